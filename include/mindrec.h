@@ -1,0 +1,245 @@
+/*
+ * mindrec.h -- C ABI of libmindrec.so, the B200 (sm_100a) implementation of the TwoTower
+ * news-recommendation hot path of tyh666/News-Recommendation-MIND.
+ *
+ * Every entry point below replaces one piece of PyTorch library work the reference does on the
+ * path  models/TwoTower.py -> models/Encoders/* -> models/Modules/Attention.py  (driven by
+ * utils/Manager.py::_train / _eval_fast).  The reference interface each one stands in for is cited
+ * as file:line (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain C: raw device pointers, explicit int64 sizes, no torch types;
+ *   - the CALLER owns every buffer (inputs, outputs, saved-for-backward, workspace); the library
+ *     allocates nothing persistent and never synchronises the device or touches the default stream;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *   - return value: 0 = MR_OK, negative = MR_ERR_*; a human-readable reason is kept per thread
+ *     and returned by mr_last_error(); nothing throws or aborts across this boundary;
+ *   - token ids / masks / labels may be int32 or int64 (`*_i64` flag) because the reference batch
+ *     dict carries int64 (utils/MIND.py:352-363);
+ *   - `precision`: MR_F32  = fp32 SIMT kernels (verification mode, 1e-5 parity with the reference)
+ *                  MR_BF16 = bf16 operands on tcgen05 tensor cores with fp32 accumulation; every
+ *                            non-GEMM step (bias, ReLU, tanh, softmax, pooling, cell state) in fp32.
+ *   - there is no CPU fallback: on a device that is not compute capability 10.x every compute entry
+ *     returns MR_ERR_NOT_SM100.
+ */
+#ifndef MINDREC_H_
+#define MINDREC_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define MR_API __attribute__((visibility("default")))
+#else
+#define MR_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  MR_OK = 0,
+  MR_ERR_BAD_SHAPE = -1,
+  MR_ERR_UNSUPPORTED = -2,
+  MR_ERR_NOT_SM100 = -3,
+  MR_ERR_LAUNCH = -4,
+  MR_ERR_NULL = -5,
+  MR_ERR_WORKSPACE = -6
+};
+
+enum { MR_F32 = 0, MR_BF16 = 1 };
+enum { MR_RNN_LSTM = 0, MR_RNN_GRU = 1 };
+
+MR_API int mr_version(void);
+MR_API const char* mr_last_error(void);
+/* MR_OK iff `device` is an sm_100-family GPU (B200). */
+MR_API int mr_device_check(int device);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches). */
+MR_API int64_t mr_launch_count(void);
+
+/* ----------------------------------------------------------------------------------------------
+ * Token-embedding gather.   models/Embeddings/BERT.py:24-41  (word_embeds = W[ids])
+ *   out[t, :] = table[ids[t], :]           ids [T], table [V,E] fp32, out [T,E] fp32
+ * Only needed when a caller wants the materialised [B,*,L,E] tensor (stand-alone module
+ * interface); the fused news encoder below never materialises it.
+ * -------------------------------------------------------------------------------------------- */
+MR_API int mr_embed_gather_f32(const void* ids, int ids_i64, const float* table, float* out,
+                        int64_t T, int64_t E, int64_t V, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Embedding-table gradient.   autograd of BERT.py:39 = embedding_dense_backward, padding_idx=0
+ *   d_table[v, :] = sum over t with ids[t]==v of d_emb[t, :];  row `padding_idx` (and every id
+ *   that does not occur) is written as zeros.  Atomic-free: a stable key sort of the token ids
+ *   followed by a two-level segmented row reduction, so the result is bit-reproducible.
+ *   d_emb is fp32 (dtype MR_F32) or bf16 (MR_BF16).
+ * -------------------------------------------------------------------------------------------- */
+MR_API int64_t mr_embed_grad_workspace_bytes(int64_t T, int64_t E, int64_t V);
+MR_API int mr_embed_grad_segreduce(const void* ids, int ids_i64, const void* d_emb, int d_emb_dtype,
+                            float* d_table, int64_t T, int64_t E, int64_t V, int64_t padding_idx,
+                            void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * CNN news encoder.   models/Encoders/CNN.py:30-51 (+ BERT.py:39 fused in front of it,
+ *                      Attention.py:5-30,56-80 fused behind it)
+ *   c[n,l,:]  = relu(conv_b + sum_tap conv_w[:, :, tap] . x[n, l+tap-1, :])     zero padded
+ *   key       = tanh(c proj_w^T + proj_b)
+ *   prob[n,:] = masked_softmax_l( query . key[n,l,:] / sqrt(H) , mask[n,:] )
+ *   news[n,:] = sum_l prob[n,l] c[n,l,:]
+ * Input is EITHER token ids (ids != NULL: rows of `table` are gathered on the fly, table is
+ * [V,E] fp32 in MR_F32 or the bf16 shadow [V,Epad] in MR_BF16) OR a dense embedding tensor
+ * (ids == NULL, emb [N*L, E] fp32).
+ * Saved for backward (caller allocated): c_save, key_save ([N*L,H] fp32, or bf16 [N*L,Hpad] in
+ * MR_BF16), prob [N,L] fp32.  c_out (optional, may be NULL) receives the fp32 token-level output
+ * the module interface returns as its first value.
+ * -------------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t N, L, E, H, V;
+  int precision;
+} mr_cnn_shape;
+
+MR_API int64_t mr_news_cnn_workspace_bytes(const mr_cnn_shape* s, int backward);
+MR_API int mr_news_cnn_fwd(const mr_cnn_shape* s,
+                    const void* ids, int ids_i64, const float* emb,
+                    const void* mask, int mask_i64,           /* NULL = no mask */
+                    const void* table,
+                    const float* conv_w, const float* conv_b, /* [H,E,3], [H] */
+                    const float* proj_w, const float* proj_b, /* [H,H], [H]   */
+                    const float* query,                       /* [H]          */
+                    void* c_save, void* key_save, float* prob, float* news,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Backward of the above.  d_news [N,H] fp32 (+ optional d_c [N*L,H] fp32 for the token-level
+ * output).  Produces d_conv_w [H,E,3], d_conv_b [H], d_proj_w [H,H], d_proj_b [H], d_query [H]
+ * (all overwritten, fp32) and d_emb [N*L,E] (fp32 in MR_F32, bf16 in MR_BF16; may be NULL when
+ * the input needs no gradient).  `table`/`ids` or `emb` are the forward inputs. */
+MR_API int mr_news_cnn_bwd(const mr_cnn_shape* s,
+                    const void* ids, int ids_i64, const float* emb, const void* table,
+                    const float* conv_w, const float* proj_w, const float* query,
+                    const void* c_save, const void* key_save, const float* prob,
+                    const float* d_news, const float* d_c,
+                    float* d_conv_w, float* d_conv_b, float* d_proj_w, float* d_proj_b,
+                    float* d_query, void* d_emb,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Recurrent user encoders.   models/Encoders/RNN.py:36-73 (RNN_User_Encoder, LSTM / GRU) and
+ *                             RNN.py:76-104 (LSTUR: h0 given, no length masking)
+ *   x [B,S,H] fp32 history vectors, lens [B] int32 (= his_mask.sum, >=1), optional h0 [B,H].
+ *   user[b,:] = hidden state after step lens[b]-1 (pack_padded_sequence + h_n semantics).
+ *   Gate order i,f,g,o (LSTM) / r,z,n (GRU); both bias vectors are added.
+ *   `reverse` != 0 runs over the flipped sequence (descend_history / LSTUR).
+ *   Saved for backward: gates [B,S,G*H] fp32 (activated gates), hs [B,S,H], cs [B,S,H] (LSTM only).
+ * -------------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t B, S, H;
+  int kind;       /* MR_RNN_LSTM | MR_RNN_GRU */
+  int reverse;
+  int precision;
+} mr_rnn_shape;
+
+MR_API int64_t mr_rnn_workspace_bytes(const mr_rnn_shape* s, int backward);
+MR_API int mr_rnn_user_fwd(const mr_rnn_shape* s, const float* x, const int32_t* lens, const float* h0,
+                    const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                    float* gates, float* hs, float* cs, float* user,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+MR_API int mr_rnn_user_bwd(const mr_rnn_shape* s, const float* x, const int32_t* lens, const float* h0,
+                    const float* w_ih, const float* w_hh,
+                    const float* gates, const float* hs, const float* cs, const float* d_user,
+                    float* d_x, float* d_h0, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Query attention pooling over a set of vectors.
+ *   models/Encoders/Pooling.py:12-25 (Attention_Pooling) and the pooling step of
+ *   MHA.py:38,71 -- scaled_dp_attention(query[1,H], r, r, mask) with key = value = r.
+ *   r [B,S,H] fp32, mask [B,S] fp32 (NULL = none), query [H] -> out [B,H], prob [B,S] (saved).
+ * Average_Pooling (Pooling.py:32-43): mean over S, mask ignored.
+ * -------------------------------------------------------------------------------------------- */
+MR_API int mr_attnpool_fwd(const float* r, const float* mask, const float* query, float* prob, float* out,
+                    int64_t B, int64_t S, int64_t H, void* stream);
+MR_API int mr_attnpool_bwd(const float* r, const float* query, const float* prob, const float* d_out,
+                    float* d_r, float* d_query_partial /* [B,H] */,
+                    int64_t B, int64_t S, int64_t H, void* stream);
+MR_API int mr_avgpool_fwd(const float* r, float* out, int64_t B, int64_t S, int64_t H, void* stream);
+MR_API int mr_avgpool_bwd(const float* d_out, float* d_r, int64_t B, int64_t S, int64_t H, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Multi-head self-attention block.   models/Modules/Attention.py:83-147 (shared q/k projection,
+ *   no output projection) as used by MHA_Encoder (MHA.py:21-39) and MHA_User_Encoder (:58-75).
+ *   qk [n,len,hn*dk], v [n,len,hn*dv] are the already projected tensors (projection GEMMs are
+ *   mr_linear_*).  mask [n,len] fp32 0/1 -> pair mask m_i*m_j (Attention.py:33-53).
+ *   ctx [n,len,hn*dv];  prob [n,hn,len,len] saved for backward.
+ * -------------------------------------------------------------------------------------------- */
+MR_API int mr_mha_core_fwd(const float* qk, const float* v, const float* mask, float* prob, float* ctx,
+                    int64_t n, int64_t len, int64_t hn, int64_t dk, int64_t dv, void* stream);
+MR_API int mr_mha_core_bwd(const float* qk, const float* v, const float* prob, const float* d_ctx,
+                    float* d_qk, float* d_v,
+                    int64_t n, int64_t len, int64_t hn, int64_t dk, int64_t dv, void* stream);
+
+/* Dense layer y = act(x W^T + b) and its gradients (nn.Linear, Attention.py:101-102; CNN.py:22).
+ *   x [M,K], w [N,K], b [N] (may be NULL), y [M,N];  act: 0 none, 1 relu, 2 tanh.
+ *   bwd: d_x = d_y W  (NULL to skip), d_w = d_y^T x, d_b = colsum(d_y); d_y is the gradient wrt
+ *   the pre-activation (callers fold the activation derivative in). */
+MR_API int64_t mr_linear_workspace_bytes(int64_t M, int64_t N, int64_t K);
+MR_API int mr_linear_fwd(const float* x, const float* w, const float* b, float* y,
+                  int64_t M, int64_t N, int64_t K, int act, int precision, void* stream);
+MR_API int mr_linear_bwd(const float* x, const float* w, const float* d_y, float* d_x, float* d_w, float* d_b,
+                  int64_t M, int64_t N, int64_t K, int precision,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+
+/* LayerNorm over the last axis, eps 1e-5 (MHA.py:18,37), with optional fused inverted-dropout keep
+ * mask (uint8, NULL = none).  mean/rstd [M] saved. */
+MR_API int mr_layernorm_fwd(const float* x, const float* gamma, const float* beta, const uint8_t* keep, float keep_scale,
+                     float* y, float* mean, float* rstd, int64_t M, int64_t H, void* stream);
+MR_API int mr_layernorm_bwd(const float* x, const float* gamma, const uint8_t* keep, float keep_scale,
+                     const float* mean, const float* rstd, const float* d_y,
+                     float* d_x, float* d_gamma_partial, float* d_beta_partial, int64_t n_partial,
+                     int64_t M, int64_t H, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Candidate scoring.   models/TwoTowerBaseModel.py:51-75 and utils/Manager.py:381-382,641
+ *   score[b,c] = <cdd[b,c,:], user[b,:]> / sqrt(H)
+ *   training: logp = log_softmax_c(score); optional fused NLL: loss_sum += -logp[b,label[b]]
+ *   eval:     prob = sigmoid(score)
+ * bwd takes d_logp [B,C] (gradient wrt the log-probabilities) and returns d_cdd, d_user.
+ * -------------------------------------------------------------------------------------------- */
+MR_API int mr_score_logsoftmax_fwd(const float* cdd, const float* user, float* logp,
+                            const void* label, int label_i64, float* loss_mean /* 1 float or NULL */,
+                            int64_t B, int64_t C, int64_t H, void* stream);
+MR_API int mr_score_logsoftmax_bwd(const float* cdd, const float* user, const float* logp, const float* d_logp,
+                            float* d_cdd, float* d_user, int64_t B, int64_t C, int64_t H, void* stream);
+/* apply_sigmoid = 0 returns the raw scores of compute_score (TwoTowerBaseModel.py:61). */
+MR_API int mr_score_sigmoid_fwd(const float* cdd, const float* user, float* prob,
+                         int64_t B, int64_t C, int64_t H, int apply_sigmoid, void* stream);
+/* Fast evaluation (TwoTowerBaseModel.py:78-84 + Manager.py:514-517), batched over impressions in
+ * CSR form: candidates of impression i are cdd_id[offsets[i] .. offsets[i+1]);
+ *   prob[j] = sigmoid(<news_table[cdd_id[j]], user[i]> / sqrt(H)). */
+MR_API int mr_score_sigmoid_gather_fwd(const float* news_table, const void* cdd_id, int id_i64,
+                                const int64_t* offsets, const float* user, float* prob,
+                                int64_t n_impr, int64_t n_cand, int64_t n_news_rows, int64_t H, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Ranking metrics per impression (CSR).   utils/Manager.py:1205-1344 (cal_metric: auc, mean_mrr,
+ * ndcg@5, ndcg@10) and Manager.py:842-850 (ordinal rank for prediction.txt).
+ *   order: descending score, ties by ascending candidate position.
+ *   metrics [n_impr,4] fp64 = (auc, mrr, ndcg@5, ndcg@10); rank [n_cand] int32 (1 = best; may be NULL).
+ * -------------------------------------------------------------------------------------------- */
+MR_API int mr_rank_metrics(const float* prob, const float* label, const int64_t* offsets,
+                    double* metrics, int32_t* rank, int64_t n_impr, int64_t n_cand, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Adam.   utils/Manager.py:404-413 (torch.optim.Adam, betas .9/.999, eps 1e-8, no weight decay)
+ *   one launch per parameter tensor; `step` is 1-based; grad_scale multiplies g first (1/world
+ *   for a summed all-reduce).  Optionally refreshes a bf16 shadow copy (row pitch `shadow_ld`
+ *   elements for rows of `row_len`; NULL = none).
+ * -------------------------------------------------------------------------------------------- */
+MR_API int mr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t step,
+                 float lr, float beta1, float beta2, float eps, float grad_scale,
+                 void* shadow_bf16, int64_t row_len, int64_t shadow_ld, void* stream);
+/* fp32 [rows, cols] -> bf16 [rows, ld] (zero padded columns). */
+MR_API int mr_cast_pad_bf16(const float* src, void* dst, int64_t rows, int64_t cols, int64_t ld, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINDREC_H_ */

@@ -1,0 +1,289 @@
+// Token-embedding gather and the atomic-free embedding-table gradient.
+//   forward : models/Embeddings/BERT.py:39            out[t,:] = W[ids[t],:]
+//   backward: autograd of the above (embedding_dense_backward with padding_idx = 0)
+//
+// Gradient algorithm (deterministic, no floating-point atomics):
+//   1. keys = token ids, values = token positions; stable LSB radix sort on the low
+//      ceil(log2 V) bits (cub::DeviceRadixSort -- integer plumbing from the CUDA toolkit);
+//   2. segment boundaries of equal ids via a flag + lower-bound search per vocabulary row;
+//   3. level 1: one warp per chunk of <= SEG_CHUNK sorted rows sums those rows of d_emb
+//      (float4 / bf16x8 coalesced row reads) -> single-chunk segments write d_table directly,
+//      longer ones write a partial row;
+//   4. level 2: one warp per multi-chunk segment adds its partial rows in order.
+//   Rows with no occurrence and the padding row are written as zeros (dense gradient, as the
+//   reference produces, so that a dense Adam step sees every row).
+#include <cub/cub.cuh>
+#include "common.cuh"
+
+namespace mr {
+
+constexpr int SEG_CHUNK = 32;
+
+__global__ void gather_rows_kernel(const void* __restrict__ ids, int is64, const float* __restrict__ table,
+                                   float* __restrict__ out, int64_t T, int64_t E, int64_t V) {
+  // one warp per row, float4 when E % 4 == 0
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  int64_t row = load_index(ids, is64, t);
+  row = row < 0 ? 0 : (row >= V ? V - 1 : row);
+  const float* src = table + row * E;
+  float* dst = out + t * E;
+  if ((E & 3) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int64_t i = lane; i < E / 4; i += 32) d4[i] = __ldg(s4 + i);
+  } else {
+    for (int64_t i = lane; i < E; i += 32) dst[i] = __ldg(src + i);
+  }
+}
+
+__global__ void make_keys_kernel(const void* __restrict__ ids, int is64, int32_t* __restrict__ keys,
+                                 int32_t* __restrict__ vals, int64_t T, int64_t V) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  int64_t row = load_index(ids, is64, t);
+  row = row < 0 ? 0 : (row >= V ? V - 1 : row);
+  keys[t] = (int32_t)row;
+  vals[t] = (int32_t)t;
+}
+
+// seg_start[v] = first sorted position whose key >= v   (v in [0, V]); binary search per row
+__global__ void seg_bounds_kernel(const int32_t* __restrict__ sorted_keys, int32_t* __restrict__ seg_start, int64_t T,
+                                  int64_t V) {
+  int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v > V) return;
+  int64_t lo = 0, hi = T;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (sorted_keys[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  seg_start[v] = (int32_t)lo;
+}
+
+// chunks per row (0 for empty / padding rows)
+__global__ void chunk_count_kernel(const int32_t* __restrict__ seg_start, int32_t* __restrict__ nchunk, int64_t V,
+                                   int64_t padding_idx) {
+  int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v > V) return;
+  if (v == V) { nchunk[v] = 0; return; }                // sentinel so the scan yields the total at [V]
+  int32_t cnt = seg_start[v + 1] - seg_start[v];
+  nchunk[v] = (v == padding_idx) ? 0 : (cnt + SEG_CHUNK - 1) / SEG_CHUNK;
+}
+
+// expands per-row chunk counts into a chunk -> row table
+__global__ void chunk_fill_kernel(const int32_t* __restrict__ nchunk, const int32_t* __restrict__ chunk_off,
+                                  int32_t* __restrict__ chunk_row, int64_t V) {
+  int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  int32_t n = nchunk[v], o = chunk_off[v];
+  for (int32_t j = 0; j < n; ++j) chunk_row[o + j] = (int32_t)v;
+}
+
+template <class T> struct RowReader;
+template <> struct RowReader<float> {
+  static constexpr int VEC = 4;
+  __device__ static void load(const float* row, int64_t i, float* o) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(row) + i);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+  __device__ static float load1(const float* row, int64_t i) { return __ldg(row + i); }
+};
+template <> struct RowReader<__nv_bfloat16> {
+  static constexpr int VEC = 8;
+  __device__ static void load(const __nv_bfloat16* row, int64_t i, float* o) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(row) + i);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); o[2 * j] = f.x; o[2 * j + 1] = f.y; }
+  }
+  __device__ static float load1(const __nv_bfloat16* row, int64_t i) { return __bfloat162float(row[i]); }
+};
+
+// level 1: warp per chunk.  MAXV = vectors per lane (E <= 32 * VEC * MAXV on the vector path)
+template <class T, int MAXV>
+__global__ void __launch_bounds__(256)
+seg_reduce_l1_kernel(const T* __restrict__ d_emb, int64_t ld, const int32_t* __restrict__ sorted_pos,
+                     const int32_t* __restrict__ seg_start, const int32_t* __restrict__ chunk_off,
+                     const int32_t* __restrict__ chunk_row, const int32_t* __restrict__ nchunk,
+                     float* __restrict__ d_table, float* __restrict__ partial, int64_t n_chunks, int64_t E, int64_t V) {
+  using R = RowReader<T>;
+  constexpr int VEC = R::VEC;
+  const int lane = threadIdx.x & 31;
+  const int64_t ch = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (ch >= n_chunks || ch >= chunk_off[V]) return;
+  const int32_t v = chunk_row[ch];
+  const int32_t j = (int32_t)ch - chunk_off[v];
+  const int32_t beg = seg_start[v] + j * SEG_CHUNK;
+  const int32_t end = min(seg_start[v + 1], beg + SEG_CHUNK);
+  float* dst = (nchunk[v] == 1) ? d_table + (int64_t)v * E : partial + ch * E;
+  const bool vec_ok = (E % VEC == 0) && (ld % VEC == 0) && (E <= 32 * VEC * MAXV);
+  if (vec_ok) {
+    float acc[MAXV][VEC];
+#pragma unroll
+    for (int a = 0; a < MAXV; ++a)
+#pragma unroll
+      for (int b = 0; b < VEC; ++b) acc[a][b] = 0.f;
+    const int64_t nv = E / VEC;
+    for (int32_t r = beg; r < end; ++r) {
+      const T* row = d_emb + (int64_t)sorted_pos[r] * ld;
+#pragma unroll
+      for (int a = 0; a < MAXV; ++a) {
+        int64_t i = lane + 32 * a;
+        if (i < nv) {
+          float t[VEC];
+          R::load(row, i, t);
+#pragma unroll
+          for (int b = 0; b < VEC; ++b) acc[a][b] += t[b];
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < MAXV; ++a) {
+      int64_t i = lane + 32 * a;
+      if (i < nv) {
+#pragma unroll
+        for (int b = 0; b < VEC; ++b) dst[i * VEC + b] = acc[a][b];
+      }
+    }
+  } else {
+    for (int64_t e = lane; e < E; e += 32) {
+      float s = 0.f;
+      for (int32_t r = beg; r < end; ++r) s += R::load1(d_emb + (int64_t)sorted_pos[r] * ld, e);
+      dst[e] = s;
+    }
+  }
+}
+
+// level 2: warp per vocabulary row; zero-fills empty rows, folds partial rows of long segments
+__global__ void __launch_bounds__(256)
+seg_reduce_l2_kernel(const int32_t* __restrict__ chunk_off, const int32_t* __restrict__ nchunk,
+                     const float* __restrict__ partial, float* __restrict__ d_table, int64_t V, int64_t E) {
+  const int lane = threadIdx.x & 31;
+  const int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (v >= V) return;
+  const int32_t n = nchunk[v];
+  if (n == 1) return;                                   // written by level 1
+  float* dst = d_table + v * E;
+  if (n == 0) {
+    for (int64_t e = lane; e < E; e += 32) dst[e] = 0.f;
+    return;
+  }
+  const float* src = partial + (int64_t)chunk_off[v] * E;
+  for (int64_t e = lane; e < E; e += 32) {
+    float s = 0.f;
+    for (int32_t j = 0; j < n; ++j) s += src[(int64_t)j * E + e];
+    dst[e] = s;
+  }
+}
+
+struct EmbedGradPlan {
+  int64_t T, E, V, max_chunks;
+  size_t cub_sort_bytes, cub_scan_bytes;
+};
+
+static EmbedGradPlan plan_embed_grad(int64_t T, int64_t E, int64_t V) {
+  EmbedGradPlan p{T, E, V, 0, 0, 0};
+  p.max_chunks = ceil_div(T, SEG_CHUNK) + V;
+  int bits = 1;
+  while ((1ll << bits) < V) ++bits;
+  cub::DeviceRadixSort::SortPairs(nullptr, p.cub_sort_bytes, (const int32_t*)nullptr, (int32_t*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)T, 0, bits);
+  cub::DeviceScan::ExclusiveSum(nullptr, p.cub_scan_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, (int)V + 1);
+  return p;
+}
+
+}  // namespace mr
+
+extern "C" {
+
+int mr_embed_gather_f32(const void* ids, int ids_i64, const float* table, float* out, int64_t T, int64_t E, int64_t V,
+                        void* stream) {
+  using namespace mr;
+  if (int rc = require_sm100()) return rc;
+  MR_REQUIRE(ids && table && out, MR_ERR_NULL, "mr_embed_gather_f32: null pointer");
+  MR_REQUIRE(T >= 0 && E >= 1 && V >= 1, MR_ERR_BAD_SHAPE, "mr_embed_gather_f32: T=%lld E=%lld V=%lld", (long long)T,
+             (long long)E, (long long)V);
+  if (T == 0) return MR_OK;
+  gather_rows_kernel<<<(unsigned)ceil_div(T, 8), 256, 0, as_stream(stream)>>>(ids, ids_i64, table, out, T, E, V);
+  MR_CHECK_LAUNCH("gather_rows_kernel");
+  return MR_OK;
+}
+
+int64_t mr_embed_grad_workspace_bytes(int64_t T, int64_t E, int64_t V) {
+  using namespace mr;
+  if (T < 0 || E < 1 || V < 1 || T >= (1ll << 31)) return -1;
+  EmbedGradPlan p = plan_embed_grad(T, E, V);
+  int64_t b = 0;
+  b += 4 * arena_bytes(T, 4);                 // keys, vals, sorted keys, sorted vals
+  b += arena_bytes(V + 1, 4);                 // seg_start
+  b += 2 * arena_bytes(V + 1, 4);             // nchunk, chunk_off
+  b += arena_bytes(p.max_chunks, 4);          // chunk_row
+  b += arena_bytes(p.max_chunks * E, 4);      // partial rows
+  b += arena_bytes((int64_t)p.cub_sort_bytes, 1) + arena_bytes((int64_t)p.cub_scan_bytes, 1);
+  return b + 256;
+}
+
+int mr_embed_grad_segreduce(const void* ids, int ids_i64, const void* d_emb, int d_emb_dtype, float* d_table, int64_t T,
+                            int64_t E, int64_t V, int64_t padding_idx, void* workspace, int64_t workspace_bytes,
+                            void* stream) {
+  using namespace mr;
+  if (int rc = require_sm100()) return rc;
+  MR_REQUIRE(ids && d_emb && d_table, MR_ERR_NULL, "mr_embed_grad_segreduce: null pointer");
+  MR_REQUIRE(T >= 0 && E >= 1 && V >= 1 && T < (1ll << 31), MR_ERR_BAD_SHAPE, "mr_embed_grad_segreduce: T=%lld E=%lld V=%lld",
+             (long long)T, (long long)E, (long long)V);
+  MR_REQUIRE(d_emb_dtype == MR_F32 || d_emb_dtype == MR_BF16, MR_ERR_UNSUPPORTED, "mr_embed_grad_segreduce: dtype %d", d_emb_dtype);
+  cudaStream_t st = as_stream(stream);
+  if (T == 0) {
+    cudaMemsetAsync(d_table, 0, sizeof(float) * V * E, st);
+    return MR_OK;
+  }
+  EmbedGradPlan p = plan_embed_grad(T, E, V);
+  Arena ar(workspace, workspace_bytes);
+  int32_t* keys = ar.take<int32_t>(T);
+  int32_t* vals = ar.take<int32_t>(T);
+  int32_t* skeys = ar.take<int32_t>(T);
+  int32_t* svals = ar.take<int32_t>(T);
+  int32_t* seg_start = ar.take<int32_t>(V + 1);
+  int32_t* nchunk = ar.take<int32_t>(V + 1);
+  int32_t* chunk_off = ar.take<int32_t>(V + 1);
+  int32_t* chunk_row = ar.take<int32_t>(p.max_chunks);
+  float* partial = ar.take<float>(p.max_chunks * E);
+  void* cub_sort = ar.take<char>((int64_t)p.cub_sort_bytes);
+  void* cub_scan = ar.take<char>((int64_t)p.cub_scan_bytes);
+  MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "mr_embed_grad_segreduce: workspace too small (%lld given)", (long long)workspace_bytes);
+
+  make_keys_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, st>>>(ids, ids_i64, keys, vals, T, V);
+  MR_CHECK_LAUNCH("make_keys_kernel");
+  int bits = 1;
+  while ((1ll << bits) < V) ++bits;
+  size_t sb = p.cub_sort_bytes;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_sort, sb, keys, skeys, vals, svals, (int)T, 0, bits, st);
+  MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "radix sort: %s", cudaGetErrorString(e));
+  count_launch(2 * ((bits + 7) / 8) + 1);
+  seg_bounds_kernel<<<(unsigned)ceil_div(V + 1, 256), 256, 0, st>>>(skeys, seg_start, T, V);
+  MR_CHECK_LAUNCH("seg_bounds_kernel");
+  chunk_count_kernel<<<(unsigned)ceil_div(V + 1, 256), 256, 0, st>>>(seg_start, nchunk, V, padding_idx);
+  MR_CHECK_LAUNCH("chunk_count_kernel");
+  size_t cb = p.cub_scan_bytes;
+  e = cub::DeviceScan::ExclusiveSum(cub_scan, cb, nchunk, chunk_off, (int)V + 1, st);
+  MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "scan: %s", cudaGetErrorString(e));
+  count_launch(2);
+  chunk_fill_kernel<<<(unsigned)ceil_div(V, 256), 256, 0, st>>>(nchunk, chunk_off, chunk_row, V);
+  MR_CHECK_LAUNCH("chunk_fill_kernel");
+  // The true chunk count (chunk_off[V]) is only known on the device; launch level 1 for the bound
+  // ceil(T/SEG_CHUNK)+V and let surplus warps exit (no host sync on this path).
+  const int64_t E4 = E;
+  if (d_emb_dtype == MR_F32)
+    seg_reduce_l1_kernel<float, 3><<<(unsigned)ceil_div(p.max_chunks, 8), 256, 0, st>>>(
+        static_cast<const float*>(d_emb), E4, svals, seg_start, chunk_off, chunk_row, nchunk, d_table, partial, p.max_chunks, E, V);
+  else
+    seg_reduce_l1_kernel<__nv_bfloat16, 2><<<(unsigned)ceil_div(p.max_chunks, 8), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(d_emb), E4, svals, seg_start, chunk_off, chunk_row, nchunk, d_table, partial, p.max_chunks, E, V);
+  MR_CHECK_LAUNCH("seg_reduce_l1_kernel");
+  seg_reduce_l2_kernel<<<(unsigned)ceil_div(V, 8), 256, 0, st>>>(chunk_off, nchunk, partial, d_table, V, E);
+  MR_CHECK_LAUNCH("seg_reduce_l2_kernel");
+  return MR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,475 @@
+"""torch.autograd.Function wrappers over the C ABI (libmindrec.so).
+
+PyTorch is used for memory, streams and autograd bookkeeping only: every arithmetic step on
+the hot path is a hand-written sm_100a kernel behind include/mindrec.h.  Nothing here has a
+CPU or eager-PyTorch fallback; a missing library or a non-B200 device raises.
+"""
+from __future__ import annotations
+
+from ctypes import byref, c_float, c_int
+
+import torch
+
+from . import _lib
+from ._lib import CnnShape, RnnShape, MR_BF16, MR_F32, check, index_flag, ptr, stream_ptr, workspace
+
+PRECISIONS = {"fp32": MR_F32, "f32": MR_F32, "bf16": MR_BF16}
+
+
+def pad_to(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _idx(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype not in (torch.int32, torch.int64):
+        t = t.long()
+    return t.contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# embedding gather                                                  models/Embeddings/BERT.py:39
+# --------------------------------------------------------------------------------------------
+def embed_grad(ids: torch.Tensor, d_emb: torch.Tensor, V: int, E: int, padding_idx: int = 0) -> torch.Tensor:
+    """Dense [V,E] fp32 gradient of the table from per-token gradients (atomic-free segmented
+    reduction, mr_embed_grad_segreduce)."""
+    lib = _lib.load()
+    T = ids.numel()
+    d_table = torch.empty(V, E, dtype=torch.float32, device=d_emb.device)
+    ws = workspace(lib.mr_embed_grad_workspace_bytes(T, E, V), d_emb.device)
+    dt = MR_BF16 if d_emb.dtype == torch.bfloat16 else MR_F32
+    check(lib.mr_embed_grad_segreduce(ptr(ids), index_flag(ids), ptr(d_emb), dt, ptr(d_table), T, E, V, padding_idx,
+                                      ptr(ws), ws.numel(), stream_ptr(d_emb.device)), "mr_embed_grad_segreduce")
+    return d_table
+
+
+class EmbeddingGather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, table, padding_idx):
+        lib = _lib.load()
+        ids_c = _idx(ids)
+        table_c = _f32c(table)
+        V, E = table_c.shape
+        out = torch.empty(*ids.shape, E, dtype=torch.float32, device=table.device)
+        check(lib.mr_embed_gather_f32(ptr(ids_c), index_flag(ids_c), ptr(table_c), ptr(out), ids_c.numel(), E, V,
+                                      stream_ptr(table.device)), "mr_embed_gather_f32")
+        ctx.save_for_backward(ids_c)
+        ctx.shape = (V, E)
+        ctx.padding_idx = -1 if padding_idx is None else int(padding_idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (ids_c,) = ctx.saved_tensors
+        V, E = ctx.shape
+        d_table = embed_grad(ids_c, _f32c(d_out), V, E, ctx.padding_idx)
+        return None, d_table, None
+
+
+# --------------------------------------------------------------------------------------------
+# CNN news encoder                                                  models/Encoders/CNN.py:30-51
+# --------------------------------------------------------------------------------------------
+class NewsCNN(torch.autograd.Function):
+    """(ids | emb, mask, table, conv_w, conv_b, proj_w, proj_b, query) -> (c, news).
+
+    ids path: `table` is the fp32 master table [V,E]; in bf16 mode `table_bf16` is its padded
+    bf16 shadow [V,Epad] that the kernel gathers from.  The gradient of the table is produced
+    by the segmented reduction inside backward (padding row skipped)."""
+
+    @staticmethod
+    def forward(ctx, ids, emb, mask, table, table_bf16, conv_w, conv_b, proj_w, proj_b, query, precision, want_c,
+                padding_idx):
+        lib = _lib.load()
+        dev = conv_w.device
+        H, E, _ = conv_w.shape
+        if ids is not None:
+            ids_c = _idx(ids)
+            L = ids_c.shape[-1]
+            N = ids_c.numel() // L
+            emb_c = None
+            V = table.shape[0]
+            lead = ids.shape[:-1]
+        else:
+            ids_c = None
+            emb_c = _f32c(emb)
+            L = emb_c.shape[-2]
+            N = emb_c.numel() // (L * E)
+            V = 0
+            lead = emb.shape[:-2]
+        mask_c = None if mask is None else _idx(mask)
+        shape = CnnShape(N, L, E, H, V, precision)
+        if precision == MR_BF16:
+            Hp = pad_to(H, 16)
+            c_save = torch.empty(N * L, Hp, dtype=torch.bfloat16, device=dev)
+            key_save = torch.empty(N * L, Hp, dtype=torch.bfloat16, device=dev)
+            tab = table_bf16 if ids is not None else None
+        else:
+            c_save = torch.empty(N * L, H, dtype=torch.float32, device=dev)
+            key_save = torch.empty(N * L, H, dtype=torch.float32, device=dev)
+            tab = _f32c(table) if ids is not None else None
+        prob = torch.empty(N, L, dtype=torch.float32, device=dev)
+        news = torch.empty(N, H, dtype=torch.float32, device=dev)
+        cw, cb, pw, pb, q = _f32c(conv_w), _f32c(conv_b), _f32c(proj_w), _f32c(proj_b), _f32c(query)
+        ws = workspace(lib.mr_news_cnn_workspace_bytes(byref(shape), 0), dev)
+        check(lib.mr_news_cnn_fwd(byref(shape), ptr(ids_c), index_flag(ids_c) if ids_c is not None else 0, ptr(emb_c),
+                                  ptr(mask_c), index_flag(mask_c) if mask_c is not None else 0, ptr(tab), ptr(cw),
+                                  ptr(cb), ptr(pw), ptr(pb), ptr(q), ptr(c_save), ptr(key_save), ptr(prob), ptr(news),
+                                  ptr(ws), ws.numel(), stream_ptr(dev)), "mr_news_cnn_fwd")
+        ctx.save_for_backward(ids_c, emb_c, tab, cw, pw, q, c_save, key_save, prob)
+        ctx.shape = shape
+        ctx.table_shape = None if table is None else tuple(table.shape)
+        ctx.padding_idx = -1 if padding_idx is None else int(padding_idx)
+        ctx.need_table_grad = table is not None and table.requires_grad
+        ctx.need_emb_grad = emb is not None and emb.requires_grad
+        ctx.set_materialize_grads(False)
+        news_out = news.view(*lead, H)
+        if want_c:
+            c_out = c_save if precision == MR_F32 else c_save[:, :H].float()
+            c_out = c_out.view(*lead, L, H)
+        else:
+            c_out = None
+        return c_out, news_out
+
+    @staticmethod
+    def backward(ctx, d_c, d_news):
+        lib = _lib.load()
+        ids_c, emb_c, tab, cw, pw, q, c_save, key_save, prob = ctx.saved_tensors
+        s = ctx.shape
+        dev = cw.device
+        N, L, E, H = s.N, s.L, s.E, s.H
+        d_news_c = torch.zeros(N, H, dtype=torch.float32, device=dev) if d_news is None else _f32c(d_news).view(N, H)
+        d_c_c = None if d_c is None else _f32c(d_c).view(N * L, H)
+        d_cw = torch.empty(H, E, 3, dtype=torch.float32, device=dev)
+        d_cb = torch.empty(H, dtype=torch.float32, device=dev)
+        d_pw = torch.empty(H, H, dtype=torch.float32, device=dev)
+        d_pb = torch.empty(H, dtype=torch.float32, device=dev)
+        d_q = torch.empty(H, dtype=torch.float32, device=dev)
+        need_x = ctx.need_table_grad or ctx.need_emb_grad
+        d_emb = None
+        if need_x:
+            d_emb = torch.empty(N * L, E, dtype=torch.bfloat16 if s.precision == MR_BF16 else torch.float32, device=dev)
+        ws = workspace(lib.mr_news_cnn_workspace_bytes(byref(s), 1), dev)
+        check(lib.mr_news_cnn_bwd(byref(s), ptr(ids_c), index_flag(ids_c) if ids_c is not None else 0, ptr(emb_c),
+                                  ptr(tab), ptr(cw), ptr(pw), ptr(q), ptr(c_save), ptr(key_save), ptr(prob),
+                                  ptr(d_news_c), ptr(d_c_c), ptr(d_cw), ptr(d_cb), ptr(d_pw), ptr(d_pb), ptr(d_q),
+                                  ptr(d_emb), ptr(ws), ws.numel(), stream_ptr(dev)), "mr_news_cnn_bwd")
+        d_table = None
+        d_emb_out = None
+        if ctx.need_table_grad:
+            V, _ = ctx.table_shape
+            d_table = embed_grad(ids_c.view(-1), d_emb, V, E, ctx.padding_idx)
+        elif ctx.need_emb_grad:
+            d_emb_out = d_emb.float().view(*emb_c.shape) if d_emb.dtype != torch.float32 else d_emb.view(*emb_c.shape)
+        return (None, d_emb_out, None, d_table, None, d_cw, d_cb, d_pw, d_pb, d_q.view(1, H), None, None, None)
+
+
+# --------------------------------------------------------------------------------------------
+# recurrent user encoders                                           models/Encoders/RNN.py:36-104
+# --------------------------------------------------------------------------------------------
+class RNNUser(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, lens, h0, w_ih, w_hh, b_ih, b_hh, kind, reverse, precision):
+        lib = _lib.load()
+        dev = x.device
+        xc = _f32c(x)
+        B, S, H = xc.shape
+        G = 4 if kind == _lib.MR_RNN_LSTM else 3
+        shape = RnnShape(B, S, H, kind, 1 if reverse else 0, precision)
+        lens_c = None if lens is None else lens.to(device=dev, dtype=torch.int32).contiguous()
+        h0_c = None if h0 is None else _f32c(h0)
+        wi, wh, bi, bh = _f32c(w_ih), _f32c(w_hh), _f32c(b_ih), _f32c(b_hh)
+        gates = torch.empty(B, S, G * H, dtype=torch.float32, device=dev)
+        hs = torch.empty(B, S, H, dtype=torch.float32, device=dev)
+        cs = torch.empty(B, S, H, dtype=torch.float32, device=dev)
+        user = torch.empty(B, H, dtype=torch.float32, device=dev)
+        ws = workspace(lib.mr_rnn_workspace_bytes(byref(shape), 0), dev)
+        check(lib.mr_rnn_user_fwd(byref(shape), ptr(xc), ptr(lens_c), ptr(h0_c), ptr(wi), ptr(wh), ptr(bi), ptr(bh),
+                                  ptr(gates), ptr(hs), ptr(cs), ptr(user), ptr(ws), ws.numel(), stream_ptr(dev)),
+              "mr_rnn_user_fwd")
+        ctx.save_for_backward(xc, lens_c, h0_c, wi, wh, gates, hs, cs)
+        ctx.shape = shape
+        ctx.need_h0 = h0 is not None and h0.requires_grad
+        return user.view(B, 1, H)
+
+    @staticmethod
+    def backward(ctx, d_user):
+        lib = _lib.load()
+        xc, lens_c, h0_c, wi, wh, gates, hs, cs = ctx.saved_tensors
+        s = ctx.shape
+        dev = xc.device
+        B, S, H = s.B, s.S, s.H
+        G = 4 if s.kind == _lib.MR_RNN_LSTM else 3
+        du = _f32c(d_user).view(B, H)
+        d_x = torch.empty(B, S, H, dtype=torch.float32, device=dev)
+        d_h0 = torch.empty(B, H, dtype=torch.float32, device=dev) if ctx.need_h0 else None
+        d_wi = torch.empty(G * H, H, dtype=torch.float32, device=dev)
+        d_wh = torch.empty(G * H, H, dtype=torch.float32, device=dev)
+        d_bi = torch.empty(G * H, dtype=torch.float32, device=dev)
+        d_bh = torch.empty(G * H, dtype=torch.float32, device=dev)
+        ws = workspace(lib.mr_rnn_workspace_bytes(byref(s), 1), dev)
+        check(lib.mr_rnn_user_bwd(byref(s), ptr(xc), ptr(lens_c), ptr(h0_c), ptr(wi), ptr(wh), ptr(gates), ptr(hs),
+                                  ptr(cs), ptr(du), ptr(d_x), ptr(d_h0), ptr(d_wi), ptr(d_wh), ptr(d_bi), ptr(d_bh),
+                                  ptr(ws), ws.numel(), stream_ptr(dev)), "mr_rnn_user_bwd")
+        return d_x, None, d_h0, d_wi, d_wh, d_bi, d_bh, None, None, None
+
+
+# --------------------------------------------------------------------------------------------
+# pooling user encoders                                             models/Encoders/Pooling.py
+# --------------------------------------------------------------------------------------------
+class AttnPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, r, mask, query):
+        lib = _lib.load()
+        rc = _f32c(r)
+        B, S, H = rc.shape
+        dev = rc.device
+        mc = None if mask is None else mask.to(device=dev, dtype=torch.float32).reshape(B, S).contiguous()
+        q = _f32c(query).view(-1)
+        prob = torch.empty(B, S, dtype=torch.float32, device=dev)
+        out = torch.empty(B, H, dtype=torch.float32, device=dev)
+        check(lib.mr_attnpool_fwd(ptr(rc), ptr(mc), ptr(q), ptr(prob), ptr(out), B, S, H, stream_ptr(dev)), "mr_attnpool_fwd")
+        ctx.save_for_backward(rc, q, prob)
+        return out.view(B, 1, H)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        rc, q, prob = ctx.saved_tensors
+        B, S, H = rc.shape
+        dev = rc.device
+        go = _f32c(d_out).view(B, H)
+        d_r = torch.empty_like(rc)
+        dq_part = torch.empty(B, H, dtype=torch.float32, device=dev)
+        check(lib.mr_attnpool_bwd(ptr(rc), ptr(q), ptr(prob), ptr(go), ptr(d_r), ptr(dq_part), B, S, H, stream_ptr(dev)),
+              "mr_attnpool_bwd")
+        return d_r, None, column_sum(dq_part).view(1, H)
+
+
+class AvgPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, r):
+        lib = _lib.load()
+        rc = _f32c(r)
+        B, S, H = rc.shape
+        out = torch.empty(B, H, dtype=torch.float32, device=rc.device)
+        check(lib.mr_avgpool_fwd(ptr(rc), ptr(out), B, S, H, stream_ptr(rc.device)), "mr_avgpool_fwd")
+        ctx.shape = (B, S, H)
+        return out.view(B, 1, H)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        B, S, H = ctx.shape
+        go = _f32c(d_out).view(B, H)
+        d_r = torch.empty(B, S, H, dtype=torch.float32, device=go.device)
+        check(lib.mr_avgpool_bwd(ptr(go), ptr(d_r), B, S, H, stream_ptr(go.device)), "mr_avgpool_bwd")
+        return d_r
+
+
+def column_sum(x: torch.Tensor) -> torch.Tensor:
+    """[R,C] -> [C] through the library's linear-layer bias-gradient path (fixed order)."""
+    lib = _lib.load()
+    R, C = x.shape
+    out = torch.empty(C, dtype=torch.float32, device=x.device)
+    ws = workspace(lib.mr_linear_workspace_bytes(R, C, 1), x.device)
+    check(lib.mr_linear_bwd(None, None, ptr(x), None, None, ptr(out), R, C, 1, MR_F32, ptr(ws), ws.numel(),
+                            stream_ptr(x.device)), "mr_linear_bwd(colsum)")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# scoring                                                  models/TwoTowerBaseModel.py:51-75
+# --------------------------------------------------------------------------------------------
+class ScoreLogSoftmax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cdd, user):
+        lib = _lib.load()
+        cc, uc = _f32c(cdd), _f32c(user)
+        B, C, H = cc.shape
+        logp = torch.empty(B, C, dtype=torch.float32, device=cc.device)
+        check(lib.mr_score_logsoftmax_fwd(ptr(cc), ptr(uc), ptr(logp), None, 0, None, B, C, H, stream_ptr(cc.device)),
+              "mr_score_logsoftmax_fwd")
+        ctx.save_for_backward(cc, uc, logp)
+        return logp
+
+    @staticmethod
+    def backward(ctx, d_logp):
+        lib = _lib.load()
+        cc, uc, logp = ctx.saved_tensors
+        B, C, H = cc.shape
+        g = _f32c(d_logp)
+        d_cdd = torch.empty_like(cc)
+        d_user = torch.empty(B, 1, H, dtype=torch.float32, device=cc.device)
+        check(lib.mr_score_logsoftmax_bwd(ptr(cc), ptr(uc), ptr(logp), ptr(g), ptr(d_cdd), ptr(d_user), B, C, H,
+                                          stream_ptr(cc.device)), "mr_score_logsoftmax_bwd")
+        return d_cdd, d_user
+
+
+def score_sigmoid(cdd: torch.Tensor, user: torch.Tensor, apply_sigmoid: bool = True) -> torch.Tensor:
+    """sigmoid(<cdd, user>/sqrt(H)), eval only (TwoTowerBaseModel.py:72-73,83); raw scores when
+    apply_sigmoid is False (compute_score, TwoTowerBaseModel.py:61)."""
+    lib = _lib.load()
+    cc, uc = _f32c(cdd), _f32c(user)
+    B, C, H = cc.shape
+    prob = torch.empty(B, C, dtype=torch.float32, device=cc.device)
+    check(lib.mr_score_sigmoid_fwd(ptr(cc), ptr(uc), ptr(prob), B, C, H, 1 if apply_sigmoid else 0,
+                                   stream_ptr(cc.device)), "mr_score_sigmoid_fwd")
+    return prob
+
+
+def score_sigmoid_gather(table: torch.Tensor, cdd_id: torch.Tensor, offsets: torch.Tensor, user: torch.Tensor) -> torch.Tensor:
+    """Batched fast-eval scoring over CSR impressions (TwoTowerBaseModel.py:78-84)."""
+    lib = _lib.load()
+    tc, uc = _f32c(table), _f32c(user).view(-1, table.shape[1])
+    ids = _idx(cdd_id).view(-1)
+    off = offsets.to(device=tc.device, dtype=torch.int64).contiguous()
+    n_impr = off.numel() - 1
+    prob = torch.empty(ids.numel(), dtype=torch.float32, device=tc.device)
+    check(lib.mr_score_sigmoid_gather_fwd(ptr(tc), ptr(ids), index_flag(ids), ptr(off), ptr(uc), ptr(prob), n_impr,
+                                          ids.numel(), tc.shape[0], tc.shape[1], stream_ptr(tc.device)),
+          "mr_score_sigmoid_gather_fwd")
+    return prob
+
+
+def rank_metrics(prob: torch.Tensor, label: torch.Tensor, offsets: torch.Tensor, want_rank: bool = False):
+    """Per-impression (auc, mrr, ndcg@5, ndcg@10) in fp64 and optional ordinal ranks
+    (utils/Manager.py:1205-1344, 842-850)."""
+    lib = _lib.load()
+    pc = _f32c(prob).view(-1)
+    lc = label.to(device=pc.device, dtype=torch.float32).contiguous().view(-1)
+    off = offsets.to(device=pc.device, dtype=torch.int64).contiguous()
+    n_impr = off.numel() - 1
+    metrics = torch.empty(n_impr, 4, dtype=torch.float64, device=pc.device)
+    rank = torch.empty(pc.numel(), dtype=torch.int32, device=pc.device) if want_rank else None
+    check(lib.mr_rank_metrics(ptr(pc), ptr(lc), ptr(off), ptr(metrics), ptr(rank), n_impr, pc.numel(),
+                              stream_ptr(pc.device)), "mr_rank_metrics")
+    return metrics, rank
+
+
+# --------------------------------------------------------------------------------------------
+# optimiser                                                         utils/Manager.py:404-413
+# --------------------------------------------------------------------------------------------
+def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, shadow=None):
+    lib = _lib.load()
+    n = p.numel()
+    row_len, ld = (0, 0)
+    if shadow is not None:
+        row_len, ld = p.shape[-1], shadow.shape[-1]
+    check(lib.mr_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), n, step, c_float(lr), c_float(beta1), c_float(beta2),
+                           c_float(eps), c_float(grad_scale), ptr(shadow), row_len, ld, stream_ptr(p.device)),
+          "mr_adam_step")
+
+
+def cast_pad_bf16(src: torch.Tensor, ld: int) -> torch.Tensor:
+    lib = _lib.load()
+    sc = _f32c(src)
+    rows, cols = sc.shape
+    dst = torch.empty(rows, ld, dtype=torch.bfloat16, device=sc.device)
+    check(lib.mr_cast_pad_bf16(ptr(sc), ptr(dst), rows, cols, ld, stream_ptr(sc.device)), "mr_cast_pad_bf16")
+    return dst
+
+
+# --------------------------------------------------------------------------------------------
+# MHA building blocks                          models/Modules/Attention.py:83-147, Encoders/MHA.py
+# --------------------------------------------------------------------------------------------
+class Linear(torch.autograd.Function):
+    """y = act(x W^T + b)  (act: 0 none)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        lib = _lib.load()
+        xc, wc = _f32c(x), _f32c(w)
+        bc = None if b is None else _f32c(b)
+        N, K = wc.shape
+        M = xc.numel() // K
+        y = torch.empty(*x.shape[:-1], N, dtype=torch.float32, device=xc.device)
+        check(lib.mr_linear_fwd(ptr(xc), ptr(wc), ptr(bc), ptr(y), M, N, K, act, MR_F32, stream_ptr(xc.device)),
+              "mr_linear_fwd")
+        if act != 0:
+            raise RuntimeError("ops.Linear only differentiates act=0")
+        ctx.save_for_backward(xc, wc)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, d_y):
+        lib = _lib.load()
+        xc, wc = ctx.saved_tensors
+        N, K = wc.shape
+        M = xc.numel() // K
+        g = _f32c(d_y).view(M, N)
+        d_x = torch.empty_like(xc)
+        d_w = torch.empty_like(wc)
+        d_b = torch.empty(N, dtype=torch.float32, device=xc.device) if ctx.has_bias else None
+        ws = workspace(lib.mr_linear_workspace_bytes(M, N, K), xc.device)
+        check(lib.mr_linear_bwd(ptr(xc), ptr(wc), ptr(g), ptr(d_x), ptr(d_w), ptr(d_b), M, N, K, MR_F32, ptr(ws),
+                                ws.numel(), stream_ptr(xc.device)), "mr_linear_bwd")
+        return d_x, d_w, d_b, None
+
+
+class MHACore(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qk, v, mask, head_num):
+        lib = _lib.load()
+        qc, vc = _f32c(qk), _f32c(v)
+        n, length, dkh = qc.shape
+        dk, dv = dkh // head_num, vc.shape[-1] // head_num
+        mc = None if mask is None else mask.to(device=qc.device, dtype=torch.float32).reshape(n, length).contiguous()
+        prob = torch.empty(n, head_num, length, length, dtype=torch.float32, device=qc.device)
+        out = torch.empty(n, length, head_num * dv, dtype=torch.float32, device=qc.device)
+        check(lib.mr_mha_core_fwd(ptr(qc), ptr(vc), ptr(mc), ptr(prob), ptr(out), n, length, head_num, dk, dv,
+                                  stream_ptr(qc.device)), "mr_mha_core_fwd")
+        ctx.save_for_backward(qc, vc, prob)
+        ctx.dims = (n, length, head_num, dk, dv)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        qc, vc, prob = ctx.saved_tensors
+        n, length, hn, dk, dv = ctx.dims
+        g = _f32c(d_out)
+        d_qk, d_v = torch.empty_like(qc), torch.empty_like(vc)
+        check(lib.mr_mha_core_bwd(ptr(qc), ptr(vc), ptr(prob), ptr(g), ptr(d_qk), ptr(d_v), n, length, hn, dk, dv,
+                                  stream_ptr(qc.device)), "mr_mha_core_bwd")
+        return d_qk, d_v, None, None
+
+
+class LayerNorm(torch.autograd.Function):
+    N_PARTIAL = 296
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, keep, keep_scale):
+        lib = _lib.load()
+        xc, gc, bc = _f32c(x), _f32c(gamma), _f32c(beta)
+        H = xc.shape[-1]
+        M = xc.numel() // H
+        kc = None if keep is None else keep.contiguous()
+        y = torch.empty_like(xc)
+        mean = torch.empty(M, dtype=torch.float32, device=xc.device)
+        rstd = torch.empty(M, dtype=torch.float32, device=xc.device)
+        check(lib.mr_layernorm_fwd(ptr(xc), ptr(gc), ptr(bc), ptr(kc), c_float(keep_scale), ptr(y), ptr(mean),
+                                   ptr(rstd), M, H, stream_ptr(xc.device)), "mr_layernorm_fwd")
+        ctx.save_for_backward(xc, gc, kc, mean, rstd)
+        ctx.keep_scale = keep_scale
+        return y
+
+    @staticmethod
+    def backward(ctx, d_y):
+        lib = _lib.load()
+        xc, gc, kc, mean, rstd = ctx.saved_tensors
+        H = xc.shape[-1]
+        M = xc.numel() // H
+        g = _f32c(d_y)
+        d_x = torch.empty_like(xc)
+        npart = LayerNorm.N_PARTIAL
+        dg = torch.empty(npart, H, dtype=torch.float32, device=xc.device)
+        db = torch.empty(npart, H, dtype=torch.float32, device=xc.device)
+        check(lib.mr_layernorm_bwd(ptr(xc), ptr(gc), ptr(kc), c_float(ctx.keep_scale), ptr(mean), ptr(rstd), ptr(g),
+                                   ptr(d_x), ptr(dg), ptr(db), npart, M, H, stream_ptr(xc.device)), "mr_layernorm_bwd")
+        return d_x, column_sum(dg), column_sum(db), None, None

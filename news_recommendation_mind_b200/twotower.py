@@ -1,0 +1,132 @@
+"""TwoTower model: drop-in for models/TwoTower.py + models/TwoTowerBaseModel.py.
+
+Same constructor ``TwoTower(manager, embedding, encoderN, encoderU)``, same methods
+(forward / encode_news / encode_user / compute_score / predict_fast / init_encoding /
+destroy_encoding / init_embedding / destroy_embedding), same attributes (.device, .hidden_dim,
+.name), same state-dict keys.  ``x`` is the batch dict produced by utils/MIND.py (CPU tensors);
+the model moves what it needs to its device exactly as the reference does.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .modules import BERT_Embedding, CNN_Encoder
+
+
+class TwoTowerBaseModel(nn.Module):
+    """models/TwoTowerBaseModel.py:6-84."""
+
+    def __init__(self, manager):
+        super().__init__()
+        self.scale = manager.scale
+        self.cdd_size = manager.cdd_size
+        self.mode = "test" if manager.mode == "test" else "dev"
+        self.impr_size = manager.impr_size
+        self.batch_size_news = manager.batch_size_news
+        self.encoding = False
+        self.his_size = manager.his_size
+        self.signal_length = manager.signal_length
+        self.device = manager.device
+        self.hidden_dim = manager.bert_dim
+
+    def init_encoding(self):
+        self.encoding = True
+
+    def destroy_encoding(self):
+        self.encoding = False
+
+    def init_embedding(self, news_reprs: torch.Tensor = None):
+        """Prepare fast inference.  The reference reloads ``news.pt`` from disk on every rank
+        (TwoTowerBaseModel.py:34-39); passing the table directly (e.g. the all-gathered shards
+        of evaluate.encode_all_news) skips the disk round trip."""
+        if news_reprs is None:
+            cache_directory = "data/cache/tensors/{}/{}/{}/".format(self.name, self.scale, self.mode)
+            news_reprs = torch.load(cache_directory + "news.pt", map_location=torch.device(self.device))
+        self.news_reprs = nn.Embedding.from_pretrained(news_reprs.to(self.device).float())
+
+    def destroy_embedding(self):
+        self.news_reprs = None
+        del self.news_reprs
+
+    def compute_score(self, cdd_news_repr, user_repr):
+        """[B,C,H] x [B,1,H] -> raw scores [B,C] = <cdd, user>/sqrt(H) (TwoTowerBaseModel.py:51-62).
+        Kept for API parity (no autograd); forward() uses the fused score+log-softmax / sigmoid kernels."""
+        return ops.score_sigmoid(cdd_news_repr, user_repr, apply_sigmoid=False)
+
+    def _logits(self, cdd_repr, user_repr):
+        if self.training:
+            return ops.ScoreLogSoftmax.apply(cdd_repr, user_repr)
+        return ops.score_sigmoid(cdd_repr, user_repr)
+
+    def forward(self, x):
+        cdd_repr = self.encode_news(x)
+        user_repr, kid = self.encode_user(x)
+        return self._logits(cdd_repr, user_repr), kid
+
+    def predict_fast(self, x):
+        cdd_id = x["cdd_id"].to(self.device)
+        user_repr, _ = self.encode_user(x)
+        B, n = cdd_id.shape
+        offsets = torch.arange(0, (B + 1) * n, n, dtype=torch.int64, device=cdd_id.device)
+        prob = ops.score_sigmoid_gather(self.news_reprs.weight, cdd_id, offsets, user_repr)
+        return prob.view(B, n)
+
+
+class TwoTower(TwoTowerBaseModel):
+    """models/TwoTower.py:3-49."""
+
+    def __init__(self, manager, embedding, encoderN, encoderU):
+        super().__init__(manager)
+        self.embedding = embedding
+        self.encoderN = encoderN
+        self.encoderU = encoderU
+        self.hidden_dim = manager.hidden_dim
+        manager.name = "__".join(["twotower", manager.encoderN, manager.encoderU])
+        self.name = manager.name
+        self._fused = isinstance(embedding, BERT_Embedding) and isinstance(encoderN, CNN_Encoder)
+
+    # ---- news side ---------------------------------------------------------------------------
+    def _encode_titles(self, ids, mask):
+        if self._fused:
+            return self.encoderN.encode_ids(self.embedding, ids, mask)
+        return self.encoderN(self.embedding(ids), mask)[1]
+
+    def encode_news(self, x):
+        cdd_news = x["cdd_encoded_index"].to(self.device, non_blocking=True)
+        cdd_attn_mask = x["cdd_attn_mask"].to(self.device, non_blocking=True)
+        return self._encode_titles(cdd_news, cdd_attn_mask)
+
+    # ---- user side ---------------------------------------------------------------------------
+    def _encode_user_from(self, his_news_repr, x):
+        return self.encoderU(his_news_repr, his_mask=x["his_mask"], user_id=x["user_id"].to(self.device, non_blocking=True))
+
+    def encode_user(self, x):
+        his_news = x["his_encoded_index"].to(self.device, non_blocking=True)
+        his_attn_mask = x["his_attn_mask"].to(self.device, non_blocking=True)
+        his_news_repr = self._encode_titles(his_news, his_attn_mask)
+        return self._encode_user_from(his_news_repr, x), None
+
+    # ---- whole model ---------------------------------------------------------------------------
+    def forward(self, x):
+        """Same result as encode_news + encode_user + score (TwoTowerBaseModel.py:65-75), but the
+        candidate and history titles go through the news encoder as ONE batch so that the big
+        kernels see B*(C+S) titles per launch instead of two launches."""
+        if not self._fused:
+            return super().forward(x)
+        cdd = x["cdd_encoded_index"].to(self.device, non_blocking=True)
+        his = x["his_encoded_index"].to(self.device, non_blocking=True)
+        cm = x["cdd_attn_mask"].to(self.device, non_blocking=True)
+        hm = x["his_attn_mask"].to(self.device, non_blocking=True)
+        B, C, L = cdd.shape
+        S = his.shape[1]
+        ids = torch.cat([cdd.reshape(B * C, L), his.reshape(B * S, L)], dim=0)
+        mask = torch.cat([cm.reshape(B * C, L), hm.reshape(B * S, L)], dim=0)
+        news = self._encode_titles(ids, mask)
+        cdd_repr = news[: B * C].view(B, C, -1)
+        his_repr = news[B * C:].view(B, S, -1)
+        user_repr = self._encode_user_from(his_repr, x)
+        return self._logits(cdd_repr, user_repr), None

@@ -1,0 +1,70 @@
+"""CPU-side checks of the C-ABI boundary: the library builds, loads, exports every symbol that
+include/mindrec.h declares with matching arity, and refuses to compute without a B200."""
+import os
+import re
+
+import pytest
+import torch
+
+import news_recommendation_mind_b200 as mr
+from news_recommendation_mind_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "mindrec.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for m in re.finditer(r"MR_API\s+[\w\s\*]+?\b(mr_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        args = m.group(2).strip()
+        n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+        out[m.group(1)] = n
+    return out
+
+
+def test_library_builds_and_loads():
+    path = build.build()
+    assert os.path.exists(path)
+    lib = _lib.load()
+    assert lib.mr_version() >= 100
+
+
+def test_every_declared_symbol_is_exported_with_matching_arity():
+    build.build()
+    lib = _lib.load()
+    declared = _header_functions()
+    assert len(declared) >= 30
+    assert set(declared) == set(_lib.exported_symbols())
+    for name, nargs in declared.items():
+        fn = getattr(lib, name)                      # raises if not exported
+        assert len(fn.argtypes) == nargs, (name, len(fn.argtypes), nargs)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    lib = _lib.load()
+    assert lib.mr_device_check(0) != 0
+    assert b"not present" in lib.mr_last_error()
+    # product modules refuse CPU tensors loudly instead of silently computing on the host
+    from helpers import manager_for, build_model
+    man = manager_for("cnn", "lstm", 3, 4, 8, 16, 8, 2, device="cpu")
+    model = build_model(man, 50)
+    x = {"cdd_encoded_index": torch.ones(2, 3, 8, dtype=torch.long), "cdd_attn_mask": torch.ones(2, 3, 8, dtype=torch.long),
+         "his_encoded_index": torch.ones(2, 4, 8, dtype=torch.long), "his_attn_mask": torch.ones(2, 4, 8, dtype=torch.long),
+         "his_mask": torch.ones(2, 4, 1, dtype=torch.float64), "user_id": torch.ones(2, dtype=torch.long)}
+    with pytest.raises(RuntimeError):
+        model(x)
+
+
+def test_state_dict_keys_match_reference(golden):
+    from helpers import manager_for, build_model
+    for name, encn, encu in [("tt_cnn_lstm", "cnn", "lstm"), ("tt_cnn_gru", "cnn", "gru"), ("tt_cnn_attn", "cnn", "attn"),
+                             ("tt_mha_lstm", "mha", "lstm"), ("tt_cnn_lstur", "cnn", "lstur")]:
+        g = golden(name)
+        B, C, S, L, E, H, V, hn = [int(v) for v in g["meta"]]
+        model = build_model(manager_for(encn, encu, C, S, L, E, H, hn, device="cpu"), V)
+        ours = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        ref = {k: tuple(v.shape) for k, v in g["params"].items()}
+        assert ours == ref, (name, set(ours) ^ set(ref))
+        assert model.name == "twotower__%s__%s" % (encn, encu)
