@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""Benchmark of the TwoTower hot path on B200 (BASELINE.json metric: training impressions/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|fp32] [--impl reference]
+
+One "step" = one Manager._train iteration (utils/Manager.py:636-647: zero_grad, forward, NLLLoss,
+backward, Adam step) over one synthetic MIND-small-shaped batch of 256 impressions per GPU
+(TwoTower CNN news encoder + LSTM user encoder, title 32, history 50, npratio 4, 300d -> 150).
+Prints ONE JSON line (rank 0).  See the module-level contract in the task statement for the keys.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG = dict(B=256, C=5, S=50, L=32, E=300, H=150, V=30522, n_news=51282, encoderN="cnn", encoderU="lstm")
+FLOP_PER_TOKEN_FWD = 2 * 3 * CFG["E"] * CFG["H"] + 2 * CFG["H"] * CFG["H"] + 4 * CFG["H"]        # 315,600
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons of one GPU with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        mhz = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = next((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), None)
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(mhz)}
+
+
+def manager_ns(device, precision):
+    import types
+    m = types.SimpleNamespace(scale="small", mode="train", cdd_size=CFG["C"], impr_size=2000, batch_size_news=500,
+                              his_size=CFG["S"], signal_length=CFG["L"], device=device, bert_dim=CFG["E"],
+                              hidden_dim=CFG["H"], head_num=10, dropout_p=0.2, descend_history=False,
+                              encoderN=CFG["encoderN"], encoderU=CFG["encoderU"], precision=precision)
+    m.get_user_num = lambda: 94057
+    return m
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's CPU implementation of the path, timed on the box's host cores.  The reference
+    is pure Python and cannot travel to the GPU box, so this arm runs the oracle port of it
+    (oracle/twotower_oracle.py, pinned to the reference by tests/golden) with every host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import twotower_oracle as O
+    from news_recommendation_mind_b200 import data
+    torch.manual_seed(42)
+    torch.set_num_threads(os.cpu_count() or 1)
+    Bs = 64                                           # bounded sample of the 256-impression step
+    params = O.init_params(CFG["V"], CFG["E"], CFG["H"], "lstm", seed=42)
+    ids, mask = data.make_news_table(CFG["n_news"], CFG["L"])
+    state = {}
+    t_steps = []
+    for s in range(args.warmup + args.steps):
+        x = data.make_train_batch(ids, mask, Bs, CFG["C"], CFG["S"], seed=1000 + s)
+        t0 = time.perf_counter()
+        O.train_step(params, state, x, s + 1, lr=1e-4, bert_lr=6e-6, encoder_n="cnn", encoder_u="lstm")
+        if s >= args.warmup:
+            t_steps.append(time.perf_counter() - t0)
+    total = sum(t_steps)
+    val = Bs * len(t_steps) / total
+    line = {"impl": "reference", "metric": "train_impressions_per_sec", "value": val, "unit": "impressions/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(t_steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, "fp32"),
+            "cpu_baseline": {"value": val, "unit": "impressions/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "%d-impression slice of the 256-impression step, %d steps" % (Bs, len(t_steps))},
+            "e2e": {"value": val, "unit": "impressions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def config_dict(args, precision):
+    return {"workload": "TwoTower CNN+LSTM training, batch 256/GPU, title 32, his 50, npratio 4, 300d->150 "
+                        "(BASELINE configs[1])", "global_batch": CFG["B"] * args.gpus, "per_gpu_batch": CFG["B"],
+            "precision": precision, "parallelism": "dp%d" % args.gpus, "optimizer": "Adam lr 1e-4 / bert_lr 6e-6",
+            "l2": "8 distinct batches cycled; per-step working set (saved activations ~0.5-1 GB) exceeds the 126 MB L2"}
+
+
+def cpu_baseline_sample():
+    from oracle import twotower_oracle as O
+    from news_recommendation_mind_b200 import data
+    torch.set_num_threads(os.cpu_count() or 1)
+    Bs = 32
+    params = O.init_params(CFG["V"], CFG["E"], CFG["H"], "lstm", seed=42)
+    ids, mask = data.make_news_table(CFG["n_news"], CFG["L"])
+    state, ts = {}, []
+    n = 0
+    t_all = time.perf_counter()
+    for s in range(40):
+        x = data.make_train_batch(ids, mask, Bs, CFG["C"], CFG["S"], seed=2000 + s)
+        t0 = time.perf_counter()
+        O.train_step(params, state, x, s + 1, lr=1e-4, bert_lr=6e-6, encoder_n="cnn", encoder_u="lstm")
+        if s >= 1:
+            ts.append(time.perf_counter() - t0)
+            n += Bs
+        if time.perf_counter() - t_all > 15 and len(ts) >= 3:
+            break
+    return {"value": n / sum(ts), "unit": "impressions/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "oracle fp32 train step (fwd+NLL+bwd+Adam) on %d-impression slices, %d steps after 1 warm-up" % (Bs, len(ts))}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import news_recommendation_mind_b200 as mr
+    from news_recommendation_mind_b200 import _lib, build, data, ops, trainer
+    build.build()
+    lib = _lib.load()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    if lib.mr_device_check(local) != 0:
+        raise RuntimeError(lib.mr_last_error().decode())
+    torch.manual_seed(42)
+    man = manager_ns(dev, args.precision)
+    model = mr.TwoTower(man, mr.BERT_Embedding(man, vocab_size=CFG["V"]), mr.CNN_Encoder(man), mr.RNN_User_Encoder(man)).to(dev)
+    core = model
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], output_device=local,
+                                                          find_unused_parameters=False)
+    opt = trainer.FusedAdam(model, lr=1e-4, bert_lr=6e-6)
+    ids, mask = data.make_news_table(CFG["n_news"], CFG["L"])
+    NB = 8
+    host = [data.make_train_batch(ids, mask, CFG["B"], CFG["C"], CFG["S"], seed=100 * rank + i, pin=True) for i in range(NB)]
+    devb = [{k: v.to(dev) for k, v in b.items()} for b in host]
+    h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in
+              ("cdd_encoded_index", "cdd_attn_mask", "his_encoded_index", "his_attn_mask", "user_id", "label")) + CFG["B"] * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(batches, steps, read_loss):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for s in range(steps):
+            loss = trainer.train_step(model, batches[s % NB], opt)
+            if read_loss:
+                loss.item()                                   # device -> host read of the step's result
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        barrier()
+        ms = max(e0.elapsed_time(e1), 0.0)
+        if read_loss:
+            ms = max(ms, wall * 1e3)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    for s in range(max(args.warmup, 3)):
+        trainer.train_step(model, devb[s % NB], opt)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = lib.mr_launch_count()
+    ms = timed(devb, args.steps, False)
+    launches = lib.mr_launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    trainer.train_step(model, host[0], opt)
+    ms_e2e = timed(host, args.steps, True)
+
+    # dominant kernel: the fused news-encoder forward, timed alone with CUDA events on its stream
+    roof = None
+    if rank == 0:
+        x = devb[0]
+        idsd = torch.cat([x["cdd_encoded_index"].view(-1, CFG["L"]), x["his_encoded_index"].view(-1, CFG["L"])])
+        maskd = torch.cat([x["cdd_attn_mask"].view(-1, CFG["L"]), x["his_attn_mask"].view(-1, CFG["L"])])
+        with torch.no_grad():
+            for _ in range(3):
+                core.encoderN.encode_ids(core.embedding, idsd, maskd)
+            reps = 10
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                core.encoderN.encode_ids(core.embedding, idsd, maskd)
+            e1.record()
+            torch.cuda.synchronize()
+        t_k = e0.elapsed_time(e1) / reps * 1e-3
+        pk = peaks()
+        flops = FLOP_PER_TOKEN_FWD * idsd.numel()
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("news_cnn_fwd_dram_bytes_per_launch")
+        roof = {"kernel": "news_cnn_fwd (gather+conv3+ReLU+proj+tanh+softmax-pool), %d titles" % idsd.shape[0],
+                "bound": "tensor", "achieved": flops / t_k / 1e12, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                "frac": flops / t_k / 1e12 / pk["tf_burst"], "traffic": traffic, "peak_source": pk["source"] + " burst",
+                "us_per_launch": t_k * 1e6}
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        per_step = ms / args.steps
+        line = {"metric": "train_impressions_per_sec", "value": world * CFG["B"] * args.steps / (ms * 1e-3),
+                "unit": "impressions/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+                "config": config_dict(args, args.precision), "clocks": clocks,
+                "e2e": {"value": world * CFG["B"] * args.steps / (ms_e2e * 1e-3), "unit": "impressions/s",
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "gpu_launches": int(launches), "roofline": roof}
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline_sample()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("MINDREC_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -234,8 +234,15 @@ MR_API int mr_rank_metrics(const float* prob, const float* label, const int64_t*
  *   elements for rows of `row_len`; NULL = none).
  * -------------------------------------------------------------------------------------------- */
 MR_API int mr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t step,
-                 float lr, float beta1, float beta2, float eps, float grad_scale,
+                 double lr, double beta1, double beta2, double eps, double grad_scale,
                  void* shadow_bf16, int64_t row_len, int64_t shadow_ld, void* stream);
+
+/* Mean negative log-likelihood (nn.NLLLoss(), utils/Manager.py:381-382,641) over logp [B,C]:
+ *   fwd: loss[0] = -(1/B) sum_b logp[b, label[b]];   bwd: d_logp[b,c] = -(d_loss/B) [c == label[b]] */
+MR_API int mr_nll_loss_fwd(const float* logp, const void* label, int label_i64, float* loss,
+                    int64_t B, int64_t C, void* stream);
+MR_API int mr_nll_loss_bwd(const void* label, int label_i64, const float* d_loss, float* d_logp,
+                    int64_t B, int64_t C, void* stream);
 /* fp32 [rows, cols] -> bf16 [rows, ld] (zero padded columns). */
 MR_API int mr_cast_pad_bf16(const float* src, void* dst, int64_t rows, int64_t cols, int64_t ld, void* stream);
 

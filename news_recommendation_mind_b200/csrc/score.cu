@@ -52,6 +52,15 @@ __global__ void nll_mean_kernel(const float* __restrict__ logp, const void* __re
   }
 }
 
+__global__ void nll_bwd_kernel(const void* __restrict__ label, int label_i64, const float* __restrict__ d_loss,
+                               float* __restrict__ d_logp, int64_t B, int C) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  int64_t b = i / C; int c = (int)(i - b * C);
+  float g = d_loss ? d_loss[0] : 1.f;
+  d_logp[i] = (load_index(label, label_i64, b) == c) ? -g / (float)B : 0.f;
+}
+
 __global__ void __launch_bounds__(256)
 score_logsoftmax_bwd_kernel(const float* __restrict__ cdd, const float* __restrict__ user, const float* __restrict__ logp,
                             const float* __restrict__ d_logp, float* __restrict__ d_cdd, float* __restrict__ d_user,
@@ -328,6 +337,24 @@ int mr_score_logsoftmax_fwd(const float* cdd, const float* user, float* logp, co
     nll_mean_kernel<<<1, 256, 0, st>>>(logp, label, label_i64, loss_mean, B, (int)C);
     MR_CHECK_LAUNCH("nll_mean_kernel");
   }
+  return MR_OK;
+}
+
+int mr_nll_loss_fwd(const float* logp, const void* label, int label_i64, float* loss, int64_t B, int64_t C, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  MR_REQUIRE(logp && label && loss, MR_ERR_NULL, "mr_nll_loss_fwd: null pointer");
+  MR_REQUIRE(B >= 1 && C >= 1, MR_ERR_BAD_SHAPE, "mr_nll_loss_fwd: bad shape");
+  nll_mean_kernel<<<1, 256, 0, as_stream(stream)>>>(logp, label, label_i64, loss, B, (int)C);
+  MR_CHECK_LAUNCH("nll_mean_kernel");
+  return MR_OK;
+}
+
+int mr_nll_loss_bwd(const void* label, int label_i64, const float* d_loss, float* d_logp, int64_t B, int64_t C, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  MR_REQUIRE(label && d_logp, MR_ERR_NULL, "mr_nll_loss_bwd: null pointer");
+  MR_REQUIRE(B >= 1 && C >= 1, MR_ERR_BAD_SHAPE, "mr_nll_loss_bwd: bad shape");
+  nll_bwd_kernel<<<(unsigned)ceil_div(B * C, 256), 256, 0, as_stream(stream)>>>(label, label_i64, d_loss, d_logp, B, (int)C);
+  MR_CHECK_LAUNCH("nll_bwd_kernel");
   return MR_OK;
 }
 

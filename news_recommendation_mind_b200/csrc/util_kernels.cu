@@ -49,14 +49,14 @@ cudaError_t colsum(const float* x, float* out, int64_t R, int64_t C, float* part
 // ---- Adam (utils/Manager.py:404-413 -> torch.optim.Adam defaults) -----------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr_over_bc1, float inv_sqrt_bc2, float beta1,
-                            float beta2, float eps, float grad_scale, __nv_bfloat16* __restrict__ shadow,
-                            int64_t row_len, int64_t shadow_ld) {
+                            float omb1, float beta2, float omb2, float eps, float grad_scale,
+                            __nv_bfloat16* __restrict__ shadow, int64_t row_len, int64_t shadow_ld) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     float gi = g[i] * grad_scale;
-    float mi = beta1 * m[i] + (1.f - beta1) * gi;
-    float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    float mi = beta1 * m[i] + omb1 * gi;
+    float vi = beta2 * v[i] + omb2 * gi * gi;
     float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
     float pi = p[i] - lr_over_bc1 * (mi / denom);
     m[i] = mi; v[i] = vi; p[i] = pi;
@@ -81,8 +81,8 @@ __global__ void cast_pad_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
 
 extern "C" {
 
-int mr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t step, float lr, float beta1,
-                 float beta2, float eps, float grad_scale, void* shadow_bf16, int64_t row_len, int64_t shadow_ld,
+int mr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t step, double lr, double beta1,
+                 double beta2, double eps, double grad_scale, void* shadow_bf16, int64_t row_len, int64_t shadow_ld,
                  void* stream) {
   using namespace mr;
   if (int rc = require_sm100()) return rc;
@@ -91,12 +91,13 @@ int mr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int64_
   if (n == 0) return MR_OK;
   if (shadow_bf16) MR_REQUIRE(row_len > 0 && shadow_ld >= row_len && n % row_len == 0, MR_ERR_BAD_SHAPE,
                               "mr_adam_step: bad shadow geometry");
-  double bc1 = 1.0 - pow((double)beta1, (double)step);
-  double bc2 = 1.0 - pow((double)beta2, (double)step);
+  double bc1 = 1.0 - pow(beta1, (double)step);
+  double bc2 = 1.0 - pow(beta2, (double)step);
   int64_t blocks = ceil_div(n, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   adam_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)),
-                                                              beta1, beta2, eps, grad_scale,
+                                                              (float)beta1, (float)(1.0 - beta1), (float)beta2,
+                                                              (float)(1.0 - beta2), (float)eps, (float)grad_scale,
                                                               static_cast<__nv_bfloat16*>(shadow_bf16), row_len, shadow_ld);
   MR_CHECK_LAUNCH("adam_kernel");
   return MR_OK;

@@ -1,0 +1,94 @@
+"""Synthetic MIND-shaped data with the exact batch-dict schema utils/MIND.py::__getitem__ emits
+(MIND.py:352-363 train, :394-405 dev), for benchmarks and tests (there is no dataset on the box).
+
+Distributions follow SURVEY.md section 8(d): Zipfian word ids in [1000, 30522) between [CLS]=101
+and [SEP]=102, title lengths ~ N(0.8L, 0.2L) clipped to [4, L], history lengths ~ LogNormal(3.0,
+0.9) clipped to [0, S] (empty history -> his_mask[0] = 1, MIND.py:332-337), Zipfian news ids,
+positive always first (label 0, MIND.py:316-327), news 0 = the empty article [101, 102, 0, ...].
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+VOCAB = 30522
+CLS, SEP = 101, 102
+NEWS_NUM = {"small_train": 51282, "small_dev": 42416, "large_train": 101527, "large_dev": 72023, "large_test": 120961}
+USER_NUM = {"small": 94057, "large": 876956}
+
+
+def make_news_table(n_news: int, L: int, seed: int = 42, vocab: int = VOCAB):
+    """-> (encoded_news [n_news+1, L] int64, attn_mask [n_news+1, L] int64)."""
+    rng = np.random.RandomState(seed)
+    n = n_news + 1
+    length = np.clip(np.rint(rng.normal(0.8 * L, 0.2 * L, size=n)), 4, L).astype(np.int64)
+    length[0] = 2
+    words = (rng.zipf(1.1, size=(n, L)) - 1) % (vocab - 1000) + 1000
+    pos = np.arange(L)[None, :]
+    ids = np.where(pos < length[:, None], words, 0)
+    ids[:, 0] = CLS
+    ids[np.arange(n), length - 1] = SEP
+    mask = (pos < length[:, None]).astype(np.int64)
+    return torch.from_numpy(ids.astype(np.int64)), torch.from_numpy(mask)
+
+
+def _zipf_ids(rng, a, size, n_news):
+    return (rng.zipf(a, size=size) - 1) % n_news + 1
+
+
+def make_train_batch(news_ids, news_mask, B: int, C: int, S: int, seed: int, n_users: int = USER_NUM["small"],
+                     pin: bool = False):
+    """One training batch (dict of CPU tensors) in the reference schema."""
+    rng = np.random.RandomState(seed)
+    n_news = news_ids.shape[0] - 1
+    cdd_id = _zipf_ids(rng, 1.05, (B, C), n_news)
+    his_len = np.clip(np.rint(rng.lognormal(3.0, 0.9, size=B)), 0, S).astype(np.int64)
+    his_id = _zipf_ids(rng, 1.05, (B, S), n_news)
+    pos = np.arange(S)[None, :]
+    his_id = np.where(pos < his_len[:, None], his_id, 0)
+    his_mask = (pos < np.maximum(his_len, 1)[:, None]).astype(np.float64)[:, :, None]
+    cdd_t, his_t = torch.from_numpy(cdd_id), torch.from_numpy(his_id)
+    x = {
+        "user_id": torch.from_numpy(rng.randint(1, n_users + 1, size=B).astype(np.int64)),
+        "cdd_id": cdd_t, "his_id": his_t,
+        "cdd_encoded_index": news_ids[cdd_t], "his_encoded_index": news_ids[his_t],
+        "cdd_attn_mask": news_mask[cdd_t], "his_attn_mask": news_mask[his_t],
+        "cdd_mask": torch.ones(B, C, 1, dtype=torch.float64),
+        "his_mask": torch.from_numpy(his_mask),
+        "label": torch.zeros(B, dtype=torch.int64),
+    }
+    if pin:
+        x = {k: v.pin_memory() for k, v in x.items()}
+    return x
+
+
+def make_eval_impressions(news_ids, news_mask, n_impr: int, S: int, seed: int, n_users: int = USER_NUM["small"]):
+    """Dev impressions in CSR form: candidate counts ~ LogNormal(3.3, 0.8) clipped to [2, 300], labels
+    Bernoulli(0.04) with at least one positive and one negative, distinct candidates per impression
+    (no score ties).  -> dict with his_* [n_impr, S, ...], cdd_id [n_cand], offsets [n_impr+1], label [n_cand]."""
+    rng = np.random.RandomState(seed)
+    n_news = news_ids.shape[0] - 1
+    n_c = np.clip(np.rint(rng.lognormal(3.3, 0.8, size=n_impr)), 2, min(300, n_news)).astype(np.int64)
+    offsets = np.concatenate([[0], np.cumsum(n_c)])
+    cdd = np.empty(offsets[-1], dtype=np.int64)
+    lab = np.zeros(offsets[-1], dtype=np.float32)
+    for i in range(n_impr):
+        a, b = offsets[i], offsets[i + 1]
+        cdd[a:b] = rng.choice(n_news, size=b - a, replace=False) + 1
+        y = (rng.random_sample(b - a) < 0.04)
+        y[rng.randint(0, b - a)] = True
+        if y.all():
+            y[0] = False
+        lab[a:b] = y
+    his_len = np.clip(np.rint(rng.lognormal(3.0, 0.9, size=n_impr)), 0, S).astype(np.int64)
+    his_id = _zipf_ids(rng, 1.05, (n_impr, S), n_news)
+    pos = np.arange(S)[None, :]
+    his_id = np.where(pos < his_len[:, None], his_id, 0)
+    his_mask = (pos < np.maximum(his_len, 1)[:, None]).astype(np.float64)[:, :, None]
+    his_t = torch.from_numpy(his_id)
+    return {
+        "impr_index": torch.arange(n_impr), "user_id": torch.from_numpy(rng.randint(1, n_users + 1, size=n_impr).astype(np.int64)),
+        "cdd_id": torch.from_numpy(cdd), "offsets": torch.from_numpy(offsets.astype(np.int64)), "label": torch.from_numpy(lab),
+        "his_id": his_t, "his_encoded_index": news_ids[his_t], "his_attn_mask": news_mask[his_t],
+        "his_mask": torch.from_numpy(his_mask),
+    }

@@ -1,0 +1,106 @@
+"""Fast evaluation of the hot path: what utils/Manager.py::_eval_fast does (Manager.py:473-541),
+re-shaped for 8 GPUs over NVLink.
+
+reference                                   here
+---------                                   ----
+rank 0 encodes every news, torch.save to    every rank encodes a contiguous shard of the news set
+disk, barrier, all ranks torch.load         and the [ceil((N+1)/ws), H] shards are ALL-GATHERED
+(Manager.py:490-510)                        over NCCL into the replicated [N+1, H] table
+one impression per Python iteration,        impressions of this rank's contiguous partition
+.tolist() each (Manager.py:514-517)         (Partition_Sampler, utils.py:267-283) are scored in
+                                            batches: encode_user -> CSR gather+dot+sigmoid
+all_gather_object of Python lists to        per-impression AUC/MRR/nDCG@5/10 on the GPU, then an
+rank 0 + cal_metric (Manager.py:525,577)    all-reduce of (sum, count) in fp64
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n_rows: int, world: int, rank: int):
+    per = (n_rows + world - 1) // world
+    lo = min(n_rows, rank * per)
+    return lo, min(n_rows, lo + per), per
+
+
+def partition_bounds(n_items: int, world: int, rank: int):
+    """Partition_Sampler (utils.py:267-283): n // ws each, remainder to the last rank."""
+    per, extra = divmod(n_items, world)
+    start = per * rank
+    return start, start + per + (extra if rank + 1 == world else 0)
+
+
+@torch.no_grad()
+def encode_all_news(model, news_ids: torch.Tensor, news_mask: torch.Tensor, batch: int = 8192) -> torch.Tensor:
+    """[N+1, L] token table -> replicated [N+1, H] news-vector table (fp32).  Shards over ranks."""
+    rank, world = _world()
+    core = model.module if hasattr(model, "module") else model
+    dev = core.device
+    n_rows = news_ids.shape[0]
+    lo, hi, per = shard_bounds(n_rows, world, rank)
+    shard = torch.zeros(per, core.hidden_dim, dtype=torch.float32, device=dev)
+    was_training = core.training
+    core.eval()
+    core.init_encoding()
+    for a in range(lo, hi, batch):
+        b = min(hi, a + batch)
+        x = {"cdd_encoded_index": news_ids[a:b].unsqueeze(1), "cdd_attn_mask": news_mask[a:b].unsqueeze(1)}
+        shard[a - lo:b - lo] = core.encode_news(x).squeeze(-2)
+    core.destroy_encoding()
+    core.train(was_training)
+    if world == 1:
+        return shard[:n_rows]
+    full = torch.empty(world * per, core.hidden_dim, dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(full, shard)
+    return full[:n_rows]
+
+
+@torch.no_grad()
+def score_impressions(model, table: torch.Tensor, impr: dict, batch: int = 1024):
+    """Scores this rank's partition of CSR impressions.  Returns (prob [n_cand_local], label, offsets_local)."""
+    rank, world = _world()
+    core = model.module if hasattr(model, "module") else model
+    dev = core.device
+    n_impr = impr["offsets"].numel() - 1
+    i0, i1 = partition_bounds(n_impr, world, rank)
+    offs = impr["offsets"]
+    c0, c1 = int(offs[i0]), int(offs[i1])
+    cdd = impr["cdd_id"][c0:c1].to(dev, non_blocking=True)
+    local_off = (offs[i0:i1 + 1] - c0).to(dev)
+    prob = torch.empty(c1 - c0, dtype=torch.float32, device=dev)
+    was_training = core.training
+    core.eval()
+    for a in range(i0, i1, batch):
+        b = min(i1, a + batch)
+        x = {"his_encoded_index": impr["his_encoded_index"][a:b], "his_attn_mask": impr["his_attn_mask"][a:b],
+             "his_mask": impr["his_mask"][a:b], "user_id": impr["user_id"][a:b]}
+        user = core.encode_user(x)[0]
+        ca, cb = int(offs[a]) - c0, int(offs[b]) - c0
+        sub_off = local_off[a - i0:b - i0 + 1] - ca
+        prob[ca:cb] = ops.score_sigmoid_gather(table, cdd[ca:cb], sub_off, user)
+    core.train(was_training)
+    return prob, impr["label"][c0:c1].to(dev), local_off
+
+
+@torch.no_grad()
+def evaluate(model, news_ids, news_mask, impr, metrics=("auc", "mean_mrr", "ndcg@5", "ndcg@10")):
+    """-> dict of the reference's default metrics rounded to 4 dp (Manager.py:106,1276-1344)."""
+    rank, world = _world()
+    table = encode_all_news(model, news_ids, news_mask)
+    prob, label, off = score_impressions(model, table, impr)
+    m, _ = ops.rank_metrics(prob, label, off)
+    acc = torch.cat([m.sum(0), torch.tensor([float(m.shape[0])], dtype=torch.float64, device=m.device)])
+    if world > 1:
+        dist.all_reduce(acc)
+    mean = (acc[:4] / acc[4]).tolist()
+    names = ["auc", "mean_mrr", "ndcg@5", "ndcg@10"]
+    return {k: round(v, 4) for k, v in zip(names, mean) if k in metrics}

@@ -310,6 +310,32 @@ class ScoreLogSoftmax(torch.autograd.Function):
         return d_cdd, d_user
 
 
+class NLLMean(torch.autograd.Function):
+    """nn.NLLLoss() (mean) on log-probabilities [B,C] (utils/Manager.py:381-382,641)."""
+
+    @staticmethod
+    def forward(ctx, logp, label):
+        lib = _lib.load()
+        lc = _f32c(logp)
+        lab = _idx(label.to(lc.device))
+        B, C = lc.shape
+        loss = torch.empty(1, dtype=torch.float32, device=lc.device)
+        check(lib.mr_nll_loss_fwd(ptr(lc), ptr(lab), index_flag(lab), ptr(loss), B, C, stream_ptr(lc.device)), "mr_nll_loss_fwd")
+        ctx.save_for_backward(lab)
+        ctx.dims = (B, C)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        lib = _lib.load()
+        (lab,) = ctx.saved_tensors
+        B, C = ctx.dims
+        g = _f32c(d_loss).view(1)
+        d_logp = torch.empty(B, C, dtype=torch.float32, device=g.device)
+        check(lib.mr_nll_loss_bwd(ptr(lab), index_flag(lab), ptr(g), ptr(d_logp), B, C, stream_ptr(g.device)), "mr_nll_loss_bwd")
+        return d_logp, None
+
+
 def score_sigmoid(cdd: torch.Tensor, user: torch.Tensor, apply_sigmoid: bool = True) -> torch.Tensor:
     """sigmoid(<cdd, user>/sqrt(H)), eval only (TwoTowerBaseModel.py:72-73,83); raw scores when
     apply_sigmoid is False (compute_score, TwoTowerBaseModel.py:61)."""
@@ -360,8 +386,8 @@ def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale
     row_len, ld = (0, 0)
     if shadow is not None:
         row_len, ld = p.shape[-1], shadow.shape[-1]
-    check(lib.mr_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), n, step, c_float(lr), c_float(beta1), c_float(beta2),
-                           c_float(eps), c_float(grad_scale), ptr(shadow), row_len, ld, stream_ptr(p.device)),
+    check(lib.mr_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), n, step, float(lr), float(beta1), float(beta2),
+                           float(eps), float(grad_scale), ptr(shadow), row_len, ld, stream_ptr(p.device)),
           "mr_adam_step")
 
 

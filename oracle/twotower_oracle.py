@@ -372,3 +372,34 @@ def train_step(params: Dict[str, Tensor], state: Dict[str, Tuple[Tensor, Tensor]
             m, v = state[k]
             adam_step(params[k], g, m, v, step, bert_lr if "bert" in k else lr)
     return float(loss.detach()), out
+
+
+def init_params(V: int, E: int, H: int, encoder_u: str = "lstm", seed: int = 42) -> Dict[str, Tensor]:
+    """Fresh CNN + LSTM/GRU TwoTower parameters with the reference's initialisers: xavier-normal conv /
+    projection / query (CNN.py:12-24), orthogonal recurrent weights (RNN.py:46-48), PyTorch defaults
+    for the biases, token table N(0, 0.02^2) standing in for the downloaded BERT table (BERT.py:16-21)."""
+    g = torch.Generator().manual_seed(seed)
+    G = 4 if encoder_u == "lstm" else 3
+
+    def uniform(shape, bound):
+        return (torch.rand(shape, generator=g) * 2 - 1) * bound
+
+    def xavier(shape, fan_in, fan_out):
+        return torch.randn(shape, generator=g) * math.sqrt(2.0 / (fan_in + fan_out))
+
+    def orthogonal(rows, cols):
+        q, r = torch.linalg.qr(torch.randn(rows, cols, generator=g))
+        return q * torch.sign(torch.diagonal(r))
+
+    return {
+        "embedding.bert_word_embedding.weight": torch.randn(V, E, generator=g) * 0.02,
+        "encoderN.cnn.weight": xavier((H, E, 3), E * 3, H * 3),
+        "encoderN.cnn.bias": uniform((H,), 1.0 / math.sqrt(3 * E)),
+        "encoderN.query_words": xavier((1, H), H, 1),
+        "encoderN.wordQueryProject.weight": xavier((H, H), H, H),
+        "encoderN.wordQueryProject.bias": uniform((H,), 1.0 / math.sqrt(H)),
+        "encoderU.rnn.weight_ih_l0": orthogonal(G * H, H),
+        "encoderU.rnn.weight_hh_l0": orthogonal(G * H, H),
+        "encoderU.rnn.bias_ih_l0": uniform((G * H,), 1.0 / math.sqrt(H)),
+        "encoderU.rnn.bias_hh_l0": uniform((G * H,), 1.0 / math.sqrt(H)),
+    }
