@@ -243,6 +243,13 @@ MR_API int mr_nll_loss_fwd(const float* logp, const void* label, int label_i64, 
                     int64_t B, int64_t C, void* stream);
 MR_API int mr_nll_loss_bwd(const void* label, int label_i64, const float* d_loss, float* d_logp,
                     int64_t B, int64_t C, void* stream);
+/* Diagnostic: one tcgen05 tile D[128,N] = A x B^T (bf16 operands, fp32 accumulate) built with the
+ * same shared-memory descriptors the production kernels use (csrc/tc05.cuh); a_mn/b_mn select
+ * K-major (rows = M/N index) or MN-major (rows = K index) operands, a_shift reads A `a_shift` rows
+ * later (zero halo).  Used by tests/test_gpu_tc.py to pin the descriptor conventions on hardware. */
+MR_API int mr_tc_selftest(const float* a, int64_t ra, int64_t ca, const float* b, int64_t rb, int64_t cb, float* d,
+                   int a_mn, int b_mn, int64_t N, int64_t K, int64_t a_shift, int64_t halo, int swap, void* stream);
+
 /* fp32 [rows, cols] -> bf16 [rows, ld] (zero padded columns). */
 MR_API int mr_cast_pad_bf16(const float* src, void* dst, int64_t rows, int64_t cols, int64_t ld, void* stream);
 

@@ -1,0 +1,106 @@
+// Self-test of the tcgen05 building blocks (descriptor conventions of tc05.cuh): one CTA stages two
+// small fp32 matrices into the bf16 panel layout, runs D = A x B^T on the tensor core for every
+// combination of operand majorness / row shift the production kernels rely on, and returns D.
+// tests/test_gpu_tc.py compares it with a bf16-rounded fp32 matmul.
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace mr {
+
+struct SelfTestArgs {
+  const float* a; int ra, ca;   // source A, row-major [ra, ca]
+  const float* b; int rb, cb;   // source B, row-major [rb, cb]
+  float* d;                     // out [128, N] fp32
+  int a_mn, b_mn;               // 0: rows are the M/N index, cols are K;  1: rows are K, cols are M/N
+  int N, K;                     // MMA N (multiple of 16, <= 256) and total K (multiple of 16)
+  int a_shift, halo;            // A operand starts `a_shift` rows later (|a_shift| <= halo)
+  int swap;                     // debug: swap the LBO / SBO fields
+};
+
+__global__ void __launch_bounds__(128, 1) tc_selftest_kernel(SelfTestArgs p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int a_rows = (p.ra + 2 * p.halo) | 1, b_rows = p.rb | 1;
+  const uint32_t a_ps = a_rows * 16, b_ps = b_rows * 16;           // panel strides (bytes)
+  const int a_panels = p.ca / 8, b_panels = p.cb / 8;
+  uint8_t* sa = smem;
+  uint8_t* sb = smem + (size_t)a_panels * a_ps;
+  const size_t total = (size_t)a_panels * a_ps + (size_t)b_panels * b_ps;
+  for (size_t i = tid * 16; i < total; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, 256);
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  for (int i = tid; i < p.ra * p.ca; i += 128) {
+    int r = i / p.ca, c = i % p.ca;
+    *reinterpret_cast<__nv_bfloat16*>(sa + (size_t)(c / 8) * a_ps + (size_t)(r + p.halo) * 16 + (c % 8) * 2) =
+        __float2bfloat16(p.a[i]);
+  }
+  for (int i = tid; i < p.rb * p.cb; i += 128) {
+    int r = i / p.cb, c = i % p.cb;
+    *reinterpret_cast<__nv_bfloat16*>(sb + (size_t)(c / 8) * b_ps + (size_t)r * 16 + (c % 8) * 2) = __float2bfloat16(p.b[i]);
+  }
+  tc::fence_proxy_async();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = tc::make_idesc(128, p.N, p.a_mn, p.b_mn);
+    const uint32_t abase = tc::smem_u32(sa) + (uint32_t)(p.halo + p.a_shift) * 16, bbase = tc::smem_u32(sb);
+    for (int ks = 0; ks < p.K / 16; ++ks) {
+      uint32_t a_addr, a_lbo, a_sbo, b_addr, b_lbo, b_sbo;
+      if (!p.a_mn) { a_addr = abase + 2 * ks * a_ps; a_lbo = a_ps; a_sbo = 128; }
+      else { a_addr = abase + ks * 256; a_lbo = 128; a_sbo = a_ps; }
+      if (!p.b_mn) { b_addr = bbase + 2 * ks * b_ps; b_lbo = b_ps; b_sbo = 128; }
+      else { b_addr = bbase + ks * 256; b_lbo = 128; b_sbo = b_ps; }
+      if (p.swap) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
+      tc::umma(tmem, tc::make_desc(a_addr, a_lbo, a_sbo), tc::make_desc(b_addr, b_lbo, b_sbo), idesc, ks > 0);
+    }
+    tc::umma_commit(&bar);
+  }
+  tc::mbar_wait(&bar, 0);
+  tc::tc_fence_after();
+  for (int c0 = 0; c0 < p.N; c0 += 16) {
+    uint32_t v[16];
+    tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) p.d[(size_t)tid * p.N + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+}  // namespace mr
+
+extern "C" {
+
+int mr_tc_selftest(const float* a, int64_t ra, int64_t ca, const float* b, int64_t rb, int64_t cb, float* d, int a_mn,
+                   int b_mn, int64_t N, int64_t K, int64_t a_shift, int64_t halo, int swap, void* stream) {
+  using namespace mr;
+  if (int rc = require_sm100()) return rc;
+  MR_REQUIRE(a && b && d, MR_ERR_NULL, "mr_tc_selftest: null pointer");
+  MR_REQUIRE(N % 16 == 0 && N >= 16 && N <= 256 && K % 16 == 0 && K >= 16, MR_ERR_BAD_SHAPE, "mr_tc_selftest: N=%lld K=%lld",
+             (long long)N, (long long)K);
+  MR_REQUIRE(ca % 8 == 0 && cb % 8 == 0 && halo >= 0 && a_shift >= -halo && a_shift <= halo, MR_ERR_BAD_SHAPE,
+             "mr_tc_selftest: bad operand shapes");
+  if (!a_mn) MR_REQUIRE(ra == 128 && ca >= K, MR_ERR_BAD_SHAPE, "A (K-major) must be [128, >=K]");
+  else MR_REQUIRE(ca == 128 && ra >= K, MR_ERR_BAD_SHAPE, "A (MN-major) must be [>=K, 128]");
+  if (!b_mn) MR_REQUIRE(rb >= N && cb >= K, MR_ERR_BAD_SHAPE, "B (K-major) must be [>=N, >=K]");
+  else MR_REQUIRE(cb >= N && rb >= K, MR_ERR_BAD_SHAPE, "B (MN-major) must be [>=K, >=N]");
+  SelfTestArgs p{a, (int)ra, (int)ca, b, (int)rb, (int)cb, d, a_mn, b_mn, (int)N, (int)K, (int)a_shift, (int)halo, swap};
+  size_t smem = (size_t)(ca / 8) * (((ra + 2 * halo) | 1) * 16) + (size_t)(cb / 8) * ((rb | 1) * 16) + 128;
+  MR_REQUIRE(smem <= 220 * 1024, MR_ERR_BAD_SHAPE, "mr_tc_selftest: operands need %zu bytes of shared memory", smem);
+  cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  tc_selftest_kernel<<<1, 128, smem, as_stream(stream)>>>(p);
+  MR_CHECK_LAUNCH("tc_selftest_kernel");
+  return MR_OK;
+}
+
+}  // extern "C"
