@@ -43,291 +43,6 @@ struct TapGemmArgs {
   uint32_t a_slot_bytes, b_slot_bytes, a_ps;
 };
 
-__device__ __forceinline__ float tanh_fast(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-__global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArgs p) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* sA = smem;
-  uint8_t* sB = sA + (size_t)p.ns_a * p.a_slot_bytes;
-  float* sbias = reinterpret_cast<float*>(sB + (size_t)p.ns_b * p.b_slot_bytes);
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(sbias + 512);
-  uint64_t* a_empty = a_full + TG_MAX_SLOTS;
-  uint64_t* b_full = a_empty + TG_MAX_SLOTS;
-  uint64_t* b_empty = b_full + TG_MAX_SLOTS;
-  uint64_t* t_full = b_empty + TG_MAX_SLOTS;
-  uint64_t* t_empty = t_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_total = p.nsz[0] + (p.n_sub > 1 ? p.nsz[1] : 0);
-  const int acc_stages = n_total <= 256 ? 2 : 1;
-  const int n_chunks = (p.K + TG_KC - 1) / TG_KC;
-
-  // ---- one-time setup ----------------------------------------------------------------------
-  {
-    const uint32_t a_bytes = (uint32_t)p.ns_a * p.a_slot_bytes;
-    for (uint32_t i = tid * 16; i < a_bytes; i += TG_THREADS * 16) *reinterpret_cast<uint4*>(sA + i) = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < 512; i += TG_THREADS) sbias[i] = (p.bias != nullptr && i < p.n_valid) ? p.bias[i] : 0.f;
-    if (tid == 0) {
-      for (int i = 0; i < TG_MAX_SLOTS; ++i) {
-        tc::mbar_init(&a_full[i], 128);
-        tc::mbar_init(&a_empty[i], 1);
-        tc::mbar_init(&b_full[i], 1);
-        tc::mbar_init(&b_empty[i], 1);
-      }
-      for (int i = 0; i < 2; ++i) {
-        tc::mbar_init(&t_full[i], 1);
-        tc::mbar_init(&t_empty[i], 128);
-      }
-      tc::fence_barrier_init();
-    }
-    if (warp == 4) tc::tmem_alloc(tmem_slot, 512);
-    tc::fence_proxy_async();
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-  }
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp < 4) {
-    // =================================== epilogue ===========================================
-    const int r = tid;
-    const int g = r % p.G, l = r / p.G;
-    int it = 0;
-    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      const int stage = it % acc_stages;
-      const uint32_t ph = (uint32_t)(it / acc_stages) & 1u;
-      tc::mbar_wait(&t_full[stage], ph);
-      tc::tc_fence_after();
-      const int64_t title = tile * p.G + g;
-      const bool valid = (l < p.L) && (title < p.n_titles);
-      const int64_t t = title * p.L + l;
-      const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(stage * 256);
-      int col0 = 0;
-      for (int sub = 0; sub < p.n_sub; ++sub) {
-        for (int c0 = 0; c0 < p.nsz[sub]; c0 += 32) {
-          uint32_t v[32];
-          const int n0 = col0 + c0;
-          if (p.nsz[sub] - c0 >= 32) {
-            tc::tmem_ld32(tbase + n0, v);
-          } else {
-            uint32_t h[16];
-            tc::tmem_ld16(tbase + n0, h);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { v[j] = h[j]; v[16 + j] = 0u; }
-          }
-          tc::tmem_ld_wait();
-          const int width = (p.nsz[sub] - c0 >= 32) ? 32 : 16;
-          if (valid) {
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            if (p.epi == TG_EPI_BIAS_RELU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j] + sbias[n0 + j], 0.f);
-            } else if (p.epi == TG_EPI_BIAS_TANH) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = tanh_fast(f[j] + sbias[n0 + j]);
-            } else if (p.epi == TG_EPI_RELUGRAD) {
-              const uint4* q0 = reinterpret_cast<const uint4*>(p.e0 + t * p.lde + n0);
-              const uint4* q1 = reinterpret_cast<const uint4*>(p.e1 + t * p.lde + n0);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                if (u * 8 < width) {
-                  uint4 x0 = __ldg(q0 + u), x1 = __ldg(q1 + u);
-                  const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&x0);
-                  const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&x1);
-#pragma unroll
-                  for (int w = 0; w < 4; ++w) {
-                    float2 d = __bfloat1622float2(h0[w]), c = __bfloat1622float2(h1[w]);
-                    f[u * 8 + 2 * w] = c.x > 0.f ? f[u * 8 + 2 * w] + d.x : 0.f;
-                    f[u * 8 + 2 * w + 1] = c.y > 0.f ? f[u * 8 + 2 * w + 1] + d.y : 0.f;
-                  }
-                }
-              }
-            }
-            uint4* dst = reinterpret_cast<uint4*>(p.out + t * p.ldo + n0);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (u * 8 < width) {
-                uint4 o;
-                o.x = tc::pack_bf16(f[u * 8 + 0], f[u * 8 + 1]);
-                o.y = tc::pack_bf16(f[u * 8 + 2], f[u * 8 + 3]);
-                o.z = tc::pack_bf16(f[u * 8 + 4], f[u * 8 + 5]);
-                o.w = tc::pack_bf16(f[u * 8 + 6], f[u * 8 + 7]);
-                dst[u] = o;
-              }
-            }
-          }
-        }
-        col0 += p.nsz[sub];
-      }
-      tc::tc_fence_before();
-      tc::mbar_arrive(&t_empty[stage]);
-    }
-  } else if (warp == 4) {
-    // =================================== MMA issuer ==========================================
-    if (lane == 0) {
-      uint32_t idesc[2];
-      idesc[0] = tc::make_idesc(128, p.nsz[0], 0, 0);
-      idesc[1] = tc::make_idesc(128, p.n_sub > 1 ? p.nsz[1] : 16, 0, 0);
-      const uint32_t b_ps = (uint32_t)n_total * 16;
-      const int ctr = (p.taps - 1) / 2;
-      uint32_t ia = 0, ib = 0;
-      int it = 0;
-      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-        const int stage = it % acc_stages;
-        const uint32_t ph = (uint32_t)(it / acc_stages) & 1u;
-        tc::mbar_wait(&t_empty[stage], ph ^ 1u);
-        tc::tc_fence_after();
-        const uint32_t dcol = tmem + (uint32_t)(stage * 256);
-        bool first = true;
-        for (int c = 0; c < n_chunks; ++c) {
-          const int kc = min(TG_KC, p.K - c * TG_KC);
-          const uint32_t sa = ia % (uint32_t)p.ns_a;
-          tc::mbar_wait(&a_full[sa], (ia / (uint32_t)p.ns_a) & 1u);
-          const uint32_t a_slot = tc::smem_u32(sA) + sa * p.a_slot_bytes;
-          for (int tap = 0; tap < p.taps; ++tap) {
-            const uint32_t sb = ib % (uint32_t)p.ns_b;
-            tc::mbar_wait(&b_full[sb], (ib / (uint32_t)p.ns_b) & 1u);
-            tc::tc_fence_after();
-            const uint32_t b_slot = tc::smem_u32(sB) + sb * p.b_slot_bytes;
-            const int shift = p.dir * (tap - ctr) * p.G;
-            const uint32_t a0 = a_slot + (uint32_t)(p.halo + shift) * 16u;
-            for (int ks = 0; ks < kc / 16; ++ks) {
-              const uint64_t da = tc::make_desc(a0 + (uint32_t)(2 * ks) * p.a_ps, p.a_ps, 128);
-              uint32_t roff = 0, coff = 0;
-              for (int sub = 0; sub < p.n_sub; ++sub) {
-                const uint64_t db = tc::make_desc(b_slot + roff * 16u + (uint32_t)(2 * ks) * b_ps, b_ps, 128);
-                tc::umma(dcol + coff, da, db, idesc[sub], first ? 0u : 1u);
-                roff += (uint32_t)p.nsz[sub];
-                coff += (uint32_t)p.nsz[sub];
-              }
-              first = false;
-            }
-            tc::umma_commit(&b_empty[sb]);
-            ++ib;
-          }
-          tc::umma_commit(&a_empty[sa]);
-          ++ia;
-        }
-        tc::umma_commit(&t_full[stage]);
-      }
-    }
-  } else if (warp == 5) {
-    // =================================== weight producer ====================================
-    if (lane == 0) {
-      uint32_t ib = 0;
-      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        for (int c = 0; c < n_chunks; ++c) {
-          const int kc = min(TG_KC, p.K - c * TG_KC);
-          const uint32_t bytes = (uint32_t)(kc / 8) * (uint32_t)n_total * 16u;
-          for (int tap = 0; tap < p.taps; ++tap) {
-            const uint32_t sb = ib % (uint32_t)p.ns_b;
-            tc::mbar_wait(&b_empty[sb], ((ib / (uint32_t)p.ns_b) & 1u) ^ 1u);
-            tc::mbar_arrive_expect_tx(&b_full[sb], bytes);
-            tc::bulk_g2s(tc::smem_u32(sB) + sb * p.b_slot_bytes, p.wpack + (size_t)(c * p.taps + tap) * p.b_slot_bytes, bytes,
-                         &b_full[sb]);
-            ++ib;
-          }
-        }
-      }
-    }
-  } else {
-    // =================================== A producers ========================================
-    const int ptid = tid - 192;            // 0..127
-    const int rgrp = ptid >> 3, j = ptid & 7;
-    uint32_t ia = 0, signaled = 0;
-    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const __nv_bfloat16* rowp[8];
-#pragma unroll
-      for (int s = 0; s < 8; ++s) {
-        const int r = rgrp + 16 * s;
-        const int g = r % p.G, l = r / p.G;
-        const int64_t title = tile * p.G + g;
-        const __nv_bfloat16* q = nullptr;
-        if (l < p.L && title < p.n_titles) {
-          const int64_t t = title * p.L + l;
-          if (p.ids != nullptr) {
-            int64_t id = load_index(p.ids, p.ids_i64, t);
-            id = id < 0 ? 0 : (id >= p.V ? p.V - 1 : id);
-            q = p.a + id * p.lda;
-          } else {
-            q = p.a + t * p.lda;
-          }
-        }
-        rowp[s] = q;
-      }
-      for (int c = 0; c < n_chunks; ++c) {
-        const int kc = min(TG_KC, p.K - c * TG_KC);
-        const uint32_t sa = ia % (uint32_t)p.ns_a;
-        tc::mbar_wait(&a_empty[sa], ((ia / (uint32_t)p.ns_a) & 1u) ^ 1u);
-        if (j * 8 < kc) {
-          const uint32_t dst0 = tc::smem_u32(sA) + sa * p.a_slot_bytes + (uint32_t)j * p.a_ps + (uint32_t)(p.halo + rgrp) * 16u;
-          const int col = c * TG_KC + j * 8;
-#pragma unroll
-          for (int s = 0; s < 8; ++s) {
-            const __nv_bfloat16* q = rowp[s];
-            tc::cp_async16(dst0 + (uint32_t)(16 * s) * 16u, q != nullptr ? (const void*)(q + col) : (const void*)p.a, q != nullptr ? 16u : 0u);
-          }
-        }
-        tc::cp_async_commit();
-        ++ia;
-        if (ia - signaled > (uint32_t)TG_CP_DEPTH) {
-          tc::cp_async_wait<TG_CP_DEPTH>();
-          tc::fence_proxy_async();
-          tc::mbar_arrive(&a_full[signaled % (uint32_t)p.ns_a]);
-          ++signaled;
-        }
-      }
-    }
-    tc::cp_async_wait<0>();
-    tc::fence_proxy_async();
-    while (signaled < ia) {
-      tc::mbar_arrive(&a_full[signaled % (uint32_t)p.ns_a]);
-      ++signaled;
-    }
-  }
-
-  // ---- teardown ----------------------------------------------------------------------------
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 4) tc::tmem_dealloc(tmem, 512);
-}
-
-// Packs fp32 weights into the [chunk][tap] panel blocks the kernel streams:
-//   W[tap][n, k] = src[n*sn + k*sk + tap*st]  for n < n_valid, k < k_valid, else 0
-__global__ void tapgemm_pack_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int taps, int n_total, int K,
-                                    int n_valid, int k_valid, int64_t sn, int64_t sk, int64_t st, uint32_t slot_bytes) {
-  const int n_chunks = (K + TG_KC - 1) / TG_KC;
-  const int64_t total = (int64_t)n_chunks * taps * (TG_KC / 8) * n_total;      // 16-byte units
-  for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (int64_t)gridDim.x * blockDim.x) {
-    const int n = (int)(u % n_total);
-    int64_t rest = u / n_total;
-    const int panel = (int)(rest % (TG_KC / 8));
-    rest /= (TG_KC / 8);
-    const int tap = (int)(rest % taps);
-    const int c = (int)(rest / taps);
-    const int k0 = c * TG_KC + panel * 8;
-    if (k0 >= K) continue;
-    uint32_t w[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float lo = 0.f, hi = 0.f;
-      const int k = k0 + 2 * e;
-      if (n < n_valid && k < k_valid) lo = src[n * sn + k * sk + tap * st];
-      if (n < n_valid && k + 1 < k_valid) hi = src[n * sn + (k + 1) * sk + tap * st];
-      w[e] = tc::pack_bf16(lo, hi);
-    }
-    uint8_t* o = dst + (size_t)(c * taps + tap) * slot_bytes + (size_t)panel * n_total * 16 + (size_t)n * 16;
-    *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-}
-
 // ---- host side -------------------------------------------------------------------------------
 struct TapGemmPlan {
   TapGemmArgs args;
