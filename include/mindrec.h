@@ -75,6 +75,7 @@ MR_API int mr_embed_gather_f32(const void* ids, int ids_i64, const float* table,
  * -------------------------------------------------------------------------------------------- */
 MR_API int64_t mr_embed_grad_workspace_bytes(int64_t T, int64_t E, int64_t V);
 MR_API int mr_embed_grad_segreduce(const void* ids, int ids_i64, const void* d_emb, int d_emb_dtype,
+                            int64_t d_emb_ld /* row pitch of d_emb in elements, 0 = E; pad columns must be 0 */,
                             float* d_table, int64_t T, int64_t E, int64_t V, int64_t padding_idx,
                             void* workspace, int64_t workspace_bytes, void* stream);
 
@@ -86,10 +87,10 @@ MR_API int mr_embed_grad_segreduce(const void* ids, int ids_i64, const void* d_e
  *   prob[n,:] = masked_softmax_l( query . key[n,l,:] / sqrt(H) , mask[n,:] )
  *   news[n,:] = sum_l prob[n,l] c[n,l,:]
  * Input is EITHER token ids (ids != NULL: rows of `table` are gathered on the fly, table is
- * [V,E] fp32 in MR_F32 or the bf16 shadow [V,Epad] in MR_BF16) OR a dense embedding tensor
- * (ids == NULL, emb [N*L, E] fp32).
- * Saved for backward (caller allocated): c_save, key_save ([N*L,H] fp32, or bf16 [N*L,Hpad] in
- * MR_BF16), prob [N,L] fp32.  c_out (optional, may be NULL) receives the fp32 token-level output
+ * [V,E] fp32 in MR_F32 or the bf16 shadow [V, align_up(E,64)] (zero padded) in MR_BF16) OR a dense
+ * embedding tensor (ids == NULL, emb [N*L, E] fp32).
+ * Saved for backward (caller allocated): c_save, key_save ([N*L,H] fp32, or bf16 [N*L, align_up(H,16)]
+ * in MR_BF16), prob [N,L] fp32.  MR_BF16 limits: H <= 256, L <= 128.  c_out (optional, may be NULL) receives the fp32 token-level output
  * the module interface returns as its first value.
  * -------------------------------------------------------------------------------------------- */
 typedef struct {
@@ -110,8 +111,8 @@ MR_API int mr_news_cnn_fwd(const mr_cnn_shape* s,
 
 /* Backward of the above.  d_news [N,H] fp32 (+ optional d_c [N*L,H] fp32 for the token-level
  * output).  Produces d_conv_w [H,E,3], d_conv_b [H], d_proj_w [H,H], d_proj_b [H], d_query [H]
- * (all overwritten, fp32) and d_emb [N*L,E] (fp32 in MR_F32, bf16 in MR_BF16; may be NULL when
- * the input needs no gradient).  `table`/`ids` or `emb` are the forward inputs. */
+ * (all overwritten, fp32) and d_emb (fp32 [N*L,E] in MR_F32, bf16 [N*L, align_up(E,16)] with zero
+ * padding columns in MR_BF16; may be NULL when the input needs no gradient).  `table`/`ids` or `emb` are the forward inputs. */
 MR_API int mr_news_cnn_bwd(const mr_cnn_shape* s,
                     const void* ids, int ids_i64, const float* emb, const void* table,
                     const float* conv_w, const float* proj_w, const float* query,

@@ -33,7 +33,7 @@ _SIGNATURES = {
     "mr_launch_count": (I64, []),
     "mr_embed_gather_f32": (c_int, [P, c_int, P, P, I64, I64, I64, P]),
     "mr_embed_grad_workspace_bytes": (I64, [I64, I64, I64]),
-    "mr_embed_grad_segreduce": (c_int, [P, c_int, P, c_int, P, I64, I64, I64, I64, P, I64, P]),
+    "mr_embed_grad_segreduce": (c_int, [P, c_int, P, c_int, I64, P, I64, I64, I64, I64, P, I64, P]),
     "mr_news_cnn_workspace_bytes": (I64, [POINTER(CnnShape), c_int]),
     "mr_news_cnn_fwd": (c_int, [POINTER(CnnShape), P, c_int, P, P, c_int, P, P, P, P, P, P, P, P, P, P, P, I64, P]),
     "mr_news_cnn_bwd": (c_int, [POINTER(CnnShape), P, c_int, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P]),

@@ -117,14 +117,16 @@ seg_reduce_l1_kernel(const T* __restrict__ d_emb, int64_t ld, const int32_t* __r
   const int32_t beg = seg_start[v] + j * SEG_CHUNK;
   const int32_t end = min(seg_start[v + 1], beg + SEG_CHUNK);
   float* dst = (nchunk[v] == 1) ? d_table + (int64_t)v * E : partial + ch * E;
-  const bool vec_ok = (E % VEC == 0) && (ld % VEC == 0) && (E <= 32 * VEC * MAXV);
+  // vector path: rows are read in VEC-wide pieces up to the row pitch (columns in [E, ld) are padding the
+  // producer keeps at zero); only the first E sums are written back.
+  const int64_t nv = (E + VEC - 1) / VEC;
+  const bool vec_ok = (ld % VEC == 0) && (nv * VEC <= ld) && (nv <= 32 * MAXV);
   if (vec_ok) {
     float acc[MAXV][VEC];
 #pragma unroll
     for (int a = 0; a < MAXV; ++a)
 #pragma unroll
       for (int b = 0; b < VEC; ++b) acc[a][b] = 0.f;
-    const int64_t nv = E / VEC;
     for (int32_t r = beg; r < end; ++r) {
       const T* row = d_emb + (int64_t)sorted_pos[r] * ld;
 #pragma unroll
@@ -143,7 +145,8 @@ seg_reduce_l1_kernel(const T* __restrict__ d_emb, int64_t ld, const int32_t* __r
       int64_t i = lane + 32 * a;
       if (i < nv) {
 #pragma unroll
-        for (int b = 0; b < VEC; ++b) dst[i * VEC + b] = acc[a][b];
+        for (int b = 0; b < VEC; ++b)
+          if (i * VEC + b < E) dst[i * VEC + b] = acc[a][b];
       }
     }
   } else {
@@ -224,9 +227,9 @@ int64_t mr_embed_grad_workspace_bytes(int64_t T, int64_t E, int64_t V) {
   return b + 256;
 }
 
-int mr_embed_grad_segreduce(const void* ids, int ids_i64, const void* d_emb, int d_emb_dtype, float* d_table, int64_t T,
-                            int64_t E, int64_t V, int64_t padding_idx, void* workspace, int64_t workspace_bytes,
-                            void* stream) {
+int mr_embed_grad_segreduce(const void* ids, int ids_i64, const void* d_emb, int d_emb_dtype, int64_t d_emb_ld,
+                            float* d_table, int64_t T, int64_t E, int64_t V, int64_t padding_idx, void* workspace,
+                            int64_t workspace_bytes, void* stream) {
   using namespace mr;
   if (int rc = require_sm100()) return rc;
   MR_REQUIRE(ids && d_emb && d_table, MR_ERR_NULL, "mr_embed_grad_segreduce: null pointer");
@@ -273,12 +276,13 @@ int mr_embed_grad_segreduce(const void* ids, int ids_i64, const void* d_emb, int
   MR_CHECK_LAUNCH("chunk_fill_kernel");
   // The true chunk count (chunk_off[V]) is only known on the device; launch level 1 for the bound
   // ceil(T/SEG_CHUNK)+V and let surplus warps exit (no host sync on this path).
-  const int64_t E4 = E;
+  const int64_t E4 = d_emb_ld > 0 ? d_emb_ld : E;
+  MR_REQUIRE(E4 >= E, MR_ERR_BAD_SHAPE, "mr_embed_grad_segreduce: row pitch %lld < E=%lld", (long long)E4, (long long)E);
   if (d_emb_dtype == MR_F32)
     seg_reduce_l1_kernel<float, 3><<<(unsigned)ceil_div(p.max_chunks, 8), 256, 0, st>>>(
         static_cast<const float*>(d_emb), E4, svals, seg_start, chunk_off, chunk_row, nchunk, d_table, partial, p.max_chunks, E, V);
   else
-    seg_reduce_l1_kernel<__nv_bfloat16, 2><<<(unsigned)ceil_div(p.max_chunks, 8), 256, 0, st>>>(
+    seg_reduce_l1_kernel<__nv_bfloat16, 3><<<(unsigned)ceil_div(p.max_chunks, 8), 256, 0, st>>>(
         static_cast<const __nv_bfloat16*>(d_emb), E4, svals, seg_start, chunk_off, chunk_row, nchunk, d_table, partial, p.max_chunks, E, V);
   MR_CHECK_LAUNCH("seg_reduce_l1_kernel");
   seg_reduce_l2_kernel<<<(unsigned)ceil_div(V, 8), 256, 0, st>>>(chunk_off, nchunk, partial, d_table, V, E);

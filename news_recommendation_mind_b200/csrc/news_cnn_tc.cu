@@ -14,6 +14,7 @@
 #include "news_cnn_tc.cuh"
 #include "pool_kernels.cuh"
 #include "tapgemm.cuh"
+#include "tokred.cuh"
 #include "gemm_simt.cuh"
 
 namespace mr {
@@ -33,15 +34,21 @@ static inline int64_t table_ld(const mr_cnn_shape* s) { return align_up(s->E, 64
 int64_t news_cnn_tc_workspace_bytes(const mr_cnn_shape* s, int backward) {
   const int64_t T = s->N * s->L, Hp = hp_of(s), Kp = kp_of(s);
   int64_t b = 256;
-  b += arena_bytes(tapgemm_pack_bytes(3, (int)Hp, (int)Kp), 1);     // conv weights
-  b += arena_bytes(tapgemm_pack_bytes(1, (int)Hp, (int)Hp), 1);     // proj weights
-  b += arena_bytes(T * Kp, 2);                                      // dense-embedding input as bf16
-  if (backward) {
-    b += 2 * arena_bytes(T * Hp, 2);                                // dkp, dc_pool / dconv
-    b += arena_bytes(tapgemm_pack_bytes(3, (int)Kp, (int)Hp), 1);   // dgrad weights
-    b += arena_bytes(s->N * s->H, 4);                               // dq partial
-    b += arena_bytes(colsum_chunks(T) * Hp, 4);
+  if (!backward) {
+    b += arena_bytes(tapgemm_pack_bytes(3, (int)Hp, (int)Kp), 1);     // conv weights
+    b += arena_bytes(tapgemm_pack_bytes(1, (int)Hp, (int)Hp), 1);     // proj weights
+    b += arena_bytes(T * Kp, 2);                                      // dense-embedding input as bf16
+    return b;
   }
+  b += arena_bytes(tapgemm_pack_bytes(1, (int)Hp, (int)Hp), 1);
+  b += arena_bytes(T * Kp, 2);
+  b += 2 * arena_bytes(T * Hp, 2);                                    // dkp, dc_pool / dconv
+  b += arena_bytes(tapgemm_pack_bytes(3, 512, (int)Hp), 1);           // dgrad weights (one 512-column block)
+  b += arena_bytes(s->N * s->H, 4);                                   // dq partial
+  b += arena_bytes(colsum_chunks(T) * Hp, 4);
+  const int64_t pc = tokred_partial_bytes(s->N, (int)s->L, 3, (int)Kp, (int)Hp);
+  const int64_t pp = tokred_partial_bytes(s->N, (int)s->L, 1, (int)Hp, (int)Hp);
+  b += arena_bytes(pc > pp ? pc : pp, 1);
   return b;
 }
 
@@ -96,9 +103,107 @@ int news_cnn_tc_fwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
   return MR_OK;
 }
 
-int news_cnn_tc_bwd(const mr_cnn_shape*, const void*, int, const float*, const void*, const float*, const float*,
-                    const float*, const void*, const void*, const float*, const float*, const float*, float*, float*,
-                    float*, float*, float*, void*, void*, int64_t, cudaStream_t) {
-  return set_err(MR_ERR_UNSUPPORTED, "MR_BF16 news encoder backward not built yet");
+__global__ void add_rows_bf16_kernel(__nv_bfloat16* __restrict__ dst, int64_t ld, const float* __restrict__ add, int64_t rows,
+                                     int64_t cols) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  int64_t r = i / cols, c = i - r * cols;
+  dst[r * ld + c] = __float2bfloat16(__bfloat162float(dst[r * ld + c]) + add[i]);
+}
+
+int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const float* emb, const void* table,
+                    const float* conv_w, const float* proj_w, const float* query, const void* c_save, const void* key_save,
+                    const float* prob, const float* d_news, const float* d_c, float* d_conv_w, float* d_conv_b,
+                    float* d_proj_w, float* d_proj_b, float* d_query, void* d_emb, void* ws, int64_t wsb, cudaStream_t st) {
+  if (int rc = check_tc(s, "mr_news_cnn_bwd")) return rc;
+  const int64_t N = s->N, L = s->L, E = s->E, H = s->H, T = N * L, Hp = hp_of(s), Kp = kp_of(s);
+  const __nv_bfloat16* c = static_cast<const __nv_bfloat16*>(c_save);
+  const __nv_bfloat16* key = static_cast<const __nv_bfloat16*>(key_save);
+  Arena ar(ws, wsb);
+  uint8_t* wpb = ar.take<uint8_t>(tapgemm_pack_bytes(1, (int)Hp, (int)Hp));          // Wq (transposed use)
+  __nv_bfloat16* xa = ids ? nullptr : ar.take<__nv_bfloat16>(T * Kp);
+  __nv_bfloat16* dkp = ar.take<__nv_bfloat16>(T * Hp);
+  __nv_bfloat16* dcv = ar.take<__nv_bfloat16>(T * Hp);                               // dc_pool, then dconv in place
+  const int64_t nblk = d_emb ? ceil_div(Kp, 512) : 0;
+  uint8_t* wdg = d_emb ? ar.take<uint8_t>(tapgemm_pack_bytes(3, 512, (int)Hp)) : nullptr;
+  float* dqp = ar.take<float>(N * H);
+  float* cp = ar.take<float>(colsum_chunks(T) * Hp);
+  const int64_t pb_conv = tokred_partial_bytes(N, (int)L, 3, (int)Kp, (int)Hp);
+  const int64_t pb_proj = tokred_partial_bytes(N, (int)L, 1, (int)Hp, (int)Hp);
+  float* partial = ar.take<float>((pb_conv > pb_proj ? pb_conv : pb_proj) / 4);
+  MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "mr_news_cnn_bwd: workspace too small (%lld given)", (long long)wsb);
+  MR_REQUIRE(3 * Hp <= 512, MR_ERR_UNSUPPORTED, "mr_news_cnn_bwd: hidden_dim %lld > 160 is not supported by the bf16 backward", (long long)H);
+
+  // 1. pooling backward: dkp = grad wrt the projection pre-activation, dcv = p * d_news   (Attention.py:77-80)
+  cnn_pool_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(c, key, Hp, prob, query, d_news, dkp, dcv, Hp, dqp, N, (int)L, (int)H);
+  MR_CHECK_LAUNCH("cnn_pool_bwd_kernel");
+  if (d_c) {
+    add_rows_bf16_kernel<<<(unsigned)ceil_div(T * H, 256), 256, 0, st>>>(dcv, Hp, d_c, T, H);
+    MR_CHECK_LAUNCH("add_rows_bf16_kernel");
+  }
+  cudaError_t e = colsum(dqp, d_query, N, H, cp, st);
+  MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "colsum dq: %s", cudaGetErrorString(e));
+  e = colsum_bf16(dkp, Hp, d_proj_b, T, H, cp, st);
+  MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "colsum dbq: %s", cudaGetErrorString(e));
+
+  // 2. d_proj_w[n,k] = sum_t dkp[t,n] c[t,k]
+  {
+    TokRedArgs a{};
+    TokRedPlan plan;
+    a.n_titles = N; a.L = (int)L; a.taps = 1;
+    a.ids = nullptr; a.p = c; a.ldp = Hp; a.KP = (int)Hp;
+    a.q = dkp; a.ldq = Hp; a.NQ = (int)Hp; a.partial = partial;
+    if (int rc = tokred_plan(a, &plan)) return rc;
+    if (int rc = tokred_launch(plan, st)) return rc;
+    if (int rc = tokred_reduce(plan, d_proj_w, (int)H, (int)H, H, 1, 0, st)) return rc;
+  }
+  // 3. dconv = relu'(c) * (dc_pool + dkp Wq)   (in place over dcv)
+  {
+    if (int rc = tapgemm_pack(proj_w, wpb, 1, (int)Hp, (int)Hp, (int)H, (int)H, 1, H, 0, st)) return rc;
+    TapGemmArgs a{};
+    TapGemmPlan plan;
+    a.n_titles = N; a.L = (int)L; a.taps = 1; a.dir = 1; a.K = (int)Hp;
+    a.n_sub = 1; a.nsz[0] = (int)Hp;
+    a.ids = nullptr; a.a = dkp; a.lda = Hp;
+    a.wpack = wpb; a.epi = TG_EPI_RELUGRAD; a.bias = nullptr; a.n_valid = (int)H;
+    a.e0 = dcv; a.e1 = c; a.lde = Hp; a.out = dcv; a.ldo = Hp;
+    if (int rc = tapgemm_plan(a, &plan)) return rc;
+    if (int rc = tapgemm_launch(plan, st)) return rc;
+  }
+  e = colsum_bf16(dcv, Hp, d_conv_b, T, H, cp, st);
+  MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "colsum dbc: %s", cudaGetErrorString(e));
+  // 4. d_conv_w[h,e,tap] = sum_t x[t+tap-1, e] dconv[t, h]
+  {
+    if (!ids) {
+      cast_rows_bf16_kernel<<<(unsigned)ceil_div(T * Kp, 256), 256, 0, st>>>(emb, xa, T, E, Kp);
+      MR_CHECK_LAUNCH("cast_rows_bf16_kernel");
+    }
+    TokRedArgs a{};
+    TokRedPlan plan;
+    a.n_titles = N; a.L = (int)L; a.taps = 3;
+    if (ids) { a.ids = ids; a.ids_i64 = ids_i64; a.p = static_cast<const __nv_bfloat16*>(table); a.ldp = table_ld(s); a.V = s->V; }
+    else { a.ids = nullptr; a.p = xa; a.ldp = Kp; }
+    a.KP = (int)Kp; a.q = dcv; a.ldq = Hp; a.NQ = (int)Hp; a.partial = partial;
+    if (int rc = tokred_plan(a, &plan)) return rc;
+    if (int rc = tokred_launch(plan, st)) return rc;
+    if (int rc = tokred_reduce(plan, d_conv_w, (int)E, (int)H, 3 * E, 3, 1, st)) return rc;
+  }
+  // 5. d_emb[t, e] = sum_tap sum_h dconv[t-(tap-1), h] conv_w[h, e, tap]
+  for (int64_t blk = 0; blk < nblk; ++blk) {
+    const int64_t n0 = blk * 512;
+    const int64_t nb = (Kp - n0) < 512 ? (Kp - n0) : 512;
+    TapGemmArgs a{};
+    TapGemmPlan plan;
+    a.n_titles = N; a.L = (int)L; a.taps = 3; a.dir = -1; a.K = (int)Hp;
+    if (nb <= 256) { a.n_sub = 1; a.nsz[0] = (int)nb; }
+    else { a.n_sub = 2; a.nsz[0] = (int)align_up(nb / 2, 16); a.nsz[1] = (int)(nb - a.nsz[0]); }
+    if (int rc = tapgemm_pack(conv_w + n0 * 3, wdg, 3, (int)nb, (int)Hp, (int)((E - n0) < nb ? (E - n0) : nb), (int)H, 3, 3 * E, 1, st)) return rc;
+    a.ids = nullptr; a.a = dcv; a.lda = Hp;
+    a.wpack = wdg; a.epi = TG_EPI_STORE; a.bias = nullptr; a.n_valid = (int)nb;
+    a.out = static_cast<__nv_bfloat16*>(d_emb) + n0; a.ldo = Kp;
+    if (int rc = tapgemm_plan(a, &plan)) return rc;
+    if (int rc = tapgemm_launch(plan, st)) return rc;
+  }
+  return MR_OK;
 }
 }  // namespace mr

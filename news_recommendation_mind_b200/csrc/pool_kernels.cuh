@@ -148,6 +148,12 @@ cnn_pool_bwd_kernel(const T* __restrict__ c, const T* __restrict__ key, int64_t 
     }
     if (h < H) dq_partial[n * H + h] = dq;
   }
+  // padding columns [H, ldo) feed tensor-core GEMMs in the bf16 path: keep them exactly zero
+  for (int64_t i = lane; i < (int64_t)L * (ldo - H); i += 32) {
+    const int64_t l = i / (ldo - H), h = H + i % (ldo - H);
+    dk[l * ldo + h] = from_f<TO>(0.f);
+    dcp[l * ldo + h] = from_f<TO>(0.f);
+  }
 }
 
 }  // namespace mr

@@ -1,0 +1,219 @@
+// Token-reduction GEMM (tokred.cuh): kernel, planning, launch and the fixed-order partial reduction.
+#include "tokred.cuh"
+#include "tapgemm.cuh"   // sm_count()
+
+namespace mr {
+
+constexpr int TR_MAX_STAGES = 4;
+
+__global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * p.stage_bytes);
+  uint64_t* empty = full + TR_MAX_STAGES;
+  uint64_t* done = empty + TR_MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m = blockIdx.x / p.S, s = blockIdx.x % p.S;
+  const bool has_tiles = (int64_t)s < p.n_tiles;
+
+  {
+    const uint32_t bytes = (uint32_t)p.n_stages * p.stage_bytes;
+    for (uint32_t i = tid * 16; i < bytes; i += TR_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+      for (int i = 0; i < TR_MAX_STAGES; ++i) {
+        tc::mbar_init(&full[i], 128);
+        tc::mbar_init(&empty[i], 1);
+      }
+      tc::mbar_init(done, 1);
+      tc::fence_barrier_init();
+    }
+    if (warp == 4) tc::tmem_alloc(tmem_slot, 512);
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+  }
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    // ---- epilogue: TMEM -> fp32 partial -------------------------------------------------------
+    float* dst = p.partial + ((size_t)(m * p.S + s) * p.taps * 128 + tid) * p.NQ;
+    if (has_tiles) {
+      tc::mbar_wait(done, 0);
+      tc::tc_fence_after();
+    }
+    for (int tap = 0; tap < p.taps; ++tap) {
+      float* d = dst + (size_t)tap * 128 * p.NQ;
+      for (int c0 = 0; c0 < p.NQ; c0 += 16) {
+        uint32_t v[16];
+        if (has_tiles) {
+          tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tap * p.NQ + c0), v);
+          tc::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<uint4*>(d + c0 + 4 * u) = make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+      }
+    }
+  } else if (warp == 4) {
+    // ---- MMA issuer ---------------------------------------------------------------------------
+    if (lane == 0 && has_tiles) {
+      const uint32_t idesc = tc::make_idesc(128, p.NQ, 1, 1);
+      const int ctr = (p.taps - 1) / 2;
+      uint32_t it = 0;
+      for (int64_t tile = s; tile < p.n_tiles; tile += p.S, ++it) {
+        const uint32_t st = it % (uint32_t)p.n_stages;
+        tc::mbar_wait(&full[st], (it / (uint32_t)p.n_stages) & 1u);
+        tc::tc_fence_after();
+        const uint32_t pbase = tc::smem_u32(smem) + st * p.stage_bytes;
+        const uint32_t qbase = pbase + p.p_bytes;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int shift = (tap - ctr) * p.G;
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t da = tc::make_desc(pbase + (uint32_t)(p.halo + shift + 16 * ks) * 16u, 128, p.p_ps);
+            const uint64_t db = tc::make_desc(qbase + (uint32_t)(16 * ks) * 16u, 128, p.q_ps);
+            tc::umma(tmem + (uint32_t)(tap * p.NQ), da, db, idesc, (it == 0 && ks == 0) ? 0u : 1u);
+          }
+        }
+        tc::umma_commit(&empty[st]);
+      }
+      tc::umma_commit(done);
+    }
+  } else if (has_tiles) {
+    // ---- producers: stage P (slice m of its columns) and Q for every tile of this CTA ---------------
+    const int ptid = tid - 160;            // 0..127
+    const int rgrp = ptid >> 3, j = ptid & 7;
+    const int q_panels = p.NQ / 8;
+    uint32_t it = 0;
+    for (int64_t tile = s; tile < p.n_tiles; tile += p.S, ++it) {
+      const uint32_t st = it % (uint32_t)p.n_stages;
+      tc::mbar_wait(&empty[st], ((it / (uint32_t)p.n_stages) & 1u) ^ 1u);
+      const uint32_t pbase = tc::smem_u32(smem) + st * p.stage_bytes;
+      const uint32_t qbase = pbase + p.p_bytes;
+#pragma unroll
+      for (int ss = 0; ss < 8; ++ss) {
+        const int r = rgrp + 16 * ss;
+        const int g = r % p.G, l = r / p.G;
+        const int64_t title = tile * p.G + g;
+        const bool valid = (l < p.L) && (title < p.n_titles);
+        const int64_t t = title * p.L + l;
+        const __nv_bfloat16* prow = nullptr;
+        if (valid) {
+          if (p.ids != nullptr) {
+            int64_t id = load_index(p.ids, p.ids_i64, t);
+            id = id < 0 ? 0 : (id >= p.V ? p.V - 1 : id);
+            prow = p.p + id * p.ldp;
+          } else {
+            prow = p.p + t * p.ldp;
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int col = (m * 16 + j + 8 * h) * 8;
+          const bool ok = valid && col < p.KP;
+          tc::cp_async16(pbase + (uint32_t)(j + 8 * h) * p.p_ps + (uint32_t)(p.halo + r) * 16u,
+                         ok ? (const void*)(prow + col) : (const void*)p.q, ok ? 16u : 0u);
+        }
+        const __nv_bfloat16* qrow = p.q + t * p.ldq;
+        for (int jj = j; jj < q_panels; jj += 8)
+          tc::cp_async16(qbase + (uint32_t)jj * p.q_ps + (uint32_t)r * 16u, valid ? (const void*)(qrow + jj * 8) : (const void*)p.q,
+                         valid ? 16u : 0u);
+      }
+      tc::cp_async_commit();
+      tc::cp_async_wait<0>();
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&full[st]);
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc(tmem, 512);
+}
+
+__global__ void tokred_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dst, int S, int taps, int NQ,
+                                     int i_valid, int j_valid, int64_t dj, int64_t di, int64_t dt) {
+  const int64_t total = (int64_t)taps * i_valid * j_valid;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = (int)(idx % j_valid);
+  const int i = (int)((idx / j_valid) % i_valid);
+  const int tap = (int)(idx / ((int64_t)j_valid * i_valid));
+  const int m = i / 128, il = i % 128;
+  const float* src = partial + (((size_t)m * S * taps + tap) * 128 + il) * NQ + j;
+  const size_t stride = (size_t)taps * 128 * NQ;
+  float acc = 0.f;
+  for (int s = 0; s < S; ++s) acc += src[(size_t)s * stride];
+  dst[j * dj + i * di + tap * dt] = acc;
+}
+
+static void tokred_geometry(int64_t n_titles, int L, int taps, int KP, int* G, int* n_mtiles, int* S, int64_t* n_tiles) {
+  int g = 128 / L;
+  if (g > 16) g = 16;
+  if (g < 1) g = 1;
+  *G = g;
+  *n_tiles = ceil_div(n_titles, (int64_t)g);
+  *n_mtiles = (KP + 127) / 128;
+  int64_t s = sm_count() / *n_mtiles;
+  if (s > *n_tiles) s = *n_tiles;
+  if (s < 1) s = 1;
+  *S = (int)s;
+}
+
+int64_t tokred_partial_bytes(int64_t n_titles, int L, int taps, int KP, int NQ) {
+  int G, n_mtiles, S;
+  int64_t n_tiles;
+  tokred_geometry(n_titles, L < 1 ? 1 : (L > 128 ? 128 : L), taps, KP, &G, &n_mtiles, &S, &n_tiles);
+  return (int64_t)n_mtiles * S * taps * 128 * NQ * 4;
+}
+
+int tokred_plan(TokRedArgs& a, TokRedPlan* plan) {
+  MR_REQUIRE(a.L >= 1 && a.L <= 128, MR_ERR_UNSUPPORTED, "token-reduction gemm: signal_length %d not in [1,128]", a.L);
+  MR_REQUIRE(a.taps == 1 || a.taps == 3, MR_ERR_BAD_SHAPE, "token-reduction gemm: taps=%d", a.taps);
+  MR_REQUIRE(a.KP >= 8 && a.KP % 8 == 0, MR_ERR_BAD_SHAPE, "token-reduction gemm: KP=%d", a.KP);
+  MR_REQUIRE(a.NQ >= 16 && a.NQ % 16 == 0 && a.NQ <= 256 && a.taps * a.NQ <= 512, MR_ERR_UNSUPPORTED,
+             "token-reduction gemm: taps*NQ = %d*%d exceeds the 512 TMEM columns", a.taps, a.NQ);
+  tokred_geometry(a.n_titles, a.L, a.taps, a.KP, &a.G, &a.n_mtiles, &a.S, &a.n_tiles);
+  a.halo = a.taps > 1 ? a.G : 0;
+  a.p_ps = (uint32_t)(((128 + 2 * a.halo) | 1) * 16);
+  a.q_ps = 129 * 16;
+  a.p_bytes = 16 * a.p_ps;
+  a.stage_bytes = a.p_bytes + (uint32_t)(a.NQ / 8) * a.q_ps;
+  const size_t fixed = (2 * TR_MAX_STAGES + 1) * 8 + 16;
+  int ns = (int)((227 * 1024 - fixed - 128) / a.stage_bytes);
+  if (ns > TR_MAX_STAGES) ns = TR_MAX_STAGES;
+  MR_REQUIRE(ns >= 1, MR_ERR_UNSUPPORTED, "token-reduction gemm: stage of %u bytes does not fit shared memory", a.stage_bytes);
+  a.n_stages = ns;
+  plan->args = a;
+  plan->smem_bytes = (size_t)ns * a.stage_bytes + fixed;
+  plan->grid = a.n_mtiles * a.S;
+  return MR_OK;
+}
+
+int tokred_launch(const TokRedPlan& plan, cudaStream_t stream) {
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tokred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "token-reduction gemm: shared-memory opt-in failed: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  tokred_kernel<<<plan.grid, TR_THREADS, plan.smem_bytes, stream>>>(plan.args);
+  MR_CHECK_LAUNCH("tokred_kernel");
+  return MR_OK;
+}
+
+int tokred_reduce(const TokRedPlan& plan, float* dst, int i_valid, int j_valid, int64_t dj, int64_t di, int64_t dt,
+                  cudaStream_t stream) {
+  const TokRedArgs& a = plan.args;
+  const int64_t total = (int64_t)a.taps * i_valid * j_valid;
+  tokred_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(a.partial, dst, a.S, a.taps, a.NQ, i_valid, j_valid,
+                                                                          dj, di, dt);
+  MR_CHECK_LAUNCH("tokred_reduce_kernel");
+  return MR_OK;
+}
+
+}  // namespace mr

@@ -8,7 +8,12 @@ int64_t colsum_chunks(int64_t R) {
   return c < 1 ? 1 : (c > 592 ? 592 : c);
 }
 
-__global__ void colsum_partial_kernel(const float* __restrict__ x, float* __restrict__ partial, int64_t R, int64_t C,
+template <class T> __device__ __forceinline__ float cs_load(const T* p);
+template <> __device__ __forceinline__ float cs_load<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float cs_load<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <class T>
+__global__ void colsum_partial_kernel(const T* __restrict__ x, int64_t ld, float* __restrict__ partial, int64_t R, int64_t C,
                                       int64_t rows_per_chunk) {
   __shared__ float sm[8][33];
   const int cx = threadIdx.x, ry = threadIdx.y;
@@ -17,7 +22,7 @@ __global__ void colsum_partial_kernel(const float* __restrict__ x, float* __rest
   const int64_t r1 = min(R, r0 + rows_per_chunk);
   float s = 0.f;
   if (c < C)
-    for (int64_t r = r0 + ry; r < r1; r += 8) s += x[r * C + c];
+    for (int64_t r = r0 + ry; r < r1; r += 8) s += cs_load<T>(x + r * ld + c);
   sm[ry][cx] = s;
   __syncthreads();
   if (ry == 0 && c < C) {
@@ -36,14 +41,21 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, float* __
   out[c] = s;
 }
 
-cudaError_t colsum(const float* x, float* out, int64_t R, int64_t C, float* partial, cudaStream_t st) {
+template <class T>
+static cudaError_t colsum_t(const T* x, int64_t ld, float* out, int64_t R, int64_t C, float* partial, cudaStream_t st) {
   int64_t chunks = colsum_chunks(R);
   int64_t rpc = ceil_div(R, chunks);
   dim3 grid((unsigned)ceil_div(C, 32), (unsigned)chunks), block(32, 8);
-  colsum_partial_kernel<<<grid, block, 0, st>>>(x, partial, R, C, rpc);
+  colsum_partial_kernel<T><<<grid, block, 0, st>>>(x, ld, partial, R, C, rpc);
   colsum_final_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(partial, out, chunks, C);
   count_launch(2);
   return cudaGetLastError();
+}
+cudaError_t colsum(const float* x, float* out, int64_t R, int64_t C, float* partial, cudaStream_t st) {
+  return colsum_t<float>(x, C, out, R, C, partial, st);
+}
+cudaError_t colsum_bf16(const __nv_bfloat16* x, int64_t ld, float* out, int64_t R, int64_t C, float* partial, cudaStream_t st) {
+  return colsum_t<__nv_bfloat16>(x, ld, out, R, C, partial, st);
 }
 
 // ---- Adam (utils/Manager.py:404-413 -> torch.optim.Adam defaults) -----------------------------

@@ -43,7 +43,8 @@ def embed_grad(ids: torch.Tensor, d_emb: torch.Tensor, V: int, E: int, padding_i
     d_table = torch.empty(V, E, dtype=torch.float32, device=d_emb.device)
     ws = workspace(lib.mr_embed_grad_workspace_bytes(T, E, V), d_emb.device)
     dt = MR_BF16 if d_emb.dtype == torch.bfloat16 else MR_F32
-    check(lib.mr_embed_grad_segreduce(ptr(ids), index_flag(ids), ptr(d_emb), dt, ptr(d_table), T, E, V, padding_idx,
+    ld = d_emb.shape[-1]
+    check(lib.mr_embed_grad_segreduce(ptr(ids), index_flag(ids), ptr(d_emb), dt, ld, ptr(d_table), T, E, V, padding_idx,
                                       ptr(ws), ws.numel(), stream_ptr(d_emb.device)), "mr_embed_grad_segreduce")
     return d_table
 
@@ -152,7 +153,10 @@ class NewsCNN(torch.autograd.Function):
         need_x = ctx.need_table_grad or ctx.need_emb_grad
         d_emb = None
         if need_x:
-            d_emb = torch.empty(N * L, E, dtype=torch.bfloat16 if s.precision == MR_BF16 else torch.float32, device=dev)
+            if s.precision == MR_BF16:      # row pitch = E rounded up to 16 (16-byte aligned tensor-core epilogue stores)
+                d_emb = torch.empty(N * L, pad_to(E, 16), dtype=torch.bfloat16, device=dev)
+            else:
+                d_emb = torch.empty(N * L, E, dtype=torch.float32, device=dev)
         ws = workspace(lib.mr_news_cnn_workspace_bytes(byref(s), 1), dev)
         check(lib.mr_news_cnn_bwd(byref(s), ptr(ids_c), index_flag(ids_c) if ids_c is not None else 0, ptr(emb_c),
                                   ptr(tab), ptr(cw), ptr(pw), ptr(q), ptr(c_save), ptr(key_save), ptr(prob),
@@ -164,7 +168,7 @@ class NewsCNN(torch.autograd.Function):
             V, _ = ctx.table_shape
             d_table = embed_grad(ids_c.view(-1), d_emb, V, E, ctx.padding_idx)
         elif ctx.need_emb_grad:
-            d_emb_out = d_emb.float().view(*emb_c.shape) if d_emb.dtype != torch.float32 else d_emb.view(*emb_c.shape)
+            d_emb_out = d_emb[:, :E].float().view(*emb_c.shape) if d_emb.dtype != torch.float32 else d_emb.view(*emb_c.shape)
         return (None, d_emb_out, None, d_table, None, d_cw, d_cb, d_pw, d_pb, d_q.view(1, H), None, None, None)
 
 

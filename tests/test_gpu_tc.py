@@ -118,3 +118,116 @@ def test_news_cnn_bf16_forward(N, L, E, H):
     dead = (ln == 0)
     if dead.any():
         assert float(news[dead.cuda()].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,C,S,L,E,H", [(8, 5, 50, 32, 300, 150), (3, 2, 7, 30, 300, 150), (2, 3, 5, 48, 64, 32), (2, 2, 3, 20, 768, 150)])
+def test_twotower_bf16_training_step_vs_fp32_oracle(B, C, S, L, E, H):
+    """Whole TwoTower training step (CNN news encoder on tcgen05 in bf16, LSTM user encoder) against the fp32
+    oracle.  north_star bound for bf16 logits is 1e-3 relative.  Gradients of the news encoder are sums with heavy
+    cancellation (softmax backward sums to zero over each title), which amplifies the 2^-9 operand rounding of
+    bf16 to a few percent relative L2 against the fp32 oracle; the tight check of the backward kernels is
+    test_news_cnn_bf16_backward (same rounding points, <= 5e-3)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from helpers import build_model, manager_for, rel_err, random_batch
+    from oracle import twotower_oracle as O
+    gen = torch.Generator().manual_seed(42)
+    torch.manual_seed(42)
+    V = 3000
+    man = manager_for("cnn", "lstm", C, S, L, E, H, 10, precision="bf16")
+    model = build_model(man, V)
+    with torch.no_grad():
+        model.embedding.weight.normal_(0, 0.3)
+    x = random_batch(gen, B, C, S, L, V)
+    params = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    ref = O.forward(params, x, True, encoder_n="cnn", encoder_u="lstm")
+    O.nll_loss(ref, x["label"]).backward()
+    model.train()
+    logp = model(x)[0]
+    torch.nn.NLLLoss()(logp, x["label"].cuda()).backward()
+    torch.cuda.synchronize()
+    e_logit = rel_err(logp, ref)
+    print("logp rel err %.3e" % e_logit)
+    worst = 0.0
+    for k, p in model.named_parameters():
+        e = rel_err(p.grad, params[k].grad)
+        print("  grad %-40s rel err %.3e" % (k, e))
+        worst = max(worst, e)
+    assert e_logit < 1e-3, e_logit
+    assert worst < 8e-2, worst
+    assert float(model.embedding.weight.grad[0].abs().max()) == 0.0
+
+
+def cnn_encoder_bf16_backward_emulation(table, ids, mask, conv_w, conv_b, proj_w, proj_b, query, g):
+    """float64 restatement of the backward of oracle.twotower_oracle.cnn_news_encoder (autograd of CNN.py:30-51,
+    softmax backward of Attention.py:77-80) with bf16 rounding at the points where the MR_BF16 kernels store
+    bf16: c, key, dkey_pre, p*d_news, dconv, d_emb."""
+    import math
+    c, news, p = cnn_encoder_bf16_emulation(table, ids, mask, conv_w, conv_b, proj_w, proj_b, query)
+    N, L = ids.shape
+    H, E = conv_w.shape[0], conv_w.shape[1]
+    c = c.reshape(N, L, H)
+    x = _bf(table)[ids.cpu()].reshape(N, L, E)
+    wq = _bf(proj_w)
+    key = _bf(torch.tanh(c @ wq.t() + proj_b.detach().cpu().double()).float())
+    q = query.detach().cpu().double().view(H)
+    g = g.detach().cpu().double().view(N, 1, H)
+    dp = (g * c).sum(-1)
+    dot = (p * dp).sum(-1, keepdim=True)
+    ds = p * (dp - dot) / math.sqrt(H)
+    d_q = (ds.unsqueeze(-1) * key).sum((0, 1))
+    dkp = _bf((ds.unsqueeze(-1) * q * (1 - key * key)).float())
+    dcp = _bf((p.unsqueeze(-1) * g).float())
+    dconv = _bf(((c > 0).double() * (dcp + dkp @ wq)).float())
+    d_proj_b = dkp.sum((0, 1))
+    d_proj_w = torch.einsum("nlh,nlk->hk", dkp, c)
+    d_conv_b = dconv.sum((0, 1))
+    xpad = torch.nn.functional.pad(x, (0, 0, 1, 1))
+    d_conv_w = torch.stack([torch.einsum("nlh,nle->he", dconv, xpad[:, tap:tap + L]) for tap in range(3)], dim=-1)
+    gpad = torch.nn.functional.pad(dconv, (0, 0, 1, 1))
+    cw = _bf(conv_w)
+    d_x = sum(gpad[:, 2 - tap:2 - tap + L] @ cw[:, :, tap] for tap in range(3))
+    d_x = _bf(d_x.float())
+    d_table = torch.zeros(table.shape, dtype=torch.float64).index_add_(0, ids.cpu().reshape(-1), d_x.reshape(-1, E))
+    d_table[0] = 0
+    return {"cnn.weight": d_conv_w, "cnn.bias": d_conv_b, "wordQueryProject.weight": d_proj_w,
+            "wordQueryProject.bias": d_proj_b, "query_words": d_q.view(1, H), "table": d_table}
+
+
+@pytest.mark.parametrize("N,L,E,H", [(37, 32, 300, 150), (23, 30, 300, 150), (9, 48, 64, 32), (130, 20, 768, 150), (515, 32, 300, 150)])
+def test_news_cnn_bf16_backward(N, L, E, H):
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from helpers import manager_for, rel_err
+    import news_recommendation_mind_b200 as mr
+    torch.manual_seed(N + L)
+    V = 997
+    man = manager_for("cnn", "lstm", 5, 50, L, E, H, 10, precision="bf16")
+    emb = mr.BERT_Embedding(man, vocab_size=V).cuda()
+    enc = mr.CNN_Encoder(man).cuda()
+    with torch.no_grad():
+        emb.weight.normal_(0, 0.3)
+        enc.cnn.bias.normal_(0, 0.1)
+    gen = torch.Generator().manual_seed(1)
+    ln = torch.randint(0, L + 1, (N,), generator=gen)
+    ln[0] = L
+    ids = torch.randint(1, V, (N, L), generator=gen)
+    mask = (torch.arange(L)[None, :] < ln[:, None]).long()
+    ids = ids * mask
+    g = torch.randn(N, H, generator=gen)
+    news = enc.encode_ids(emb, ids.cuda(), mask.cuda())
+    (news * g.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    exp = cnn_encoder_bf16_backward_emulation(emb.weight, ids, mask, enc.cnn.weight, enc.cnn.bias, enc.wordQueryProject.weight,
+                                              enc.wordQueryProject.bias, enc.query_words, g)
+    worst = 0.0
+    for k, p in enc.named_parameters():
+        e = rel_err(p.grad, exp[k])
+        print("  %-28s %.3e" % (k, e))
+        worst = max(worst, e)
+    e = rel_err(emb.weight.grad, exp["table"])
+    print("  %-28s %.3e" % ("table", e))
+    worst = max(worst, e)
+    assert float(emb.weight.grad[0].abs().max()) == 0.0          # padding_idx = 0 row (BERT.py:16-21)
+    # same rounding points, so only accumulation order, tanh.approx and bf16 ties differ
+    assert worst < 5e-3, worst
