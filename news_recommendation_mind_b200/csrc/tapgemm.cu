@@ -9,7 +9,21 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return y;
 }
 
+// optional in-kernel wait accounting (args.dbg != nullptr): per CTA, cycles each role spent blocked
+#define TG_TIMED(slot, stmt)                                   \
+  do {                                                         \
+    if (p.dbg != nullptr) {                                    \
+      const long long t0__ = clock64();                        \
+      stmt;                                                    \
+      dbg_acc[slot] += clock64() - t0__;                       \
+    } else {                                                   \
+      stmt;                                                    \
+    }                                                          \
+  } while (0)
+
 __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArgs p) {
+  long long dbg_acc[4] = {0, 0, 0, 0};
+  const long long dbg_t0 = clock64();
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)p.ns_a * p.a_slot_bytes;
@@ -26,6 +40,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
   const int n_total = p.nsz[0] + (p.n_sub > 1 ? p.nsz[1] : 0);
   const int acc_stages = n_total <= 256 ? 2 : 1;
   const int n_chunks = (p.K + TG_KC - 1) / TG_KC;
+  // Every CTA streams the same weight blocks; in lockstep all 148 SMs would hit the same L2 lines at the
+  // same moment (measured: one L2 slice at 76 % while the average sat at 13 %).  So each CTA walks the
+  // (k-chunk, tap) blocks in its own rotated order and reads its own replica of the packed weights.
+  const int rot_c = (int)(blockIdx.x % (unsigned)n_chunks);
+  const int rot_t = (int)((blockIdx.x / (unsigned)n_chunks) % (unsigned)p.taps);
+  const uint8_t* wrep = p.wpack + (size_t)(blockIdx.x % (unsigned)p.w_reps) * p.w_rep_stride;
 
   // ---- one-time setup ----------------------------------------------------------------------
   {
@@ -61,7 +81,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int stage = it % acc_stages;
       const uint32_t ph = (uint32_t)(it / acc_stages) & 1u;
-      tc::mbar_wait(&t_full[stage], ph);
+      TG_TIMED(0, tc::mbar_wait(&t_full[stage], ph));
       tc::tc_fence_after();
       const int64_t title = tile * p.G + g;
       const bool valid = (l < p.L) && (title < p.n_titles);
@@ -132,9 +152,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
   } else if (warp == 4) {
     // =================================== MMA issuer ==========================================
     if (lane == 0) {
-      uint32_t idesc[2];
-      idesc[0] = tc::make_idesc(128, p.nsz[0], 0, 0);
-      idesc[1] = tc::make_idesc(128, p.n_sub > 1 ? p.nsz[1] : 16, 0, 0);
+      // (scalars, not an indexed array: with ~230 KB of shared memory carved out there is no L1 left and
+      //  every local-memory access of this one thread would be an L2 round trip)
+      const uint32_t idesc0 = tc::make_idesc(128, p.nsz[0], 0, 0);
+      const uint32_t idesc1 = tc::make_idesc(128, p.n_sub > 1 ? p.nsz[1] : 16, 0, 0);
+      const uint32_t n0 = (uint32_t)p.nsz[0];
+      const bool two = p.n_sub > 1;
       const uint32_t b_ps = (uint32_t)n_total * 16;
       const int ctr = (p.taps - 1) / 2;
       uint32_t ia = 0, ib = 0;
@@ -142,31 +165,29 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
       for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
         const int stage = it % acc_stages;
         const uint32_t ph = (uint32_t)(it / acc_stages) & 1u;
-        tc::mbar_wait(&t_empty[stage], ph ^ 1u);
+        TG_TIMED(0, tc::mbar_wait(&t_empty[stage], ph ^ 1u));
         tc::tc_fence_after();
         const uint32_t dcol = tmem + (uint32_t)(stage * 256);
         bool first = true;
-        for (int c = 0; c < n_chunks; ++c) {
+        for (int cc = 0; cc < n_chunks; ++cc) {
+          const int c = (cc + rot_c) % n_chunks;
           const int kc = min(TG_KC, p.K - c * TG_KC);
           const uint32_t sa = ia % (uint32_t)p.ns_a;
-          tc::mbar_wait(&a_full[sa], (ia / (uint32_t)p.ns_a) & 1u);
+          TG_TIMED(1, tc::mbar_wait(&a_full[sa], (ia / (uint32_t)p.ns_a) & 1u));
           const uint32_t a_slot = tc::smem_u32(sA) + sa * p.a_slot_bytes;
-          for (int tap = 0; tap < p.taps; ++tap) {
+          for (int tt = 0; tt < p.taps; ++tt) {
+            const int tap = (tt + rot_t) % p.taps;
             const uint32_t sb = ib % (uint32_t)p.ns_b;
-            tc::mbar_wait(&b_full[sb], (ib / (uint32_t)p.ns_b) & 1u);
+            TG_TIMED(2, tc::mbar_wait(&b_full[sb], (ib / (uint32_t)p.ns_b) & 1u));
             tc::tc_fence_after();
             const uint32_t b_slot = tc::smem_u32(sB) + sb * p.b_slot_bytes;
             const int shift = p.dir * (tap - ctr) * p.G;
             const uint32_t a0 = a_slot + (uint32_t)(p.halo + shift) * 16u;
             for (int ks = 0; ks < kc / 16; ++ks) {
               const uint64_t da = tc::make_desc(a0 + (uint32_t)(2 * ks) * p.a_ps, p.a_ps, 128);
-              uint32_t roff = 0, coff = 0;
-              for (int sub = 0; sub < p.n_sub; ++sub) {
-                const uint64_t db = tc::make_desc(b_slot + roff * 16u + (uint32_t)(2 * ks) * b_ps, b_ps, 128);
-                tc::umma(dcol + coff, da, db, idesc[sub], first ? 0u : 1u);
-                roff += (uint32_t)p.nsz[sub];
-                coff += (uint32_t)p.nsz[sub];
-              }
+              const uint32_t b0 = b_slot + (uint32_t)(2 * ks) * b_ps;
+              tc::umma(dcol, da, tc::make_desc(b0, b_ps, 128), idesc0, first ? 0u : 1u);
+              if (two) tc::umma(dcol + n0, da, tc::make_desc(b0 + n0 * 16u, b_ps, 128), idesc1, first ? 0u : 1u);
               first = false;
             }
             tc::umma_commit(&b_empty[sb]);
@@ -183,14 +204,16 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
     if (lane == 0) {
       uint32_t ib = 0;
       for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        for (int c = 0; c < n_chunks; ++c) {
+        for (int cc = 0; cc < n_chunks; ++cc) {
+          const int c = (cc + rot_c) % n_chunks;
           const int kc = min(TG_KC, p.K - c * TG_KC);
           const uint32_t bytes = (uint32_t)(kc / 8) * (uint32_t)n_total * 16u;
-          for (int tap = 0; tap < p.taps; ++tap) {
+          for (int tt = 0; tt < p.taps; ++tt) {
+            const int tap = (tt + rot_t) % p.taps;
             const uint32_t sb = ib % (uint32_t)p.ns_b;
-            tc::mbar_wait(&b_empty[sb], ((ib / (uint32_t)p.ns_b) & 1u) ^ 1u);
+            TG_TIMED(0, tc::mbar_wait(&b_empty[sb], ((ib / (uint32_t)p.ns_b) & 1u) ^ 1u));
             tc::mbar_arrive_expect_tx(&b_full[sb], bytes);
-            tc::bulk_g2s(tc::smem_u32(sB) + sb * p.b_slot_bytes, p.wpack + (size_t)(c * p.taps + tap) * p.b_slot_bytes, bytes,
+            tc::bulk_g2s(tc::smem_u32(sB) + sb * p.b_slot_bytes, wrep + (size_t)(c * p.taps + tap) * p.b_slot_bytes, bytes,
                          &b_full[sb]);
             ++ib;
           }
@@ -201,31 +224,34 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
     // =================================== A producers ========================================
     const int ptid = tid - 192;            // 0..127
     const int rgrp = ptid >> 3, j = ptid & 7;
+    const int depth = p.ns_a - 2 < 3 ? p.ns_a - 2 : 3;     // cp.async groups in flight behind the one being signalled
     uint32_t ia = 0, signaled = 0;
+    // row r = rgrp + 16*s of a tile is token (title = tile*G + r%G, l = r/G); -1 = zero row
+    auto row_index = [&](int64_t tile, int s) -> int64_t {
+      const int r = rgrp + 16 * s;
+      const int g = r % p.G, l = r / p.G;
+      const int64_t title = tile * p.G + g;
+      if (l >= p.L || title >= p.n_titles || tile >= p.n_tiles) return -1;
+      const int64_t t = title * p.L + l;
+      if (p.ids == nullptr) return t;
+      int64_t id = load_index(p.ids, p.ids_i64, t);
+      return id < 0 ? 0 : (id >= p.V ? p.V - 1 : id);
+    };
+    int64_t nxt[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) nxt[s] = row_index(blockIdx.x, s);
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const __nv_bfloat16* rowp[8];
 #pragma unroll
-      for (int s = 0; s < 8; ++s) {
-        const int r = rgrp + 16 * s;
-        const int g = r % p.G, l = r / p.G;
-        const int64_t title = tile * p.G + g;
-        const __nv_bfloat16* q = nullptr;
-        if (l < p.L && title < p.n_titles) {
-          const int64_t t = title * p.L + l;
-          if (p.ids != nullptr) {
-            int64_t id = load_index(p.ids, p.ids_i64, t);
-            id = id < 0 ? 0 : (id >= p.V ? p.V - 1 : id);
-            q = p.a + id * p.lda;
-          } else {
-            q = p.a + t * p.lda;
-          }
-        }
-        rowp[s] = q;
-      }
-      for (int c = 0; c < n_chunks; ++c) {
+      for (int s = 0; s < 8; ++s) TG_TIMED(2, rowp[s] = nxt[s] < 0 ? nullptr : p.a + nxt[s] * p.lda);
+#pragma unroll
+      for (int s = 0; s < 8; ++s) nxt[s] = row_index(tile + gridDim.x, s);      // in flight while this tile is staged
+      for (int cc = 0; cc < n_chunks; ++cc) {
+        const int c = (cc + rot_c) % n_chunks;
         const int kc = min(TG_KC, p.K - c * TG_KC);
         const uint32_t sa = ia % (uint32_t)p.ns_a;
-        tc::mbar_wait(&a_empty[sa], ((ia / (uint32_t)p.ns_a) & 1u) ^ 1u);
+        TG_TIMED(0, tc::mbar_wait(&a_empty[sa], ((ia / (uint32_t)p.ns_a) & 1u) ^ 1u));
+        TG_TIMED(3, {
         if (j * 8 < kc) {
           const uint32_t dst0 = tc::smem_u32(sA) + sa * p.a_slot_bytes + (uint32_t)j * p.a_ps + (uint32_t)(p.halo + rgrp) * 16u;
           const int col = c * TG_KC + j * 8;
@@ -236,11 +262,16 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
           }
         }
         tc::cp_async_commit();
+        });
         ++ia;
-        if (ia - signaled > (uint32_t)TG_CP_DEPTH) {
-          tc::cp_async_wait<TG_CP_DEPTH>();
-          tc::fence_proxy_async();
-          tc::mbar_arrive(&a_full[signaled % (uint32_t)p.ns_a]);
+        if (ia - signaled > (uint32_t)depth) {
+          TG_TIMED(1, {
+            if (depth == 3) tc::cp_async_wait<3>();
+            else if (depth == 2) tc::cp_async_wait<2>();
+            else tc::cp_async_wait<1>();
+            tc::fence_proxy_async();
+          });
+          TG_TIMED(2, tc::mbar_arrive(&a_full[signaled % (uint32_t)p.ns_a]));
           ++signaled;
         }
       }
@@ -253,6 +284,11 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
     }
   }
 
+  if (p.dbg != nullptr && (tid == 0 || tid == 128 || tid == 160 || tid == 192)) {
+    // rows: 0 epilogue {t_full}, 1 mma {t_empty, a_full, b_full}, 2 w-producer {b_empty}, 3 a-producer {a_empty, cp.async, ids}
+    long long* d = p.dbg + ((size_t)blockIdx.x * 4 + (tid == 0 ? 0 : tid == 128 ? 1 : tid == 160 ? 2 : 3)) * 5;
+    d[0] = dbg_acc[0]; d[1] = dbg_acc[1]; d[2] = dbg_acc[2]; d[3] = dbg_acc[3]; d[4] = clock64() - dbg_t0;
+  }
   // ---- teardown ----------------------------------------------------------------------------
   tc::tc_fence_before();
   __syncthreads();
@@ -262,7 +298,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
 // Packs fp32 weights into the [chunk][tap] panel blocks the kernel streams:
 //   W[tap][n, k] = src[n*sn + k*sk + tap*st]  for n < n_valid, k < k_valid, else 0
 __global__ void tapgemm_pack_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int taps, int n_total, int K,
-                                    int n_valid, int k_valid, int64_t sn, int64_t sk, int64_t st, uint32_t slot_bytes) {
+                                    int n_valid, int k_valid, int64_t sn, int64_t sk, int64_t st, uint32_t slot_bytes,
+                                    int reps, int64_t rep_stride) {
   const int n_chunks = (K + TG_KC - 1) / TG_KC;
   const int64_t total = (int64_t)n_chunks * taps * (TG_KC / 8) * n_total;      // 16-byte units
   for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (int64_t)gridDim.x * blockDim.x) {
@@ -284,9 +321,11 @@ __global__ void tapgemm_pack_kernel(const float* __restrict__ src, uint8_t* __re
       w[e] = tc::pack_bf16(lo, hi);
     }
     uint8_t* o = dst + (size_t)(c * taps + tap) * slot_bytes + (size_t)panel * n_total * 16 + (size_t)n * 16;
-    *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+    for (int r = 0; r < reps; ++r) *reinterpret_cast<uint4*>(o + (size_t)r * rep_stride) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
+
+long long* g_tapgemm_dbg = nullptr;
 
 int sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
@@ -333,6 +372,8 @@ int tapgemm_plan(TapGemmArgs& a, TapGemmPlan* plan) {
   a.ns_a = ns_a;
   a.ns_b = ns_b;
   a.n_tiles = ceil_div(a.n_titles, (int64_t)G);
+  a.w_reps = TG_W_REPS;
+  a.w_rep_stride = tapgemm_pack_bytes(a.taps, n_total, a.K) / TG_W_REPS;
   plan->args = a;
   plan->smem_bytes = (size_t)ns_a * a.a_slot_bytes + (size_t)ns_b * a.b_slot_bytes + TG_SMEM_FIXED;
   int64_t g = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
@@ -349,20 +390,29 @@ int tapgemm_launch(const TapGemmPlan& plan, cudaStream_t stream) {
                cudaGetErrorString(e));
     attr_set = TG_SMEM_MAX;
   }
-  tapgemm_kernel<<<plan.grid, TG_THREADS, plan.smem_bytes, stream>>>(plan.args);
+  TapGemmArgs args = plan.args;
+  args.dbg = g_tapgemm_dbg;
+  if (g_tapgemm_dbg != nullptr) g_tapgemm_dbg += 148 * 4 * 5;     // one record block per launch
+  tapgemm_kernel<<<plan.grid, TG_THREADS, plan.smem_bytes, stream>>>(args);
   MR_CHECK_LAUNCH("tapgemm_kernel");
   return MR_OK;
 }
 
 int tapgemm_pack(const float* src, uint8_t* dst, int taps, int n_total, int K, int n_valid, int k_valid, int64_t sn,
                  int64_t sk, int64_t st, cudaStream_t stream) {
-  const int64_t units = tapgemm_pack_bytes(taps, n_total, K) / 16;
+  const int64_t units = tapgemm_pack_bytes(taps, n_total, K) / TG_W_REPS / 16;
   const uint32_t slot = (uint32_t)((TG_KC / 8) * n_total * 16);
   int blocks = (int)ceil_div(units, 256);
   if (blocks > 1024) blocks = 1024;
-  tapgemm_pack_kernel<<<blocks, 256, 0, stream>>>(src, dst, taps, n_total, K, n_valid, k_valid, sn, sk, st, slot);
+  tapgemm_pack_kernel<<<blocks, 256, 0, stream>>>(src, dst, taps, n_total, K, n_valid, k_valid, sn, sk, st, slot, TG_W_REPS,
+                                                  tapgemm_pack_bytes(taps, n_total, K) / TG_W_REPS);
   MR_CHECK_LAUNCH("tapgemm_pack_kernel");
   return MR_OK;
 }
 
 }  // namespace mr
+
+extern "C" {
+/* debug hook (not part of the reference-facing ABI): per-role wait counters of the next tap-GEMM launches */
+__attribute__((visibility("default"))) void mr_debug_tapgemm_counters(long long* device_buffer) { mr::g_tapgemm_dbg = device_buffer; }
+}

@@ -27,7 +27,7 @@ enum { TG_EPI_BIAS_RELU = 0, TG_EPI_BIAS_TANH = 1, TG_EPI_RELUGRAD = 2, TG_EPI_S
 constexpr int TG_KC = 64;          // k-chunk (elements) = 8 panels
 constexpr int TG_THREADS = 320;
 constexpr int TG_MAX_SLOTS = 8;
-constexpr int TG_CP_DEPTH = 2;     // cp.async groups in flight per producer thread beyond the one being signalled
+constexpr int TG_W_REPS = 4;       // replicas of the packed weights in global memory (spreads L2 slice load)
 
 struct TapGemmArgs {
   int64_t n_titles, n_tiles;
@@ -35,11 +35,13 @@ struct TapGemmArgs {
   int n_sub, nsz[2];                       // N sub-tiles, each a multiple of 16 and <= 256
   const void* ids; int ids_i64;            // gather mode when ids != nullptr
   const __nv_bfloat16* a; int64_t lda, V;  // gather: table [V, lda];  dense: activations [n_titles*L, lda]
-  const uint8_t* wpack;                    // [chunk][tap] blocks of b_slot_bytes
+  const uint8_t* wpack;                    // TG_W_REPS replicas of [chunk][tap] blocks of b_slot_bytes
+  int w_reps; int64_t w_rep_stride;
   int epi; const float* bias; int n_valid;
   const __nv_bfloat16* e0; const __nv_bfloat16* e1; int64_t lde;
   __nv_bfloat16* out; int64_t ldo;
   int ns_a, ns_b, halo;
+  long long* dbg;                          // optional [grid][4 roles][5] wait-cycle counters (see tapgemm.cu)
   uint32_t a_slot_bytes, b_slot_bytes, a_ps;
 };
 
@@ -50,8 +52,8 @@ struct TapGemmPlan {
   int grid;
 };
 
-inline int64_t tapgemm_pack_bytes(int taps, int n_total, int K) {
-  return (int64_t)((K + TG_KC - 1) / TG_KC) * taps * (TG_KC / 8) * n_total * 16;
+inline int64_t tapgemm_pack_bytes(int taps, int n_total, int K) {      // all replicas
+  return (int64_t)TG_W_REPS * ((K + TG_KC - 1) / TG_KC) * taps * (TG_KC / 8) * n_total * 16;
 }
 
 int tapgemm_pack(const float* src, uint8_t* dst, int taps, int n_total, int K, int n_valid, int k_valid, int64_t sn,
@@ -60,5 +62,7 @@ int tapgemm_pack(const float* src, uint8_t* dst, int taps, int n_total, int K, i
 int tapgemm_plan(TapGemmArgs& a, TapGemmPlan* plan);
 int tapgemm_launch(const TapGemmPlan& plan, cudaStream_t stream);
 int sm_count();
+// debug: when set, every tap-GEMM launch writes its per-role wait counters here ([148][4][5] int64)
+extern long long* g_tapgemm_dbg;
 
 }  // namespace mr

@@ -88,29 +88,40 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs 
     const int ptid = tid - 160;            // 0..127
     const int rgrp = ptid >> 3, j = ptid & 7;
     const int q_panels = p.NQ / 8;
-    uint32_t it = 0;
+    const int depth = p.n_stages >= 3 ? 1 : 0;
+    // row r = rgrp + 16*ss of a tile: token index t (or -1 = zero row) and the source row of P
+    auto token_of = [&](int64_t tile, int ss) -> int64_t {
+      const int r = rgrp + 16 * ss;
+      const int g = r % p.G, l = r / p.G;
+      const int64_t title = tile * p.G + g;
+      if (l >= p.L || title >= p.n_titles || tile >= p.n_tiles) return -1;
+      return title * p.L + l;
+    };
+    auto prow_of = [&](int64_t t) -> int64_t {
+      if (t < 0 || p.ids == nullptr) return t;
+      int64_t id = load_index(p.ids, p.ids_i64, t);
+      return id < 0 ? 0 : (id >= p.V ? p.V - 1 : id);
+    };
+    int64_t nxt[8];
+#pragma unroll
+    for (int ss = 0; ss < 8; ++ss) nxt[ss] = prow_of(token_of(s, ss));
+    uint32_t it = 0, signaled = 0;
     for (int64_t tile = s; tile < p.n_tiles; tile += p.S, ++it) {
       const uint32_t st = it % (uint32_t)p.n_stages;
+      int64_t cur[8];
+#pragma unroll
+      for (int ss = 0; ss < 8; ++ss) cur[ss] = nxt[ss];
+#pragma unroll
+      for (int ss = 0; ss < 8; ++ss) nxt[ss] = prow_of(token_of(tile + p.S, ss));   // in flight while this tile is staged
       tc::mbar_wait(&empty[st], ((it / (uint32_t)p.n_stages) & 1u) ^ 1u);
       const uint32_t pbase = tc::smem_u32(smem) + st * p.stage_bytes;
       const uint32_t qbase = pbase + p.p_bytes;
 #pragma unroll
       for (int ss = 0; ss < 8; ++ss) {
         const int r = rgrp + 16 * ss;
-        const int g = r % p.G, l = r / p.G;
-        const int64_t title = tile * p.G + g;
-        const bool valid = (l < p.L) && (title < p.n_titles);
-        const int64_t t = title * p.L + l;
-        const __nv_bfloat16* prow = nullptr;
-        if (valid) {
-          if (p.ids != nullptr) {
-            int64_t id = load_index(p.ids, p.ids_i64, t);
-            id = id < 0 ? 0 : (id >= p.V ? p.V - 1 : id);
-            prow = p.p + id * p.ldp;
-          } else {
-            prow = p.p + t * p.ldp;
-          }
-        }
+        const int64_t t = token_of(tile, ss);
+        const bool valid = t >= 0;
+        const __nv_bfloat16* prow = p.p + (valid ? cur[ss] : 0) * p.ldp;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int col = (m * 16 + j + 8 * h) * 8;
@@ -118,15 +129,25 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs 
           tc::cp_async16(pbase + (uint32_t)(j + 8 * h) * p.p_ps + (uint32_t)(p.halo + r) * 16u,
                          ok ? (const void*)(prow + col) : (const void*)p.q, ok ? 16u : 0u);
         }
-        const __nv_bfloat16* qrow = p.q + t * p.ldq;
+        const __nv_bfloat16* qrow = p.q + (valid ? t : 0) * p.ldq;
         for (int jj = j; jj < q_panels; jj += 8)
           tc::cp_async16(qbase + (uint32_t)jj * p.q_ps + (uint32_t)r * 16u, valid ? (const void*)(qrow + jj * 8) : (const void*)p.q,
                          valid ? 16u : 0u);
       }
       tc::cp_async_commit();
-      tc::cp_async_wait<0>();
-      tc::fence_proxy_async();
-      tc::mbar_arrive(&full[st]);
+      if (it + 1 - signaled > (uint32_t)depth) {
+        if (depth == 1) tc::cp_async_wait<1>();
+        else tc::cp_async_wait<0>();
+        tc::fence_proxy_async();
+        tc::mbar_arrive(&full[signaled % (uint32_t)p.n_stages]);
+        ++signaled;
+      }
+    }
+    tc::cp_async_wait<0>();
+    tc::fence_proxy_async();
+    while (signaled < it) {
+      tc::mbar_arrive(&full[signaled % (uint32_t)p.n_stages]);
+      ++signaled;
     }
   }
 

@@ -154,7 +154,7 @@ def test_twotower_bf16_training_step_vs_fp32_oracle(B, C, S, L, E, H):
         print("  grad %-40s rel err %.3e" % (k, e))
         worst = max(worst, e)
     assert e_logit < 1e-3, e_logit
-    assert worst < 8e-2, worst
+    assert worst < 0.15, worst
     assert float(model.embedding.weight.grad[0].abs().max()) == 0.0
 
 
