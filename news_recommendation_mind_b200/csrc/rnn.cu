@@ -10,6 +10,7 @@
 //      three GEMMs (d_x, d_W_ih, d_W_hh) and column sums for the biases.
 // pos(s) = s, or S-1-s when `reverse` (the reference flips the padded history *before* packing).
 #include "gemm_simt.cuh"
+#include "rnn_res.cuh"
 
 namespace mr {
 
@@ -309,15 +310,17 @@ int mr_rnn_user_fwd(const mr_rnn_shape* s, const float* x, const int32_t* lens, 
   cudaError_t e = gemm_simt<true, false>((int64_t)B * S, GH, H, xv, Transposed{w_ih, H},
                                          TwoBiasEpi{xp, GH, b_ih, s->kind == MR_RNN_LSTM ? b_hh : nullptr}, 1, nullptr, st);
   MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "rnn input projection: %s", cudaGetErrorString(e));
+  // steps past a sequence's length are never written by the kernel: clear the saved tensors
+  cudaMemsetAsync(gates, 0, sizeof(float) * (int64_t)B * S * GH, st);
+  cudaMemsetAsync(hs, 0, sizeof(float) * (int64_t)B * S * H, st);
+  cudaMemsetAsync(cs, 0, sizeof(float) * (int64_t)B * S * H, st);
+  if (s->precision == MR_BF16 && rnn_res_supported(s->kind, H))
+    return rnn_res_fwd(s->kind, xp, w_hh, b_hh, h0, lens, gates, hs, cs, user, B, S, H, st);
   dim3 tg((unsigned)ceil_div(H, 32), (unsigned)ceil_div(GH, 32)), tb(32, 8);
   transpose_kernel<<<tg, tb, 0, st>>>(w_hh, whhT, GH, H);
   MR_CHECK_LAUNCH("transpose_kernel");
   size_t smem = sizeof(float) * (2 * RNN_BPC * H + RNN_BPC * GH);
   unsigned grid = (unsigned)ceil_div(B, RNN_BPC);
-  // steps past a sequence's length are never written by the kernel: clear the saved tensors
-  cudaMemsetAsync(gates, 0, sizeof(float) * (int64_t)B * S * GH, st);
-  cudaMemsetAsync(hs, 0, sizeof(float) * (int64_t)B * S * H, st);
-  cudaMemsetAsync(cs, 0, sizeof(float) * (int64_t)B * S * H, st);
   if (s->kind == MR_RNN_LSTM) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(rnn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     rnn_fwd_kernel<0><<<grid, RNN_THREADS, smem, st>>>(xp, whhT, b_hh, h0, lens, gates, hs, cs, user, B, S, H);
@@ -358,14 +361,16 @@ int mr_rnn_user_bwd(const mr_rnn_shape* s, const float* x, const int32_t* lens, 
   if (s->kind == MR_RNN_LSTM) dgh = dgi;
   size_t smem = sizeof(float) * (2 * RNN_BPC * H + RNN_BPC * GH);
   unsigned grid = (unsigned)ceil_div(B, RNN_BPC);
-  if (s->kind == MR_RNN_LSTM) {
+  if (s->precision == MR_BF16 && rnn_res_supported(s->kind, H)) {
+    if (int rc = rnn_res_bwd(s->kind, w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H, st)) return rc;
+  } else if (s->kind == MR_RNN_LSTM) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(rnn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     rnn_bwd_kernel<0><<<grid, RNN_THREADS, smem, st>>>(w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H);
   } else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(rnn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     rnn_bwd_kernel<1><<<grid, RNN_THREADS, smem, st>>>(w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H);
   }
-  MR_CHECK_LAUNCH("rnn_bwd_kernel");
+  if (!(s->precision == MR_BF16 && rnn_res_supported(s->kind, H))) MR_CHECK_LAUNCH("rnn_bwd_kernel");
   cudaError_t e;
   if (d_x) {
     e = gemm_simt<true, true>(BS, H, GH, RowMajor{dgi, GH}, RowMajor{w_ih, H}, SeqStoreEpi{d_x, S, H, s->reverse}, 1, nullptr, st);

@@ -1,0 +1,19 @@
+// Persistent recurrence kernels with the recurrent weights resident in shared memory (MR_BF16 path of
+// the LSTM / GRU user encoders, models/Encoders/RNN.py:36-104).  See rnn_res.cu.
+#pragma once
+#include "common.cuh"
+
+namespace mr {
+
+// true when W_hh (bf16) plus the per-step scratch fits one SM's shared memory for this shape
+bool rnn_res_supported(int kind, int H);
+int rnn_res_bpc(int kind, int B, int H);
+
+// xp: [B,S,G*H] fp32 input projection (+ biases), indexed by step; w_hh [G*H, H] fp32; the rest as rnn.cu
+int rnn_res_fwd(int kind, const float* xp, const float* w_hh, const float* b_hh, const float* h0, const int32_t* lens,
+                float* gates, float* hs, float* cs, float* user, int B, int S, int H, cudaStream_t st);
+int rnn_res_bwd(int kind, const float* w_hh, const float* h0, const int32_t* lens, const float* gates, const float* hs,
+                const float* cs, const float* d_user, float* dgi, float* dgh, float* d_h0, int B, int S, int H,
+                cudaStream_t st);
+
+}  // namespace mr

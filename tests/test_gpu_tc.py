@@ -231,3 +231,42 @@ def test_news_cnn_bf16_backward(N, L, E, H):
     assert float(emb.weight.grad[0].abs().max()) == 0.0          # padding_idx = 0 row (BERT.py:16-21)
     # same rounding points, so only accumulation order, tanh.approx and bf16 ties differ
     assert worst < 5e-3, worst
+
+
+@pytest.mark.parametrize("kind,B,S,H,rev", [("lstm", 256, 50, 150, False), ("gru", 37, 20, 150, False), ("lstm", 5, 7, 64, True),
+                                             ("gru", 300, 11, 96, True), ("lstm", 700, 9, 150, False)])
+def test_rnn_user_encoder_resident_weights(kind, B, S, H, rev):
+    """MR_BF16 recurrent user encoder (persistent kernel, W_hh resident in shared memory as bf16) against the
+    oracle's LSTM / GRU (RNN.py:50-73) evaluated with W_hh rounded to bf16 -- the one rounding the kernel
+    applies; everything else is fp32, so outputs and gradients agree to 1e-4."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from helpers import manager_for, rel_err
+    import news_recommendation_mind_b200 as mr
+    from oracle import twotower_oracle as O
+    torch.manual_seed(B + S)
+    man = manager_for("cnn", kind, 5, S, 32, 300, H, 10, precision="bf16", descend_history=rev)
+    enc = mr.RNN_User_Encoder(man).cuda()
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(B, S, H, generator=gen) * 0.5
+    ln = torch.randint(1, S + 1, (B,), generator=gen)
+    ln[0] = S
+    his_mask = (torch.arange(S)[None, :] < ln[:, None]).double().unsqueeze(-1)
+    g = torch.randn(B, 1, H, generator=gen)
+    xc = x.cuda().requires_grad_(True)
+    out = enc(xc, his_mask=his_mask)
+    (out * g.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    p = {k: v.detach().cpu().double().requires_grad_(True) for k, v in enc.rnn.named_parameters()}
+    whh = p["weight_hh_l0"].detach().float().bfloat16().double().requires_grad_(True)
+    xo = x.double().requires_grad_(True)
+    fn = O.lstm_user_encoder if kind == "lstm" else O.gru_user_encoder
+    ref = fn(xo, his_mask, p["weight_ih_l0"], whh, p["bias_ih_l0"], p["bias_hh_l0"], descend_history=rev)
+    (ref * g.double()).sum().backward()
+    errs = {"out": rel_err(out, ref), "d_x": rel_err(xc.grad, xo.grad),
+            "d_w_ih": rel_err(enc.rnn.weight_ih_l0.grad, p["weight_ih_l0"].grad),
+            "d_w_hh": rel_err(enc.rnn.weight_hh_l0.grad, whh.grad),
+            "d_b_ih": rel_err(enc.rnn.bias_ih_l0.grad, p["bias_ih_l0"].grad),
+            "d_b_hh": rel_err(enc.rnn.bias_hh_l0.grad, p["bias_hh_l0"].grad)}
+    print(kind, B, S, H, {k: "%.2e" % v for k, v in errs.items()})
+    assert max(errs.values()) < 1e-4, errs
