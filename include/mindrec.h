@@ -249,7 +249,8 @@ MR_API int mr_nll_loss_bwd(const void* label, int label_i64, const float* d_loss
  * K-major (rows = M/N index) or MN-major (rows = K index) operands, a_shift reads A `a_shift` rows
  * later (zero halo).  Used by tests/test_gpu_tc.py to pin the descriptor conventions on hardware. */
 MR_API int mr_tc_selftest(const float* a, int64_t ra, int64_t ca, const float* b, int64_t rb, int64_t cb, float* d,
-                   int a_mn, int b_mn, int64_t N, int64_t K, int64_t a_shift, int64_t halo, int swap, void* stream);
+                   int a_mn, int b_mn, int64_t N, int64_t K, int64_t a_shift, int64_t halo, int swap,
+                   int a_layout, int b_layout, int base_off_mode, void* stream);
 
 /* fp32 [rows, cols] -> bf16 [rows, ld] (zero padded columns). */
 MR_API int mr_cast_pad_bf16(const float* src, void* dst, int64_t rows, int64_t cols, int64_t ld, void* stream);

@@ -60,7 +60,7 @@ _SIGNATURES = {
     "mr_nll_loss_fwd": (c_int, [P, P, c_int, P, I64, I64, P]),
     "mr_nll_loss_bwd": (c_int, [P, c_int, P, P, I64, I64, P]),
     "mr_cast_pad_bf16": (c_int, [P, P, I64, I64, I64, P]),
-    "mr_tc_selftest": (c_int, [P, I64, I64, P, I64, I64, P, c_int, c_int, I64, I64, I64, I64, c_int, P]),
+    "mr_tc_selftest": (c_int, [P, I64, I64, P, I64, I64, P, c_int, c_int, I64, I64, I64, I64, c_int, c_int, c_int, c_int, P]),
 }
 
 _lib = None

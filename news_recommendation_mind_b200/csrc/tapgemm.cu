@@ -21,11 +21,21 @@ __device__ __forceinline__ float tanh_fast(float x) {
     }                                                          \
   } while (0)
 
+// ring position + phase bit, advanced without integer division (the role loops are latency bound:
+// every instruction on their critical path shows up in the tile rate)
+struct Ring {
+  uint32_t pos, phase, n;
+  __device__ __forceinline__ explicit Ring(uint32_t n_) : pos(0), phase(0), n(n_) {}
+  __device__ __forceinline__ void next() {
+    if (++pos == n) { pos = 0; phase ^= 1u; }
+  }
+};
+
 __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArgs p) {
   long long dbg_acc[4] = {0, 0, 0, 0};
   const long long dbg_t0 = clock64();
-  extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* sA = smem;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;                      // A slots: [rows_alloc x 128 B], 1024-byte aligned (swizzle period)
   uint8_t* sB = sA + (size_t)p.ns_a * p.a_slot_bytes;
   float* sbias = reinterpret_cast<float*>(sB + (size_t)p.ns_b * p.b_slot_bytes);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(sbias + 512);
@@ -36,13 +46,14 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int n_total = p.nsz[0] + (p.n_sub > 1 ? p.nsz[1] : 0);
-  const int acc_stages = n_total <= 256 ? 2 : 1;
+  const uint32_t acc_stages = n_total <= 256 ? 2u : 1u;
   const int n_chunks = (p.K + TG_KC - 1) / TG_KC;
+  const int last_kc = p.K - (n_chunks - 1) * TG_KC;
   // Every CTA streams the same weight blocks; in lockstep all 148 SMs would hit the same L2 lines at the
-  // same moment (measured: one L2 slice at 76 % while the average sat at 13 %).  So each CTA walks the
-  // (k-chunk, tap) blocks in its own rotated order and reads its own replica of the packed weights.
+  // same moment.  So each CTA walks the (k-chunk, tap) blocks in its own rotated order and reads its own
+  // replica of the packed weights.
   const int rot_c = (int)(blockIdx.x % (unsigned)n_chunks);
   const int rot_t = (int)((blockIdx.x / (unsigned)n_chunks) % (unsigned)p.taps);
   const uint8_t* wrep = p.wpack + (size_t)(blockIdx.x % (unsigned)p.w_reps) * p.w_rep_stride;
@@ -77,22 +88,23 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
     // =================================== epilogue ===========================================
     const int r = tid;
     const int g = r % p.G, l = r / p.G;
-    int it = 0;
-    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      const int stage = it % acc_stages;
-      const uint32_t ph = (uint32_t)(it / acc_stages) & 1u;
-      TG_TIMED(0, tc::mbar_wait(&t_full[stage], ph));
+    const bool row_ok = l < p.L;
+    const int64_t row_off = (int64_t)g * p.L + l;            // token offset inside the tile's G titles
+    Ring acc(acc_stages);
+    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      TG_TIMED(0, tc::mbar_wait(&t_full[acc.pos], acc.phase));
       tc::tc_fence_after();
-      const int64_t title = tile * p.G + g;
-      const bool valid = (l < p.L) && (title < p.n_titles);
-      const int64_t t = title * p.L + l;
-      const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(stage * 256);
+      const bool valid = row_ok && (tile * p.G + g < p.n_titles);
+      const int64_t t = tile * p.G * p.L + row_off;
+      const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + acc.pos * 256u;
       int col0 = 0;
       for (int sub = 0; sub < p.n_sub; ++sub) {
-        for (int c0 = 0; c0 < p.nsz[sub]; c0 += 32) {
+        const int nsub = sub == 0 ? p.nsz[0] : p.nsz[1];
+        for (int c0 = 0; c0 < nsub; c0 += 32) {
           uint32_t v[32];
           const int n0 = col0 + c0;
-          if (p.nsz[sub] - c0 >= 32) {
+          const bool wide = nsub - c0 >= 32;
+          if (wide) {
             tc::tmem_ld32(tbase + n0, v);
           } else {
             uint32_t h[16];
@@ -100,8 +112,16 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
 #pragma unroll
             for (int j = 0; j < 16; ++j) { v[j] = h[j]; v[16 + j] = 0u; }
           }
+          // operands of the RELUGRAD epilogue are fetched while the TMEM load is in flight
+          uint4 x0[4], x1[4];
+          if (p.epi == TG_EPI_RELUGRAD && valid) {
+            const uint4* q0 = reinterpret_cast<const uint4*>(p.e0 + t * p.lde + n0);
+            const uint4* q1 = reinterpret_cast<const uint4*>(p.e1 + t * p.lde + n0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (u < 2 || wide) { x0[u] = __ldg(q0 + u); x1[u] = __ldg(q1 + u); }
+          }
           tc::tmem_ld_wait();
-          const int width = (p.nsz[sub] - c0 >= 32) ? 32 : 16;
           if (valid) {
             float f[32];
 #pragma unroll
@@ -113,14 +133,11 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = tanh_fast(f[j] + sbias[n0 + j]);
             } else if (p.epi == TG_EPI_RELUGRAD) {
-              const uint4* q0 = reinterpret_cast<const uint4*>(p.e0 + t * p.lde + n0);
-              const uint4* q1 = reinterpret_cast<const uint4*>(p.e1 + t * p.lde + n0);
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
-                if (u * 8 < width) {
-                  uint4 x0 = __ldg(q0 + u), x1 = __ldg(q1 + u);
-                  const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&x0);
-                  const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&x1);
+                if (u < 2 || wide) {
+                  const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&x0[u]);
+                  const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&x1[u]);
 #pragma unroll
                   for (int w = 0; w < 4; ++w) {
                     float2 d = __bfloat1622float2(h0[w]), c = __bfloat1622float2(h1[w]);
@@ -133,7 +150,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
             uint4* dst = reinterpret_cast<uint4*>(p.out + t * p.ldo + n0);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              if (u * 8 < width) {
+              if (u < 2 || wide) {
                 uint4 o;
                 o.x = tc::pack_bf16(f[u * 8 + 0], f[u * 8 + 1]);
                 o.y = tc::pack_bf16(f[u * 8 + 2], f[u * 8 + 3]);
@@ -144,79 +161,96 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
             }
           }
         }
-        col0 += p.nsz[sub];
+        col0 += nsub;
       }
       tc::tc_fence_before();
-      tc::mbar_arrive(&t_empty[stage]);
+      tc::mbar_arrive(&t_empty[acc.pos]);
+      acc.next();
     }
   } else if (warp == 4) {
     // =================================== MMA issuer ==========================================
-    if (lane == 0) {
-      // (scalars, not an indexed array: with ~230 KB of shared memory carved out there is no L1 left and
-      //  every local-memory access of this one thread would be an L2 round trip)
-      const uint32_t idesc0 = tc::make_idesc(128, p.nsz[0], 0, 0);
-      const uint32_t idesc1 = tc::make_idesc(128, p.n_sub > 1 ? p.nsz[1] : 16, 0, 0);
-      const uint32_t n0 = (uint32_t)p.nsz[0];
-      const bool two = p.n_sub > 1;
-      const uint32_t b_ps = (uint32_t)n_total * 16;
-      const int ctr = (p.taps - 1) / 2;
-      uint32_t ia = 0, ib = 0;
-      int it = 0;
-      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-        const int stage = it % acc_stages;
-        const uint32_t ph = (uint32_t)(it / acc_stages) & 1u;
-        TG_TIMED(0, tc::mbar_wait(&t_empty[stage], ph ^ 1u));
-        tc::tc_fence_after();
-        const uint32_t dcol = tmem + (uint32_t)(stage * 256);
-        bool first = true;
-        for (int cc = 0; cc < n_chunks; ++cc) {
-          const int c = (cc + rot_c) % n_chunks;
-          const int kc = min(TG_KC, p.K - c * TG_KC);
-          const uint32_t sa = ia % (uint32_t)p.ns_a;
-          TG_TIMED(1, tc::mbar_wait(&a_full[sa], (ia / (uint32_t)p.ns_a) & 1u));
-          const uint32_t a_slot = tc::smem_u32(sA) + sa * p.a_slot_bytes;
-          for (int tt = 0; tt < p.taps; ++tt) {
-            const int tap = (tt + rot_t) % p.taps;
-            const uint32_t sb = ib % (uint32_t)p.ns_b;
-            TG_TIMED(2, tc::mbar_wait(&b_full[sb], (ib / (uint32_t)p.ns_b) & 1u));
-            tc::tc_fence_after();
-            const uint32_t b_slot = tc::smem_u32(sB) + sb * p.b_slot_bytes;
-            const int shift = p.dir * (tap - ctr) * p.G;
-            const uint32_t a0 = a_slot + (uint32_t)(p.halo + shift) * 16u;
-            for (int ks = 0; ks < kc / 16; ++ks) {
-              const uint64_t da = tc::make_desc(a0 + (uint32_t)(2 * ks) * p.a_ps, p.a_ps, 128);
-              const uint32_t b0 = b_slot + (uint32_t)(2 * ks) * b_ps;
-              tc::umma(dcol, da, tc::make_desc(b0, b_ps, 128), idesc0, first ? 0u : 1u);
-              if (two) tc::umma(dcol + n0, da, tc::make_desc(b0 + n0 * 16u, b_ps, 128), idesc1, first ? 0u : 1u);
-              first = false;
+    // The whole warp walks the loop (warp-uniform control flow, so descriptor arithmetic stays in uniform
+    // registers); one elected lane issues tcgen05.mma / tcgen05.commit.  Descriptors are built once per
+    // block and advanced by adding to their low word (start address field, 16-byte units).
+    const uint32_t idesc0 = tc::make_idesc(128, p.nsz[0], 0, 0);
+    const uint32_t idesc1 = tc::make_idesc(128, p.n_sub > 1 ? p.nsz[1] : 16, 0, 0);
+    const uint32_t n0 = (uint32_t)p.nsz[0];
+    const bool two = p.n_sub > 1;
+    const uint32_t b_ps = (uint32_t)n_total * 16;
+    const uint64_t a_hi = tc::make_desc_sw(0, 16, 1024, 2, 0) & 0xFFFFFFFF00000000ull;
+    const uint64_t b_desc0 = tc::make_desc(0, b_ps, 128);
+    const uint32_t b_kstep = (2u * b_ps) >> 4;             // k-step of 16 elements = two panels
+    const uint32_t sA0 = tc::smem_u32(sA), sB0 = tc::smem_u32(sB);
+    // operand row offset (in 16-byte units of the start-address field) of each tap: (halo + shift) * 128 B
+    const int ctr = (p.taps - 1) / 2;
+    const uint32_t tap_off0 = (uint32_t)(p.halo + p.dir * (0 - ctr) * p.G) * 8u;
+    const uint32_t tap_off1 = (uint32_t)(p.halo + p.dir * (1 - ctr) * p.G) * 8u;
+    const uint32_t tap_off2 = (uint32_t)(p.halo + p.dir * (2 - ctr) * p.G) * 8u;
+    Ring ra(p.ns_a), rb(p.ns_b), acc(acc_stages);
+    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      TG_TIMED(0, tc::mbar_wait(&t_empty[acc.pos], acc.phase ^ 1u));
+      tc::tc_fence_after();
+      const uint32_t dcol = tmem + acc.pos * 256u;
+      uint32_t accum = 0;
+      int c = rot_c;
+      for (int cc = 0; cc < n_chunks; ++cc) {
+        const int nks = (c == n_chunks - 1 ? last_kc : TG_KC) >> 4;
+        TG_TIMED(1, tc::mbar_wait(&a_full[ra.pos], ra.phase));
+        const uint32_t a_slot16 = (sA0 + ra.pos * p.a_slot_bytes) >> 4;
+        int tap = rot_t;
+        for (int tt = 0; tt < p.taps; ++tt) {
+          TG_TIMED(2, tc::mbar_wait(&b_full[rb.pos], rb.phase));
+          tc::tc_fence_after();
+          const uint32_t b_slot = sB0 + rb.pos * p.b_slot_bytes;
+          const uint32_t toff = tap == 0 ? tap_off0 : (tap == 1 ? tap_off1 : tap_off2);
+          const uint64_t da0 = a_hi | (uint64_t)((a_slot16 + toff) & 0x3FFFu);
+          const uint64_t db0 = b_desc0 | (uint64_t)((b_slot >> 4) & 0x3FFFu);
+          const uint64_t db1 = b_desc0 | (uint64_t)(((b_slot + n0 * 16u) >> 4) & 0x3FFFu);
+          const bool last_tap = tt == p.taps - 1;
+          TG_TIMED(3, {
+          if (tc::elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              if (ks < nks) {
+                tc::umma(dcol, da0 + (uint64_t)(2 * ks), db0 + (uint64_t)(ks * b_kstep), idesc0, accum | (uint32_t)ks);
+                if (two) tc::umma(dcol + n0, da0 + (uint64_t)(2 * ks), db1 + (uint64_t)(ks * b_kstep), idesc1, accum | (uint32_t)ks);
+              }
             }
-            tc::umma_commit(&b_empty[sb]);
-            ++ib;
+            tc::umma_commit(&b_empty[rb.pos]);
+            if (last_tap) tc::umma_commit(&a_empty[ra.pos]);
+            if (last_tap && cc == n_chunks - 1) tc::umma_commit(&t_full[acc.pos]);
           }
-          tc::umma_commit(&a_empty[sa]);
-          ++ia;
+          __syncwarp();
+          });
+          accum = 1;
+          rb.next();
+          if (++tap == p.taps) tap = 0;
         }
-        tc::umma_commit(&t_full[stage]);
+        ra.next();
+        if (++c == n_chunks) c = 0;
       }
+      acc.next();
     }
   } else if (warp == 5) {
     // =================================== weight producer ====================================
-    if (lane == 0) {
-      uint32_t ib = 0;
+    if ((tid & 31) == 0) {
+      const uint32_t sB0 = tc::smem_u32(sB);
+      const uint32_t full_bytes = (uint32_t)(TG_KC / 8) * (uint32_t)n_total * 16u;
+      const uint32_t last_bytes = (uint32_t)(last_kc / 8) * (uint32_t)n_total * 16u;
+      Ring rb(p.ns_b);
       for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        int c = rot_c;
         for (int cc = 0; cc < n_chunks; ++cc) {
-          const int c = (cc + rot_c) % n_chunks;
-          const int kc = min(TG_KC, p.K - c * TG_KC);
-          const uint32_t bytes = (uint32_t)(kc / 8) * (uint32_t)n_total * 16u;
+          const uint32_t bytes = c == n_chunks - 1 ? last_bytes : full_bytes;
+          int tap = rot_t;
           for (int tt = 0; tt < p.taps; ++tt) {
-            const int tap = (tt + rot_t) % p.taps;
-            const uint32_t sb = ib % (uint32_t)p.ns_b;
-            TG_TIMED(0, tc::mbar_wait(&b_empty[sb], ((ib / (uint32_t)p.ns_b) & 1u) ^ 1u));
-            tc::mbar_arrive_expect_tx(&b_full[sb], bytes);
-            tc::bulk_g2s(tc::smem_u32(sB) + sb * p.b_slot_bytes, wrep + (size_t)(c * p.taps + tap) * p.b_slot_bytes, bytes,
-                         &b_full[sb]);
-            ++ib;
+            TG_TIMED(0, tc::mbar_wait(&b_empty[rb.pos], rb.phase ^ 1u));
+            tc::mbar_arrive_expect_tx(&b_full[rb.pos], bytes);
+            tc::bulk_g2s(sB0 + rb.pos * p.b_slot_bytes, wrep + (size_t)(c * p.taps + tap) * p.b_slot_bytes, bytes, &b_full[rb.pos]);
+            rb.next();
+            if (++tap == p.taps) tap = 0;
           }
+          if (++c == n_chunks) c = 0;
         }
       }
     }
@@ -224,68 +258,82 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
     // =================================== A producers ========================================
     const int ptid = tid - 192;            // 0..127
     const int rgrp = ptid >> 3, j = ptid & 7;
-    const int depth = p.ns_a - 2 < 3 ? p.ns_a - 2 : 3;     // cp.async groups in flight behind the one being signalled
-    uint32_t ia = 0, signaled = 0;
-    // row r = rgrp + 16*s of a tile is token (title = tile*G + r%G, l = r/G); -1 = zero row
-    auto row_index = [&](int64_t tile, int s) -> int64_t {
+    const uint32_t depth = (uint32_t)(p.ns_a - 2 < 3 ? p.ns_a - 2 : 3);   // cp.async groups in flight behind the signalled one
+    const uint32_t sA0 = tc::smem_u32(sA);
+    // this thread stages the 16-byte piece j of rows r = rgrp + 16*s (s = 0..7) of every k-chunk.  Row r is
+    // token (title = tile*G + r%G, position = r/G); the geometry is tile independent, so it is computed once.
+    int64_t row_off[8];      // token offset inside the tile's G titles, -1 = permanent zero row
+    int row_g[8];
+    uint32_t dst_off[8];     // row-linear SWIZZLE_128B: row at (halo + r) * 128, piece j at ((j ^ row) & 7) * 16
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
       const int r = rgrp + 16 * s;
       const int g = r % p.G, l = r / p.G;
-      const int64_t title = tile * p.G + g;
-      if (l >= p.L || title >= p.n_titles || tile >= p.n_tiles) return -1;
-      const int64_t t = title * p.L + l;
+      row_g[s] = g;
+      row_off[s] = l < p.L ? (int64_t)g * p.L + l : -1;
+      const uint32_t row = (uint32_t)(p.halo + r);
+      dst_off[s] = row * 128u + ((((uint32_t)j ^ row) & 7u) << 4);
+    }
+    auto row_index = [&](int64_t tile, int s) -> int64_t {
+      if (row_off[s] < 0 || tile >= p.n_tiles || tile * p.G + row_g[s] >= p.n_titles) return -1;
+      const int64_t t = tile * p.G * p.L + row_off[s];
       if (p.ids == nullptr) return t;
-      int64_t id = load_index(p.ids, p.ids_i64, t);
+      const int64_t id = load_index(p.ids, p.ids_i64, t);
       return id < 0 ? 0 : (id >= p.V ? p.V - 1 : id);
     };
     int64_t nxt[8];
 #pragma unroll
     for (int s = 0; s < 8; ++s) nxt[s] = row_index(blockIdx.x, s);
+    Ring ra(p.ns_a), sig(p.ns_a);
+    uint32_t pending = 0;                  // committed but not yet signalled k-chunks
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const __nv_bfloat16* rowp[8];
 #pragma unroll
-      for (int s = 0; s < 8; ++s) TG_TIMED(2, rowp[s] = nxt[s] < 0 ? nullptr : p.a + nxt[s] * p.lda);
+      for (int s = 0; s < 8; ++s) TG_TIMED(2, rowp[s] = nxt[s] < 0 ? nullptr : p.a + nxt[s] * p.lda + j * 8);
 #pragma unroll
       for (int s = 0; s < 8; ++s) nxt[s] = row_index(tile + gridDim.x, s);      // in flight while this tile is staged
+      int c = rot_c;
       for (int cc = 0; cc < n_chunks; ++cc) {
-        const int c = (cc + rot_c) % n_chunks;
-        const int kc = min(TG_KC, p.K - c * TG_KC);
-        const uint32_t sa = ia % (uint32_t)p.ns_a;
-        TG_TIMED(0, tc::mbar_wait(&a_empty[sa], ((ia / (uint32_t)p.ns_a) & 1u) ^ 1u));
+        const int kc = c == n_chunks - 1 ? last_kc : TG_KC;
+        TG_TIMED(0, tc::mbar_wait(&a_empty[ra.pos], ra.phase ^ 1u));
         TG_TIMED(3, {
-        if (j * 8 < kc) {
-          const uint32_t dst0 = tc::smem_u32(sA) + sa * p.a_slot_bytes + (uint32_t)j * p.a_ps + (uint32_t)(p.halo + rgrp) * 16u;
-          const int col = c * TG_KC + j * 8;
+          if (j * 8 < kc) {
+            const uint32_t slot = sA0 + ra.pos * p.a_slot_bytes;
+            const int col = c * TG_KC;
 #pragma unroll
-          for (int s = 0; s < 8; ++s) {
-            const __nv_bfloat16* q = rowp[s];
-            tc::cp_async16(dst0 + (uint32_t)(16 * s) * 16u, q != nullptr ? (const void*)(q + col) : (const void*)p.a, q != nullptr ? 16u : 0u);
+            for (int s = 0; s < 8; ++s) {
+              const __nv_bfloat16* q = rowp[s];
+              tc::cp_async16(slot + dst_off[s], q != nullptr ? (const void*)(q + col) : (const void*)p.a, q != nullptr ? 16u : 0u);
+            }
           }
-        }
-        tc::cp_async_commit();
+          tc::cp_async_commit();
         });
-        ++ia;
-        if (ia - signaled > (uint32_t)depth) {
+        ra.next();
+        if (++c == n_chunks) c = 0;
+        if (++pending > depth) {
           TG_TIMED(1, {
             if (depth == 3) tc::cp_async_wait<3>();
             else if (depth == 2) tc::cp_async_wait<2>();
             else tc::cp_async_wait<1>();
             tc::fence_proxy_async();
           });
-          TG_TIMED(2, tc::mbar_arrive(&a_full[signaled % (uint32_t)p.ns_a]));
-          ++signaled;
+          tc::mbar_arrive(&a_full[sig.pos]);
+          sig.next();
+          --pending;
         }
       }
     }
     tc::cp_async_wait<0>();
     tc::fence_proxy_async();
-    while (signaled < ia) {
-      tc::mbar_arrive(&a_full[signaled % (uint32_t)p.ns_a]);
-      ++signaled;
+    while (pending > 0) {
+      tc::mbar_arrive(&a_full[sig.pos]);
+      sig.next();
+      --pending;
     }
   }
 
   if (p.dbg != nullptr && (tid == 0 || tid == 128 || tid == 160 || tid == 192)) {
-    // rows: 0 epilogue {t_full}, 1 mma {t_empty, a_full, b_full}, 2 w-producer {b_empty}, 3 a-producer {a_empty, cp.async, ids}
+    // rows: 0 epilogue {t_full}, 1 mma {t_empty, a_full, b_full}, 2 w-producer {b_empty}, 3 a-producer {a_empty, cp.wait, ids, cp.issue}
     long long* d = p.dbg + ((size_t)blockIdx.x * 4 + (tid == 0 ? 0 : tid == 128 ? 1 : tid == 160 ? 2 : 3)) * 5;
     d[0] = dbg_acc[0]; d[1] = dbg_acc[1]; d[2] = dbg_acc[2]; d[3] = dbg_acc[3]; d[4] = clock64() - dbg_t0;
   }
@@ -356,8 +404,8 @@ int tapgemm_plan(TapGemmArgs& a, TapGemmPlan* plan) {
   if (G > 16) G = 16;
   a.G = G;
   a.halo = a.taps > 1 ? G : 0;
-  a.a_ps = (uint32_t)(((128 + 2 * a.halo) | 1) * 16);
-  a.a_slot_bytes = (TG_KC / 8) * a.a_ps;
+  a.a_ps = 0;
+  a.a_slot_bytes = (uint32_t)(align_up(128 + 2 * a.halo, 8) * 128);      // one k-chunk of 64 columns, SWIZZLE_128B rows
   a.b_slot_bytes = (uint32_t)((TG_KC / 8) * n_total * 16);
   const int n_chunks = (a.K + TG_KC - 1) / TG_KC;
   int ns_a = n_chunks + 1;

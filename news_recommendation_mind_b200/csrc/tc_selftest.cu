@@ -15,19 +15,34 @@ struct SelfTestArgs {
   int N, K;                     // MMA N (multiple of 16, <= 256) and total K (multiple of 16)
   int a_shift, halo;            // A operand starts `a_shift` rows later (|a_shift| <= halo)
   int swap;                     // debug: swap the LBO / SBO fields
+  int a_layout, b_layout;       // 0 = SWIZZLE_NONE panel layout; 2/4/6 = row-linear SWIZZLE_128B/64B/32B (tc05.cuh)
+  int base_off_mode;            // swizzled operands: 0 = base_offset field 0, 1 = (start >> 7) & 7
 };
 
+// row-linear swizzled layout: rows of RB = 128/64/32 bytes (CB = RB/2 bf16 columns per block), consecutive
+// rows RB bytes apart, 16-byte chunks XOR-ed with the row's position inside the 1024-byte swizzle period
+__device__ __forceinline__ int sw_rb(int layout) { return layout == 2 ? 128 : (layout == 4 ? 64 : 32); }
+__device__ __forceinline__ size_t sw_off(int layout, size_t blk_stride, int row, int col) {
+  const int rb = sw_rb(layout), cb = rb / 2;
+  const int blk = col / cb, cc = col % cb;
+  const size_t rowb = (size_t)row * rb;
+  const int x = (int)((rowb >> 7) & (rb / 16 - 1));
+  return (size_t)blk * blk_stride + rowb + (size_t)(((cc / 8) ^ x) * 16) + (cc % 8) * 2;
+}
+
 __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(SelfTestArgs p) {
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int a_rows = (p.ra + 2 * p.halo) | 1, b_rows = p.rb | 1;
-  const uint32_t a_ps = a_rows * 16, b_ps = b_rows * 16;           // panel strides (bytes)
-  const int a_panels = p.ca / 8, b_panels = p.cb / 8;
+  uint32_t a_ps = a_rows * 16, b_ps = b_rows * 16;                 // panel / block strides (bytes)
+  int a_panels = p.ca / 8, b_panels = p.cb / 8;
+  if (p.a_layout) { a_ps = (uint32_t)((p.ra + 2 * p.halo + 7) / 8 * 8) * sw_rb(p.a_layout); a_panels = (p.ca * 2 + sw_rb(p.a_layout) - 1) / sw_rb(p.a_layout); }
+  if (p.b_layout) { b_ps = (uint32_t)((p.rb + 7) / 8 * 8) * sw_rb(p.b_layout); b_panels = (p.cb * 2 + sw_rb(p.b_layout) - 1) / sw_rb(p.b_layout); }
   uint8_t* sa = smem;
-  uint8_t* sb = smem + (size_t)a_panels * a_ps;
-  const size_t total = (size_t)a_panels * a_ps + (size_t)b_panels * b_ps;
+  uint8_t* sb = smem + ((size_t)a_panels * a_ps + 1023) / 1024 * 1024;
+  const size_t total = ((size_t)a_panels * a_ps + 1023) / 1024 * 1024 + (size_t)b_panels * b_ps;
   for (size_t i = tid * 16; i < total; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
   if (warp == 0) tc::tmem_alloc(&tmem_slot, 256);
   if (tid == 0) {
@@ -37,12 +52,14 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(SelfTestArgs p) {
   __syncthreads();
   for (int i = tid; i < p.ra * p.ca; i += 128) {
     int r = i / p.ca, c = i % p.ca;
-    *reinterpret_cast<__nv_bfloat16*>(sa + (size_t)(c / 8) * a_ps + (size_t)(r + p.halo) * 16 + (c % 8) * 2) =
-        __float2bfloat16(p.a[i]);
+    const size_t off = p.a_layout ? sw_off(p.a_layout, a_ps, r + p.halo, c)
+                                  : (size_t)(c / 8) * a_ps + (size_t)(r + p.halo) * 16 + (c % 8) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(sa + off) = __float2bfloat16(p.a[i]);
   }
   for (int i = tid; i < p.rb * p.cb; i += 128) {
     int r = i / p.cb, c = i % p.cb;
-    *reinterpret_cast<__nv_bfloat16*>(sb + (size_t)(c / 8) * b_ps + (size_t)r * 16 + (c % 8) * 2) = __float2bfloat16(p.b[i]);
+    const size_t off = p.b_layout ? sw_off(p.b_layout, b_ps, r, c) : (size_t)(c / 8) * b_ps + (size_t)r * 16 + (c % 8) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(sb + off) = __float2bfloat16(p.b[i]);
   }
   tc::fence_proxy_async();
   tc::tc_fence_before();
@@ -59,7 +76,22 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(SelfTestArgs p) {
       if (!p.b_mn) { b_addr = bbase + 2 * ks * b_ps; b_lbo = b_ps; b_sbo = 128; }
       else { b_addr = bbase + ks * 256; b_lbo = 128; b_sbo = b_ps; }
       if (p.swap) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
-      tc::umma(tmem, tc::make_desc(a_addr, a_lbo, a_sbo), tc::make_desc(b_addr, b_lbo, b_sbo), idesc, ks > 0);
+      uint64_t da = tc::make_desc(a_addr, a_lbo, a_sbo), db = tc::make_desc(b_addr, b_lbo, b_sbo);
+      if (p.a_layout) {
+        const int rb = sw_rb(p.a_layout), kpb = rb / 32;        // k-steps of 16 elements per block
+        uint32_t st;
+        if (!p.a_mn) { st = tc::smem_u32(sa) + (uint32_t)(ks / kpb) * a_ps + (uint32_t)(p.halo + p.a_shift) * rb + (uint32_t)(ks % kpb) * 32; a_lbo = 16; a_sbo = 8 * rb; }
+        else { st = tc::smem_u32(sa) + (uint32_t)(p.halo + p.a_shift + 16 * ks) * rb; a_lbo = a_ps; a_sbo = 8 * rb; }
+        da = tc::make_desc_sw(st, a_lbo, a_sbo, p.a_layout, p.base_off_mode ? ((st >> 7) & 7u) : 0u);
+      }
+      if (p.b_layout) {
+        const int rb = sw_rb(p.b_layout), kpb = rb / 32;
+        uint32_t st;
+        if (!p.b_mn) { st = tc::smem_u32(sb) + (uint32_t)(ks / kpb) * b_ps + (uint32_t)(ks % kpb) * 32; b_lbo = 16; b_sbo = 8 * rb; }
+        else { st = tc::smem_u32(sb) + (uint32_t)(16 * ks) * rb; b_lbo = b_ps; b_sbo = 8 * rb; }
+        db = tc::make_desc_sw(st, b_lbo, b_sbo, p.b_layout, p.base_off_mode ? ((st >> 7) & 7u) : 0u);
+      }
+      tc::umma(tmem, da, db, idesc, ks > 0);
     }
     tc::umma_commit(&bar);
   }
@@ -82,7 +114,8 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(SelfTestArgs p) {
 extern "C" {
 
 int mr_tc_selftest(const float* a, int64_t ra, int64_t ca, const float* b, int64_t rb, int64_t cb, float* d, int a_mn,
-                   int b_mn, int64_t N, int64_t K, int64_t a_shift, int64_t halo, int swap, void* stream) {
+                   int b_mn, int64_t N, int64_t K, int64_t a_shift, int64_t halo, int swap, int a_layout, int b_layout,
+                   int base_off_mode, void* stream) {
   using namespace mr;
   if (int rc = require_sm100()) return rc;
   MR_REQUIRE(a && b && d, MR_ERR_NULL, "mr_tc_selftest: null pointer");
@@ -94,8 +127,16 @@ int mr_tc_selftest(const float* a, int64_t ra, int64_t ca, const float* b, int64
   else MR_REQUIRE(ca == 128 && ra >= K, MR_ERR_BAD_SHAPE, "A (MN-major) must be [>=K, 128]");
   if (!b_mn) MR_REQUIRE(rb >= N && cb >= K, MR_ERR_BAD_SHAPE, "B (K-major) must be [>=N, >=K]");
   else MR_REQUIRE(cb >= N && rb >= K, MR_ERR_BAD_SHAPE, "B (MN-major) must be [>=K, >=N]");
-  SelfTestArgs p{a, (int)ra, (int)ca, b, (int)rb, (int)cb, d, a_mn, b_mn, (int)N, (int)K, (int)a_shift, (int)halo, swap};
-  size_t smem = (size_t)(ca / 8) * (((ra + 2 * halo) | 1) * 16) + (size_t)(cb / 8) * ((rb | 1) * 16) + 128;
+  SelfTestArgs p{a, (int)ra, (int)ca, b, (int)rb, (int)cb, d, a_mn, b_mn, (int)N, (int)K, (int)a_shift, (int)halo, swap,
+                 a_layout, b_layout, base_off_mode};
+  auto okl = [](int l) { return l == 0 || l == 2 || l == 4 || l == 6; };
+  MR_REQUIRE(okl(a_layout) && okl(b_layout), MR_ERR_BAD_SHAPE, "mr_tc_selftest: layouts must be 0, 2, 4 or 6");
+  auto opbytes = [](int layout, int64_t rows, int64_t cols) -> size_t {
+    if (!layout) return (size_t)(cols / 8) * ((rows | 1) * 16);
+    const int64_t rbytes = layout == 2 ? 128 : (layout == 4 ? 64 : 32);
+    return (size_t)((cols * 2 + rbytes - 1) / rbytes) * (size_t)((rows + 7) / 8 * 8) * rbytes;
+  };
+  size_t smem = (opbytes(a_layout, ra + 2 * halo, ca) + 1023) / 1024 * 1024 + opbytes(b_layout, rb, cb) + 1024;
   MR_REQUIRE(smem <= 220 * 1024, MR_ERR_BAD_SHAPE, "mr_tc_selftest: operands need %zu bytes of shared memory", smem);
   cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   tc_selftest_kernel<<<1, 128, smem, as_stream(stream)>>>(p);

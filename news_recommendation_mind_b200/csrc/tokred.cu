@@ -7,7 +7,7 @@ namespace mr {
 constexpr int TR_MAX_STAGES = 4;
 
 __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs p) {
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * p.stage_bytes);
   uint64_t* empty = full + TR_MAX_STAGES;
   uint64_t* done = empty + TR_MAX_STAGES;
@@ -60,10 +60,13 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs 
       }
     }
   } else if (warp == 4) {
-    // ---- MMA issuer ---------------------------------------------------------------------------
-    if (lane == 0 && has_tiles) {
+    // ---- MMA issuer (warp-uniform loop, one elected lane issues) --------------------------------------
+    if (has_tiles) {
       const uint32_t idesc = tc::make_idesc(128, p.NQ, 1, 1);
       const int ctr = (p.taps - 1) / 2;
+      const uint64_t a_tmpl = tc::make_desc_sw(0, p.p_ps, 1024, 2, 0);
+      const uint64_t b_tmpl = tc::make_desc_sw(0, p.q_ps, 8 * p.q_rb, p.q_layout, 0);
+      const uint32_t a_kstep = (16u * 128u) >> 4, b_kstep = (16u * p.q_rb) >> 4;      // 16 token rows per k-step
       uint32_t it = 0;
       for (int64_t tile = s; tile < p.n_tiles; tile += p.S, ++it) {
         const uint32_t st = it % (uint32_t)p.n_stages;
@@ -71,17 +74,22 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs 
         tc::tc_fence_after();
         const uint32_t pbase = tc::smem_u32(smem) + st * p.stage_bytes;
         const uint32_t qbase = pbase + p.p_bytes;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int shift = (tap - ctr) * p.G;
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t da = tc::make_desc(pbase + (uint32_t)(p.halo + shift + 16 * ks) * 16u, 128, p.p_ps);
-            const uint64_t db = tc::make_desc(qbase + (uint32_t)(16 * ks) * 16u, 128, p.q_ps);
-            tc::umma(tmem + (uint32_t)(tap * p.NQ), da, db, idesc, (it == 0 && ks == 0) ? 0u : 1u);
+        const uint64_t db0 = b_tmpl | (uint64_t)((qbase >> 4) & 0x3FFFu);
+        if (tc::elect_one()) {
+          for (int tap = 0; tap < p.taps; ++tap) {
+            const int shift = (tap - ctr) * p.G;
+            const uint64_t da0 = a_tmpl | (uint64_t)(((pbase + (uint32_t)(p.halo + shift) * 128u) >> 4) & 0x3FFFu);
+            const uint32_t dcol = tmem + (uint32_t)(tap * p.NQ);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              tc::umma(dcol, da0 + (uint64_t)(ks * a_kstep), db0 + (uint64_t)(ks * b_kstep), idesc, (it | (uint32_t)ks) ? 1u : 0u);
           }
+          tc::umma_commit(&empty[st]);
         }
-        tc::umma_commit(&empty[st]);
+        __syncwarp();
       }
-      tc::umma_commit(done);
+      if (tc::elect_one()) tc::umma_commit(done);
+      __syncwarp();
     }
   } else if (has_tiles) {
     // ---- producers: stage P (slice m of its columns) and Q for every tile of this CTA ---------------
@@ -122,17 +130,22 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs 
         const int64_t t = token_of(tile, ss);
         const bool valid = t >= 0;
         const __nv_bfloat16* prow = p.p + (valid ? cur[ss] : 0) * p.ldp;
+        const uint32_t prow_s = (uint32_t)(p.halo + r);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < 2; ++h) {          // P: two 64-column blocks, SWIZZLE_128B rows
           const int col = (m * 16 + j + 8 * h) * 8;
           const bool ok = valid && col < p.KP;
-          tc::cp_async16(pbase + (uint32_t)(j + 8 * h) * p.p_ps + (uint32_t)(p.halo + r) * 16u,
+          tc::cp_async16(pbase + (uint32_t)h * p.p_ps + prow_s * 128u + ((((uint32_t)j ^ prow_s) & 7u) << 4),
                          ok ? (const void*)(prow + col) : (const void*)p.q, ok ? 16u : 0u);
         }
         const __nv_bfloat16* qrow = p.q + (valid ? t : 0) * p.ldq;
-        for (int jj = j; jj < q_panels; jj += 8)
-          tc::cp_async16(qbase + (uint32_t)jj * p.q_ps + (uint32_t)r * 16u, valid ? (const void*)(qrow + jj * 8) : (const void*)p.q,
+        const uint32_t ppb = p.q_rb >> 4;      // 16-byte pieces per row of a Q block (8 / 4 / 2)
+        const uint32_t qx = (((uint32_t)r * p.q_rb) >> 7) & (ppb - 1);
+        for (int jj = j; jj < q_panels; jj += 8) {
+          const uint32_t blk = (uint32_t)jj / ppb, q = (uint32_t)jj % ppb;
+          tc::cp_async16(qbase + blk * p.q_ps + (uint32_t)r * p.q_rb + ((q ^ qx) << 4), valid ? (const void*)(qrow + jj * 8) : (const void*)p.q,
                          valid ? 16u : 0u);
+        }
       }
       tc::cp_async_commit();
       if (it + 1 - signaled > (uint32_t)depth) {
@@ -200,10 +213,14 @@ int tokred_plan(TokRedArgs& a, TokRedPlan* plan) {
              "token-reduction gemm: taps*NQ = %d*%d exceeds the 512 TMEM columns", a.taps, a.NQ);
   tokred_geometry(a.n_titles, a.L, a.taps, a.KP, &a.G, &a.n_mtiles, &a.S, &a.n_tiles);
   a.halo = a.taps > 1 ? a.G : 0;
-  a.p_ps = (uint32_t)(((128 + 2 * a.halo) | 1) * 16);
-  a.q_ps = 129 * 16;
-  a.p_bytes = 16 * a.p_ps;
-  a.stage_bytes = a.p_bytes + (uint32_t)(a.NQ / 8) * a.q_ps;
+  // P: two 64-column blocks of [rows x 128 B] (SWIZZLE_128B);  Q: NQ columns in blocks of 64 / 32 / 16 columns
+  // (SWIZZLE_128B / 64B / 32B -- the widest row that divides NQ), 128 rows each; every block 1024-byte aligned
+  a.p_ps = (uint32_t)(align_up(128 + 2 * a.halo, 8) * 128);
+  a.p_bytes = 2 * a.p_ps;
+  a.q_layout = a.NQ % 64 == 0 ? 2 : (a.NQ % 32 == 0 ? 4 : 6);
+  a.q_rb = a.q_layout == 2 ? 128u : (a.q_layout == 4 ? 64u : 32u);
+  a.q_ps = 128 * a.q_rb;
+  a.stage_bytes = (uint32_t)align_up(a.p_bytes + (uint32_t)(a.NQ * 2 / a.q_rb) * a.q_ps, 1024);
   const size_t fixed = (2 * TR_MAX_STAGES + 1) * 8 + 16;
   int ns = (int)((227 * 1024 - fixed - 128) / a.stage_bytes);
   if (ns > TR_MAX_STAGES) ns = TR_MAX_STAGES;

@@ -28,7 +28,8 @@ struct TokRedArgs {
   const __nv_bfloat16* q; int64_t ldq; int NQ;      // NQ: columns of Q (multiple of 16, taps*NQ <= 512)
   float* partial;                                   // [n_mtiles][S][taps][128][NQ]
   int n_mtiles, S, halo, n_stages;
-  uint32_t p_ps, q_ps, p_bytes, stage_bytes;
+  uint32_t p_ps, q_ps, p_bytes, stage_bytes, q_rb;   // block strides (bytes), Q row bytes
+  int q_layout;                                        // UMMA layout type of Q (2 / 4 / 6)
 };
 
 struct TokRedPlan {

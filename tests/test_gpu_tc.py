@@ -10,11 +10,11 @@ from news_recommendation_mind_b200._lib import check, ptr, stream_ptr
 pytestmark = pytest.mark.gpu
 
 
-def run_tile(a, b, a_mn, b_mn, N, K, shift, halo, swap=0):
+def run_tile(a, b, a_mn, b_mn, N, K, shift, halo, swap=0, a_layout=0, b_layout=0, base_off_mode=0):
     lib = _lib.load()
     d = torch.empty(128, N, dtype=torch.float32, device="cuda")
     check(lib.mr_tc_selftest(ptr(a), a.shape[0], a.shape[1], ptr(b), b.shape[0], b.shape[1], ptr(d), a_mn, b_mn, N, K,
-                             shift, halo, swap, stream_ptr("cuda")), "mr_tc_selftest")
+                             shift, halo, swap, a_layout, b_layout, base_off_mode, stream_ptr("cuda")), "mr_tc_selftest")
     torch.cuda.synchronize()
     return d
 
