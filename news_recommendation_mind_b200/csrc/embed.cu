@@ -158,10 +158,16 @@ seg_reduce_l1_kernel(const T* __restrict__ d_emb, int64_t ld, const int32_t* __r
   }
 }
 
-// level 2: warp per vocabulary row; zero-fills empty rows, folds partial rows of long segments
+// level 2: warp per vocabulary row; zero-fills empty rows, folds the partial rows of short multi-chunk
+// segments; rows with more than SEG_HEAVY chunks (frequent tokens: [CLS], [SEP], the head of the Zipf
+// distribution) are queued for the heavy path below instead of being summed by one warp.
+constexpr int SEG_HEAVY = 8;
+constexpr int SEG_SPLIT = 4;      // CTAs per heavy row
+
 __global__ void __launch_bounds__(256)
 seg_reduce_l2_kernel(const int32_t* __restrict__ chunk_off, const int32_t* __restrict__ nchunk,
-                     const float* __restrict__ partial, float* __restrict__ d_table, int64_t V, int64_t E) {
+                     const float* __restrict__ partial, float* __restrict__ d_table, int64_t V, int64_t E,
+                     int32_t* __restrict__ heavy_count, int32_t* __restrict__ heavy_rows, int32_t max_heavy) {
   const int lane = threadIdx.x & 31;
   const int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (v >= V) return;
@@ -172,6 +178,13 @@ seg_reduce_l2_kernel(const int32_t* __restrict__ chunk_off, const int32_t* __res
     for (int64_t e = lane; e < E; e += 32) dst[e] = 0.f;
     return;
   }
+  if (n > SEG_HEAVY) {
+    if (lane == 0) {
+      const int32_t slot = atomicAdd(heavy_count, 1);   // integer bookkeeping only: the order of the list does
+      if (slot < max_heavy) heavy_rows[slot] = (int32_t)v;   // not influence any floating-point sum
+    }
+    return;
+  }
   const float* src = partial + (int64_t)chunk_off[v] * E;
   for (int64_t e = lane; e < E; e += 32) {
     float s = 0.f;
@@ -180,14 +193,57 @@ seg_reduce_l2_kernel(const int32_t* __restrict__ chunk_off, const int32_t* __res
   }
 }
 
+// heavy rows: CTA (h, sp) sums the sp-th quarter of row heavy_rows[h]'s partial rows, four independent
+// accumulators per column combined in a fixed order; heavy_final adds the SEG_SPLIT results in order.
+__global__ void __launch_bounds__(256)
+seg_reduce_heavy_kernel(const int32_t* __restrict__ chunk_off, const int32_t* __restrict__ nchunk,
+                        const float* __restrict__ partial, float* __restrict__ partial2,
+                        const int32_t* __restrict__ heavy_count, const int32_t* __restrict__ heavy_rows, int64_t E) {
+  const int h = blockIdx.x / SEG_SPLIT, sp = blockIdx.x % SEG_SPLIT;
+  if (h >= *heavy_count) return;
+  const int32_t v = heavy_rows[h];
+  const int32_t n = nchunk[v];
+  const int32_t per = (n + SEG_SPLIT - 1) / SEG_SPLIT;
+  const int32_t j0 = sp * per, j1 = min(n, j0 + per);
+  const float* src = partial + (int64_t)chunk_off[v] * E;
+  float* dst = partial2 + (int64_t)blockIdx.x * E;
+  for (int64_t e = threadIdx.x; e < E; e += blockDim.x) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int32_t j = j0;
+    for (; j + 3 < j1; j += 4) {
+      a0 += src[(int64_t)j * E + e];
+      a1 += src[(int64_t)(j + 1) * E + e];
+      a2 += src[(int64_t)(j + 2) * E + e];
+      a3 += src[(int64_t)(j + 3) * E + e];
+    }
+    for (; j < j1; ++j) a0 += src[(int64_t)j * E + e];
+    dst[e] = (a0 + a1) + (a2 + a3);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+seg_reduce_heavy_final_kernel(const float* __restrict__ partial2, float* __restrict__ d_table,
+                              const int32_t* __restrict__ heavy_count, const int32_t* __restrict__ heavy_rows, int64_t E) {
+  const int h = blockIdx.x;
+  if (h >= *heavy_count) return;
+  const int32_t v = heavy_rows[h];
+  for (int64_t e = threadIdx.x; e < E; e += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int sp = 0; sp < SEG_SPLIT; ++sp) s += partial2[((int64_t)h * SEG_SPLIT + sp) * E + e];
+    d_table[(int64_t)v * E + e] = s;
+  }
+}
+
 struct EmbedGradPlan {
-  int64_t T, E, V, max_chunks;
+  int64_t T, E, V, max_chunks, max_heavy;
   size_t cub_sort_bytes, cub_scan_bytes;
 };
 
 static EmbedGradPlan plan_embed_grad(int64_t T, int64_t E, int64_t V) {
-  EmbedGradPlan p{T, E, V, 0, 0, 0};
+  EmbedGradPlan p{T, E, V, 0, 0, 0, 0};
   p.max_chunks = ceil_div(T, SEG_CHUNK) + V;
+  p.max_heavy = T / ((int64_t)SEG_CHUNK * SEG_HEAVY) + 1;       // rows with more than SEG_HEAVY chunks
   int bits = 1;
   while ((1ll << bits) < V) ++bits;
   cub::DeviceRadixSort::SortPairs(nullptr, p.cub_sort_bytes, (const int32_t*)nullptr, (int32_t*)nullptr,
@@ -223,6 +279,7 @@ int64_t mr_embed_grad_workspace_bytes(int64_t T, int64_t E, int64_t V) {
   b += 2 * arena_bytes(V + 1, 4);             // nchunk, chunk_off
   b += arena_bytes(p.max_chunks, 4);          // chunk_row
   b += arena_bytes(p.max_chunks * E, 4);      // partial rows
+  b += arena_bytes(p.max_heavy + 1, 4) + arena_bytes(p.max_heavy * SEG_SPLIT * E, 4);   // heavy list, heavy partials
   b += arena_bytes((int64_t)p.cub_sort_bytes, 1) + arena_bytes((int64_t)p.cub_scan_bytes, 1);
   return b + 256;
 }
@@ -252,6 +309,8 @@ int mr_embed_grad_segreduce(const void* ids, int ids_i64, const void* d_emb, int
   int32_t* chunk_off = ar.take<int32_t>(V + 1);
   int32_t* chunk_row = ar.take<int32_t>(p.max_chunks);
   float* partial = ar.take<float>(p.max_chunks * E);
+  int32_t* heavy = ar.take<int32_t>(p.max_heavy + 1);            // [0] = count, [1..] = rows
+  float* partial2 = ar.take<float>(p.max_heavy * SEG_SPLIT * E);
   void* cub_sort = ar.take<char>((int64_t)p.cub_sort_bytes);
   void* cub_scan = ar.take<char>((int64_t)p.cub_scan_bytes);
   MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "mr_embed_grad_segreduce: workspace too small (%lld given)", (long long)workspace_bytes);
@@ -285,8 +344,15 @@ int mr_embed_grad_segreduce(const void* ids, int ids_i64, const void* d_emb, int
     seg_reduce_l1_kernel<__nv_bfloat16, 3><<<(unsigned)ceil_div(p.max_chunks, 8), 256, 0, st>>>(
         static_cast<const __nv_bfloat16*>(d_emb), E4, svals, seg_start, chunk_off, chunk_row, nchunk, d_table, partial, p.max_chunks, E, V);
   MR_CHECK_LAUNCH("seg_reduce_l1_kernel");
-  seg_reduce_l2_kernel<<<(unsigned)ceil_div(V, 8), 256, 0, st>>>(chunk_off, nchunk, partial, d_table, V, E);
+  cudaMemsetAsync(heavy, 0, sizeof(int32_t), st);
+  seg_reduce_l2_kernel<<<(unsigned)ceil_div(V, 8), 256, 0, st>>>(chunk_off, nchunk, partial, d_table, V, E, heavy, heavy + 1,
+                                                                 (int32_t)p.max_heavy);
   MR_CHECK_LAUNCH("seg_reduce_l2_kernel");
+  seg_reduce_heavy_kernel<<<(unsigned)(p.max_heavy * SEG_SPLIT), 256, 0, st>>>(chunk_off, nchunk, partial, partial2, heavy,
+                                                                             heavy + 1, E);
+  MR_CHECK_LAUNCH("seg_reduce_heavy_kernel");
+  seg_reduce_heavy_final_kernel<<<(unsigned)p.max_heavy, 256, 0, st>>>(partial2, d_table, heavy, heavy + 1, E);
+  MR_CHECK_LAUNCH("seg_reduce_heavy_final_kernel");
   return MR_OK;
 }
 

@@ -27,6 +27,16 @@ __global__ void cast_rows_bf16_kernel(const float* __restrict__ src, __nv_bfloat
   dst[i] = __float2bfloat16(c < cols ? src[r * cols + c] : 0.f);
 }
 
+// ---- optional per-launch timing of the dominant kernel (conv forward tap GEMM) with CUDA events on the
+// launching stream; bench.py switches it on for the timed region and reads the average afterwards -------------
+constexpr int CONV_EVT_SLOTS = 256;
+static struct ConvTiming {
+  bool enabled = false;
+  cudaEvent_t beg[CONV_EVT_SLOTS], end[CONV_EVT_SLOTS];
+  bool created = false;
+  int64_t count = 0;
+} g_conv_timing;
+
 static inline int64_t hp_of(const mr_cnn_shape* s) { return align_up(s->H, 16); }
 static inline int64_t kp_of(const mr_cnn_shape* s) { return align_up(s->E, 16); }
 static inline int64_t table_ld(const mr_cnn_shape* s) { return align_up(s->E, 64); }
@@ -88,7 +98,14 @@ int news_cnn_tc_fwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
   a.wpack = wconv; a.epi = TG_EPI_BIAS_RELU; a.bias = conv_b; a.n_valid = (int)H;
   a.out = c; a.ldo = Hp;
   if (int rc = tapgemm_plan(a, &plan)) return rc;
+  const bool timed = g_conv_timing.enabled;
+  const int slot = (int)(g_conv_timing.count % CONV_EVT_SLOTS);
+  if (timed) cudaEventRecord(g_conv_timing.beg[slot], st);
   if (int rc = tapgemm_launch(plan, st)) return rc;
+  if (timed) {
+    cudaEventRecord(g_conv_timing.end[slot], st);
+    ++g_conv_timing.count;
+  }
   // projection: key = tanh(c Wq^T + bq)
   TapGemmArgs b{};
   b.n_titles = N; b.L = (int)L; b.taps = 1; b.dir = 1; b.K = (int)Hp;
@@ -207,3 +224,37 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
   return MR_OK;
 }
 }  // namespace mr
+
+extern "C" {
+/* bench hooks: time every conv-forward tap-GEMM launch with CUDA events on its own stream */
+__attribute__((visibility("default"))) int mr_debug_conv_timing(int enable) {
+  using namespace mr;
+  if (enable && !g_conv_timing.created) {
+    for (int i = 0; i < CONV_EVT_SLOTS; ++i) {
+      if (cudaEventCreate(&g_conv_timing.beg[i]) != cudaSuccess || cudaEventCreate(&g_conv_timing.end[i]) != cudaSuccess)
+        return set_err(MR_ERR_LAUNCH, "mr_debug_conv_timing: cannot create events");
+    }
+    g_conv_timing.created = true;
+  }
+  g_conv_timing.enabled = enable != 0;
+  if (enable) g_conv_timing.count = 0;
+  return MR_OK;
+}
+/* after a device synchronise: number of timed launches (<= 256 kept) and their mean duration in ms */
+__attribute__((visibility("default"))) int mr_debug_conv_timing_read(int64_t* launches, float* mean_ms) {
+  using namespace mr;
+  const int64_t n = g_conv_timing.count < CONV_EVT_SLOTS ? g_conv_timing.count : CONV_EVT_SLOTS;
+  double tot = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_conv_timing.beg[i], g_conv_timing.end[i]) != cudaSuccess) {
+      cudaGetLastError();
+      return set_err(MR_ERR_LAUNCH, "mr_debug_conv_timing_read: events not complete (synchronise first)");
+    }
+    tot += ms;
+  }
+  if (launches) *launches = g_conv_timing.count;
+  if (mean_ms) *mean_ms = n ? (float)(tot / n) : 0.f;
+  return MR_OK;
+}
+}

@@ -57,11 +57,29 @@ def encode_all_news(model, news_ids: torch.Tensor, news_mask: torch.Tensor, batc
         shard[a - lo:b - lo] = core.encode_news(x).squeeze(-2)
     core.destroy_encoding()
     core.train(was_training)
+    return gather_news_shards(shard, n_rows)
+
+
+def gather_news_shards(shard: torch.Tensor, n_rows: int) -> torch.Tensor:
+    """All-gather of the per-rank [ceil(n_rows/ws), H] shards into the replicated [n_rows, H] table -- replaces
+    the reference's torch.save / barrier / torch.load round trip through the file system (Manager.py:503-510)."""
+    _, world = _world()
     if world == 1:
         return shard[:n_rows]
-    full = torch.empty(world * per, core.hidden_dim, dtype=torch.float32, device=dev)
-    dist.all_gather_into_tensor(full, shard)
+    full = torch.empty(world * shard.shape[0], shard.shape[1], dtype=shard.dtype, device=shard.device)
+    dist.all_gather_into_tensor(full, shard.contiguous())
     return full[:n_rows]
+
+
+def reduce_metric_sums(per_impression: torch.Tensor) -> torch.Tensor:
+    """[n_local, 4] fp64 per-impression (auc, mrr, ndcg@5, ndcg@10) -> global means [4] (all-reduce of sums and
+    the impression count; replaces all_gather_object + rank-0 cal_metric, Manager.py:525,577)."""
+    _, world = _world()
+    acc = torch.cat([per_impression.sum(0), torch.tensor([float(per_impression.shape[0])], dtype=torch.float64,
+                                                          device=per_impression.device)])
+    if world > 1:
+        dist.all_reduce(acc)
+    return acc[:4] / acc[4]
 
 
 @torch.no_grad()
@@ -98,9 +116,6 @@ def evaluate(model, news_ids, news_mask, impr, metrics=("auc", "mean_mrr", "ndcg
     table = encode_all_news(model, news_ids, news_mask)
     prob, label, off = score_impressions(model, table, impr)
     m, _ = ops.rank_metrics(prob, label, off)
-    acc = torch.cat([m.sum(0), torch.tensor([float(m.shape[0])], dtype=torch.float64, device=m.device)])
-    if world > 1:
-        dist.all_reduce(acc)
-    mean = (acc[:4] / acc[4]).tolist()
+    mean = reduce_metric_sums(m).tolist()
     names = ["auc", "mean_mrr", "ndcg@5", "ndcg@10"]
     return {k: round(v, 4) for k, v in zip(names, mean) if k in metrics}
