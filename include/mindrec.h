@@ -98,6 +98,10 @@ typedef struct {
   int precision;
 } mr_cnn_shape;
 
+/* Token ids whose table rows the MR_BF16 gather keeps in shared memory (at most 4; e.g. PAD, [CLS], [SEP] --
+ * in MIND-shaped batches they are >25 % of all positions and every SM would otherwise hit the same few L2
+ * lines).  Purely a performance hint: results are identical.  Process-wide, set before launching. */
+MR_API int mr_news_cnn_set_hot_tokens(const int64_t* ids, int n);
 MR_API int64_t mr_news_cnn_workspace_bytes(const mr_cnn_shape* s, int backward);
 MR_API int mr_news_cnn_fwd(const mr_cnn_shape* s,
                     const void* ids, int ids_i64, const float* emb,

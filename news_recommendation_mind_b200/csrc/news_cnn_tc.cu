@@ -115,7 +115,15 @@ int news_cnn_tc_fwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
   b.out = key; b.ldo = Hp;
   if (int rc = tapgemm_plan(b, &plan)) return rc;
   if (int rc = tapgemm_launch(plan, st)) return rc;
-  cnn_pool_fwd_kernel<__nv_bfloat16><<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(c, key, Hp, mask, mask_i64, query, prob, news, N, (int)L, (int)H);
+  if (L <= 32 && Hp <= 256) {
+    const unsigned grid = (unsigned)ceil_div(N, 8);
+    if (Hp <= 64) cnn_pool_fwd_bf16_kernel<1><<<grid, 256, 0, st>>>(c, key, Hp, mask, mask_i64, query, prob, news, N, (int)L, (int)H);
+    else if (Hp <= 128) cnn_pool_fwd_bf16_kernel<2><<<grid, 256, 0, st>>>(c, key, Hp, mask, mask_i64, query, prob, news, N, (int)L, (int)H);
+    else if (Hp <= 192) cnn_pool_fwd_bf16_kernel<3><<<grid, 256, 0, st>>>(c, key, Hp, mask, mask_i64, query, prob, news, N, (int)L, (int)H);
+    else cnn_pool_fwd_bf16_kernel<4><<<grid, 256, 0, st>>>(c, key, Hp, mask, mask_i64, query, prob, news, N, (int)L, (int)H);
+  } else {
+    cnn_pool_fwd_kernel<__nv_bfloat16><<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(c, key, Hp, mask, mask_i64, query, prob, news, N, (int)L, (int)H);
+  }
   MR_CHECK_LAUNCH("cnn_pool_fwd_kernel");
   return MR_OK;
 }
@@ -152,7 +160,15 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
   MR_REQUIRE(3 * Hp <= 512, MR_ERR_UNSUPPORTED, "mr_news_cnn_bwd: hidden_dim %lld > 160 is not supported by the bf16 backward", (long long)H);
 
   // 1. pooling backward: dkp = grad wrt the projection pre-activation, dcv = p * d_news   (Attention.py:77-80)
-  cnn_pool_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(c, key, Hp, prob, query, d_news, dkp, dcv, Hp, dqp, N, (int)L, (int)H);
+  if (L <= 32 && Hp <= 256) {
+    const unsigned grid = (unsigned)ceil_div(N, 8);
+    if (Hp <= 64) cnn_pool_bwd_bf16_kernel<1><<<grid, 256, 0, st>>>(c, key, Hp, prob, query, d_news, dkp, dcv, dqp, N, (int)L, (int)H);
+    else if (Hp <= 128) cnn_pool_bwd_bf16_kernel<2><<<grid, 256, 0, st>>>(c, key, Hp, prob, query, d_news, dkp, dcv, dqp, N, (int)L, (int)H);
+    else if (Hp <= 192) cnn_pool_bwd_bf16_kernel<3><<<grid, 256, 0, st>>>(c, key, Hp, prob, query, d_news, dkp, dcv, dqp, N, (int)L, (int)H);
+    else cnn_pool_bwd_bf16_kernel<4><<<grid, 256, 0, st>>>(c, key, Hp, prob, query, d_news, dkp, dcv, dqp, N, (int)L, (int)H);
+  } else {
+    cnn_pool_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(c, key, Hp, prob, query, d_news, dkp, dcv, Hp, dqp, N, (int)L, (int)H);
+  }
   MR_CHECK_LAUNCH("cnn_pool_bwd_kernel");
   if (d_c) {
     add_rows_bf16_kernel<<<(unsigned)ceil_div(T * H, 256), 256, 0, st>>>(dcv, Hp, d_c, T, H);

@@ -157,3 +157,174 @@ cnn_pool_bwd_kernel(const T* __restrict__ c, const T* __restrict__ key, int64_t 
 }
 
 }  // namespace mr
+
+// ------------------------------------------------------------------------------------------------------
+// bf16 fast path (titles of at most 32 tokens, row pitch ld = Hp a multiple of 8 and <= 256 columns).
+// One warp per title.  Row dot products run 4 rows at a time with 8 lanes per row and 16-byte loads (a row
+// group reads 128 contiguous bytes), reduced with 3 shuffle levels; the pooled sum / the per-row outputs give
+// each of the first Hp/8 lanes one 8-column piece, so every row is one coalesced 16-byte load per lane and
+// the 32 row loads of a title are independent (memory-level parallelism instead of a shuffle chain per row).
+// ------------------------------------------------------------------------------------------------------
+namespace mr {
+
+__device__ __forceinline__ void bf8_to_f(const uint4& v, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 f_to_bf8(const float* f) {
+  uint4 o;
+  __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(f[4], f[5]), d = __floats2bfloat162_rn(f[6], f[7]);
+  o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+  o.z = *reinterpret_cast<uint32_t*>(&c); o.w = *reinterpret_cast<uint32_t*>(&d);
+  return o;
+}
+
+// row scores: out (valid in every lane l < L) = sum_h vec[h] * x[l, h];  vec is given as this lane's slices
+// for the "8 lanes per row" mapping: vr[i][0..7] = vec[(part + 8 i) * 8 ..], part = lane & 7
+template <int MAXP>     // MAXP = ceil(pieces / 8) <= 4
+__device__ __forceinline__ float row_dots_bf16(const __nv_bfloat16* __restrict__ x, int64_t ld, int L, int pieces,
+                                               const float (&vr)[MAXP][8], int lane) {
+  const int rr = lane >> 3, part = lane & 7;
+  float mine = 0.f;
+  for (int it = 0; it < 8; ++it) {
+    const int l = it * 4 + rr;
+    float d = 0.f;
+    if (l < L) {
+      const uint4* row = reinterpret_cast<const uint4*>(x + (int64_t)l * ld);
+      uint4 v[MAXP];
+#pragma unroll
+      for (int i = 0; i < MAXP; ++i)
+        if (part + 8 * i < pieces) v[i] = __ldg(row + part + 8 * i);
+#pragma unroll
+      for (int i = 0; i < MAXP; ++i)
+        if (part + 8 * i < pieces) {
+          float f[8];
+          bf8_to_f(v[i], f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d = fmaf(vr[i][e], f[e], d);
+        }
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 4);
+    const float sv = __shfl_sync(0xffffffffu, d, (lane & 3) * 8);
+    if ((lane >> 2) == it) mine = sv;
+  }
+  return mine;
+}
+
+template <int MAXP>
+__global__ void __launch_bounds__(256)
+cnn_pool_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ c, const __nv_bfloat16* __restrict__ key, int64_t ld,
+                         const void* __restrict__ mask, int mask_i64, const float* __restrict__ q, float* __restrict__ prob,
+                         float* __restrict__ news, int64_t N, int L, int H) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int pieces = (int)(ld / 8);
+  const __nv_bfloat16* kn = key + n * L * ld;
+  const __nv_bfloat16* cn = c + n * L * ld;
+  float qr[MAXP][8];
+#pragma unroll
+  for (int i = 0; i < MAXP; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int h = ((lane & 7) + 8 * i) * 8 + e;
+      qr[i][e] = h < H ? __ldg(q + h) : 0.f;
+    }
+  const float s = row_dots_bf16<MAXP>(kn, ld, L, pieces, qr, lane) * rsqrtf((float)H);
+  const bool keep = lane < L && (mask ? (load_index(mask, mask_i64, n * L + lane) != 0) : true);
+  const float mx = warp_max(keep ? s : -INFINITY);
+  const float ex = keep ? expf(s - mx) : 0.f;
+  const float sum = warp_sum(ex);
+  const float p = sum > 0.f ? ex / sum : 0.f;             // all-masked title -> zeros (XSoftmax, Attention.py:66-74)
+  if (lane < L) prob[n * L + lane] = p;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  const uint4* cp = reinterpret_cast<const uint4*>(cn) + lane;
+#pragma unroll 8
+  for (int l = 0; l < L; ++l) {
+    const float pl = __shfl_sync(0xffffffffu, p, l);
+    if (lane < pieces) {
+      float f[8];
+      bf8_to_f(__ldg(cp + (int64_t)l * pieces), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(pl, f[e], acc[e]);
+    }
+  }
+  if (lane < pieces) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int h = lane * 8 + e;
+      if (h < H) news[n * H + h] = acc[e];
+    }
+  }
+}
+
+template <int MAXP>
+__global__ void __launch_bounds__(256)
+cnn_pool_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ c, const __nv_bfloat16* __restrict__ key, int64_t ld,
+                         const float* __restrict__ prob, const float* __restrict__ q, const float* __restrict__ d_news,
+                         __nv_bfloat16* __restrict__ dkp, __nv_bfloat16* __restrict__ dc_pool, float* __restrict__ dq_partial,
+                         int64_t N, int L, int H) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int pieces = (int)(ld / 8);
+  const __nv_bfloat16* kn = key + n * L * ld;
+  const __nv_bfloat16* cn = c + n * L * ld;
+  const float* dn = d_news + n * H;
+  float dr[MAXP][8];
+#pragma unroll
+  for (int i = 0; i < MAXP; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int h = ((lane & 7) + 8 * i) * 8 + e;
+      dr[i][e] = h < H ? __ldg(dn + h) : 0.f;
+    }
+  const float dp = row_dots_bf16<MAXP>(cn, ld, L, pieces, dr, lane);        // <d_news, c[l]>
+  const float p = lane < L ? prob[n * L + lane] : 0.f;
+  const float dot = warp_sum(p * dp);
+  const float ds = p * (dp - dot) * rsqrtf((float)H);                       // softmax backward (Attention.py:77-80)
+  // this lane's 8-column piece of q and d_news
+  float qv[8], dv[8], dq[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int h = lane * 8 + e;
+    qv[e] = (lane < pieces && h < H) ? __ldg(q + h) : 0.f;
+    dv[e] = (lane < pieces && h < H) ? __ldg(dn + h) : 0.f;
+    dq[e] = 0.f;
+  }
+  const uint4* kp = reinterpret_cast<const uint4*>(kn) + lane;
+  uint4* dko = reinterpret_cast<uint4*>(dkp + n * L * ld) + lane;
+  uint4* dco = reinterpret_cast<uint4*>(dc_pool + n * L * ld) + lane;
+#pragma unroll 4
+  for (int l = 0; l < L; ++l) {
+    const float dsl = __shfl_sync(0xffffffffu, ds, l);
+    const float pl = __shfl_sync(0xffffffffu, p, l);
+    if (lane < pieces) {
+      float k[8], o1[8], o2[8];
+      bf8_to_f(__ldg(kp + (int64_t)l * pieces), k);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        dq[e] = fmaf(dsl, k[e], dq[e]);
+        o1[e] = dsl * qv[e] * (1.f - k[e] * k[e]);
+        o2[e] = pl * dv[e];
+      }
+      dko[(int64_t)l * pieces] = f_to_bf8(o1);
+      dco[(int64_t)l * pieces] = f_to_bf8(o2);
+    }
+  }
+  if (lane < pieces) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int h = lane * 8 + e;
+      if (h < H) dq_partial[n * H + h] = dq[e];
+    }
+  }
+}
+
+}  // namespace mr

@@ -45,6 +45,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
   uint64_t* t_full = b_empty + TG_MAX_SLOTS;
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint8_t* hot = reinterpret_cast<uint8_t*>(tmem_slot + 4);          // [n_hot][hot_pitch] bf16 rows (gather mode)
+  const uint32_t hot_pitch = (uint32_t)((p.K * 2 + 15) / 16 * 16);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int n_total = p.nsz[0] + (p.n_sub > 1 ? p.nsz[1] : 0);
@@ -63,6 +65,11 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
     const uint32_t a_bytes = (uint32_t)p.ns_a * p.a_slot_bytes;
     for (uint32_t i = tid * 16; i < a_bytes; i += TG_THREADS * 16) *reinterpret_cast<uint4*>(sA + i) = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < 512; i += TG_THREADS) sbias[i] = (p.bias != nullptr && i < p.n_valid) ? p.bias[i] : 0.f;
+    if (p.ids != nullptr)
+      for (uint32_t i = tid; i < (uint32_t)p.n_hot * (hot_pitch / 16); i += TG_THREADS) {
+        const uint32_t h = i / (hot_pitch / 16), q = i % (hot_pitch / 16);
+        reinterpret_cast<uint4*>(hot + (size_t)h * hot_pitch)[q] = __ldg(reinterpret_cast<const uint4*>(p.a + p.hot_ids[h] * p.lda) + q);
+      }
     if (tid == 0) {
       for (int i = 0; i < TG_MAX_SLOTS; ++i) {
         tc::mbar_init(&a_full[i], 128);
@@ -274,12 +281,17 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
       const uint32_t row = (uint32_t)(p.halo + r);
       dst_off[s] = row * 128u + ((((uint32_t)j ^ row) & 7u) << 4);
     }
+    // -> source row (token id in gather mode, token index otherwise); -1 = zero row; -2-h = hot row h (smem copy)
     auto row_index = [&](int64_t tile, int s) -> int64_t {
       if (row_off[s] < 0 || tile >= p.n_tiles || tile * p.G + row_g[s] >= p.n_titles) return -1;
       const int64_t t = tile * p.G * p.L + row_off[s];
       if (p.ids == nullptr) return t;
-      const int64_t id = load_index(p.ids, p.ids_i64, t);
-      return id < 0 ? 0 : (id >= p.V ? p.V - 1 : id);
+      int64_t id = load_index(p.ids, p.ids_i64, t);
+      id = id < 0 ? 0 : (id >= p.V ? p.V - 1 : id);
+#pragma unroll
+      for (int h = 0; h < TG_MAX_HOT; ++h)
+        if (h < p.n_hot && id == p.hot_ids[h]) id = -2 - h;
+      return id;
     };
     int64_t nxt[8];
 #pragma unroll
@@ -289,7 +301,14 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const __nv_bfloat16* rowp[8];
 #pragma unroll
-      for (int s = 0; s < 8; ++s) TG_TIMED(2, rowp[s] = nxt[s] < 0 ? nullptr : p.a + nxt[s] * p.lda + j * 8);
+      for (int s = 0; s < 8; ++s) {
+        if (nxt[s] >= 0) rowp[s] = p.a + nxt[s] * p.lda + j * 8;
+        else if (nxt[s] == -1) rowp[s] = nullptr;
+        else rowp[s] = reinterpret_cast<const __nv_bfloat16*>(hot + (size_t)(-2 - nxt[s]) * hot_pitch) + j * 8;   // shared memory
+      }
+      uint32_t hot_mask = 0;
+#pragma unroll
+      for (int s = 0; s < 8; ++s) hot_mask |= (nxt[s] <= -2 ? 1u : 0u) << s;
 #pragma unroll
       for (int s = 0; s < 8; ++s) nxt[s] = row_index(tile + gridDim.x, s);      // in flight while this tile is staged
       int c = rot_c;
@@ -303,7 +322,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
               const __nv_bfloat16* q = rowp[s];
-              tc::cp_async16(slot + dst_off[s], q != nullptr ? (const void*)(q + col) : (const void*)p.a, q != nullptr ? 16u : 0u);
+              if ((hot_mask >> s) & 1u) {          // hot token: 16-byte smem -> smem copy (covered by the fence below)
+                const uint4 v = *reinterpret_cast<const uint4*>(q + col);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot + dst_off[s]), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+              } else {
+                tc::cp_async16(slot + dst_off[s], q != nullptr ? (const void*)(q + col) : (const void*)p.a, q != nullptr ? 16u : 0u);
+              }
             }
           }
           tc::cp_async_commit();
@@ -389,6 +413,13 @@ int sm_count() {
 constexpr size_t TG_SMEM_MAX = 227 * 1024;
 constexpr size_t TG_SMEM_FIXED = 512 * 4 + (4 * TG_MAX_SLOTS + 4) * 8 + 16;   // bias + barriers + tmem slot
 
+static int64_t g_hot_ids[TG_MAX_HOT] = {0, 0, 0, 0};
+static int g_n_hot = 0;
+int hot_tokens(int64_t* out) {
+  for (int i = 0; i < g_n_hot; ++i) out[i] = g_hot_ids[i];
+  return g_n_hot;
+}
+
 int tapgemm_plan(TapGemmArgs& a, TapGemmPlan* plan) {
   MR_REQUIRE(a.L >= 1 && a.L <= 128, MR_ERR_UNSUPPORTED, "tap gemm: signal_length %d not in [1,128] (bf16 path)", a.L);
   MR_REQUIRE(a.K >= 16 && a.K % 16 == 0, MR_ERR_BAD_SHAPE, "tap gemm: K=%d must be a positive multiple of 16", a.K);
@@ -411,7 +442,15 @@ int tapgemm_plan(TapGemmArgs& a, TapGemmPlan* plan) {
   int ns_a = n_chunks + 1;
   if (ns_a < 4) ns_a = 4;
   if (ns_a > 6) ns_a = 6;
-  size_t left = TG_SMEM_MAX - TG_SMEM_FIXED - 128;
+  a.n_hot = 0;
+  if (a.ids != nullptr) {
+    int64_t hot[TG_MAX_HOT];
+    const int n = hot_tokens(hot);
+    for (int i = 0; i < n; ++i)
+      if (hot[i] >= 0 && hot[i] < a.V) a.hot_ids[a.n_hot++] = hot[i];
+  }
+  const size_t hot_bytes = (size_t)a.n_hot * ((size_t)(a.K * 2 + 15) / 16 * 16);
+  size_t left = TG_SMEM_MAX - TG_SMEM_FIXED - hot_bytes - 128;
   while (ns_a > 4 && (size_t)ns_a * a.a_slot_bytes + 2 * (size_t)a.b_slot_bytes > left) --ns_a;
   MR_REQUIRE((size_t)ns_a * a.a_slot_bytes + 2 * (size_t)a.b_slot_bytes <= left, MR_ERR_UNSUPPORTED,
              "tap gemm: tile does not fit shared memory (N=%d)", n_total);
@@ -423,7 +462,7 @@ int tapgemm_plan(TapGemmArgs& a, TapGemmPlan* plan) {
   a.w_reps = TG_W_REPS;
   a.w_rep_stride = tapgemm_pack_bytes(a.taps, n_total, a.K) / TG_W_REPS;
   plan->args = a;
-  plan->smem_bytes = (size_t)ns_a * a.a_slot_bytes + (size_t)ns_b * a.b_slot_bytes + TG_SMEM_FIXED;
+  plan->smem_bytes = (size_t)ns_a * a.a_slot_bytes + (size_t)ns_b * a.b_slot_bytes + TG_SMEM_FIXED + hot_bytes;
   int64_t g = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
   plan->grid = (int)(g < 1 ? 1 : g);
   return MR_OK;
@@ -461,6 +500,13 @@ int tapgemm_pack(const float* src, uint8_t* dst, int taps, int n_total, int K, i
 }  // namespace mr
 
 extern "C" {
+int mr_news_cnn_set_hot_tokens(const int64_t* ids, int n) {
+  using namespace mr;
+  MR_REQUIRE(n >= 0 && n <= TG_MAX_HOT && (n == 0 || ids != nullptr), MR_ERR_BAD_SHAPE, "mr_news_cnn_set_hot_tokens: n=%d (max %d)", n, TG_MAX_HOT);
+  for (int i = 0; i < n; ++i) g_hot_ids[i] = ids[i];
+  g_n_hot = n;
+  return MR_OK;
+}
 /* debug hook (not part of the reference-facing ABI): per-role wait counters of the next tap-GEMM launches */
 __attribute__((visibility("default"))) void mr_debug_tapgemm_counters(long long* device_buffer) { mr::g_tapgemm_dbg = device_buffer; }
 }

@@ -34,6 +34,8 @@ struct TapGemmArgs {
   int L, G, taps, dir, K;
   int n_sub, nsz[2];                       // N sub-tiles, each a multiple of 16 and <= 256
   const void* ids; int ids_i64;            // gather mode when ids != nullptr
+  int64_t hot_ids[4]; int n_hot;           // gather mode: table rows kept in shared memory (PAD/[CLS]/[SEP]: every
+                                           // CTA would otherwise hammer the same few L2 lines)
   const __nv_bfloat16* a; int64_t lda, V;  // gather: table [V, lda];  dense: activations [n_titles*L, lda]
   const uint8_t* wpack;                    // TG_W_REPS replicas of [chunk][tap] blocks of b_slot_bytes
   int w_reps; int64_t w_rep_stride;
@@ -62,6 +64,9 @@ int tapgemm_pack(const float* src, uint8_t* dst, int taps, int n_total, int K, i
 int tapgemm_plan(TapGemmArgs& a, TapGemmPlan* plan);
 int tapgemm_launch(const TapGemmPlan& plan, cudaStream_t stream);
 int sm_count();
+constexpr int TG_MAX_HOT = 4;
+// process-wide list of "hot" token ids (set through mr_news_cnn_set_hot_tokens); n <= TG_MAX_HOT
+int hot_tokens(int64_t* out);
 // debug: when set, every tap-GEMM launch writes its per-role wait counters here ([148][4][5] int64)
 extern long long* g_tapgemm_dbg;
 

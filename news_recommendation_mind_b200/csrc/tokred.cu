@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs 
   uint64_t* empty = full + TR_MAX_STAGES;
   uint64_t* done = empty + TR_MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  uint8_t* hot = reinterpret_cast<uint8_t*>(tmem_slot + 2);          // [n_hot][256 B]: this CTA's 128-column slice of the hot rows
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m = blockIdx.x / p.S, s = blockIdx.x % p.S;
@@ -20,6 +21,14 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs 
   {
     const uint32_t bytes = (uint32_t)p.n_stages * p.stage_bytes;
     for (uint32_t i = tid * 16; i < bytes; i += TR_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+    if (p.ids != nullptr)
+      for (int i = tid; i < p.n_hot * 16; i += TR_THREADS) {
+        const int h = i >> 4, q = i & 15;
+        const int col = (m * 16 + q) * 8;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (col < p.KP) v = __ldg(reinterpret_cast<const uint4*>(p.p + p.hot_ids[h] * p.ldp + col));
+        reinterpret_cast<uint4*>(hot + (size_t)h * 256)[q] = v;
+      }
     if (tid == 0) {
       for (int i = 0; i < TR_MAX_STAGES; ++i) {
         tc::mbar_init(&full[i], 128);
@@ -105,10 +114,15 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs 
       if (l >= p.L || title >= p.n_titles || tile >= p.n_tiles) return -1;
       return title * p.L + l;
     };
+    // source row of P: token index (dense), token id (gather), -1 = zero row, -2-h = hot row h (shared memory)
     auto prow_of = [&](int64_t t) -> int64_t {
       if (t < 0 || p.ids == nullptr) return t;
       int64_t id = load_index(p.ids, p.ids_i64, t);
-      return id < 0 ? 0 : (id >= p.V ? p.V - 1 : id);
+      id = id < 0 ? 0 : (id >= p.V ? p.V - 1 : id);
+#pragma unroll
+      for (int h = 0; h < 4; ++h)
+        if (h < p.n_hot && id == p.hot_ids[h]) id = -2 - h;
+      return id;
     };
     int64_t nxt[8];
 #pragma unroll
@@ -129,14 +143,20 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs 
         const int r = rgrp + 16 * ss;
         const int64_t t = token_of(tile, ss);
         const bool valid = t >= 0;
-        const __nv_bfloat16* prow = p.p + (valid ? cur[ss] : 0) * p.ldp;
+        const bool is_hot = valid && cur[ss] <= -2;
+        const __nv_bfloat16* prow = p.p + (valid && !is_hot ? cur[ss] : 0) * p.ldp;
         const uint32_t prow_s = (uint32_t)(p.halo + r);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {          // P: two 64-column blocks, SWIZZLE_128B rows
           const int col = (m * 16 + j + 8 * h) * 8;
           const bool ok = valid && col < p.KP;
-          tc::cp_async16(pbase + (uint32_t)h * p.p_ps + prow_s * 128u + ((((uint32_t)j ^ prow_s) & 7u) << 4),
-                         ok ? (const void*)(prow + col) : (const void*)p.q, ok ? 16u : 0u);
+          const uint32_t dst = pbase + (uint32_t)h * p.p_ps + prow_s * 128u + ((((uint32_t)j ^ prow_s) & 7u) << 4);
+          if (is_hot) {
+            const uint4 v = reinterpret_cast<const uint4*>(hot + (size_t)(-2 - cur[ss]) * 256)[j + 8 * h];
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+          } else {
+            tc::cp_async16(dst, ok ? (const void*)(prow + col) : (const void*)p.q, ok ? 16u : 0u);
+          }
         }
         const __nv_bfloat16* qrow = p.q + (valid ? t : 0) * p.ldq;
         const uint32_t ppb = p.q_rb >> 4;      // 16-byte pieces per row of a Q block (8 / 4 / 2)
@@ -221,7 +241,14 @@ int tokred_plan(TokRedArgs& a, TokRedPlan* plan) {
   a.q_rb = a.q_layout == 2 ? 128u : (a.q_layout == 4 ? 64u : 32u);
   a.q_ps = 128 * a.q_rb;
   a.stage_bytes = (uint32_t)align_up(a.p_bytes + (uint32_t)(a.NQ * 2 / a.q_rb) * a.q_ps, 1024);
-  const size_t fixed = (2 * TR_MAX_STAGES + 1) * 8 + 16;
+  a.n_hot = 0;
+  if (a.ids != nullptr) {
+    int64_t hot[TG_MAX_HOT];
+    const int n = hot_tokens(hot);
+    for (int i = 0; i < n; ++i)
+      if (hot[i] >= 0 && hot[i] < a.V) a.hot_ids[a.n_hot++] = hot[i];
+  }
+  const size_t fixed = (2 * TR_MAX_STAGES + 1) * 8 + 16 + 4 * 256;
   int ns = (int)((227 * 1024 - fixed - 128) / a.stage_bytes);
   if (ns > TR_MAX_STAGES) ns = TR_MAX_STAGES;
   MR_REQUIRE(ns >= 1, MR_ERR_UNSUPPORTED, "token-reduction gemm: stage of %u bytes does not fit shared memory", a.stage_bytes);

@@ -24,6 +24,7 @@ struct TokRedArgs {
   int64_t n_titles, n_tiles;
   int L, G, taps;
   const void* ids; int ids_i64;
+  int64_t hot_ids[4]; int n_hot;                    // gather mode: table rows kept in shared memory (see tapgemm.cuh)
   const __nv_bfloat16* p; int64_t ldp, V; int KP;   // KP: columns of P to reduce (multiple of 8)
   const __nv_bfloat16* q; int64_t ldq; int NQ;      // NQ: columns of Q (multiple of 16, taps*NQ <= 512)
   float* partial;                                   // [n_mtiles][S][taps][128][NQ]

@@ -16,6 +16,7 @@ parameters under the reference's names and initialisers -- their own forward is 
 """
 from __future__ import annotations
 
+import ctypes
 import os
 
 import torch
@@ -63,6 +64,11 @@ class BERT_Embedding(nn.Module):
                 self.bert_word_embedding.weight.normal_(0.0, 0.02)
         self._shadow = None
         self._shadow_key = None
+        # PAD / [CLS] / [SEP] of the BERT vocabulary (utils/Manager.py special-token table; MIND.py:103-127 puts
+        # [CLS] first, [SEP] last and pads with 0): kept in shared memory by the fused gather
+        hot = [t for t in getattr(manager, "hot_token_ids", (0, 101, 102)) if 0 <= t < vocab_size][:4]
+        arr = (ctypes.c_int64 * max(len(hot), 1))(*hot)
+        _lib.check(_lib.load().mr_news_cnn_set_hot_tokens(arr, len(hot)), "mr_news_cnn_set_hot_tokens")
 
     @property
     def weight(self) -> torch.Tensor:
