@@ -53,7 +53,7 @@ int64_t news_cnn_tc_workspace_bytes(const mr_cnn_shape* s, int backward) {
   b += arena_bytes(tapgemm_pack_bytes(1, (int)Hp, (int)Hp), 1);
   b += arena_bytes(T * Kp, 2);
   b += 2 * arena_bytes(T * Hp, 2);                                    // dkp, dc_pool / dconv
-  b += arena_bytes(tapgemm_pack_bytes(3, 512, (int)Hp), 1);           // dgrad weights (one 512-column block)
+  b += arena_bytes(tapgemm_pack_bytes(3, 256, (int)Hp), 1);           // dgrad weights (one block of <= 256 columns)
   b += arena_bytes(s->N * s->H, 4);                                   // dq partial
   b += arena_bytes(colsum_chunks(T) * Hp, 4);
   const int64_t pc = tokred_partial_bytes(s->N, (int)s->L, 3, (int)Kp, (int)Hp);
@@ -149,8 +149,10 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
   __nv_bfloat16* xa = ids ? nullptr : ar.take<__nv_bfloat16>(T * Kp);
   __nv_bfloat16* dkp = ar.take<__nv_bfloat16>(T * Hp);
   __nv_bfloat16* dcv = ar.take<__nv_bfloat16>(T * Hp);                               // dc_pool, then dconv in place
-  const int64_t nblk = d_emb ? ceil_div(Kp, 512) : 0;
-  uint8_t* wdg = d_emb ? ar.take<uint8_t>(tapgemm_pack_bytes(3, 512, (int)Hp)) : nullptr;
+  // d_emb columns are produced in blocks of at most 256 so that the TMEM accumulator stays double buffered
+  const int64_t nblk = d_emb ? ceil_div(Kp, 256) : 0;
+  const int64_t nbsz = nblk ? align_up(ceil_div(Kp, nblk), 16) : 0;
+  uint8_t* wdg = d_emb ? ar.take<uint8_t>(tapgemm_pack_bytes(3, 256, (int)Hp)) : nullptr;
   float* dqp = ar.take<float>(N * H);
   float* cp = ar.take<float>(colsum_chunks(T) * Hp);
   const int64_t pb_conv = tokred_partial_bytes(N, (int)L, 3, (int)Kp, (int)Hp);
@@ -223,13 +225,12 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
   }
   // 5. d_emb[t, e] = sum_tap sum_h dconv[t-(tap-1), h] conv_w[h, e, tap]
   for (int64_t blk = 0; blk < nblk; ++blk) {
-    const int64_t n0 = blk * 512;
-    const int64_t nb = (Kp - n0) < 512 ? (Kp - n0) : 512;
+    const int64_t n0 = blk * nbsz;
+    const int64_t nb = (Kp - n0) < nbsz ? (Kp - n0) : nbsz;
     TapGemmArgs a{};
     TapGemmPlan plan;
     a.n_titles = N; a.L = (int)L; a.taps = 3; a.dir = -1; a.K = (int)Hp;
-    if (nb <= 256) { a.n_sub = 1; a.nsz[0] = (int)nb; }
-    else { a.n_sub = 2; a.nsz[0] = (int)align_up(nb / 2, 16); a.nsz[1] = (int)(nb - a.nsz[0]); }
+    a.n_sub = 1; a.nsz[0] = (int)nb;
     if (int rc = tapgemm_pack(conv_w + n0 * 3, wdg, 3, (int)nb, (int)Hp, (int)((E - n0) < nb ? (E - n0) : nb), (int)H, 3, 3 * E, 1, st)) return rc;
     a.ids = nullptr; a.a = dcv; a.lda = Hp;
     a.wpack = wdg; a.epi = TG_EPI_STORE; a.bias = nullptr; a.n_valid = (int)nb;

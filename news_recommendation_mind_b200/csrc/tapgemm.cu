@@ -1,5 +1,7 @@
 // Host side of the tap GEMM (tapgemm.cuh): shared-memory carve-up, weight packing, launch.
 #include "tapgemm.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace mr {
 
@@ -31,7 +33,7 @@ struct Ring {
   }
 };
 
-__global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArgs p) {
+__global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArgs p, const __grid_constant__ CUtensorMap tmap) {
   long long dbg_acc[4] = {0, 0, 0, 0};
   const long long dbg_t0 = clock64();
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
       }
     if (tid == 0) {
       for (int i = 0; i < TG_MAX_SLOTS; ++i) {
-        tc::mbar_init(&a_full[i], 128);
+        tc::mbar_init(&a_full[i], p.use_tma ? 1 : 128);
         tc::mbar_init(&a_empty[i], 1);
         tc::mbar_init(&b_full[i], 1);
         tc::mbar_init(&b_empty[i], 1);
@@ -261,8 +263,61 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
         }
       }
     }
+  } else if (p.use_tma) {
+    // =================================== A producer (TMA) ===================================
+    // One warp.  Dense activations: ONE 3-D tile load per k-chunk -- the tensor map views the [T, ld] matrix as
+    // (column, title, position), so the box {64, G, L} arrives in shared memory already in the position-major
+    // row order r = l*G + g, 128-byte swizzled by the copy engine.  Token table: lane i gathers rows 4i..4i+3
+    // of the tile with one tile::gather4 (4 token ids -> 4 x 128 B); rows outside the titles use row index V,
+    // which is out of bounds and therefore zero filled.
+    if (warp == 6) {
+      const int lane = tid & 31;
+      if (lane == 0) tc::tma_prefetch_desc(&tmap);
+      const uint32_t sA0 = tc::smem_u32(sA) + (uint32_t)p.halo * 128u;
+      const uint32_t dense_bytes = (uint32_t)(p.G * p.L) * 128u;
+      int64_t row_off[4];
+      int row_g[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = 4 * lane + k;
+        const int g = r % p.G, l = r / p.G;
+        row_g[k] = g;
+        row_off[k] = l < p.L ? (int64_t)g * p.L + l : -1;
+      }
+      auto row_id = [&](int64_t tile, int k) -> int {
+        if (p.ids == nullptr || row_off[k] < 0 || tile >= p.n_tiles || tile * p.G + row_g[k] >= p.n_titles) return (int)p.V;
+        const int64_t id = load_index(p.ids, p.ids_i64, tile * p.G * p.L + row_off[k]);
+        return (int)(id < 0 ? 0 : (id >= p.V ? p.V - 1 : id));
+      };
+      int nxt[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) nxt[k] = row_id(blockIdx.x, k);
+      Ring ra(p.ns_a);
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        int rid[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rid[k] = nxt[k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) nxt[k] = row_id(tile + gridDim.x, k);      // ids of the next tile, in flight
+        int c = rot_c;
+        for (int cc = 0; cc < n_chunks; ++cc) {
+          TG_TIMED(0, tc::mbar_wait(&a_empty[ra.pos], ra.phase ^ 1u));
+          const uint32_t slot = sA0 + ra.pos * p.a_slot_bytes;
+          if (p.ids != nullptr) {
+            if (lane == 0) tc::mbar_arrive_expect_tx(&a_full[ra.pos], 128u * 128u);
+            __syncwarp();
+            tc::tma_gather4(slot + (uint32_t)lane * 512u, &tmap, c * TG_KC, rid[0], rid[1], rid[2], rid[3], &a_full[ra.pos]);
+          } else if (lane == 0) {
+            tc::mbar_arrive_expect_tx(&a_full[ra.pos], dense_bytes);
+            tc::tma_load_3d(slot, &tmap, c * TG_KC, (int)(tile * p.G), 0, &a_full[ra.pos]);
+          }
+          ra.next();
+          if (++c == n_chunks) c = 0;
+        }
+      }
+    }
   } else {
-    // =================================== A producers ========================================
+    // =================================== A producers (cp.async) =============================
     const int ptid = tid - 192;            // 0..127
     const int rgrp = ptid >> 3, j = ptid & 7;
     const uint32_t depth = (uint32_t)(p.ns_a - 2 < 3 ? p.ns_a - 2 : 3);   // cp.async groups in flight behind the signalled one
@@ -399,6 +454,24 @@ __global__ void tapgemm_pack_kernel(const float* __restrict__ src, uint8_t* __re
 
 long long* g_tapgemm_dbg = nullptr;
 
+bool use_tma_default() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MINDREC_TMA");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+bool use_tma_gather() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MINDREC_TMA_GATHER");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
+
 int sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
   int dev = 0;
@@ -434,7 +507,10 @@ int tapgemm_plan(TapGemmArgs& a, TapGemmPlan* plan) {
   int G = 128 / a.L;
   if (G > 16) G = 16;
   a.G = G;
-  a.halo = a.taps > 1 ? G : 0;
+  // dense activations: TMA tile loads.  Token-table gather: cp.async + the hot-row shared-memory cache by default
+  // (PAD/[CLS]/[SEP] rows hammer a few L2 lines when fetched by every SM; MINDREC_TMA_GATHER=1 selects gather4).
+  a.use_tma = use_tma_default() && (a.ids == nullptr || use_tma_gather()) ? 1 : 0;
+  a.halo = a.taps > 1 ? (int)align_up(G, 8) : 0;      // multiple of 8 rows: tile rows start on a 1024-byte swizzle period
   a.a_ps = 0;
   a.a_slot_bytes = (uint32_t)(align_up(128 + 2 * a.halo, 8) * 128);      // one k-chunk of 64 columns, SWIZZLE_128B rows
   a.b_slot_bytes = (uint32_t)((TG_KC / 8) * n_total * 16);
@@ -461,6 +537,17 @@ int tapgemm_plan(TapGemmArgs& a, TapGemmPlan* plan) {
   a.n_tiles = ceil_div(a.n_titles, (int64_t)G);
   a.w_reps = TG_W_REPS;
   a.w_rep_stride = tapgemm_pack_bytes(a.taps, n_total, a.K) / TG_W_REPS;
+  if (a.use_tma) {
+    if (a.ids != nullptr) {
+      if (int rc = tma_encode_2d(&plan->tmap, a.a, (uint64_t)a.lda, (uint64_t)a.V, (uint64_t)a.lda * 2, TG_KC, 1, 128)) return rc;
+    } else {
+      if (int rc = tma_encode_3d(&plan->tmap, a.a, (uint64_t)a.lda, (uint64_t)a.n_titles, (uint64_t)a.L, (uint64_t)a.L * a.lda * 2,
+                                 (uint64_t)a.lda * 2, TG_KC, (uint32_t)G, (uint32_t)a.L, 128))
+        return rc;
+    }
+  } else {
+    memset(&plan->tmap, 0, sizeof(plan->tmap));
+  }
   plan->args = a;
   plan->smem_bytes = (size_t)ns_a * a.a_slot_bytes + (size_t)ns_b * a.b_slot_bytes + TG_SMEM_FIXED + hot_bytes;
   int64_t g = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
@@ -480,7 +567,7 @@ int tapgemm_launch(const TapGemmPlan& plan, cudaStream_t stream) {
   TapGemmArgs args = plan.args;
   args.dbg = g_tapgemm_dbg;
   if (g_tapgemm_dbg != nullptr) g_tapgemm_dbg += 148 * 4 * 5;     // one record block per launch
-  tapgemm_kernel<<<plan.grid, TG_THREADS, plan.smem_bytes, stream>>>(args);
+  tapgemm_kernel<<<plan.grid, TG_THREADS, plan.smem_bytes, stream>>>(args, plan.tmap);
   MR_CHECK_LAUNCH("tapgemm_kernel");
   return MR_OK;
 }

@@ -20,6 +20,7 @@
 #pragma once
 #include "common.cuh"
 #include "tc05.cuh"
+#include "tma.cuh"
 
 namespace mr {
 
@@ -43,12 +44,14 @@ struct TapGemmArgs {
   const __nv_bfloat16* e0; const __nv_bfloat16* e1; int64_t lde;
   __nv_bfloat16* out; int64_t ldo;
   int ns_a, ns_b, halo;
+  int use_tma;                             // A tiles staged by TMA (3-D tile load / gather4) instead of cp.async
   long long* dbg;                          // optional [grid][4 roles][5] wait-cycle counters (see tapgemm.cu)
   uint32_t a_slot_bytes, b_slot_bytes, a_ps;
 };
 
 // ---- host side -------------------------------------------------------------------------------
 struct TapGemmPlan {
+  alignas(64) CUtensorMap tmap;            // A operand: 2-D table (gather4) or 3-D [cols, title, position] view
   TapGemmArgs args;
   size_t smem_bytes;
   int grid;
@@ -64,6 +67,8 @@ int tapgemm_pack(const float* src, uint8_t* dst, int taps, int n_total, int K, i
 int tapgemm_plan(TapGemmArgs& a, TapGemmPlan* plan);
 int tapgemm_launch(const TapGemmPlan& plan, cudaStream_t stream);
 int sm_count();
+bool use_tma_gather();
+bool use_tma_default();                  // MINDREC_TMA=0 switches the producers back to cp.async
 constexpr int TG_MAX_HOT = 4;
 // process-wide list of "hot" token ids (set through mr_news_cnn_set_hot_tokens); n <= TG_MAX_HOT
 int hot_tokens(int64_t* out);

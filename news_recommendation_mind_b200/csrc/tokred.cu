@@ -6,7 +6,20 @@ namespace mr {
 
 constexpr int TR_MAX_STAGES = 4;
 
+#define TR_TIMED(slot, stmt)                                   \
+  do {                                                         \
+    if (p.dbg != nullptr) {                                    \
+      const long long t0__ = clock64();                        \
+      stmt;                                                    \
+      dbg_acc[slot] += clock64() - t0__;                       \
+    } else {                                                   \
+      stmt;                                                    \
+    }                                                          \
+  } while (0)
+
 __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs p) {
+  long long dbg_acc[4] = {0, 0, 0, 0};
+  const long long dbg_t0 = clock64();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * p.stage_bytes);
   uint64_t* empty = full + TR_MAX_STAGES;
@@ -79,11 +92,12 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs 
       uint32_t it = 0;
       for (int64_t tile = s; tile < p.n_tiles; tile += p.S, ++it) {
         const uint32_t st = it % (uint32_t)p.n_stages;
-        tc::mbar_wait(&full[st], (it / (uint32_t)p.n_stages) & 1u);
+        TR_TIMED(0, tc::mbar_wait(&full[st], (it / (uint32_t)p.n_stages) & 1u));
         tc::tc_fence_after();
         const uint32_t pbase = tc::smem_u32(smem) + st * p.stage_bytes;
         const uint32_t qbase = pbase + p.p_bytes;
         const uint64_t db0 = b_tmpl | (uint64_t)((qbase >> 4) & 0x3FFFu);
+        TR_TIMED(1, {
         if (tc::elect_one()) {
           for (int tap = 0; tap < p.taps; ++tap) {
             const int shift = (tap - ctr) * p.G;
@@ -96,6 +110,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs 
           tc::umma_commit(&empty[st]);
         }
         __syncwarp();
+        });
       }
       if (tc::elect_one()) tc::umma_commit(done);
       __syncwarp();
@@ -105,14 +120,29 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs 
     const int ptid = tid - 160;            // 0..127
     const int rgrp = ptid >> 3, j = ptid & 7;
     const int q_panels = p.NQ / 8;
-    const int depth = p.n_stages >= 3 ? 1 : 0;
-    // row r = rgrp + 16*ss of a tile: token index t (or -1 = zero row) and the source row of P
-    auto token_of = [&](int64_t tile, int ss) -> int64_t {
+    const uint32_t depth = p.n_stages >= 3 ? 1u : 0u;
+    const uint32_t ppb_shift = p.q_rb == 128 ? 3u : (p.q_rb == 64 ? 2u : 1u);       // log2(16-byte pieces per Q row)
+    const uint32_t ppb_mask = (1u << ppb_shift) - 1u;
+    // tile-independent geometry of this thread's rows r = rgrp + 16*ss (token = tile*G*L + row_off)
+    int64_t row_off[8];
+    int row_g[8];
+    uint32_t p_dst[8], q_dst[8], q_x[8];
+#pragma unroll
+    for (int ss = 0; ss < 8; ++ss) {
       const int r = rgrp + 16 * ss;
       const int g = r % p.G, l = r / p.G;
-      const int64_t title = tile * p.G + g;
-      if (l >= p.L || title >= p.n_titles || tile >= p.n_tiles) return -1;
-      return title * p.L + l;
+      row_g[ss] = g;
+      row_off[ss] = l < p.L ? (int64_t)g * p.L + l : -1;
+      const uint32_t prow_s = (uint32_t)(p.halo + r);
+      p_dst[ss] = prow_s * 128u + ((((uint32_t)j ^ prow_s) & 7u) << 4);
+      q_dst[ss] = (uint32_t)r * p.q_rb;
+      q_x[ss] = (((uint32_t)r * p.q_rb) >> 7) & ppb_mask;
+    }
+    const int pcol0 = (m * 16 + j) * 8, pcol1 = pcol0 + 64;
+    const bool pok0 = pcol0 < p.KP, pok1 = pcol1 < p.KP;
+    auto token_of = [&](int64_t tile, int ss) -> int64_t {
+      if (row_off[ss] < 0 || tile >= p.n_tiles || tile * p.G + row_g[ss] >= p.n_titles) return -1;
+      return tile * p.G * p.L + row_off[ss];
     };
     // source row of P: token index (dense), token id (gather), -1 = zero row, -2-h = hot row h (shared memory)
     auto prow_of = [&](int64_t t) -> int64_t {
@@ -135,43 +165,41 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs 
       for (int ss = 0; ss < 8; ++ss) cur[ss] = nxt[ss];
 #pragma unroll
       for (int ss = 0; ss < 8; ++ss) nxt[ss] = prow_of(token_of(tile + p.S, ss));   // in flight while this tile is staged
-      tc::mbar_wait(&empty[st], ((it / (uint32_t)p.n_stages) & 1u) ^ 1u);
+      TR_TIMED(0, tc::mbar_wait(&empty[st], ((it / (uint32_t)p.n_stages) & 1u) ^ 1u));
+      const long long t_issue0 = clock64();
       const uint32_t pbase = tc::smem_u32(smem) + st * p.stage_bytes;
       const uint32_t qbase = pbase + p.p_bytes;
 #pragma unroll
       for (int ss = 0; ss < 8; ++ss) {
-        const int r = rgrp + 16 * ss;
         const int64_t t = token_of(tile, ss);
         const bool valid = t >= 0;
         const bool is_hot = valid && cur[ss] <= -2;
-        const __nv_bfloat16* prow = p.p + (valid && !is_hot ? cur[ss] : 0) * p.ldp;
-        const uint32_t prow_s = (uint32_t)(p.halo + r);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {          // P: two 64-column blocks, SWIZZLE_128B rows
-          const int col = (m * 16 + j + 8 * h) * 8;
-          const bool ok = valid && col < p.KP;
-          const uint32_t dst = pbase + (uint32_t)h * p.p_ps + prow_s * 128u + ((((uint32_t)j ^ prow_s) & 7u) << 4);
-          if (is_hot) {
-            const uint4 v = reinterpret_cast<const uint4*>(hot + (size_t)(-2 - cur[ss]) * 256)[j + 8 * h];
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-          } else {
-            tc::cp_async16(dst, ok ? (const void*)(prow + col) : (const void*)p.q, ok ? 16u : 0u);
-          }
+        const uint32_t d0 = pbase + p_dst[ss];
+        if (is_hot) {                               // hot token: 16-byte smem -> smem copies
+          const uint4* hrow = reinterpret_cast<const uint4*>(hot + (size_t)(-2 - cur[ss]) * 256);
+          const uint4 v0 = hrow[j], v1 = hrow[j + 8];
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d0), "r"(v0.x), "r"(v0.y), "r"(v0.z), "r"(v0.w) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d0 + p.p_ps), "r"(v1.x), "r"(v1.y), "r"(v1.z), "r"(v1.w) : "memory");
+        } else {
+          const __nv_bfloat16* prow = p.p + (valid ? cur[ss] : 0) * p.ldp;
+          tc::cp_async16(d0, valid && pok0 ? (const void*)(prow + pcol0) : (const void*)p.q, valid && pok0 ? 16u : 0u);
+          tc::cp_async16(d0 + p.p_ps, valid && pok1 ? (const void*)(prow + pcol1) : (const void*)p.q, valid && pok1 ? 16u : 0u);
         }
         const __nv_bfloat16* qrow = p.q + (valid ? t : 0) * p.ldq;
-        const uint32_t ppb = p.q_rb >> 4;      // 16-byte pieces per row of a Q block (8 / 4 / 2)
-        const uint32_t qx = (((uint32_t)r * p.q_rb) >> 7) & (ppb - 1);
         for (int jj = j; jj < q_panels; jj += 8) {
-          const uint32_t blk = (uint32_t)jj / ppb, q = (uint32_t)jj % ppb;
-          tc::cp_async16(qbase + blk * p.q_ps + (uint32_t)r * p.q_rb + ((q ^ qx) << 4), valid ? (const void*)(qrow + jj * 8) : (const void*)p.q,
+          const uint32_t blk = (uint32_t)jj >> ppb_shift, q = (uint32_t)jj & ppb_mask;
+          tc::cp_async16(qbase + blk * p.q_ps + q_dst[ss] + ((q ^ q_x[ss]) << 4), valid ? (const void*)(qrow + jj * 8) : (const void*)p.q,
                          valid ? 16u : 0u);
         }
       }
       tc::cp_async_commit();
-      if (it + 1 - signaled > (uint32_t)depth) {
+      dbg_acc[2] += clock64() - t_issue0;
+      if (it + 1 - signaled > depth) {
+        TR_TIMED(1, {
         if (depth == 1) tc::cp_async_wait<1>();
         else tc::cp_async_wait<0>();
         tc::fence_proxy_async();
+        });
         tc::mbar_arrive(&full[signaled % (uint32_t)p.n_stages]);
         ++signaled;
       }
@@ -184,6 +212,11 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs 
     }
   }
 
+  if (p.dbg != nullptr && (tid == 128 || tid == 160)) {
+    // rows: 1 mma {full wait, issue}, 3 producer {empty wait, cp.wait, issue}
+    long long* d = p.dbg + ((size_t)blockIdx.x * 4 + (tid == 128 ? 1 : 3)) * 5;
+    d[0] = dbg_acc[0]; d[1] = dbg_acc[1]; d[2] = dbg_acc[2]; d[3] = dbg_acc[3]; d[4] = clock64() - dbg_t0;
+  }
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 4) tc::tmem_dealloc(tmem, 512);
@@ -266,7 +299,10 @@ int tokred_launch(const TokRedPlan& plan, cudaStream_t stream) {
     MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "token-reduction gemm: shared-memory opt-in failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  tokred_kernel<<<plan.grid, TR_THREADS, plan.smem_bytes, stream>>>(plan.args);
+  TokRedArgs args = plan.args;
+  args.dbg = g_tapgemm_dbg;
+  if (g_tapgemm_dbg != nullptr) g_tapgemm_dbg += 148 * 4 * 5;
+  tokred_kernel<<<plan.grid, TR_THREADS, plan.smem_bytes, stream>>>(args);
   MR_CHECK_LAUNCH("tokred_kernel");
   return MR_OK;
 }

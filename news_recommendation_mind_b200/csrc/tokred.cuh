@@ -30,6 +30,7 @@ struct TokRedArgs {
   float* partial;                                   // [n_mtiles][S][taps][128][NQ]
   int n_mtiles, S, halo, n_stages;
   uint32_t p_ps, q_ps, p_bytes, stage_bytes, q_rb;   // block strides (bytes), Q row bytes
+  long long* dbg;                                      // optional wait counters (debug)
   int q_layout;                                        // UMMA layout type of Q (2 / 4 / 6)
 };
 

@@ -27,7 +27,7 @@ enc.encode_ids(emb, ids, mask).sum().backward()
 torch.cuda.synchronize()
 lib.mr_debug_tapgemm_counters(None)
 b = buf.double().cpu()
-names = ["conv fwd", "proj fwd", "relugrad", "dgrad"]
+names = ["conv fwd", "proj fwd", "tokred proj (mma: full-wait, issue | prod: empty-wait, cp.wait, issue)", "relugrad", "tokred conv", "dgrad"]
 roles = ["epilogue  {t_full,-,-}", "mma       {t_empty,a_full,b_full}", "w-producer{b_empty,-,-}", "a-producer{a_empty,cp.wait,ids+arrive,cp.issue}"]
 for i in range(NL):
     if b[i].abs().sum() == 0:
