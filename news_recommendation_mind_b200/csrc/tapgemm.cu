@@ -336,24 +336,33 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
       const uint32_t row = (uint32_t)(p.halo + r);
       dst_off[s] = row * 128u + ((((uint32_t)j ^ row) & 7u) << 4);
     }
-    // -> source row (token id in gather mode, token index otherwise); -1 = zero row; -2-h = hot row h (smem copy)
-    auto row_index = [&](int64_t tile, int s) -> int64_t {
+    // token index of row s of a tile (-1 = zero row); the id load is issued one tile ahead and classified at the
+    // top of the next iteration, so its latency overlaps the staging of the current tile
+    auto row_token = [&](int64_t tile, int s) -> int64_t {
       if (row_off[s] < 0 || tile >= p.n_tiles || tile * p.G + row_g[s] >= p.n_titles) return -1;
-      const int64_t t = tile * p.G * p.L + row_off[s];
-      if (p.ids == nullptr) return t;
-      int64_t id = load_index(p.ids, p.ids_i64, t);
-      id = id < 0 ? 0 : (id >= p.V ? p.V - 1 : id);
+      return tile * p.G * p.L + row_off[s];
+    };
+    auto raw_of = [&](int64_t t) -> int64_t { return (t < 0 || p.ids == nullptr) ? t : load_index(p.ids, p.ids_i64, t); };
+    // -> source row (token id in gather mode, token index otherwise); -1 = zero row; -2-h = hot row h (smem copy)
+    auto classify = [&](int64_t t, int64_t raw) -> int64_t {
+      if (t < 0 || p.ids == nullptr) return t;
+      int64_t id = raw < 0 ? 0 : (raw >= p.V ? p.V - 1 : raw);
 #pragma unroll
       for (int h = 0; h < TG_MAX_HOT; ++h)
         if (h < p.n_hot && id == p.hot_ids[h]) id = -2 - h;
       return id;
     };
-    int64_t nxt[8];
+    int64_t raw[8];
 #pragma unroll
-    for (int s = 0; s < 8; ++s) nxt[s] = row_index(blockIdx.x, s);
+    for (int s = 0; s < 8; ++s) raw[s] = raw_of(row_token(blockIdx.x, s));
     Ring ra(p.ns_a), sig(p.ns_a);
     uint32_t pending = 0;                  // committed but not yet signalled k-chunks
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      int64_t nxt[8];
+#pragma unroll
+      for (int s = 0; s < 8; ++s) nxt[s] = classify(row_token(tile, s), raw[s]);
+#pragma unroll
+      for (int s = 0; s < 8; ++s) raw[s] = raw_of(row_token(tile + gridDim.x, s));      // in flight while this tile is staged
       const __nv_bfloat16* rowp[8];
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
@@ -364,8 +373,6 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
       uint32_t hot_mask = 0;
 #pragma unroll
       for (int s = 0; s < 8; ++s) hot_mask |= (nxt[s] <= -2 ? 1u : 0u) << s;
-#pragma unroll
-      for (int s = 0; s < 8; ++s) nxt[s] = row_index(tile + gridDim.x, s);      // in flight while this tile is staged
       int c = rot_c;
       for (int cc = 0; cc < n_chunks; ++cc) {
         const int kc = c == n_chunks - 1 ? last_kc : TG_KC;

@@ -1,6 +1,7 @@
 // Token-reduction GEMM (tokred.cuh): kernel, planning, launch and the fixed-order partial reduction.
 #include "tokred.cuh"
 #include "tapgemm.cuh"   // sm_count()
+#include <string.h>
 
 namespace mr {
 
@@ -17,7 +18,8 @@ constexpr int TR_MAX_STAGES = 4;
     }                                                          \
   } while (0)
 
-__global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs p) {
+__global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs p, const __grid_constant__ CUtensorMap pmap,
+                                                              const __grid_constant__ CUtensorMap qmap) {
   long long dbg_acc[4] = {0, 0, 0, 0};
   const long long dbg_t0 = clock64();
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -44,7 +46,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs 
       }
     if (tid == 0) {
       for (int i = 0; i < TR_MAX_STAGES; ++i) {
-        tc::mbar_init(&full[i], 128);
+        tc::mbar_init(&full[i], (p.p_tma ? 0 : 128) + (p.q_tma ? 1 : 0));
         tc::mbar_init(&empty[i], 1);
       }
       tc::mbar_init(done, 1);
@@ -144,31 +146,47 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs 
       if (row_off[ss] < 0 || tile >= p.n_tiles || tile * p.G + row_g[ss] >= p.n_titles) return -1;
       return tile * p.G * p.L + row_off[ss];
     };
+    // raw id of a token (the load is issued one tile ahead and only classified at the top of the next iteration,
+    // so its latency overlaps the staging of the current tile)
+    auto raw_of = [&](int64_t t) -> int64_t { return (t < 0 || p.ids == nullptr) ? t : load_index(p.ids, p.ids_i64, t); };
     // source row of P: token index (dense), token id (gather), -1 = zero row, -2-h = hot row h (shared memory)
-    auto prow_of = [&](int64_t t) -> int64_t {
+    auto classify = [&](int64_t t, int64_t raw) -> int64_t {
       if (t < 0 || p.ids == nullptr) return t;
-      int64_t id = load_index(p.ids, p.ids_i64, t);
-      id = id < 0 ? 0 : (id >= p.V ? p.V - 1 : id);
+      int64_t id = raw < 0 ? 0 : (raw >= p.V ? p.V - 1 : raw);
 #pragma unroll
       for (int h = 0; h < 4; ++h)
         if (h < p.n_hot && id == p.hot_ids[h]) id = -2 - h;
       return id;
     };
-    int64_t nxt[8];
+    int64_t raw[8];
 #pragma unroll
-    for (int ss = 0; ss < 8; ++ss) nxt[ss] = prow_of(token_of(s, ss));
+    for (int ss = 0; ss < 8; ++ss) raw[ss] = raw_of(token_of(s, ss));
     uint32_t it = 0, signaled = 0;
     for (int64_t tile = s; tile < p.n_tiles; tile += p.S, ++it) {
       const uint32_t st = it % (uint32_t)p.n_stages;
       int64_t cur[8];
 #pragma unroll
-      for (int ss = 0; ss < 8; ++ss) cur[ss] = nxt[ss];
+      for (int ss = 0; ss < 8; ++ss) cur[ss] = classify(token_of(tile, ss), raw[ss]);
 #pragma unroll
-      for (int ss = 0; ss < 8; ++ss) nxt[ss] = prow_of(token_of(tile + p.S, ss));   // in flight while this tile is staged
+      for (int ss = 0; ss < 8; ++ss) raw[ss] = raw_of(token_of(tile + p.S, ss));   // in flight while this tile is staged
       TR_TIMED(0, tc::mbar_wait(&empty[st], ((it / (uint32_t)p.n_stages) & 1u) ^ 1u));
       const long long t_issue0 = clock64();
       const uint32_t pbase = tc::smem_u32(smem) + st * p.stage_bytes;
       const uint32_t qbase = pbase + p.p_bytes;
+      if (p.q_tma && ptid == 0) {
+        // TMA: one 3-D tile load per Q block (and per P block when P is dense); the box arrives in the
+        // position-major row order, swizzled by the copy engine
+        const uint32_t rows = (uint32_t)(p.G * p.L);
+        const uint32_t q_blocks = (uint32_t)(p.NQ * 2) / p.q_rb;
+        tc::mbar_arrive_expect_tx(&full[st], rows * (q_blocks * p.q_rb + (p.p_tma ? 256u : 0u)));
+        for (uint32_t b = 0; b < q_blocks; ++b)
+          tc::tma_load_3d(qbase + b * p.q_ps, &qmap, (int)(b * (p.q_rb / 2)), (int)(tile * p.G), 0, &full[st]);
+        if (p.p_tma) {
+          tc::tma_load_3d(pbase + (uint32_t)p.halo * 128u, &pmap, m * 128, (int)(tile * p.G), 0, &full[st]);
+          tc::tma_load_3d(pbase + p.p_ps + (uint32_t)p.halo * 128u, &pmap, m * 128 + 64, (int)(tile * p.G), 0, &full[st]);
+        }
+      }
+      if (p.p_tma) continue;                       // nothing left for the cp.async threads
 #pragma unroll
       for (int ss = 0; ss < 8; ++ss) {
         const int64_t t = token_of(tile, ss);
@@ -185,11 +203,13 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs 
           tc::cp_async16(d0, valid && pok0 ? (const void*)(prow + pcol0) : (const void*)p.q, valid && pok0 ? 16u : 0u);
           tc::cp_async16(d0 + p.p_ps, valid && pok1 ? (const void*)(prow + pcol1) : (const void*)p.q, valid && pok1 ? 16u : 0u);
         }
-        const __nv_bfloat16* qrow = p.q + (valid ? t : 0) * p.ldq;
-        for (int jj = j; jj < q_panels; jj += 8) {
-          const uint32_t blk = (uint32_t)jj >> ppb_shift, q = (uint32_t)jj & ppb_mask;
-          tc::cp_async16(qbase + blk * p.q_ps + q_dst[ss] + ((q ^ q_x[ss]) << 4), valid ? (const void*)(qrow + jj * 8) : (const void*)p.q,
-                         valid ? 16u : 0u);
+        if (!p.q_tma) {
+          const __nv_bfloat16* qrow = p.q + (valid ? t : 0) * p.ldq;
+          for (int jj = j; jj < q_panels; jj += 8) {
+            const uint32_t blk = (uint32_t)jj >> ppb_shift, q = (uint32_t)jj & ppb_mask;
+            tc::cp_async16(qbase + blk * p.q_ps + q_dst[ss] + ((q ^ q_x[ss]) << 4), valid ? (const void*)(qrow + jj * 8) : (const void*)p.q,
+                           valid ? 16u : 0u);
+          }
         }
       }
       tc::cp_async_commit();
@@ -204,11 +224,13 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs 
         ++signaled;
       }
     }
-    tc::cp_async_wait<0>();
-    tc::fence_proxy_async();
-    while (signaled < it) {
-      tc::mbar_arrive(&full[signaled % (uint32_t)p.n_stages]);
-      ++signaled;
+    if (!p.p_tma) {
+      tc::cp_async_wait<0>();
+      tc::fence_proxy_async();
+      while (signaled < it) {
+        tc::mbar_arrive(&full[signaled % (uint32_t)p.n_stages]);
+        ++signaled;
+      }
     }
   }
 
@@ -265,7 +287,10 @@ int tokred_plan(TokRedArgs& a, TokRedPlan* plan) {
   MR_REQUIRE(a.NQ >= 16 && a.NQ % 16 == 0 && a.NQ <= 256 && a.taps * a.NQ <= 512, MR_ERR_UNSUPPORTED,
              "token-reduction gemm: taps*NQ = %d*%d exceeds the 512 TMEM columns", a.taps, a.NQ);
   tokred_geometry(a.n_titles, a.L, a.taps, a.KP, &a.G, &a.n_mtiles, &a.S, &a.n_tiles);
-  a.halo = a.taps > 1 ? a.G : 0;
+  a.q_tma = use_tma_default() ? 1 : 0;
+  a.p_tma = (a.q_tma && (a.ids == nullptr)) ? 1 : 0;
+  // TMA destinations start on a 1024-byte swizzle period (halo a multiple of 8 rows); cp.async staging has no such need
+  a.halo = a.taps > 1 ? (a.p_tma ? (int)align_up(a.G, 8) : a.G) : 0;
   // P: two 64-column blocks of [rows x 128 B] (SWIZZLE_128B);  Q: NQ columns in blocks of 64 / 32 / 16 columns
   // (SWIZZLE_128B / 64B / 32B -- the widest row that divides NQ), 128 rows each; every block 1024-byte aligned
   a.p_ps = (uint32_t)(align_up(128 + 2 * a.halo, 8) * 128);
@@ -286,6 +311,16 @@ int tokred_plan(TokRedArgs& a, TokRedPlan* plan) {
   if (ns > TR_MAX_STAGES) ns = TR_MAX_STAGES;
   MR_REQUIRE(ns >= 1, MR_ERR_UNSUPPORTED, "token-reduction gemm: stage of %u bytes does not fit shared memory", a.stage_bytes);
   a.n_stages = ns;
+  memset(&plan->pmap, 0, sizeof(CUtensorMap));
+  memset(&plan->qmap, 0, sizeof(CUtensorMap));
+  if (a.q_tma)
+    if (int rc = tma_encode_3d(&plan->qmap, a.q, (uint64_t)a.ldq, (uint64_t)a.n_titles, (uint64_t)a.L, (uint64_t)a.L * a.ldq * 2,
+                               (uint64_t)a.ldq * 2, a.q_rb / 2, (uint32_t)a.G, (uint32_t)a.L, (int)a.q_rb))
+      return rc;
+  if (a.p_tma)
+    if (int rc = tma_encode_3d(&plan->pmap, a.p, (uint64_t)a.ldp, (uint64_t)a.n_titles, (uint64_t)a.L, (uint64_t)a.L * a.ldp * 2,
+                               (uint64_t)a.ldp * 2, 64, (uint32_t)a.G, (uint32_t)a.L, 128))
+      return rc;
   plan->args = a;
   plan->smem_bytes = (size_t)ns * a.stage_bytes + fixed;
   plan->grid = a.n_mtiles * a.S;
@@ -302,7 +337,7 @@ int tokred_launch(const TokRedPlan& plan, cudaStream_t stream) {
   TokRedArgs args = plan.args;
   args.dbg = g_tapgemm_dbg;
   if (g_tapgemm_dbg != nullptr) g_tapgemm_dbg += 148 * 4 * 5;
-  tokred_kernel<<<plan.grid, TR_THREADS, plan.smem_bytes, stream>>>(args);
+  tokred_kernel<<<plan.grid, TR_THREADS, plan.smem_bytes, stream>>>(args, plan.pmap, plan.qmap);
   MR_CHECK_LAUNCH("tokred_kernel");
   return MR_OK;
 }

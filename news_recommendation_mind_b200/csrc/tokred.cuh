@@ -15,6 +15,7 @@
 #pragma once
 #include "common.cuh"
 #include "tc05.cuh"
+#include "tma.cuh"
 
 namespace mr {
 
@@ -30,11 +31,14 @@ struct TokRedArgs {
   float* partial;                                   // [n_mtiles][S][taps][128][NQ]
   int n_mtiles, S, halo, n_stages;
   uint32_t p_ps, q_ps, p_bytes, stage_bytes, q_rb;   // block strides (bytes), Q row bytes
+  int p_tma, q_tma;                                    // operand staged by TMA tile loads instead of cp.async
   long long* dbg;                                      // optional wait counters (debug)
   int q_layout;                                        // UMMA layout type of Q (2 / 4 / 6)
 };
 
 struct TokRedPlan {
+  alignas(64) CUtensorMap pmap;       // dense P: 3-D (column, title, position) view, box {64, G, L}, SWIZZLE_128B
+  alignas(64) CUtensorMap qmap;       // Q: same view, box {q_rb/2, G, L}, swizzle = q_rb
   TokRedArgs args;
   size_t smem_bytes;
   int grid;
