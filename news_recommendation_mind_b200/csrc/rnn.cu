@@ -11,6 +11,8 @@
 // pos(s) = s, or S-1-s when `reverse` (the reference flips the padded history *before* packing).
 #include "gemm_simt.cuh"
 #include "rnn_res.cuh"
+#include "tapgemm.cuh"
+#include "tokred.cuh"
 
 namespace mr {
 
@@ -258,17 +260,178 @@ struct TwoBiasEpi {
   }
 };
 
+// ---- MR_BF16: the three big GEMMs of the recurrent encoders on the tensor-core kernels -------------------------
+// rows m = b*S + s (step order: s-th step reads x[b, S-1-s] when `reverse`), padded to a multiple of 128 rows
+__global__ void seq_cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t M, int64_t Mp, int S,
+                                     int H, int Hp, int reverse) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Mp * Hp) return;
+  const int64_t m = i / Hp;
+  const int k = (int)(i - m * Hp);
+  float v = 0.f;
+  if (m < M && k < H) {
+    const int64_t b = m / S;
+    const int s = (int)(m - b * S);
+    v = x[(b * S + (reverse ? S - 1 - s : s)) * H + k];
+  }
+  out[i] = __float2bfloat16(v);
+}
+// h_{s-1} of every step (h0 or 0 at s = 0)
+__global__ void hprev_bf16_kernel(const float* __restrict__ hs, const float* __restrict__ h0, __nv_bfloat16* __restrict__ out,
+                                  int64_t M, int64_t Mp, int S, int H, int Hp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Mp * Hp) return;
+  const int64_t m = i / Hp;
+  const int k = (int)(i - m * Hp);
+  float v = 0.f;
+  if (m < M && k < H) {
+    const int64_t b = m / S;
+    const int s = (int)(m - b * S);
+    v = s > 0 ? hs[(m - 1) * H + k] : (h0 ? h0[b * H + k] : 0.f);
+  }
+  out[i] = __float2bfloat16(v);
+}
+__global__ void cast_rows_pad_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t M, int64_t Mp,
+                                          int C, int Cp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Mp * Cp) return;
+  const int64_t m = i / Cp;
+  const int c = (int)(i - m * Cp);
+  dst[i] = __float2bfloat16((m < M && c < C) ? src[m * C + c] : 0.f);
+}
+// d_x[b, pos(s), :] = tmp[(b,s), :H]
+__global__ void unseq_copy_kernel(const float* __restrict__ tmp, float* __restrict__ d_x, int64_t M, int S, int H, int Hp, int reverse) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * H) return;
+  const int64_t m = i / H;
+  const int k = (int)(i - m * H);
+  const int64_t b = m / S;
+  const int s = (int)(m - b * S);
+  d_x[(b * S + (reverse ? S - 1 - s : s)) * H + k] = tmp[m * Hp + k];
+}
+
+struct RnnTcGeom {
+  int64_t M, Mp, Hp, GH, GHp, nblk, nbsz;
+};
+static RnnTcGeom rnn_tc_geom(const mr_rnn_shape* s) {
+  RnnTcGeom g;
+  g.M = s->B * s->S;
+  g.Mp = align_up(g.M, 128);
+  g.Hp = align_up(s->H, 16);
+  g.GH = (s->kind == MR_RNN_LSTM ? 4 : 3) * s->H;
+  g.GHp = align_up(g.GH, 16);
+  g.nblk = ceil_div(g.GHp, 256);
+  g.nbsz = align_up(ceil_div(g.GHp, g.nblk), 16);
+  return g;
+}
+static bool rnn_tc_ok(const mr_rnn_shape* s) { return s->precision == MR_BF16 && align_up(s->H, 16) <= 256; }
+static int64_t rnn_tc_ws(const mr_rnn_shape* s, int backward) {
+  const RnnTcGeom g = rnn_tc_geom(s);
+  int64_t b = arena_bytes(g.Mp * g.Hp, 2);                                      // x as bf16, step order
+  if (!backward) return b + arena_bytes(tapgemm_pack_bytes(1, (int)g.nbsz, (int)g.Hp), 1);
+  b += arena_bytes(g.Mp * g.Hp, 2);                                             // h_{s-1}
+  b += 2 * arena_bytes(g.Mp * g.GHp, 2);                                        // dgi, dgh as bf16
+  b += arena_bytes(tapgemm_pack_bytes(1, (int)g.Hp, (int)g.GHp), 1);            // W_ih for d_x
+  b += arena_bytes(g.M * g.Hp, 4);                                              // d_x in step order
+  b += arena_bytes(tokred_partial_bytes(g.Mp / 128, 128, 1, (int)g.GHp, (int)g.Hp), 1);
+  return b;
+}
+
+// xp = x_seq W_ih^T + b_ih (+ b_hh)
+static int rnn_tc_input_proj(const mr_rnn_shape* s, const float* x, const float* w_ih, const float* b_ih, const float* b_hh2,
+                             float* xp, Arena& ar, cudaStream_t st) {
+  const RnnTcGeom g = rnn_tc_geom(s);
+  const int H = (int)s->H;
+  __nv_bfloat16* xb = ar.take<__nv_bfloat16>(g.Mp * g.Hp);
+  uint8_t* wp = ar.take<uint8_t>(tapgemm_pack_bytes(1, (int)g.nbsz, (int)g.Hp));
+  MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "mr_rnn_user_fwd: workspace too small");
+  seq_cast_bf16_kernel<<<(unsigned)ceil_div(g.Mp * g.Hp, 256), 256, 0, st>>>(x, xb, g.M, g.Mp, (int)s->S, H, (int)g.Hp, s->reverse);
+  MR_CHECK_LAUNCH("seq_cast_bf16_kernel");
+  for (int64_t blk = 0; blk < g.nblk; ++blk) {
+    const int64_t n0 = blk * g.nbsz;
+    const int64_t nb = (g.GHp - n0) < g.nbsz ? (g.GHp - n0) : g.nbsz;
+    const int64_t nv = (g.GH - n0) < nb ? (g.GH - n0) : nb;
+    if (nv <= 0) break;
+    if (int rc = tapgemm_pack(w_ih + n0 * H, wp, 1, (int)nb, (int)g.Hp, (int)nv, H, H, 1, 0, st)) return rc;
+    TapGemmArgs a{};
+    TapGemmPlan plan;
+    a.n_titles = g.Mp / 128; a.L = 128; a.taps = 1; a.dir = 1; a.K = (int)g.Hp;
+    a.n_sub = 1; a.nsz[0] = (int)nb;
+    a.ids = nullptr; a.a = xb; a.lda = g.Hp;
+    a.wpack = wp; a.epi = TG_EPI_BIAS_F32; a.bias = b_ih + n0; a.bias2 = b_hh2 ? b_hh2 + n0 : nullptr; a.n_valid = (int)nv;
+    a.n_rows = g.M; a.out_f32 = xp + n0; a.ldo = align_up(g.GH, 4); a.n_store = (int)align_up(nv, 4);
+    if (int rc = tapgemm_plan(a, &plan)) return rc;
+    if (int rc = tapgemm_launch(plan, st)) return rc;
+  }
+  return MR_OK;
+}
+
+// d_x, d_w_ih, d_w_hh from the gate gradients
+static int rnn_tc_grad_gemms(const mr_rnn_shape* s, const float* x, const float* h0, const float* w_ih, const float* hs,
+                             const float* dgi, const float* dgh, float* d_x, float* d_w_ih, float* d_w_hh, Arena& ar,
+                             cudaStream_t st) {
+  const RnnTcGeom g = rnn_tc_geom(s);
+  const int H = (int)s->H, S = (int)s->S;
+  __nv_bfloat16* xb = ar.take<__nv_bfloat16>(g.Mp * g.Hp);
+  __nv_bfloat16* hb = ar.take<__nv_bfloat16>(g.Mp * g.Hp);
+  __nv_bfloat16* gib = ar.take<__nv_bfloat16>(g.Mp * g.GHp);
+  __nv_bfloat16* ghb = ar.take<__nv_bfloat16>(g.Mp * g.GHp);
+  uint8_t* wp = ar.take<uint8_t>(tapgemm_pack_bytes(1, (int)g.Hp, (int)g.GHp));
+  float* tmp = ar.take<float>(g.M * g.Hp);
+  float* partial = ar.take<float>(tokred_partial_bytes(g.Mp / 128, 128, 1, (int)g.GHp, (int)g.Hp) / 4);
+  MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "mr_rnn_user_bwd: workspace too small");
+  seq_cast_bf16_kernel<<<(unsigned)ceil_div(g.Mp * g.Hp, 256), 256, 0, st>>>(x, xb, g.M, g.Mp, S, H, (int)g.Hp, s->reverse);
+  MR_CHECK_LAUNCH("seq_cast_bf16_kernel");
+  hprev_bf16_kernel<<<(unsigned)ceil_div(g.Mp * g.Hp, 256), 256, 0, st>>>(hs, h0, hb, g.M, g.Mp, S, H, (int)g.Hp);
+  MR_CHECK_LAUNCH("hprev_bf16_kernel");
+  cast_rows_pad_bf16_kernel<<<(unsigned)ceil_div(g.Mp * g.GHp, 256), 256, 0, st>>>(dgi, gib, g.M, g.Mp, (int)g.GH, (int)g.GHp);
+  MR_CHECK_LAUNCH("cast_rows_pad_bf16_kernel");
+  if (dgh != dgi) {
+    cast_rows_pad_bf16_kernel<<<(unsigned)ceil_div(g.Mp * g.GHp, 256), 256, 0, st>>>(dgh, ghb, g.M, g.Mp, (int)g.GH, (int)g.GHp);
+    MR_CHECK_LAUNCH("cast_rows_pad_bf16_kernel");
+  } else {
+    ghb = gib;
+  }
+  if (d_x) {        // d_x_seq[m, k] = sum_n dgi[m, n] W_ih[n, k]
+    if (int rc = tapgemm_pack(w_ih, wp, 1, (int)g.Hp, (int)g.GHp, H, (int)g.GH, 1, H, 0, st)) return rc;
+    TapGemmArgs a{};
+    TapGemmPlan plan;
+    a.n_titles = g.Mp / 128; a.L = 128; a.taps = 1; a.dir = 1; a.K = (int)g.GHp;
+    a.n_sub = 1; a.nsz[0] = (int)g.Hp;
+    a.ids = nullptr; a.a = gib; a.lda = g.GHp;
+    a.wpack = wp; a.epi = TG_EPI_BIAS_F32; a.bias = nullptr; a.bias2 = nullptr; a.n_valid = H;
+    a.n_rows = g.M; a.out_f32 = tmp; a.ldo = g.Hp; a.n_store = (int)g.Hp;
+    if (int rc = tapgemm_plan(a, &plan)) return rc;
+    if (int rc = tapgemm_launch(plan, st)) return rc;
+    unseq_copy_kernel<<<(unsigned)ceil_div(g.M * H, 256), 256, 0, st>>>(tmp, d_x, g.M, S, H, (int)g.Hp, s->reverse);
+    MR_CHECK_LAUNCH("unseq_copy_kernel");
+  }
+  for (int which = 0; which < 2; ++which) {   // d_w_ih[n,k] = sum_m dgi[m,n] x[m,k];  d_w_hh[n,k] = sum_m dgh[m,n] h_{s-1}[m,k]
+    TokRedArgs a{};
+    TokRedPlan plan;
+    a.n_titles = g.Mp / 128; a.L = 128; a.taps = 1;
+    a.ids = nullptr; a.p = which == 0 ? gib : ghb; a.ldp = g.GHp; a.KP = (int)g.GHp;
+    a.q = which == 0 ? xb : hb; a.ldq = g.Hp; a.NQ = (int)g.Hp; a.partial = partial;
+    if (int rc = tokred_plan(a, &plan)) return rc;
+    if (int rc = tokred_launch(plan, st)) return rc;
+    if (int rc = tokred_reduce(plan, which == 0 ? d_w_ih : d_w_hh, (int)g.GH, H, 1, H, 0, st)) return rc;
+  }
+  return MR_OK;
+}
+
 static int64_t rnn_ws(const mr_rnn_shape* s, int backward) {
   const int64_t G = s->kind == MR_RNN_LSTM ? 4 : 3, GH = G * s->H, BS = s->B * s->S;
   int64_t b = 0;
   if (!backward) {
-    b += arena_bytes(BS * GH, 4);           // xp
+    b += arena_bytes(BS * align_up(GH, 4), 4);   // xp
     b += arena_bytes(s->H * GH, 4);         // whhT
+    if (rnn_tc_ok(s)) b += rnn_tc_ws(s, 0);
     return b + 256;
   }
   b += 2 * arena_bytes(BS * GH, 4);         // dgi, dgh
   b += arena_bytes(64 * GH * s->H, 4);      // split-K partial
   b += arena_bytes(colsum_chunks(BS) * GH, 4);
+  if (rnn_tc_ok(s)) b += rnn_tc_ws(s, 1);
   return b + 256;
 }
 
@@ -303,19 +466,24 @@ int mr_rnn_user_fwd(const mr_rnn_shape* s, const float* x, const int32_t* lens, 
   const int B = (int)s->B, S = (int)s->S, H = (int)s->H;
   const int G = s->kind == MR_RNN_LSTM ? 4 : 3, GH = G * H;
   Arena ar(workspace, workspace_bytes);
-  float* xp = ar.take<float>((int64_t)B * S * GH);
+  const int64_t ldx = rnn_tc_ok(s) ? align_up(GH, 4) : GH;       // pitch of the input projection (16-byte rows for the tensor-core epilogue)
+  float* xp = ar.take<float>((int64_t)B * S * ldx);
   float* whhT = ar.take<float>((int64_t)H * GH);
   MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "mr_rnn_user_fwd: workspace too small (%lld given)", (long long)workspace_bytes);
-  SeqView xv{x, S, H, s->reverse};
-  cudaError_t e = gemm_simt<true, false>((int64_t)B * S, GH, H, xv, Transposed{w_ih, H},
-                                         TwoBiasEpi{xp, GH, b_ih, s->kind == MR_RNN_LSTM ? b_hh : nullptr}, 1, nullptr, st);
-  MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "rnn input projection: %s", cudaGetErrorString(e));
+  if (rnn_tc_ok(s)) {
+    if (int rc = rnn_tc_input_proj(s, x, w_ih, b_ih, s->kind == MR_RNN_LSTM ? b_hh : nullptr, xp, ar, st)) return rc;
+  } else {
+    SeqView xv{x, S, H, s->reverse};
+    cudaError_t e = gemm_simt<true, false>((int64_t)B * S, GH, H, xv, Transposed{w_ih, H},
+                                           TwoBiasEpi{xp, GH, b_ih, s->kind == MR_RNN_LSTM ? b_hh : nullptr}, 1, nullptr, st);
+    MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "rnn input projection: %s", cudaGetErrorString(e));
+  }
   // steps past a sequence's length are never written by the kernel: clear the saved tensors
   cudaMemsetAsync(gates, 0, sizeof(float) * (int64_t)B * S * GH, st);
   cudaMemsetAsync(hs, 0, sizeof(float) * (int64_t)B * S * H, st);
   cudaMemsetAsync(cs, 0, sizeof(float) * (int64_t)B * S * H, st);
   if (s->precision == MR_BF16 && rnn_res_supported(s->kind, H))
-    return rnn_res_fwd(s->kind, xp, w_hh, b_hh, h0, lens, gates, hs, cs, user, B, S, H, st);
+    return rnn_res_fwd(s->kind, xp, (int)ldx, w_hh, b_hh, h0, lens, gates, hs, cs, user, B, S, H, st);
   dim3 tg((unsigned)ceil_div(H, 32), (unsigned)ceil_div(GH, 32)), tb(32, 8);
   transpose_kernel<<<tg, tb, 0, st>>>(w_hh, whhT, GH, H);
   MR_CHECK_LAUNCH("transpose_kernel");
@@ -372,16 +540,20 @@ int mr_rnn_user_bwd(const mr_rnn_shape* s, const float* x, const int32_t* lens, 
   }
   if (!(s->precision == MR_BF16 && rnn_res_supported(s->kind, H))) MR_CHECK_LAUNCH("rnn_bwd_kernel");
   cudaError_t e;
-  if (d_x) {
-    e = gemm_simt<true, true>(BS, H, GH, RowMajor{dgi, GH}, RowMajor{w_ih, H}, SeqStoreEpi{d_x, S, H, s->reverse}, 1, nullptr, st);
-    MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "rnn d_x: %s", cudaGetErrorString(e));
+  if (rnn_tc_ok(s)) {
+    if (int rc = rnn_tc_grad_gemms(s, x, h0, w_ih, hs, dgi, dgh, d_x, d_w_ih, d_w_hh, ar, st)) return rc;
+  } else {
+    if (d_x) {
+      e = gemm_simt<true, true>(BS, H, GH, RowMajor{dgi, GH}, RowMajor{w_ih, H}, SeqStoreEpi{d_x, S, H, s->reverse}, 1, nullptr, st);
+      MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "rnn d_x: %s", cudaGetErrorString(e));
+    }
+    e = gemm_simt<false, true>(GH, H, BS, Transposed{dgi, GH}, SeqViewKM{SeqView{x, S, H, s->reverse}}, StoreEpi{d_w_ih, H},
+                               pick_splits(GH, H, BS), sp, st);
+    MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "rnn d_w_ih: %s", cudaGetErrorString(e));
+    e = gemm_simt<false, true>(GH, H, BS, Transposed{dgh, GH}, PrevHiddenKM{hs, h0, S, H}, StoreEpi{d_w_hh, H},
+                               pick_splits(GH, H, BS), sp, st);
+    MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "rnn d_w_hh: %s", cudaGetErrorString(e));
   }
-  e = gemm_simt<false, true>(GH, H, BS, Transposed{dgi, GH}, SeqViewKM{SeqView{x, S, H, s->reverse}}, StoreEpi{d_w_ih, H},
-                             pick_splits(GH, H, BS), sp, st);
-  MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "rnn d_w_ih: %s", cudaGetErrorString(e));
-  e = gemm_simt<false, true>(GH, H, BS, Transposed{dgh, GH}, PrevHiddenKM{hs, h0, S, H}, StoreEpi{d_w_hh, H},
-                             pick_splits(GH, H, BS), sp, st);
-  MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "rnn d_w_hh: %s", cudaGetErrorString(e));
   e = colsum(dgi, d_b_ih, BS, GH, cp, st);
   MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "rnn d_b_ih: %s", cudaGetErrorString(e));
   e = colsum(dgh, d_b_hh, BS, GH, cp, st);

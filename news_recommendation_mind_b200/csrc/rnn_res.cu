@@ -63,7 +63,7 @@ bool rnn_res_supported(int kind, int H) { return rr_fits(kind, H, 1); }
 
 template <int KIND, int BPC>
 __global__ void __launch_bounds__(RR_THREADS, 1)
-rnn_res_fwd_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
+rnn_res_fwd_kernel(const float* __restrict__ xp, int ldx, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
                    const float* __restrict__ h0, const int32_t* __restrict__ lens, float* __restrict__ gates,
                    float* __restrict__ hs, float* __restrict__ cs, float* __restrict__ user, int B, int S, int H) {
   constexpr int G = KIND == 0 ? 4 : 3;
@@ -111,7 +111,7 @@ rnn_res_fwd_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
     float xv[G];
     const bool act = gt && s < my_len;
     if (act) {
-      const float* xps = xp + ((int64_t)b * S + s) * GH + j;
+      const float* xps = xp + ((int64_t)b * S + s) * ldx + j;
 #pragma unroll
       for (int g = 0; g < G; ++g) xv[g] = __ldg(xps + g * H);          // consumed after the matvec: latency hidden
     }
@@ -301,14 +301,14 @@ rnn_res_bwd_kernel(const float* __restrict__ w_hh, const float* __restrict__ h0,
 }
 
 template <int KIND>
-static int launch_fwd(int bpc, const float* xp, const float* w_hh, const float* b_hh, const float* h0, const int32_t* lens,
+static int launch_fwd(int bpc, const float* xp, int ldx, const float* w_hh, const float* b_hh, const float* h0, const int32_t* lens,
                       float* gates, float* hs, float* cs, float* user, int B, int S, int H, cudaStream_t st) {
   const RRGeom g = rr_geom(KIND == 0 ? MR_RNN_LSTM : MR_RNN_GRU, H, bpc);
   const unsigned grid = (unsigned)ceil_div(B, bpc);
 #define RR_LAUNCH_F(BPC)                                                                                               \
   {                                                                                                                    \
     cudaFuncSetAttribute(rnn_res_fwd_kernel<KIND, BPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.fwd_bytes); \
-    rnn_res_fwd_kernel<KIND, BPC><<<grid, RR_THREADS, g.fwd_bytes, st>>>(xp, w_hh, b_hh, h0, lens, gates, hs, cs, user, B, S, H); \
+    rnn_res_fwd_kernel<KIND, BPC><<<grid, RR_THREADS, g.fwd_bytes, st>>>(xp, ldx, w_hh, b_hh, h0, lens, gates, hs, cs, user, B, S, H); \
   }
   if (bpc == 1) RR_LAUNCH_F(1) else if (bpc == 2) RR_LAUNCH_F(2) else RR_LAUNCH_F(4)
 #undef RR_LAUNCH_F
@@ -333,11 +333,11 @@ static int launch_bwd(int bpc, const float* w_hh, const float* h0, const int32_t
   return MR_OK;
 }
 
-int rnn_res_fwd(int kind, const float* xp, const float* w_hh, const float* b_hh, const float* h0, const int32_t* lens,
+int rnn_res_fwd(int kind, const float* xp, int ldx, const float* w_hh, const float* b_hh, const float* h0, const int32_t* lens,
                 float* gates, float* hs, float* cs, float* user, int B, int S, int H, cudaStream_t st) {
   const int bpc = rnn_res_bpc(kind, B, H);
-  return kind == MR_RNN_LSTM ? launch_fwd<0>(bpc, xp, w_hh, b_hh, h0, lens, gates, hs, cs, user, B, S, H, st)
-                             : launch_fwd<1>(bpc, xp, w_hh, b_hh, h0, lens, gates, hs, cs, user, B, S, H, st);
+  return kind == MR_RNN_LSTM ? launch_fwd<0>(bpc, xp, ldx, w_hh, b_hh, h0, lens, gates, hs, cs, user, B, S, H, st)
+                             : launch_fwd<1>(bpc, xp, ldx, w_hh, b_hh, h0, lens, gates, hs, cs, user, B, S, H, st);
 }
 
 int rnn_res_bwd(int kind, const float* w_hh, const float* h0, const int32_t* lens, const float* gates, const float* hs,

@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
   {
     const uint32_t a_bytes = (uint32_t)p.ns_a * p.a_slot_bytes;
     for (uint32_t i = tid * 16; i < a_bytes; i += TG_THREADS * 16) *reinterpret_cast<uint4*>(sA + i) = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < 512; i += TG_THREADS) sbias[i] = (p.bias != nullptr && i < p.n_valid) ? p.bias[i] : 0.f;
+    for (int i = tid; i < 512; i += TG_THREADS)
+      sbias[i] = (p.bias != nullptr && i < p.n_valid) ? p.bias[i] + (p.bias2 != nullptr ? p.bias2[i] : 0.f) : 0.f;
     if (p.ids != nullptr)
       for (uint32_t i = tid; i < (uint32_t)p.n_hot * (hot_pitch / 16); i += TG_THREADS) {
         const uint32_t h = i / (hot_pitch / 16), q = i % (hot_pitch / 16);
@@ -103,8 +104,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       TG_TIMED(0, tc::mbar_wait(&t_full[acc.pos], acc.phase));
       tc::tc_fence_after();
-      const bool valid = row_ok && (tile * p.G + g < p.n_titles);
       const int64_t t = tile * p.G * p.L + row_off;
+      const bool valid = row_ok && (tile * p.G + g < p.n_titles) && t < p.n_rows;
       const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + acc.pos * 256u;
       int col0 = 0;
       for (int sub = 0; sub < p.n_sub; ++sub) {
@@ -155,6 +156,15 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
                   }
                 }
               }
+            }
+            if (p.epi == TG_EPI_BIAS_F32) {
+              float4* dst = reinterpret_cast<float4*>(p.out_f32 + t * p.ldo + n0);
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                if ((u < 4 || wide) && n0 + 4 * u < p.n_store)
+                  dst[u] = make_float4(f[4 * u] + sbias[n0 + 4 * u], f[4 * u + 1] + sbias[n0 + 4 * u + 1],
+                                       f[4 * u + 2] + sbias[n0 + 4 * u + 2], f[4 * u + 3] + sbias[n0 + 4 * u + 3]);
+              continue;
             }
             uint4* dst = reinterpret_cast<uint4*>(p.out + t * p.ldo + n0);
 #pragma unroll
@@ -542,6 +552,7 @@ int tapgemm_plan(TapGemmArgs& a, TapGemmPlan* plan) {
   a.ns_a = ns_a;
   a.ns_b = ns_b;
   a.n_tiles = ceil_div(a.n_titles, (int64_t)G);
+  if (a.n_rows <= 0) a.n_rows = a.n_titles * a.L;
   a.w_reps = TG_W_REPS;
   a.w_rep_stride = tapgemm_pack_bytes(a.taps, n_total, a.K) / TG_W_REPS;
   if (a.use_tma) {

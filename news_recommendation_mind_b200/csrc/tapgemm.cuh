@@ -24,7 +24,7 @@
 
 namespace mr {
 
-enum { TG_EPI_BIAS_RELU = 0, TG_EPI_BIAS_TANH = 1, TG_EPI_RELUGRAD = 2, TG_EPI_STORE = 3 };
+enum { TG_EPI_BIAS_RELU = 0, TG_EPI_BIAS_TANH = 1, TG_EPI_RELUGRAD = 2, TG_EPI_STORE = 3, TG_EPI_BIAS_F32 = 4 };
 constexpr int TG_KC = 64;          // k-chunk (elements) = 8 panels
 constexpr int TG_THREADS = 320;
 constexpr int TG_MAX_SLOTS = 8;
@@ -40,7 +40,9 @@ struct TapGemmArgs {
   const __nv_bfloat16* a; int64_t lda, V;  // gather: table [V, lda];  dense: activations [n_titles*L, lda]
   const uint8_t* wpack;                    // TG_W_REPS replicas of [chunk][tap] blocks of b_slot_bytes
   int w_reps; int64_t w_rep_stride;
-  int epi; const float* bias; int n_valid;
+  int epi; const float* bias; const float* bias2; int n_valid;   // bias2: optional second bias (LSTM b_ih + b_hh)
+  int64_t n_rows;                          // rows of the problem (<= n_titles * L); 0 = n_titles * L
+  float* out_f32; int n_store;             // TG_EPI_BIAS_F32: fp32 output [rows, ldo], columns >= n_store are not written
   const __nv_bfloat16* e0; const __nv_bfloat16* e1; int64_t lde;
   __nv_bfloat16* out; int64_t ldo;
   int ns_a, ns_b, halo;

@@ -236,9 +236,11 @@ def test_news_cnn_bf16_backward(N, L, E, H):
 @pytest.mark.parametrize("kind,B,S,H,rev", [("lstm", 256, 50, 150, False), ("gru", 37, 20, 150, False), ("lstm", 5, 7, 64, True),
                                              ("gru", 300, 11, 96, True), ("lstm", 700, 9, 150, False)])
 def test_rnn_user_encoder_resident_weights(kind, B, S, H, rev):
-    """MR_BF16 recurrent user encoder (persistent kernel, W_hh resident in shared memory as bf16) against the
-    oracle's LSTM / GRU (RNN.py:50-73) evaluated with W_hh rounded to bf16 -- the one rounding the kernel
-    applies; everything else is fp32, so outputs and gradients agree to 1e-4."""
+    """MR_BF16 recurrent user encoder (persistent kernel with W_hh resident in shared memory as bf16, input
+    projection and weight-gradient GEMMs on the tensor-core kernels) against the oracle's LSTM / GRU
+    (RNN.py:50-73) evaluated with the forward operand roundings the kernels apply (x, W_ih, W_hh to bf16;
+    state, gates and accumulation fp32): outputs agree to 1e-4.  The backward GEMMs additionally round the
+    gate gradients and h_{s-1} to bf16 (2^-9 relative per operand): gradients within 1e-2 relative L2."""
     import sys, os
     sys.path.insert(0, os.path.dirname(__file__))
     from helpers import manager_for, rel_err
@@ -259,14 +261,16 @@ def test_rnn_user_encoder_resident_weights(kind, B, S, H, rev):
     torch.cuda.synchronize()
     p = {k: v.detach().cpu().double().requires_grad_(True) for k, v in enc.rnn.named_parameters()}
     whh = p["weight_hh_l0"].detach().float().bfloat16().double().requires_grad_(True)
-    xo = x.double().requires_grad_(True)
+    wih = p["weight_ih_l0"].detach().float().bfloat16().double().requires_grad_(True)
+    xo = x.bfloat16().double().requires_grad_(True)
     fn = O.lstm_user_encoder if kind == "lstm" else O.gru_user_encoder
-    ref = fn(xo, his_mask, p["weight_ih_l0"], whh, p["bias_ih_l0"], p["bias_hh_l0"], descend_history=rev)
+    ref = fn(xo, his_mask, wih, whh, p["bias_ih_l0"], p["bias_hh_l0"], descend_history=rev)
     (ref * g.double()).sum().backward()
     errs = {"out": rel_err(out, ref), "d_x": rel_err(xc.grad, xo.grad),
-            "d_w_ih": rel_err(enc.rnn.weight_ih_l0.grad, p["weight_ih_l0"].grad),
+            "d_w_ih": rel_err(enc.rnn.weight_ih_l0.grad, wih.grad),
             "d_w_hh": rel_err(enc.rnn.weight_hh_l0.grad, whh.grad),
             "d_b_ih": rel_err(enc.rnn.bias_ih_l0.grad, p["bias_ih_l0"].grad),
             "d_b_hh": rel_err(enc.rnn.bias_hh_l0.grad, p["bias_hh_l0"].grad)}
     print(kind, B, S, H, {k: "%.2e" % v for k, v in errs.items()})
-    assert max(errs.values()) < 1e-4, errs
+    assert errs["out"] < 1e-4, errs
+    assert max(errs.values()) < 1e-2, errs
