@@ -424,7 +424,7 @@ static int64_t rnn_ws(const mr_rnn_shape* s, int backward) {
   int64_t b = 0;
   if (!backward) {
     b += arena_bytes(BS * align_up(GH, 4), 4);   // xp
-    b += arena_bytes(s->H * GH, 4);         // whhT
+    b += arena_bytes(s->H * GH + rnn_res_scratch_bytes(s->kind, (int)s->H) / 4, 4);         // whhT / bf16 image of W_hh
     if (rnn_tc_ok(s)) b += rnn_tc_ws(s, 0);
     return b + 256;
   }
@@ -468,7 +468,7 @@ int mr_rnn_user_fwd(const mr_rnn_shape* s, const float* x, const int32_t* lens, 
   Arena ar(workspace, workspace_bytes);
   const int64_t ldx = rnn_tc_ok(s) ? align_up(GH, 4) : GH;       // pitch of the input projection (16-byte rows for the tensor-core epilogue)
   float* xp = ar.take<float>((int64_t)B * S * ldx);
-  float* whhT = ar.take<float>((int64_t)H * GH);
+  float* whhT = ar.take<float>((int64_t)H * GH + rnn_res_scratch_bytes(s->kind, H) / 4);
   MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "mr_rnn_user_fwd: workspace too small (%lld given)", (long long)workspace_bytes);
   if (rnn_tc_ok(s)) {
     if (int rc = rnn_tc_input_proj(s, x, w_ih, b_ih, s->kind == MR_RNN_LSTM ? b_hh : nullptr, xp, ar, st)) return rc;
@@ -483,7 +483,7 @@ int mr_rnn_user_fwd(const mr_rnn_shape* s, const float* x, const int32_t* lens, 
   cudaMemsetAsync(hs, 0, sizeof(float) * (int64_t)B * S * H, st);
   cudaMemsetAsync(cs, 0, sizeof(float) * (int64_t)B * S * H, st);
   if (s->precision == MR_BF16 && rnn_res_supported(s->kind, H))
-    return rnn_res_fwd(s->kind, xp, (int)ldx, w_hh, b_hh, h0, lens, gates, hs, cs, user, B, S, H, st);
+    return rnn_res_fwd(s->kind, xp, (int)ldx, w_hh, b_hh, h0, lens, gates, hs, cs, user, B, S, H, whhT, st);
   dim3 tg((unsigned)ceil_div(H, 32), (unsigned)ceil_div(GH, 32)), tb(32, 8);
   transpose_kernel<<<tg, tb, 0, st>>>(w_hh, whhT, GH, H);
   MR_CHECK_LAUNCH("transpose_kernel");
@@ -530,7 +530,7 @@ int mr_rnn_user_bwd(const mr_rnn_shape* s, const float* x, const int32_t* lens, 
   size_t smem = sizeof(float) * (2 * RNN_BPC * H + RNN_BPC * GH);
   unsigned grid = (unsigned)ceil_div(B, RNN_BPC);
   if (s->precision == MR_BF16 && rnn_res_supported(s->kind, H)) {
-    if (int rc = rnn_res_bwd(s->kind, w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H, st)) return rc;
+    if (int rc = rnn_res_bwd(s->kind, w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H, sp, st)) return rc;
   } else if (s->kind == MR_RNN_LSTM) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(rnn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     rnn_bwd_kernel<0><<<grid, RNN_THREADS, smem, st>>>(w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H);

@@ -14,6 +14,7 @@
 // BPC = ceil(B / #SM) rounded up to 1/2/4, so B=256 runs as 128 CTAs of 2 sequences.
 #include "rnn_res.cuh"
 #include "tapgemm.cuh"   // sm_count()
+#include "tc05.cuh"
 
 namespace mr {
 
@@ -61,9 +62,42 @@ int rnn_res_bpc(int kind, int B, int H) {
 
 bool rnn_res_supported(int kind, int H) { return rr_fits(kind, H, 1); }
 
+// W_hh [GH, H] fp32 -> bf16 images of the two shared-memory layouts (done once per call; every CTA then pulls its
+// copy with a few cp.async.bulk transfers instead of 90k strided loads):
+//   wt [H][GHp]  (forward:  Wt[k][n] = W_hh[n][k], zero padded columns)      w [GH][Hp]  (backward, zero padded)
+__global__ void rnn_res_prep_kernel(const float* __restrict__ w_hh, __nv_bfloat16* __restrict__ wt, __nv_bfloat16* __restrict__ w,
+                                    int GH, int H, int GHp, int Hp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wt != nullptr && i < H * GHp) {
+    const int k = i / GHp, n = i - k * GHp;
+    wt[i] = __float2bfloat16(n < GH ? w_hh[(int64_t)n * H + k] : 0.f);
+  }
+  if (w != nullptr && i < GH * Hp) {
+    const int n = i / Hp, k = i - n * Hp;
+    w[i] = __float2bfloat16(k < H ? w_hh[(int64_t)n * H + k] : 0.f);
+  }
+}
+
+// pulls `bytes` (multiple of 16) from global into shared memory with bulk copies; all threads wait on the barrier
+__device__ __forceinline__ void bulk_fill(uint8_t* dst, const void* src, uint32_t bytes, uint64_t* bar, int tid) {
+  if (tid == 0) {
+    tc::mbar_init(bar, 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    tc::mbar_arrive_expect_tx(bar, bytes);
+    for (uint32_t off = 0; off < bytes; off += 32768) {
+      const uint32_t n = bytes - off < 32768 ? bytes - off : 32768;
+      tc::bulk_g2s(tc::smem_u32(dst + off), static_cast<const uint8_t*>(src) + off, n, bar);
+    }
+  }
+  tc::mbar_wait(bar, 0);
+}
+
 template <int KIND, int BPC>
 __global__ void __launch_bounds__(RR_THREADS, 1)
-rnn_res_fwd_kernel(const float* __restrict__ xp, int ldx, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
+rnn_res_fwd_kernel(const float* __restrict__ xp, int ldx, const __nv_bfloat16* __restrict__ wt_g, const float* __restrict__ b_hh,
                    const float* __restrict__ h0, const int32_t* __restrict__ lens, float* __restrict__ gates,
                    float* __restrict__ hs, float* __restrict__ cs, float* __restrict__ user, int B, int S, int H) {
   constexpr int G = KIND == 0 ? 4 : 3;
@@ -76,10 +110,8 @@ rnn_res_fwd_kernel(const float* __restrict__ xp, int ldx, const float* __restric
   int* len_s = reinterpret_cast<int*>(c_s + BPC * H);
   const int tid = threadIdx.x, b0 = blockIdx.x * BPC;
 
-  for (int i = tid; i < H * GHp; i += RR_THREADS) {
-    const int k = i / GHp, n = i - k * GHp;
-    Wt[i] = __float2bfloat16(n < GH ? __ldg(w_hh + (int64_t)n * H + k) : 0.f);
-  }
+  __shared__ uint64_t w_bar;
+  bulk_fill(reinterpret_cast<uint8_t*>(Wt), wt_g, (uint32_t)(H * GHp * 2), &w_bar, tid);
   for (int i = tid; i < BPC * H; i += RR_THREADS) {
     const int bl = i / H, j = i - bl * H, b = b0 + bl;
     h_s[j * BPC + bl] = (h0 != nullptr && b < B) ? h0[(int64_t)b * H + j] : 0.f;
@@ -178,7 +210,7 @@ rnn_res_fwd_kernel(const float* __restrict__ xp, int ldx, const float* __restric
 
 template <int KIND, int BPC>
 __global__ void __launch_bounds__(RR_THREADS, 1)
-rnn_res_bwd_kernel(const float* __restrict__ w_hh, const float* __restrict__ h0, const int32_t* __restrict__ lens,
+rnn_res_bwd_kernel(const __nv_bfloat16* __restrict__ w_g, const float* __restrict__ h0, const int32_t* __restrict__ lens,
                    const float* __restrict__ gates, const float* __restrict__ hs, const float* __restrict__ cs,
                    const float* __restrict__ d_user, float* __restrict__ dgi, float* __restrict__ dgh,
                    float* __restrict__ d_h0, int B, int S, int H) {
@@ -191,10 +223,8 @@ rnn_res_bwd_kernel(const float* __restrict__ w_hh, const float* __restrict__ h0,
   int* len_s = reinterpret_cast<int*>(dp + (size_t)BPC * GH);
   const int tid = threadIdx.x, b0 = blockIdx.x * BPC;
 
-  for (int i = tid; i < GH * Hp; i += RR_THREADS) {
-    const int n = i / Hp, k = i - n * Hp;
-    W[i] = __float2bfloat16(k < H ? __ldg(w_hh + (int64_t)n * H + k) : 0.f);
-  }
+  __shared__ uint64_t w_bar;
+  bulk_fill(reinterpret_cast<uint8_t*>(W), w_g, (uint32_t)(GH * Hp * 2), &w_bar, tid);
   if (tid < BPC) {
     const int b = b0 + tid;
     const int l = b < B ? (lens ? lens[b] : S) : 0;
@@ -301,7 +331,7 @@ rnn_res_bwd_kernel(const float* __restrict__ w_hh, const float* __restrict__ h0,
 }
 
 template <int KIND>
-static int launch_fwd(int bpc, const float* xp, int ldx, const float* w_hh, const float* b_hh, const float* h0, const int32_t* lens,
+static int launch_fwd(int bpc, const float* xp, int ldx, const __nv_bfloat16* w_hh, const float* b_hh, const float* h0, const int32_t* lens,
                       float* gates, float* hs, float* cs, float* user, int B, int S, int H, cudaStream_t st) {
   const RRGeom g = rr_geom(KIND == 0 ? MR_RNN_LSTM : MR_RNN_GRU, H, bpc);
   const unsigned grid = (unsigned)ceil_div(B, bpc);
@@ -317,7 +347,7 @@ static int launch_fwd(int bpc, const float* xp, int ldx, const float* w_hh, cons
 }
 
 template <int KIND>
-static int launch_bwd(int bpc, const float* w_hh, const float* h0, const int32_t* lens, const float* gates, const float* hs,
+static int launch_bwd(int bpc, const __nv_bfloat16* w_hh, const float* h0, const int32_t* lens, const float* gates, const float* hs,
                       const float* cs, const float* d_user, float* dgi, float* dgh, float* d_h0, int B, int S, int H,
                       cudaStream_t st) {
   const RRGeom g = rr_geom(KIND == 0 ? MR_RNN_LSTM : MR_RNN_GRU, H, bpc);
@@ -333,17 +363,31 @@ static int launch_bwd(int bpc, const float* w_hh, const float* h0, const int32_t
   return MR_OK;
 }
 
-int rnn_res_fwd(int kind, const float* xp, int ldx, const float* w_hh, const float* b_hh, const float* h0, const int32_t* lens,
-                float* gates, float* hs, float* cs, float* user, int B, int S, int H, cudaStream_t st) {
+int64_t rnn_res_scratch_bytes(int kind, int H) {
+  const RRGeom g = rr_geom(kind, H, 1);
+  const int64_t a = (int64_t)H * g.GHp * 2, b = (int64_t)g.GH * g.Hp * 2;
+  return (a > b ? a : b) + 256;
+}
+
+int rnn_res_fwd(int kind, const float* xp, int ldx, const float* w_hh_f32, const float* b_hh, const float* h0, const int32_t* lens,
+                float* gates, float* hs, float* cs, float* user, int B, int S, int H, void* scratch, cudaStream_t st) {
   const int bpc = rnn_res_bpc(kind, B, H);
+  const RRGeom g = rr_geom(kind, H, bpc);
+  __nv_bfloat16* w_hh = static_cast<__nv_bfloat16*>(scratch);
+  rnn_res_prep_kernel<<<(unsigned)ceil_div((int64_t)H * g.GHp, 256), 256, 0, st>>>(w_hh_f32, w_hh, nullptr, g.GH, H, g.GHp, g.Hp);
+  MR_CHECK_LAUNCH("rnn_res_prep_kernel");
   return kind == MR_RNN_LSTM ? launch_fwd<0>(bpc, xp, ldx, w_hh, b_hh, h0, lens, gates, hs, cs, user, B, S, H, st)
                              : launch_fwd<1>(bpc, xp, ldx, w_hh, b_hh, h0, lens, gates, hs, cs, user, B, S, H, st);
 }
 
-int rnn_res_bwd(int kind, const float* w_hh, const float* h0, const int32_t* lens, const float* gates, const float* hs,
+int rnn_res_bwd(int kind, const float* w_hh_f32, const float* h0, const int32_t* lens, const float* gates, const float* hs,
                 const float* cs, const float* d_user, float* dgi, float* dgh, float* d_h0, int B, int S, int H,
-                cudaStream_t st) {
+                void* scratch, cudaStream_t st) {
   const int bpc = rnn_res_bpc(kind, B, H);
+  const RRGeom g = rr_geom(kind, H, bpc);
+  __nv_bfloat16* w_hh = static_cast<__nv_bfloat16*>(scratch);
+  rnn_res_prep_kernel<<<(unsigned)ceil_div((int64_t)g.GH * g.Hp, 256), 256, 0, st>>>(w_hh_f32, nullptr, w_hh, g.GH, H, g.GHp, g.Hp);
+  MR_CHECK_LAUNCH("rnn_res_prep_kernel");
   return kind == MR_RNN_LSTM ? launch_bwd<0>(bpc, w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H, st)
                              : launch_bwd<1>(bpc, w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H, st);
 }
