@@ -3,9 +3,11 @@
 
 namespace mr {
 
+// row chunks of the first level: enough CTAs to fill the GPU (column groups x chunks), few enough that the
+// fixed-order second level (one thread per column walking the chunks) stays a few microseconds
 int64_t colsum_chunks(int64_t R) {
-  int64_t c = ceil_div(R, 256);
-  return c < 1 ? 1 : (c > 592 ? 592 : c);
+  int64_t c = ceil_div(R, 512);
+  return c < 1 ? 1 : (c > 96 ? 96 : c);
 }
 
 template <class T> __device__ __forceinline__ float cs_load(const T* p);

@@ -14,9 +14,10 @@ man = manager_for("cnn", "lstm", 5, 50, L, E, H, 10, precision="bf16")
 emb = mr.BERT_Embedding(man, vocab_size=30522).cuda()
 enc = mr.CNN_Encoder(man).cuda()
 ids_t, mask_t = data.make_news_table(51282, L)
-g = torch.Generator().manual_seed(0)
-pick = torch.randint(0, ids_t.shape[0], (N,), generator=g)
-ids = ids_t[pick].cuda(); mask = mask_t[pick].cuda()
+# the bench batch: 256 impressions x (5 candidates + 50 history slots, padded with news 0) = 14,080 titles
+xb = data.make_train_batch(ids_t, mask_t, 256, 5, 50, seed=0)
+ids = torch.cat([xb["cdd_encoded_index"].view(-1, L), xb["his_encoded_index"].view(-1, L)])[:N].cuda()
+mask = torch.cat([xb["cdd_attn_mask"].view(-1, L), xb["his_attn_mask"].view(-1, L)])[:N].cuda()
 for i in range(reps):
     if bwd:
         news = enc.encode_ids(emb, ids, mask)
