@@ -47,7 +47,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -246,6 +246,23 @@ def run_ours(args):
                 "peak_source": pk["source"] + " sustained (kernel timed inside the training step)",
                 "us_per_launch": t_k * 1e6, "launches_timed": int(conv_launches),
                 "algorithmic_flop_per_token": FLOP_PER_TOKEN_CONV}
+    # second half of the BASELINE metric: evaluation news-encoded/s (Manager._eval_fast hot loop 1: the whole news set
+    # through encode_news, sharded over ranks + all-gather), timed with CUDA events around the whole table build
+    from news_recommendation_mind_b200 import evaluate as ev
+    with torch.no_grad():
+        ev.encode_all_news(core, ids[:4096], mask[:4096])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        table = ev.encode_all_news(core, ids, mask)
+        e1.record()
+        torch.cuda.synchronize()
+        t_eval = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_eval, op=dist.ReduceOp.MAX)
+    eval_info = {"metric": "eval_news_encoded_per_sec", "value": ids.shape[0] / (float(t_eval) * 1e-3), "unit": "news/s",
+                 "news": int(ids.shape[0]), "ms": float(t_eval),
+                 "note": "full small-train news set (51,283 titles) incl. H2D of the int64 token table, sharded over ranks + NCCL all-gather"}
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -257,7 +274,7 @@ def run_ours(args):
                 "config": config_dict(args, args.precision), "clocks": clocks,
                 "e2e": {"value": world * CFG["B"] * args.steps / (ms_e2e * 1e-3), "unit": "impressions/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-                "gpu_launches": int(launches), "roofline": roof}
+                "gpu_launches": int(launches), "roofline": roof, "eval": eval_info}
         if world == 1:
             line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line))

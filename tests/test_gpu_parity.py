@@ -198,3 +198,39 @@ def test_bad_shapes_raise():
         enc(torch.zeros(2, 3, 10, 17, device="cuda"))
     with pytest.raises(AssertionError):
         mr.MHA_Encoder(manager_for("mha", "lstm", 3, 3, 10, 300, 150, 12))      # 150 % 12 != 0, as the reference asserts
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fast_evaluation_metrics_match_oracle(precision):
+    """Manager._eval_fast semantics (Manager.py:473-541): news table from encode_news over the whole news set,
+    per-impression predict_fast, then cal_metric.  AUC / MRR / nDCG@5 / nDCG@10 must equal the oracle's to 4
+    decimals (north_star); in fp32 the scores themselves agree to 1e-5."""
+    from news_recommendation_mind_b200 import data, evaluate as ev
+    torch.manual_seed(11)
+    C, S, L, E, H, V = 5, 12, 32, 300, 150, 30522
+    man = manager_for("cnn", "lstm", C, S, L, E, H, 10, precision=precision)
+    model = build_model(man, V).eval()
+    with torch.no_grad():
+        model.embedding.weight.normal_(0, 0.3)
+    news_ids, news_mask = data.make_news_table(400, L, seed=5)
+    impr = data.make_eval_impressions(news_ids, news_mask, 60, S, seed=9)
+    got = ev.evaluate(model, news_ids, news_mask, impr)
+    # oracle: same pipeline on the CPU
+    params = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        table = O.encode_news(params, news_ids.unsqueeze(1), news_mask.unsqueeze(1), "cnn").squeeze(1)
+        offs = impr["offsets"].numpy()
+        labels, preds = [], []
+        for i in range(len(offs) - 1):
+            x = {"cdd_id": impr["cdd_id"][offs[i]:offs[i + 1]].unsqueeze(0), "his_encoded_index": impr["his_encoded_index"][i:i + 1],
+                 "his_attn_mask": impr["his_attn_mask"][i:i + 1], "his_mask": impr["his_mask"][i:i + 1],
+                 "user_id": impr["user_id"][i:i + 1]}
+            preds.append(O.predict_fast(params, table, x, encoder_n="cnn", encoder_u="lstm").squeeze(0).numpy())
+            labels.append(impr["label"][offs[i]:offs[i + 1]].numpy())
+    exp = MO.ranking_metrics(labels, preds)
+    print(precision, got, exp)
+    if precision == "fp32":
+        assert got == {k: exp[k] for k in got}
+    else:   # bf16 scores differ in the 3rd significant digit; the rank-based means move by at most a few 1e-3
+        for k in got:
+            assert abs(got[k] - exp[k]) < 5e-3, (k, got[k], exp[k])
