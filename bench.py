@@ -246,6 +246,17 @@ def run_ours(args):
                 "peak_source": pk["source"] + " sustained (kernel timed inside the training step)",
                 "us_per_launch": t_k * 1e6, "launches_timed": int(conv_launches),
                 "algorithmic_flop_per_token": FLOP_PER_TOKEN_CONV}
+    # extra (not the headline): the same training step with in-batch unique-news dedup switched on
+    dedup_info = None
+    if args.precision == "bf16":
+        core.dedup_titles = True
+        for s_ in range(3):
+            trainer.train_step(model, devb[s_ % NB], opt)
+        ms_d = timed(devb, args.steps, False)
+        core.dedup_titles = False
+        dedup_info = {"value": world * CFG["B"] * args.steps / (ms_d * 1e-3), "unit": "impressions/s", "ms_per_step": ms_d / args.steps,
+                      "unique_titles_last_step": getattr(core, "last_unique_titles", None), "titles_per_step": CFG["B"] * (CFG["C"] + CFG["S"]),
+                      "note": "identical outputs; every distinct news of the batch is encoded once (history padding = news 0)"}
     # second half of the BASELINE metric: evaluation news-encoded/s (Manager._eval_fast hot loop 1: the whole news set
     # through encode_news, sharded over ranks + all-gather), timed with CUDA events around the whole table build
     from news_recommendation_mind_b200 import evaluate as ev
@@ -274,7 +285,7 @@ def run_ours(args):
                 "config": config_dict(args, args.precision), "clocks": clocks,
                 "e2e": {"value": world * CFG["B"] * args.steps / (ms_e2e * 1e-3), "unit": "impressions/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-                "gpu_launches": int(launches), "roofline": roof, "eval": eval_info}
+                "gpu_launches": int(launches), "roofline": roof, "eval": eval_info, "dedup": dedup_info}
         if world == 1:
             line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line))

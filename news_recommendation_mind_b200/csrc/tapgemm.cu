@@ -58,8 +58,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
   // Every CTA streams the same weight blocks; in lockstep all 148 SMs would hit the same L2 lines at the
   // same moment.  So each CTA walks the (k-chunk, tap) blocks in its own rotated order and reads its own
   // replica of the packed weights.
-  const int rot_c = (int)(blockIdx.x % (unsigned)n_chunks);
-  const int rot_t = (int)((blockIdx.x / (unsigned)n_chunks) % (unsigned)p.taps);
+  // (rotation changes the fp32 accumulation order per CTA, i.e. a title's result would depend on which CTA
+  //  encodes it; it is off by default so that the encoder is batch-invariant -- p.rotate enables it)
+  const int rot_c = p.rotate ? (int)(blockIdx.x % (unsigned)n_chunks) : 0;
+  const int rot_t = p.rotate ? (int)((blockIdx.x / (unsigned)n_chunks) % (unsigned)p.taps) : 0;
   const uint8_t* wrep = p.wpack + (size_t)(blockIdx.x % (unsigned)p.w_reps) * p.w_rep_stride;
 
   // ---- one-time setup ----------------------------------------------------------------------
@@ -554,6 +556,11 @@ int tapgemm_plan(TapGemmArgs& a, TapGemmPlan* plan) {
   a.n_tiles = ceil_div(a.n_titles, (int64_t)G);
   if (a.n_rows <= 0) a.n_rows = a.n_titles * a.L;
   a.w_reps = TG_W_REPS;
+  {
+    static int rot = -1;
+    if (rot < 0) { const char* e = getenv("MINDREC_ROTATE"); rot = (e != nullptr && e[0] == '1') ? 1 : 0; }
+    a.rotate = rot;
+  }
   a.w_rep_stride = tapgemm_pack_bytes(a.taps, n_total, a.K) / TG_W_REPS;
   if (a.use_tma) {
     if (a.ids != nullptr) {

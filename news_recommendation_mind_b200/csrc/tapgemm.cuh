@@ -40,6 +40,7 @@ struct TapGemmArgs {
   const __nv_bfloat16* a; int64_t lda, V;  // gather: table [V, lda];  dense: activations [n_titles*L, lda]
   const uint8_t* wpack;                    // TG_W_REPS replicas of [chunk][tap] blocks of b_slot_bytes
   int w_reps; int64_t w_rep_stride;
+  int rotate;                              // per-CTA rotated (k-chunk, tap) order (MINDREC_ROTATE=1); off = batch-invariant sums
   int epi; const float* bias; const float* bias2; int n_valid;   // bias2: optional second bias (LSTM b_ih + b_hh)
   int64_t n_rows;                          // rows of the problem (<= n_titles * L); 0 = n_titles * L
   float* out_f32; int n_store;             // TG_EPI_BIAS_F32: fp32 output [rows, ldo], columns >= n_store are not written

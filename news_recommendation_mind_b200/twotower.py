@@ -88,6 +88,10 @@ class TwoTower(TwoTowerBaseModel):
         manager.name = "__".join(["twotower", manager.encoderN, manager.encoderU])
         self.name = manager.name
         self._fused = isinstance(embedding, BERT_Embedding) and isinstance(encoderN, CNN_Encoder)
+        # opt-in (manager.dedup_titles): encode every distinct news of a batch once and gather the vectors back to
+        # the (candidate | history) slots -- identical outputs, the backward sums the slot gradients per news with
+        # the deterministic segmented reduction.  Needs cdd_id / his_id in the batch (utils/MIND.py:354-355).
+        self.dedup_titles = bool(getattr(manager, "dedup_titles", False))
 
     # ---- news side ---------------------------------------------------------------------------
     def _encode_titles(self, ids, mask):
@@ -125,7 +129,17 @@ class TwoTower(TwoTowerBaseModel):
         S = his.shape[1]
         ids = torch.cat([cdd.reshape(B * C, L), his.reshape(B * S, L)], dim=0)
         mask = torch.cat([cm.reshape(B * C, L), hm.reshape(B * S, L)], dim=0)
-        news = self._encode_titles(ids, mask)
+        if self.dedup_titles and "cdd_id" in x and "his_id" in x:
+            nid = torch.cat([x["cdd_id"].reshape(-1), x["his_id"].reshape(-1)])           # integer bookkeeping only
+            uniq, inverse = torch.unique(nid, return_inverse=True)
+            first = torch.full((uniq.numel(),), nid.numel(), dtype=torch.int64, device=nid.device)
+            first.scatter_reduce_(0, inverse, torch.arange(nid.numel(), device=nid.device), reduce="amin")
+            first, inverse = first.to(self.device, non_blocking=True), inverse.to(self.device, non_blocking=True)
+            news_u = self._encode_titles(ids.index_select(0, first), mask.index_select(0, first))
+            news = ops.EmbeddingGather.apply(inverse, news_u, None)
+            self.last_unique_titles = int(uniq.numel())
+        else:
+            news = self._encode_titles(ids, mask)
         cdd_repr = news[: B * C].view(B, C, -1)
         his_repr = news[B * C:].view(B, S, -1)
         user_repr = self._encode_user_from(his_repr, x)

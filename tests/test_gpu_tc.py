@@ -274,3 +274,34 @@ def test_rnn_user_encoder_resident_weights(kind, B, S, H, rev):
     print(kind, B, S, H, {k: "%.2e" % v for k, v in errs.items()})
     assert errs["out"] < 1e-4, errs
     assert max(errs.values()) < 1e-2, errs
+
+
+@pytest.mark.parametrize("precision,gtol", [("fp32", 1e-4), ("bf16", 0.15)])
+def test_dedup_titles_is_exact_in_forward_and_sums_gradients(precision, gtol):
+    """In-batch unique-news dedup (opt-in) must give the same log-probabilities bit for bit (the encoder is batch
+    invariant: a title's vector does not depend on where in the batch it sits) and the same gradients up to
+    summation order (fp32: 1e-4; bf16 rounds the per-token gradients after the slot sum instead of before it, so
+    the cancellation-heavy encoder gradients move by a few percent, as they do against the fp32 oracle)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from helpers import build_model, manager_for, rel_err
+    from news_recommendation_mind_b200 import data
+    torch.manual_seed(3)
+    C, S, L, E, H, V = 5, 20, 32, 300, 150, 30522
+    news_ids, news_mask = data.make_news_table(500, L, seed=2)
+    x = data.make_train_batch(news_ids, news_mask, 16, C, S, seed=4)
+    outs = []
+    for dedup in (False, True):
+        man = manager_for("cnn", "lstm", C, S, L, E, H, 10, precision=precision)
+        man.dedup_titles = dedup
+        torch.manual_seed(5)
+        model = build_model(man, V)
+        with torch.no_grad():
+            model.embedding.weight.normal_(0, 0.3)
+        model.train()
+        logp = model(x)[0]
+        torch.nn.NLLLoss()(logp, x["label"].cuda()).backward()
+        outs.append((logp.detach().clone(), {k: p.grad.detach().clone() for k, p in model.named_parameters()}))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for k in outs[0][1]:
+        assert rel_err(outs[1][1][k], outs[0][1][k]) < gtol, (k, rel_err(outs[1][1][k], outs[0][1][k]))
