@@ -82,7 +82,6 @@ int news_cnn_tc_fwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
   __nv_bfloat16* c = static_cast<__nv_bfloat16*>(c_save);
   __nv_bfloat16* key = static_cast<__nv_bfloat16*>(key_save);
 
-  if (int rc = tapgemm_pack(conv_w, wconv, 3, (int)Hp, (int)Kp, (int)H, (int)E, 3 * E, 3, 1, st)) return rc;
   if (int rc = tapgemm_pack(proj_w, wproj, 1, (int)Hp, (int)Hp, (int)H, (int)H, H, 1, 0, st)) return rc;
   if (!ids) {
     cast_rows_bf16_kernel<<<(unsigned)ceil_div(T * Kp, 256), 256, 0, st>>>(emb, xa, T, E, Kp);
@@ -97,11 +96,21 @@ int news_cnn_tc_fwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
   else { a.ids = nullptr; a.a = xa; a.lda = Kp; a.V = 0; }
   a.wpack = wconv; a.epi = TG_EPI_BIAS_RELU; a.bias = conv_b; a.n_valid = (int)H;
   a.out = c; a.ldo = Hp;
-  if (int rc = tapgemm_plan(a, &plan)) return rc;
+  const bool two_cta = tapgemm2_supported(a);       // CTA pairs with the conv weights resident in shared memory
+  if (two_cta) {
+    if (int rc = tapgemm2_pack(conv_w, wconv, 3, (int)Hp, (int)Kp, (int)H, (int)E, 3 * E, 3, 1, st)) return rc;
+  } else {
+    if (int rc = tapgemm_pack(conv_w, wconv, 3, (int)Hp, (int)Kp, (int)H, (int)E, 3 * E, 3, 1, st)) return rc;
+    if (int rc = tapgemm_plan(a, &plan)) return rc;
+  }
   const bool timed = g_conv_timing.enabled;
   const int slot = (int)(g_conv_timing.count % CONV_EVT_SLOTS);
   if (timed) cudaEventRecord(g_conv_timing.beg[slot], st);
-  if (int rc = tapgemm_launch(plan, st)) return rc;
+  if (two_cta) {
+    if (int rc = tapgemm2_run(a, wconv, st)) return rc;
+  } else {
+    if (int rc = tapgemm_launch(plan, st)) return rc;
+  }
   if (timed) {
     cudaEventRecord(g_conv_timing.end[slot], st);
     ++g_conv_timing.count;

@@ -69,6 +69,12 @@ int tapgemm_pack(const float* src, uint8_t* dst, int taps, int n_total, int K, i
 // fills the derived fields of `a` (G, halo, slots, tiles); returns MR_OK or an error
 int tapgemm_plan(TapGemmArgs& a, TapGemmPlan* plan);
 int tapgemm_launch(const TapGemmPlan& plan, cudaStream_t stream);
+// two-CTA (cta_group::2) variant with the weights resident in shared memory -- tapgemm2.cu
+bool tapgemm2_supported(const TapGemmArgs& a);
+int64_t tapgemm2_pack_bytes(int taps, int N, int K);
+int tapgemm2_pack(const float* src, uint8_t* dst, int taps, int N, int K, int n_valid, int k_valid, int64_t sn, int64_t sk,
+                  int64_t st, cudaStream_t stream);
+int tapgemm2_run(TapGemmArgs a, const uint8_t* wpack2, cudaStream_t stream);
 int sm_count();
 bool use_tma_gather();
 bool use_tma_default();                  // MINDREC_TMA=0 switches the producers back to cp.async

@@ -35,5 +35,11 @@ for i in range(NL):
     print("launch %d (%s): kernel cycles avg %.0f" % (i, names[i] if i < len(names) else "?", b[i, :, 0, 4].mean()))
     for r in range(4):
         tot = b[i, :, r, 4].mean()
+        if r == 1 and (b[i, 1::2, 1, 4] == 0).all():      # two-CTA kernel: only leaders (even CTAs) issue
+            sel = b[i, 0::2]
+            tot = sel[:, r, 4].mean()
+            print("   %-36s wait%% = %5.1f %5.1f %5.1f %5.1f  (of %.0f cycles, leaders)" % (roles[r], 100 * sel[:, r, 0].mean() / tot,
+                  100 * sel[:, r, 1].mean() / tot, 100 * sel[:, r, 2].mean() / tot, 100 * sel[:, r, 3].mean() / tot, tot))
+            continue
         print("   %-36s wait%% = %5.1f %5.1f %5.1f %5.1f  (of %.0f cycles)" % (roles[r], 100 * b[i, :, r, 0].mean() / tot,
               100 * b[i, :, r, 1].mean() / tot, 100 * b[i, :, r, 2].mean() / tot, 100 * b[i, :, r, 3].mean() / tot, tot))
