@@ -102,6 +102,10 @@ typedef struct {
  * in MIND-shaped batches they are >25 % of all positions and every SM would otherwise hit the same few L2
  * lines).  Purely a performance hint: results are identical.  Process-wide, set before launching. */
 MR_API int mr_news_cnn_set_hot_tokens(const int64_t* ids, int n);
+/* reps > 0: the bf16 table shadow passed to mr_news_cnn_fwd/bwd has n_hot*reps extra rows after row V-1; row
+ * V + h*reps + k (k < reps) is a copy of hot row h.  The gather then runs on TMA (tile::gather4) and every CTA
+ * reads its own replica of the hot rows.  0 (default): cp.async gather + shared-memory hot-row cache. */
+MR_API int mr_news_cnn_set_hot_replicas(int reps);
 MR_API int64_t mr_news_cnn_workspace_bytes(const mr_cnn_shape* s, int backward);
 MR_API int mr_news_cnn_fwd(const mr_cnn_shape* s,
                     const void* ids, int ids_i64, const float* emb,

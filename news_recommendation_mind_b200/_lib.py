@@ -35,6 +35,7 @@ _SIGNATURES = {
     "mr_embed_grad_workspace_bytes": (I64, [I64, I64, I64]),
     "mr_embed_grad_segreduce": (c_int, [P, c_int, P, c_int, I64, P, I64, I64, I64, I64, P, I64, P]),
     "mr_news_cnn_set_hot_tokens": (c_int, [POINTER(c_int64), c_int]),
+    "mr_news_cnn_set_hot_replicas": (c_int, [c_int]),
     "mr_news_cnn_workspace_bytes": (I64, [POINTER(CnnShape), c_int]),
     "mr_news_cnn_fwd": (c_int, [POINTER(CnnShape), P, c_int, P, P, c_int, P, P, P, P, P, P, P, P, P, P, P, I64, P]),
     "mr_news_cnn_bwd": (c_int, [POINTER(CnnShape), P, c_int, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P]),

@@ -297,9 +297,16 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
         row_off[k] = l < p.L ? (int64_t)g * p.L + l : -1;
       }
       auto row_id = [&](int64_t tile, int k) -> int {
-        if (p.ids == nullptr || row_off[k] < 0 || tile >= p.n_tiles || tile * p.G + row_g[k] >= p.n_titles) return (int)p.V;
-        const int64_t id = load_index(p.ids, p.ids_i64, tile * p.G * p.L + row_off[k]);
-        return (int)(id < 0 ? 0 : (id >= p.V ? p.V - 1 : id));
+        if (p.ids == nullptr || row_off[k] < 0 || tile >= p.n_tiles || tile * p.G + row_g[k] >= p.n_titles)
+          return (int)(p.V + (int64_t)p.n_hot * p.hot_reps);      // out of bounds -> zero filled
+        int64_t id = load_index(p.ids, p.ids_i64, tile * p.G * p.L + row_off[k]);
+        id = id < 0 ? 0 : (id >= p.V ? p.V - 1 : id);
+        if (p.hot_reps > 0) {          // hot rows: read this CTA's replica instead of the one row every SM wants
+#pragma unroll
+          for (int h = 0; h < TG_MAX_HOT; ++h)
+            if (h < p.n_hot && id == p.hot_ids[h]) id = p.V + (int64_t)h * p.hot_reps + (int64_t)(blockIdx.x % (unsigned)p.hot_reps);
+        }
+        return (int)id;
       };
       int nxt[4];
 #pragma unroll
@@ -507,6 +514,8 @@ constexpr size_t TG_SMEM_FIXED = 512 * 4 + (4 * TG_MAX_SLOTS + 4) * 8 + 16;   //
 
 static int64_t g_hot_ids[TG_MAX_HOT] = {0, 0, 0, 0};
 static int g_n_hot = 0;
+static int g_hot_reps = 0;
+int hot_replicas() { return g_hot_reps; }
 int hot_tokens(int64_t* out) {
   for (int i = 0; i < g_n_hot; ++i) out[i] = g_hot_ids[i];
   return g_n_hot;
@@ -528,7 +537,8 @@ int tapgemm_plan(TapGemmArgs& a, TapGemmPlan* plan) {
   a.G = G;
   // dense activations: TMA tile loads.  Token-table gather: cp.async + the hot-row shared-memory cache by default
   // (PAD/[CLS]/[SEP] rows hammer a few L2 lines when fetched by every SM; MINDREC_TMA_GATHER=1 selects gather4).
-  a.use_tma = use_tma_default() && (a.ids == nullptr || use_tma_gather()) ? 1 : 0;
+  a.hot_reps = a.ids != nullptr ? hot_replicas() : 0;
+  a.use_tma = use_tma_default() && (a.ids == nullptr || use_tma_gather() || a.hot_reps > 0) ? 1 : 0;
   a.halo = a.taps > 1 ? (int)align_up(G, 8) : 0;      // multiple of 8 rows: tile rows start on a 1024-byte swizzle period
   a.a_ps = 0;
   a.a_slot_bytes = (uint32_t)(align_up(128 + 2 * a.halo, 8) * 128);      // one k-chunk of 64 columns, SWIZZLE_128B rows
@@ -564,7 +574,9 @@ int tapgemm_plan(TapGemmArgs& a, TapGemmPlan* plan) {
   a.w_rep_stride = tapgemm_pack_bytes(a.taps, n_total, a.K) / TG_W_REPS;
   if (a.use_tma) {
     if (a.ids != nullptr) {
-      if (int rc = tma_encode_2d(&plan->tmap, a.a, (uint64_t)a.lda, (uint64_t)a.V, (uint64_t)a.lda * 2, TG_KC, 1, 128)) return rc;
+      if (int rc = tma_encode_2d(&plan->tmap, a.a, (uint64_t)a.lda, (uint64_t)(a.V + (int64_t)a.n_hot * a.hot_reps),
+                                 (uint64_t)a.lda * 2, TG_KC, 1, 128))
+        return rc;
     } else {
       if (int rc = tma_encode_3d(&plan->tmap, a.a, (uint64_t)a.lda, (uint64_t)a.n_titles, (uint64_t)a.L, (uint64_t)a.L * a.lda * 2,
                                  (uint64_t)a.lda * 2, TG_KC, (uint32_t)G, (uint32_t)a.L, 128))
@@ -612,6 +624,12 @@ int tapgemm_pack(const float* src, uint8_t* dst, int taps, int n_total, int K, i
 }  // namespace mr
 
 extern "C" {
+int mr_news_cnn_set_hot_replicas(int reps) {
+  using namespace mr;
+  MR_REQUIRE(reps >= 0 && reps <= 1024, MR_ERR_BAD_SHAPE, "mr_news_cnn_set_hot_replicas: reps=%d", reps);
+  g_hot_reps = reps;
+  return MR_OK;
+}
 int mr_news_cnn_set_hot_tokens(const int64_t* ids, int n) {
   using namespace mr;
   MR_REQUIRE(n >= 0 && n <= TG_MAX_HOT && (n == 0 || ids != nullptr), MR_ERR_BAD_SHAPE, "mr_news_cnn_set_hot_tokens: n=%d (max %d)", n, TG_MAX_HOT);

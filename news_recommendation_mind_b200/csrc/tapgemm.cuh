@@ -35,6 +35,7 @@ struct TapGemmArgs {
   int L, G, taps, dir, K;
   int n_sub, nsz[2];                       // N sub-tiles, each a multiple of 16 and <= 256
   const void* ids; int ids_i64;            // gather mode when ids != nullptr
+  int hot_reps;                            // > 0: table rows V + h*hot_reps + k (k < hot_reps) are copies of hot row h
   int64_t hot_ids[4]; int n_hot;           // gather mode: table rows kept in shared memory (PAD/[CLS]/[SEP]: every
                                            // CTA would otherwise hammer the same few L2 lines)
   const __nv_bfloat16* a; int64_t lda, V;  // gather: table [V, lda];  dense: activations [n_titles*L, lda]
@@ -81,6 +82,7 @@ bool use_tma_default();                  // MINDREC_TMA=0 switches the producers
 constexpr int TG_MAX_HOT = 4;
 // process-wide list of "hot" token ids (set through mr_news_cnn_set_hot_tokens); n <= TG_MAX_HOT
 int hot_tokens(int64_t* out);
+int hot_replicas();                      // replicas per hot row appended to the bf16 table (0 = none)
 // debug: when set, every tap-GEMM launch writes its per-role wait counters here ([148][4][5] int64)
 extern long long* g_tapgemm_dbg;
 

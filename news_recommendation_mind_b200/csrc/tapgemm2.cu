@@ -15,7 +15,9 @@
 
 namespace mr {
 
-constexpr int TG2_THREADS = 320;
+constexpr int TG2_THREADS = 448;     // warps 0-3 epilogue, 4 MMA / relay, 5 weights, 6-13 A producers
+constexpr int TG2_PROD = 256;        // producer threads
+constexpr int TG2_RPT = 128 * 8 / TG2_PROD;   // rows per producer thread (a thread owns one 16-byte piece column)
 
 struct Ring2 {
   uint32_t pos, phase, n;
@@ -143,7 +145,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG2_THREADS, 1) tapg
     }
     if (tid == 0) {
       for (int i = 0; i < TG_MAX_SLOTS; ++i) {
-        tc::mbar_init(&a_full[i], 128);
+        tc::mbar_init(&a_full[i], TG2_PROD);
         tc::mbar_init(&a_empty[i], 1);
         tc::mbar_init(&peer_full[i], 1);
       }
@@ -241,24 +243,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG2_THREADS, 1) tapg
           TG2_TIMED(2, tc::mbar_wait_cluster(&peer_full[ra.pos], ra.phase));
           tc::tc_fence_after();
           const uint32_t a_slot16 = (sA0 + ra.pos * p.a_slot_bytes) >> 4;
-          for (int tap = 0; tap < p.taps; ++tap) {
-            const uint32_t b_blk = sB0 + (uint32_t)(c * p.taps + tap) * q.b_half_slot;
-            const uint32_t toff = tap == 0 ? tap_off0 : (tap == 1 ? tap_off1 : tap_off2);
-            const uint64_t da0 = a_hi | (uint64_t)((a_slot16 + toff) & 0x3FFFu);
-            const uint64_t db0 = b_desc0 | (uint64_t)((b_blk >> 4) & 0x3FFFu);
-            const bool last_tap = tap == p.taps - 1;
-            TG2_TIMED(3, {
-            if (tc::elect_one()) {
+          // all taps of the chunk in one elected section: up to 12 MMAs back to back, one commit
+          const uint32_t b_chunk = sB0 + (uint32_t)(c * p.taps) * q.b_half_slot;
+          const bool last_chunk = c == n_chunks - 1;
+          TG2_TIMED(3, {
+          if (tc::elect_one()) {
+            for (int tap = 0; tap < p.taps; ++tap) {
+              const uint32_t toff = tap == 0 ? tap_off0 : (tap == 1 ? tap_off1 : tap_off2);
+              const uint64_t da0 = a_hi | (uint64_t)((a_slot16 + toff) & 0x3FFFu);
+              const uint64_t db0 = b_desc0 | (uint64_t)(((b_chunk + (uint32_t)tap * q.b_half_slot) >> 4) & 0x3FFFu);
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                if (ks < nks) tc::umma2(dcol, da0 + (uint64_t)(2 * ks), db0 + (uint64_t)(ks * b_kstep), idesc, accum | (uint32_t)ks);
-              if (last_tap) tc::umma2_commit(&a_empty[ra.pos]);
-              if (last_tap && c == n_chunks - 1) tc::umma2_commit(&t_full[acc.pos]);
+                if (ks < nks) tc::umma2(dcol, da0 + (uint64_t)(2 * ks), db0 + (uint64_t)(ks * b_kstep), idesc, accum | (uint32_t)(tap | ks));
             }
-            __syncwarp();
-            });
-            accum = 1;
+            tc::umma2_commit(&a_empty[ra.pos]);
+            if (last_chunk) tc::umma2_commit(&t_full[acc.pos]);
           }
+          __syncwarp();
+          });
+          accum = 1;
           ra.next();
         }
         acc.next();
@@ -296,12 +299,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG2_THREADS, 1) tapg
     const int rgrp = ptid >> 3, j = ptid & 7;
     const uint32_t depth = (uint32_t)(p.ns_a - 2 < 3 ? p.ns_a - 2 : 3);
     const uint32_t sA0 = tc::smem_u32(sA);
-    int64_t row_off[8];
-    int row_g[8];
-    uint32_t dst_off[8];
+    int64_t row_off[TG2_RPT];
+    int row_g[TG2_RPT];
+    uint32_t dst_off[TG2_RPT];
 #pragma unroll
-    for (int s = 0; s < 8; ++s) {
-      const int r = rgrp + 16 * s;
+    for (int s = 0; s < TG2_RPT; ++s) {
+      const int r = rgrp + (TG2_PROD / 8) * s;
       const int g = r % p.G, l = r / p.G;
       row_g[s] = g;
       row_off[s] = l < p.L ? (int64_t)g * p.L + l : -1;
@@ -321,22 +324,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG2_THREADS, 1) tapg
         if (h < p.n_hot && id == p.hot_ids[h]) id = -2 - h;
       return id;
     };
-    int64_t raw[8];
+    int64_t raw[TG2_RPT];
 #pragma unroll
-    for (int s = 0; s < 8; ++s) raw[s] = raw_of(row_token(2 * pair0 + rank, s));
+    for (int s = 0; s < TG2_RPT; ++s) raw[s] = raw_of(row_token(2 * pair0 + rank, s));
     Ring2 ra(p.ns_a), sig(p.ns_a);
     uint32_t pending = 0;
     for (int64_t pair = pair0; pair < q.n_pairs; pair += pair_step) {
       const int64_t tile = 2 * pair + rank;
-      int64_t cur[8];
+      int64_t cur[TG2_RPT];
 #pragma unroll
-      for (int s = 0; s < 8; ++s) cur[s] = classify(row_token(tile, s), raw[s]);
+      for (int s = 0; s < TG2_RPT; ++s) cur[s] = classify(row_token(tile, s), raw[s]);
 #pragma unroll
-      for (int s = 0; s < 8; ++s) raw[s] = raw_of(row_token(tile + 2 * pair_step, s));
-      const __nv_bfloat16* rowp[8];
+      for (int s = 0; s < TG2_RPT; ++s) raw[s] = raw_of(row_token(tile + 2 * pair_step, s));
+      const __nv_bfloat16* rowp[TG2_RPT];
       uint32_t hot_mask = 0;
 #pragma unroll
-      for (int s = 0; s < 8; ++s) {
+      for (int s = 0; s < TG2_RPT; ++s) {
         if (cur[s] >= 0) rowp[s] = p.a + cur[s] * p.lda + j * 8;
         else if (cur[s] == -1) rowp[s] = nullptr;
         else rowp[s] = reinterpret_cast<const __nv_bfloat16*>(hot + (size_t)(-2 - cur[s]) * hot_pitch) + j * 8;
@@ -349,7 +352,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG2_THREADS, 1) tapg
           const uint32_t slot = sA0 + ra.pos * p.a_slot_bytes;
           const int col = c * TG_KC;
 #pragma unroll
-          for (int s = 0; s < 8; ++s) {
+          for (int s = 0; s < TG2_RPT; ++s) {
             const __nv_bfloat16* src = rowp[s];
             if ((hot_mask >> s) & 1u) {
               const uint4 v = *reinterpret_cast<const uint4*>(src + col);

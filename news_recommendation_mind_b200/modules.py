@@ -69,6 +69,10 @@ class BERT_Embedding(nn.Module):
         hot = [t for t in getattr(manager, "hot_token_ids", (0, 101, 102)) if 0 <= t < vocab_size][:4]
         arr = (ctypes.c_int64 * max(len(hot), 1))(*hot)
         _lib.check(_lib.load().mr_news_cnn_set_hot_tokens(arr, len(hot)), "mr_news_cnn_set_hot_tokens")
+        # optional: `hot_replicas` copies of every hot row appended to the bf16 shadow (TMA gather4 path)
+        self.hot_ids = hot
+        self.hot_reps = int(getattr(manager, "hot_replicas", os.environ.get("MINDREC_HOT_REPS", "0")))
+        _lib.check(_lib.load().mr_news_cnn_set_hot_replicas(self.hot_reps), "mr_news_cnn_set_hot_replicas")
 
     @property
     def weight(self) -> torch.Tensor:
@@ -80,13 +84,22 @@ class BERT_Embedding(nn.Module):
         w = self.weight
         key = (w.data_ptr(), w._version, tuple(w.shape))
         if self._shadow is None or self._shadow_key != key:
-            self._shadow = ops.cast_pad_bf16(w.detach(), ops.pad_to(w.shape[1], 64))
+            self._shadow = ops.cast_pad_bf16(w.detach(), ops.pad_to(w.shape[1], 64), extra_rows=len(self.hot_ids) * self.hot_reps)
+            self._replicate_hot(self._shadow)
             self._shadow_key = key
         return self._shadow
+
+    def _replicate_hot(self, shadow: torch.Tensor) -> None:
+        """rows V + h*reps .. V + (h+1)*reps of the shadow <- hot row h (byte copies of bf16 rows)."""
+        V = self.weight.shape[0]
+        for h, t in enumerate(self.hot_ids):
+            if self.hot_reps > 0:
+                shadow[V + h * self.hot_reps: V + (h + 1) * self.hot_reps] = shadow[t]
 
     def mark_shadow_fresh(self, shadow: torch.Tensor) -> None:
         """Called by the fused optimiser, which rewrites the shadow inside the Adam kernel."""
         w = self.weight
+        self._replicate_hot(shadow)
         self._shadow = shadow
         self._shadow_key = (w.data_ptr(), w._version, tuple(w.shape))
 

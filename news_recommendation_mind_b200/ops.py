@@ -395,11 +395,11 @@ def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale
           "mr_adam_step")
 
 
-def cast_pad_bf16(src: torch.Tensor, ld: int) -> torch.Tensor:
+def cast_pad_bf16(src: torch.Tensor, ld: int, extra_rows: int = 0) -> torch.Tensor:
     lib = _lib.load()
     sc = _f32c(src)
     rows, cols = sc.shape
-    dst = torch.empty(rows, ld, dtype=torch.bfloat16, device=sc.device)
+    dst = torch.empty(rows + extra_rows, ld, dtype=torch.bfloat16, device=sc.device)
     check(lib.mr_cast_pad_bf16(ptr(sc), ptr(dst), rows, cols, ld, stream_ptr(sc.device)), "mr_cast_pad_bf16")
     return dst
 
