@@ -10,7 +10,7 @@ from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_float, c_int
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmindrec.so")
+LIB_PATH = os.environ.get("MINDREC_LIB") or os.path.join(HERE, "libmindrec.so")   # MINDREC_LIB: A/B of two builds (scripts/)
 
 MR_F32, MR_BF16 = 0, 1
 MR_RNN_LSTM, MR_RNN_GRU = 0, 1

@@ -180,6 +180,8 @@ struct BiasActEpi {         // out = act(v + bias[n]); act 0 none, 1 relu, 2 tan
 // `partial` needs colsum_chunks(R) * C floats.
 int64_t colsum_chunks(int64_t R);
 cudaError_t colsum(const float* x, float* out, int64_t R, int64_t C, float* partial, cudaStream_t st);
+// out[c] = sum_r x[r*ld + c], R small (one launch)
+cudaError_t colsum_small(const float* x, int64_t ld, float* out, int64_t R, int64_t C, cudaStream_t st);
 cudaError_t colsum_bf16(const __nv_bfloat16* x, int64_t ld, float* out, int64_t R, int64_t C, float* partial, cudaStream_t st);
 
 }  // namespace mr

@@ -123,7 +123,7 @@ static int bwd_f32(const mr_cnn_shape* s, const void* ids, int ids_i64, const fl
   cudaError_t e;
   conv_w_permute_kernel<<<(unsigned)ceil_div(3 * E * H, 256), 256, 0, st>>>(conv_w, nullptr, wd, (int)E, (int)H);
   MR_CHECK_LAUNCH("conv_w_permute_kernel");
-  cnn_pool_bwd_kernel<float, float><<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(c, key, H, prob, query, d_news, dkp, dc, H, dqp, N, (int)L, (int)H);
+  cnn_pool_bwd_kernel<float, float><<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(c, key, H, prob, query, d_news, dkp, dc, H, dqp, nullptr, N, (int)L, (int)H);
   MR_CHECK_LAUNCH("cnn_pool_bwd_kernel");
   e = colsum(dqp, d_query, N, H, cp, st);
   MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "colsum dq: %s", cudaGetErrorString(e));

@@ -54,7 +54,11 @@ int64_t news_cnn_tc_workspace_bytes(const mr_cnn_shape* s, int backward) {
   b += arena_bytes(T * Kp, 2);
   b += 2 * arena_bytes(T * Hp, 2);                                    // dkp, dc_pool / dconv
   b += arena_bytes(tapgemm_pack_bytes(3, 256, (int)Hp), 1);           // dgrad weights (one block of <= 256 columns)
-  b += arena_bytes(s->N * s->H, 4);                                   // dq partial
+  b += 2 * arena_bytes(s->N * s->H, 4);                               // dq / dbq partials (generic pooling path)
+  b += arena_bytes(s->N * Hp, 4);                                     // d_news padded to the row pitch
+  b += arena_bytes(ceil_div(s->N, 8) * 2 * Hp, 4);                    // per-CTA (dq | dbq) partials of the fast pooling backward
+  b += arena_bytes((int64_t)sm_count() * 4 * Hp, 4);                  // per-warp column sums of dconv (conv-bias gradient)
+  b += arena_bytes(T * 32, 1);                                        // relu'(c) as a bit mask, 32 bytes per token
   b += arena_bytes(colsum_chunks(T) * Hp, 4);
   const int64_t pc = tokred_partial_bytes(s->N, (int)s->L, 3, (int)Kp, (int)Hp);
   const int64_t pp = tokred_partial_bytes(s->N, (int)s->L, 1, (int)Hp, (int)Hp);
@@ -163,6 +167,11 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
   const int64_t nbsz = nblk ? align_up(ceil_div(Kp, nblk), 16) : 0;
   uint8_t* wdg = d_emb ? ar.take<uint8_t>(tapgemm_pack_bytes(3, 256, (int)Hp)) : nullptr;
   float* dqp = ar.take<float>(N * H);
+  float* dbp = ar.take<float>(N * H);
+  float* dnp = ar.take<float>(N * Hp);
+  float* ppart = ar.take<float>(ceil_div(N, 8) * 2 * Hp);
+  float* csum = ar.take<float>((int64_t)sm_count() * 4 * Hp);
+  uint8_t* cmask = ar.take<uint8_t>(T * 32);
   float* cp = ar.take<float>(colsum_chunks(T) * Hp);
   const int64_t pb_conv = tokred_partial_bytes(N, (int)L, 3, (int)Kp, (int)Hp);
   const int64_t pb_proj = tokred_partial_bytes(N, (int)L, 1, (int)Hp, (int)Hp);
@@ -170,25 +179,35 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
   MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "mr_news_cnn_bwd: workspace too small (%lld given)", (long long)wsb);
   MR_REQUIRE(3 * Hp <= 512, MR_ERR_UNSUPPORTED, "mr_news_cnn_bwd: hidden_dim %lld > 160 is not supported by the bf16 backward", (long long)H);
 
-  // 1. pooling backward: dkp = grad wrt the projection pre-activation, dcv = p * d_news   (Attention.py:77-80)
-  if (L <= 32 && Hp <= 256) {
+  // 1. pooling backward (Attention.py:77-80): dkp = grad wrt the projection pre-activation, d_query, d_proj_b.
+  //    Fast path (titles of <= 32 tokens): p * d_news is NOT materialised -- the RELUGRAD_POOL epilogue of step 3 forms
+  //    it from prob and the padded copy of d_news; generic path: dcv = p * d_news.
+  const bool fast_pool = L <= 32 && Hp <= 160;
+  cudaError_t e;
+  if (fast_pool) {
     const unsigned grid = (unsigned)ceil_div(N, 8);
-    if (Hp <= 64) cnn_pool_bwd_bf16_kernel<1><<<grid, 256, 0, st>>>(c, key, Hp, prob, query, d_news, dkp, dcv, dqp, N, (int)L, (int)H);
-    else if (Hp <= 128) cnn_pool_bwd_bf16_kernel<2><<<grid, 256, 0, st>>>(c, key, Hp, prob, query, d_news, dkp, dcv, dqp, N, (int)L, (int)H);
-    else if (Hp <= 192) cnn_pool_bwd_bf16_kernel<3><<<grid, 256, 0, st>>>(c, key, Hp, prob, query, d_news, dkp, dcv, dqp, N, (int)L, (int)H);
-    else cnn_pool_bwd_bf16_kernel<4><<<grid, 256, 0, st>>>(c, key, Hp, prob, query, d_news, dkp, dcv, dqp, N, (int)L, (int)H);
+    if (Hp <= 64) cnn_pool_bwd_bf16_kernel<1><<<grid, 256, 0, st>>>(c, key, Hp, prob, query, d_news, dkp, dnp, ppart, cmask, N, (int)L, (int)H);
+    else if (Hp <= 128) cnn_pool_bwd_bf16_kernel<2><<<grid, 256, 0, st>>>(c, key, Hp, prob, query, d_news, dkp, dnp, ppart, cmask, N, (int)L, (int)H);
+    else cnn_pool_bwd_bf16_kernel<3><<<grid, 256, 0, st>>>(c, key, Hp, prob, query, d_news, dkp, dnp, ppart, cmask, N, (int)L, (int)H);
+    MR_CHECK_LAUNCH("cnn_pool_bwd_bf16_kernel");
+    cnn_pool_bwd_final_kernel<<<(unsigned)ceil_div(2 * Hp, 32), 256, 0, st>>>(ppart, (int64_t)grid, (int)Hp, (int)H, d_query, d_proj_b);
+    MR_CHECK_LAUNCH("cnn_pool_bwd_final_kernel");
+    if (d_c) {                                   // gradient arriving at the token representations (stand-alone CNN module)
+      cast_rows_bf16_kernel<<<(unsigned)ceil_div(T * Hp, 256), 256, 0, st>>>(d_c, dcv, T, H, Hp);
+      MR_CHECK_LAUNCH("cast_rows_bf16_kernel");
+    }
   } else {
-    cnn_pool_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(c, key, Hp, prob, query, d_news, dkp, dcv, Hp, dqp, N, (int)L, (int)H);
+    cnn_pool_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(c, key, Hp, prob, query, d_news, dkp, dcv, Hp, dqp, dbp, N, (int)L, (int)H);
+    MR_CHECK_LAUNCH("cnn_pool_bwd_kernel");
+    if (d_c) {
+      add_rows_bf16_kernel<<<(unsigned)ceil_div(T * H, 256), 256, 0, st>>>(dcv, Hp, d_c, T, H);
+      MR_CHECK_LAUNCH("add_rows_bf16_kernel");
+    }
+    e = colsum(dqp, d_query, N, H, cp, st);
+    MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "colsum dq: %s", cudaGetErrorString(e));
+    e = colsum(dbp, d_proj_b, N, H, cp, st);
+    MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "colsum dbq: %s", cudaGetErrorString(e));
   }
-  MR_CHECK_LAUNCH("cnn_pool_bwd_kernel");
-  if (d_c) {
-    add_rows_bf16_kernel<<<(unsigned)ceil_div(T * H, 256), 256, 0, st>>>(dcv, Hp, d_c, T, H);
-    MR_CHECK_LAUNCH("add_rows_bf16_kernel");
-  }
-  cudaError_t e = colsum(dqp, d_query, N, H, cp, st);
-  MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "colsum dq: %s", cudaGetErrorString(e));
-  e = colsum_bf16(dkp, Hp, d_proj_b, T, H, cp, st);
-  MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "colsum dbq: %s", cudaGetErrorString(e));
 
   // 2. d_proj_w[n,k] = sum_t dkp[t,n] c[t,k]
   {
@@ -201,7 +220,8 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
     if (int rc = tokred_launch(plan, st)) return rc;
     if (int rc = tokred_reduce(plan, d_proj_w, (int)H, (int)H, H, 1, 0, st)) return rc;
   }
-  // 3. dconv = relu'(c) * (dc_pool + dkp Wq)   (in place over dcv)
+  // 3. dconv = relu'(c) * (p * d_news + dkp Wq)   -> dcv;  the conv-bias gradient (column sums of dconv) comes out of
+  //    the same epilogue as per-warp partials
   {
     if (int rc = tapgemm_pack(proj_w, wpb, 1, (int)Hp, (int)Hp, (int)H, (int)H, 1, H, 0, st)) return rc;
     TapGemmArgs a{};
@@ -209,13 +229,20 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
     a.n_titles = N; a.L = (int)L; a.taps = 1; a.dir = 1; a.K = (int)Hp;
     a.n_sub = 1; a.nsz[0] = (int)Hp;
     a.ids = nullptr; a.a = dkp; a.lda = Hp;
-    a.wpack = wpb; a.epi = TG_EPI_RELUGRAD; a.bias = nullptr; a.n_valid = (int)H;
-    a.e0 = dcv; a.e1 = c; a.lde = Hp; a.out = dcv; a.ldo = Hp;
+    a.wpack = wpb; a.bias = nullptr; a.n_valid = (int)H;
+    if (fast_pool) {
+      a.epi = TG_EPI_RELUGRAD_POOL; a.e0 = d_c ? dcv : nullptr; a.prob = prob; a.dnp = dnp; a.ldn = Hp; a.cmask = cmask;
+    } else {
+      a.epi = TG_EPI_RELUGRAD; a.e0 = dcv;
+    }
+    a.e1 = c; a.lde = Hp; a.out = dcv; a.ldo = Hp;
+    a.colsum_out = csum;
     if (int rc = tapgemm_plan(a, &plan)) return rc;
+    MR_REQUIRE(plan.grid <= sm_count(), MR_ERR_LAUNCH, "mr_news_cnn_bwd: tap-GEMM grid %d exceeds the column-sum partials", plan.grid);
     if (int rc = tapgemm_launch(plan, st)) return rc;
+    e = colsum_small(csum, Hp, d_conv_b, (int64_t)plan.grid * 4, H, st);
+    MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "colsum dbc: %s", cudaGetErrorString(e));
   }
-  e = colsum_bf16(dcv, Hp, d_conv_b, T, H, cp, st);
-  MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "colsum dbc: %s", cudaGetErrorString(e));
   // 4. d_conv_w[h,e,tap] = sum_t x[t+tap-1, e] dconv[t, h]
   {
     if (!ids) {

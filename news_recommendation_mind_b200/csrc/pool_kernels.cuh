@@ -75,13 +75,9 @@ cnn_pool_fwd_kernel(const T* __restrict__ c, const T* __restrict__ key, int64_t 
   }
 }
 
-// backward: d_news [N,H] -> dkp (grad wrt proj pre-activation) and dc_pool, both TO [.., ldo];
-// dq partial per title.
-template <class T, class TO>
-__global__ void __launch_bounds__(256)
-cnn_pool_bwd_kernel(const T* __restrict__ c, const T* __restrict__ key, int64_t ld, const float* __restrict__ prob,
-                    const float* __restrict__ q, const float* __restrict__ d_news, TO* __restrict__ dkp,
-                    TO* __restrict__ dc_pool, int64_t ldo, float* __restrict__ dq_partial, int64_t N, int L, int H);
+// backward: d_news [N,H] -> dkp (grad wrt proj pre-activation) and, when dc_pool != nullptr, dc_pool = p * d_news,
+// both TO [.., ldo]; per-title partials of dq and (when dbq_partial != nullptr) of the projection-bias gradient
+// sum_l dkp[l, :].
 
 template <class TO> __device__ __forceinline__ TO from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
@@ -91,7 +87,8 @@ template <class T, class TO>
 __global__ void __launch_bounds__(256)
 cnn_pool_bwd_kernel(const T* __restrict__ c, const T* __restrict__ key, int64_t ld, const float* __restrict__ prob,
                     const float* __restrict__ q, const float* __restrict__ d_news, TO* __restrict__ dkp,
-                    TO* __restrict__ dc_pool, int64_t ldo, float* __restrict__ dq_partial, int64_t N, int L, int H) {
+                    TO* __restrict__ dc_pool, int64_t ldo, float* __restrict__ dq_partial, float* __restrict__ dbq_partial,
+                    int64_t N, int L, int H) {
   const int lane = threadIdx.x & 31;
   const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= N) return;
@@ -99,7 +96,7 @@ cnn_pool_bwd_kernel(const T* __restrict__ c, const T* __restrict__ key, int64_t 
   const T* kn = key + n * L * ld;
   const T* cn = c + n * L * ld;
   TO* dk = dkp + n * L * ldo;
-  TO* dcp = dc_pool + n * L * ldo;
+  TO* dcp = dc_pool ? dc_pool + n * L * ldo : nullptr;
   const float* dn = d_news + n * H;
   // dp[l] = <d_news, c[l]>, kept in lane l%32 / register l/32
   float p[PL_MAXR], dp[PL_MAXR];
@@ -130,7 +127,7 @@ cnn_pool_bwd_kernel(const T* __restrict__ c, const T* __restrict__ key, int64_t 
     int h = h0 + lane;
     float qh = h < H ? __ldg(q + h) : 0.f;
     float dnh = h < H ? __ldg(dn + h) : 0.f;
-    float dq = 0.f;
+    float dq = 0.f, db = 0.f;
 #pragma unroll
     for (int r = 0; r < PL_MAXR; ++r) {
       if (r * 32 >= L) break;
@@ -141,18 +138,23 @@ cnn_pool_bwd_kernel(const T* __restrict__ c, const T* __restrict__ key, int64_t 
         if (h < H) {
           float k = to_f(kn[(int64_t)l * ld + h]);
           dq = fmaf(dsl, k, dq);
-          dk[(int64_t)l * ldo + h] = from_f<TO>(dsl * qh * (1.f - k * k));
-          dcp[(int64_t)l * ldo + h] = from_f<TO>(pl * dnh);
+          const float o = dsl * qh * (1.f - k * k);
+          db += o;
+          dk[(int64_t)l * ldo + h] = from_f<TO>(o);
+          if (dcp) dcp[(int64_t)l * ldo + h] = from_f<TO>(pl * dnh);
         }
       }
     }
-    if (h < H) dq_partial[n * H + h] = dq;
+    if (h < H) {
+      dq_partial[n * H + h] = dq;
+      if (dbq_partial) dbq_partial[n * H + h] = db;
+    }
   }
   // padding columns [H, ldo) feed tensor-core GEMMs in the bf16 path: keep them exactly zero
   for (int64_t i = lane; i < (int64_t)L * (ldo - H); i += 32) {
     const int64_t l = i / (ldo - H), h = H + i % (ldo - H);
     dk[l * ldo + h] = from_f<TO>(0.f);
-    dcp[l * ldo + h] = from_f<TO>(0.f);
+    if (dcp) dcp[l * ldo + h] = from_f<TO>(0.f);
   }
 }
 
@@ -264,66 +266,114 @@ cnn_pool_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ c, const __nv_bfloat1
   }
 }
 
+// Backward.  Writes dkp = grad wrt the projection pre-activation (bf16 [T, ld]), dnp = d_news padded to the row
+// pitch ld (fp32 [N, ld]) and cmask = one bit per element of c (c > 0; 32 bytes per token row, ld <= 256): the
+// RELUGRAD_POOL epilogue of the tap GEMM forms relu'(c) * (p[t] * d_news[n, :] + ...) from them -- dc_pool is never
+// materialised and c is not read again.  The gradients of the pooling query and of the projection bias
+// (sum over tokens of dkp, taken before the bf16 rounding) are reduced over the CTA's 8 titles in a fixed order and
+// written as one partial row per CTA: part[blockIdx][0][ld] = dq, part[blockIdx][1][ld] = dbq.
 template <int MAXP>
 __global__ void __launch_bounds__(256)
 cnn_pool_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ c, const __nv_bfloat16* __restrict__ key, int64_t ld,
                          const float* __restrict__ prob, const float* __restrict__ q, const float* __restrict__ d_news,
-                         __nv_bfloat16* __restrict__ dkp, __nv_bfloat16* __restrict__ dc_pool, float* __restrict__ dq_partial,
-                         int64_t N, int L, int H) {
-  const int lane = threadIdx.x & 31;
-  const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (n >= N) return;
+                         __nv_bfloat16* __restrict__ dkp, float* __restrict__ dnp, float* __restrict__ part,
+                         uint8_t* __restrict__ cmask, int64_t N, int L, int H) {
+  __shared__ float red[8][2][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   const int pieces = (int)(ld / 8);
-  const __nv_bfloat16* kn = key + n * L * ld;
-  const __nv_bfloat16* cn = c + n * L * ld;
-  const float* dn = d_news + n * H;
-  float dr[MAXP][8];
+  float dq[8], db[8];
 #pragma unroll
-  for (int i = 0; i < MAXP; ++i)
+  for (int e = 0; e < 8; ++e) { dq[e] = 0.f; db[e] = 0.f; }
+  if (n < N) {
+    const __nv_bfloat16* kn = key + n * L * ld;
+    const __nv_bfloat16* cn = c + n * L * ld;
+    const float* dn = d_news + n * H;
+    float dr[MAXP][8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int h = ((lane & 7) + 8 * i) * 8 + e;
-      dr[i][e] = h < H ? __ldg(dn + h) : 0.f;
-    }
-  const float dp = row_dots_bf16<MAXP>(cn, ld, L, pieces, dr, lane);        // <d_news, c[l]>
-  const float p = lane < L ? prob[n * L + lane] : 0.f;
-  const float dot = warp_sum(p * dp);
-  const float ds = p * (dp - dot) * rsqrtf((float)H);                       // softmax backward (Attention.py:77-80)
-  // this lane's 8-column piece of q and d_news
-  float qv[8], dv[8], dq[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int h = lane * 8 + e;
-    qv[e] = (lane < pieces && h < H) ? __ldg(q + h) : 0.f;
-    dv[e] = (lane < pieces && h < H) ? __ldg(dn + h) : 0.f;
-    dq[e] = 0.f;
-  }
-  const uint4* kp = reinterpret_cast<const uint4*>(kn) + lane;
-  uint4* dko = reinterpret_cast<uint4*>(dkp + n * L * ld) + lane;
-  uint4* dco = reinterpret_cast<uint4*>(dc_pool + n * L * ld) + lane;
-#pragma unroll 4
-  for (int l = 0; l < L; ++l) {
-    const float dsl = __shfl_sync(0xffffffffu, ds, l);
-    const float pl = __shfl_sync(0xffffffffu, p, l);
-    if (lane < pieces) {
-      float k[8], o1[8], o2[8];
-      bf8_to_f(__ldg(kp + (int64_t)l * pieces), k);
+    for (int i = 0; i < MAXP; ++i)
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        dq[e] = fmaf(dsl, k[e], dq[e]);
-        o1[e] = dsl * qv[e] * (1.f - k[e] * k[e]);
-        o2[e] = pl * dv[e];
+        const int h = ((lane & 7) + 8 * i) * 8 + e;
+        dr[i][e] = h < H ? __ldg(dn + h) : 0.f;
       }
-      dko[(int64_t)l * pieces] = f_to_bf8(o1);
-      dco[(int64_t)l * pieces] = f_to_bf8(o2);
+    const float dp = row_dots_bf16<MAXP>(cn, ld, L, pieces, dr, lane);        // <d_news, c[l]>
+    const float p = lane < L ? prob[n * L + lane] : 0.f;
+    const float dot = warp_sum(p * dp);
+    const float ds = p * (dp - dot) * rsqrtf((float)H);                       // softmax backward (Attention.py:77-80)
+    // this lane's 8-column piece of q and d_news
+    float qv[8], dv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int h = lane * 8 + e;
+      qv[e] = (lane < pieces && h < H) ? __ldg(q + h) : 0.f;
+      dv[e] = (lane < pieces && h < H) ? __ldg(dn + h) : 0.f;
+    }
+    if (lane < pieces) {
+      float4* o = reinterpret_cast<float4*>(dnp + n * ld + lane * 8);
+      o[0] = make_float4(dv[0], dv[1], dv[2], dv[3]);
+      o[1] = make_float4(dv[4], dv[5], dv[6], dv[7]);
+    }
+    const uint4* kp = reinterpret_cast<const uint4*>(kn) + lane;
+    const uint4* cpp = reinterpret_cast<const uint4*>(cn) + lane;
+    uint4* dko = reinterpret_cast<uint4*>(dkp + n * L * ld) + lane;
+    uint8_t* cmo = cmask + n * L * 32 + lane;          // byte `piece` of the 32-byte row: (c[l, 8 piece + e] > 0) in bit e
+#pragma unroll 4
+    for (int l = 0; l < L; ++l) {
+      const float dsl = __shfl_sync(0xffffffffu, ds, l);
+      if (lane < pieces) {
+        float k[8], o1[8], cv[8];
+        bf8_to_f(__ldg(kp + (int64_t)l * pieces), k);
+        bf8_to_f(__ldg(cpp + (int64_t)l * pieces), cv);
+        uint32_t bits = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bits |= (cv[e] > 0.f ? 1u : 0u) << e;
+        cmo[(int64_t)l * 32] = (uint8_t)bits;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          dq[e] = fmaf(dsl, k[e], dq[e]);
+          o1[e] = dsl * qv[e] * (1.f - k[e] * k[e]);
+          db[e] += o1[e];
+        }
+        dko[(int64_t)l * pieces] = f_to_bf8(o1);
+      }
     }
   }
   if (lane < pieces) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int h = lane * 8 + e;
-      if (h < H) dq_partial[n * H + h] = dq[e];
+      red[warp][0][lane * 8 + e] = dq[e];
+      red[warp][1][lane * 8 + e] = db[e];
     }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * (int)ld; i += 256) {
+    const int which = i >= (int)ld, col = i - which * (int)ld;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][which][col];
+    part[(int64_t)blockIdx.x * 2 * ld + i] = s;
+  }
+}
+
+// part [rows][2][ld] -> d_query[h] = sum_rows part[.][0][h],  d_proj_b[h] = sum_rows part[.][1][h]   (h < H), fixed order
+static __global__ void __launch_bounds__(256)
+cnn_pool_bwd_final_kernel(const float* __restrict__ part, int64_t rows, int ld, int H, float* __restrict__ d_query,
+                          float* __restrict__ d_proj_b) {
+  __shared__ float sm[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  float s = 0.f;
+  if (col < 2 * ld)
+    for (int64_t r = ry; r < rows; r += 8) s += part[r * 2 * ld + col];
+  sm[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && col < 2 * ld) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][cx];
+    const int which = col >= ld, h = col - which * ld;
+    if (h < H) (which ? d_proj_b : d_query)[h] = t;
   }
 }
 

@@ -33,6 +33,9 @@ struct Ring {
   }
 };
 
+// POOL = true: the instantiation whose epilogue is TG_EPI_RELUGRAD_POOL (kept apart so that neither epilogue pays for the
+// other's registers and instructions)
+template <bool POOL>
 __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArgs p, const __grid_constant__ CUtensorMap tmap) {
   long long dbg_acc[4] = {0, 0, 0, 0};
   const long long dbg_t0 = clock64();
@@ -103,11 +106,120 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
     const bool row_ok = l < p.L;
     const int64_t row_off = (int64_t)g * p.L + l;            // token offset inside the tile's G titles
     Ring acc(acc_stages);
+    float colacc[8];                      // column sums of the stored rows: lane j, slot ci <-> column 32 ci + j
+#pragma unroll
+    for (int ci = 0; ci < 8; ++ci) colacc[ci] = 0.f;
+    const int lane = tid & 31;
+    float* sdn = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(hot) + 15) & ~(uintptr_t)15);     // POOL: [2][G][dn_pitch]
+    const int dn_pitch = n_total + 4;        // +16 B per row: the G rows read by one LDS.128 fall into different banks
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      TG_TIMED(0, tc::mbar_wait(&t_full[acc.pos], acc.phase));
-      tc::tc_fence_after();
       const int64_t t = tile * p.G * p.L + row_off;
       const bool valid = row_ok && (tile * p.G + g < p.n_titles) && t < p.n_rows;
+      if constexpr (POOL) {
+        // ---- dconv = relu'(c) * (acc + p[t] d_news[title] (+ e0)) ; the c row (<= 160 columns) and p[t] are requested
+        // BEFORE the accumulator is waited for, so one memory latency per tile is exposed at most ----------------
+        uint32_t cm[5] = {0u, 0u, 0u, 0u, 0u};       // bit j of cm[ci]: c[t, 32 ci + j] > 0 (sign mask written by the pooling backward)
+        float pt = 0.f;
+        if (valid) {
+          const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(p.cmask + t * 32));
+          cm[4] = __ldg(reinterpret_cast<const uint32_t*>(p.cmask + t * 32 + 16));
+          cm[0] = m0.x; cm[1] = m0.y; cm[2] = m0.z; cm[3] = m0.w;
+          pt = __ldg(p.prob + t);
+        }
+        // the tile's G rows of d_news go through shared memory (two stages, one per accumulator stage)
+        float* sd_stage = sdn + (size_t)acc.pos * p.G * dn_pitch;
+        {
+          const int pieces = n_total >> 2;
+          for (int i = tid; i < p.G * pieces; i += 128) {
+            const int gg = i / pieces, q = i - gg * pieces;
+            const int64_t title = tile * p.G + gg;
+            float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (title < p.n_titles) v4 = __ldg(reinterpret_cast<const float4*>(p.dnp + title * p.ldn) + q);
+            *reinterpret_cast<float4*>(sd_stage + gg * dn_pitch + 4 * q) = v4;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        const float4* dn_row = reinterpret_cast<const float4*>(sd_stage + g * dn_pitch);
+        TG_TIMED(0, tc::mbar_wait(&t_full[acc.pos], acc.phase));
+        tc::tc_fence_after();
+        const uint32_t tb = tmem + ((uint32_t)(warp * 32) << 16) + acc.pos * 256u;
+#pragma unroll
+        for (int ci = 0; ci < 5; ++ci) {
+          if (ci * 32 < n_total) {
+            const int n0 = ci * 32;
+            const bool wide = n_total - n0 >= 32;
+            uint32_t v[32];
+            if (wide) {
+              tc::tmem_ld32(tb + n0, v);
+            } else {
+              uint32_t h[16];
+              tc::tmem_ld16(tb + n0, h);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) { v[j] = h[j]; v[16 + j] = 0u; }
+            }
+            float4 dn[8];
+            uint4 x0[4];
+            if (valid) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                if (u < 4 || wide) dn[u] = dn_row[ci * 8 + u];
+              if (p.e0 != nullptr) {
+                const uint4* q0 = reinterpret_cast<const uint4*>(p.e0 + t * p.lde + n0);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (u < 2 || wide) x0[u] = __ldg(q0 + u);
+              }
+            }
+            tc::tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const bool on = valid && (u < 2 || wide);
+              const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&x0[u]);
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                const int j = u * 8 + 2 * w;
+                float a0 = 0.f, a1 = 0.f;
+                if (on) {
+                  const float4 d4 = dn[j >> 2];
+                  const float d0 = (j & 2) ? d4.z : d4.x, d1 = (j & 2) ? d4.w : d4.y;
+                  a0 = fmaf(pt, d0, __uint_as_float(v[j]));
+                  a1 = fmaf(pt, d1, __uint_as_float(v[j + 1]));
+                  if (p.e0 != nullptr) {
+                    const float2 e2 = __bfloat1622float2(h0[w]);
+                    a0 += e2.x; a1 += e2.y;
+                  }
+                  a0 = ((cm[ci] >> j) & 1u) ? a0 : 0.f;
+                  a1 = ((cm[ci] >> (j + 1)) & 1u) ? a1 : 0.f;
+                }
+                f[j] = a0; f[j + 1] = a1;
+              }
+            }
+            if (valid) {
+              uint4* dst = reinterpret_cast<uint4*>(p.out + t * p.ldo + n0);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                if (u < 2 || wide) {
+                  uint4 o;
+                  o.x = tc::pack_bf16(f[u * 8 + 0], f[u * 8 + 1]);
+                  o.y = tc::pack_bf16(f[u * 8 + 2], f[u * 8 + 3]);
+                  o.z = tc::pack_bf16(f[u * 8 + 4], f[u * 8 + 5]);
+                  o.w = tc::pack_bf16(f[u * 8 + 6], f[u * 8 + 7]);
+                  dst[u] = o;
+                }
+              }
+            }
+            if (p.colsum_out != nullptr) colacc[ci] += tc::warp_colsum32(f, lane);
+          }
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive(&t_empty[acc.pos]);
+        acc.next();
+        continue;
+      }
+      if constexpr (!POOL) {
+      TG_TIMED(0, tc::mbar_wait(&t_full[acc.pos], acc.phase));
+      tc::tc_fence_after();
       const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + acc.pos * 256u;
       int col0 = 0;
       for (int sub = 0; sub < p.n_sub; ++sub) {
@@ -134,10 +246,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
               if (u < 2 || wide) { x0[u] = __ldg(q0 + u); x1[u] = __ldg(q1 + u); }
           }
           tc::tmem_ld_wait();
-          if (valid) {
-            float f[32];
+          float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) f[j] = valid ? __uint_as_float(v[j]) : 0.f;
+          if (valid) {
             if (p.epi == TG_EPI_BIAS_RELU) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j] + sbias[n0 + j], 0.f);
@@ -181,12 +293,26 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
               }
             }
           }
+          if (p.colsum_out != nullptr && p.epi == TG_EPI_RELUGRAD) {
+            // column sums of what this warp stored (invalid rows count as zero); n_sub == 1, n_total <= 256
+            const float cs = tc::warp_colsum32(f, lane);
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci)
+              if (ci == (n0 >> 5)) colacc[ci] += cs;
+          }
         }
         col0 += nsub;
       }
       tc::tc_fence_before();
       tc::mbar_arrive(&t_empty[acc.pos]);
       acc.next();
+      }
+    }
+    if (p.colsum_out != nullptr) {
+      float* cs = p.colsum_out + ((size_t)blockIdx.x * 4 + warp) * n_total;
+#pragma unroll
+      for (int ci = 0; ci < 8; ++ci)
+        if (ci * 32 + lane < n_total) cs[ci * 32 + lane] = colacc[ci];
     }
   } else if (warp == 4) {
     // =================================== MMA issuer ==========================================
@@ -554,7 +680,12 @@ int tapgemm_plan(TapGemmArgs& a, TapGemmPlan* plan) {
     for (int i = 0; i < n; ++i)
       if (hot[i] >= 0 && hot[i] < a.V) a.hot_ids[a.n_hot++] = hot[i];
   }
-  const size_t hot_bytes = (size_t)a.n_hot * ((size_t)(a.K * 2 + 15) / 16 * 16);
+  size_t hot_bytes = (size_t)a.n_hot * ((size_t)(a.K * 2 + 15) / 16 * 16);
+  if (a.epi == TG_EPI_RELUGRAD_POOL) {
+    MR_REQUIRE(a.ids == nullptr && a.n_sub == 1 && n_total <= 160 && a.ldn % 4 == 0 && a.cmask != nullptr && a.prob != nullptr && a.dnp != nullptr,
+               MR_ERR_BAD_SHAPE, "tap gemm: RELUGRAD_POOL epilogue needs a dense A, N <= 160 and its operands");
+    hot_bytes = 16 + 2 * (size_t)G * (n_total + 4) * 4;       // two stages of the tile's d_news rows
+  }
   size_t left = TG_SMEM_MAX - TG_SMEM_FIXED - hot_bytes - 128;
   while (ns_a > 4 && (size_t)ns_a * a.a_slot_bytes + 2 * (size_t)a.b_slot_bytes > left) --ns_a;
   MR_REQUIRE((size_t)ns_a * a.a_slot_bytes + 2 * (size_t)a.b_slot_bytes <= left, MR_ERR_UNSUPPORTED,
@@ -596,7 +727,8 @@ int tapgemm_launch(const TapGemmPlan& plan, cudaStream_t stream) {
   if (plan.args.n_titles <= 0) return MR_OK;
   static thread_local size_t attr_set = 0;
   if (plan.smem_bytes > attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM_MAX);
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM_MAX);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM_MAX);
     MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "tap gemm: cannot opt in to %zu bytes of shared memory: %s", TG_SMEM_MAX,
                cudaGetErrorString(e));
     attr_set = TG_SMEM_MAX;
@@ -604,7 +736,8 @@ int tapgemm_launch(const TapGemmPlan& plan, cudaStream_t stream) {
   TapGemmArgs args = plan.args;
   args.dbg = g_tapgemm_dbg;
   if (g_tapgemm_dbg != nullptr) g_tapgemm_dbg += 148 * 4 * 5;     // one record block per launch
-  tapgemm_kernel<<<plan.grid, TG_THREADS, plan.smem_bytes, stream>>>(args, plan.tmap);
+  if (args.epi == TG_EPI_RELUGRAD_POOL) tapgemm_kernel<true><<<plan.grid, TG_THREADS, plan.smem_bytes, stream>>>(args, plan.tmap);
+  else tapgemm_kernel<false><<<plan.grid, TG_THREADS, plan.smem_bytes, stream>>>(args, plan.tmap);
   MR_CHECK_LAUNCH("tapgemm_kernel");
   return MR_OK;
 }

@@ -24,7 +24,10 @@
 
 namespace mr {
 
-enum { TG_EPI_BIAS_RELU = 0, TG_EPI_BIAS_TANH = 1, TG_EPI_RELUGRAD = 2, TG_EPI_STORE = 3, TG_EPI_BIAS_F32 = 4 };
+enum { TG_EPI_BIAS_RELU = 0, TG_EPI_BIAS_TANH = 1, TG_EPI_RELUGRAD = 2, TG_EPI_STORE = 3, TG_EPI_BIAS_F32 = 4,
+       // out = relu'(e1) * (acc + prob[t] * dnp[title, :] (+ e0)): the pooling gradient p * d_news is formed here instead of
+       // being read back from memory, and relu'(e1) comes as a 1-bit-per-column mask (n_total <= 160)
+       TG_EPI_RELUGRAD_POOL = 5 };
 constexpr int TG_KC = 64;          // k-chunk (elements) = 8 panels
 constexpr int TG_THREADS = 320;
 constexpr int TG_MAX_SLOTS = 8;
@@ -46,6 +49,9 @@ struct TapGemmArgs {
   int64_t n_rows;                          // rows of the problem (<= n_titles * L); 0 = n_titles * L
   float* out_f32; int n_store;             // TG_EPI_BIAS_F32: fp32 output [rows, ldo], columns >= n_store are not written
   const __nv_bfloat16* e0; const __nv_bfloat16* e1; int64_t lde;
+  const float* prob; const float* dnp; int64_t ldn;   // TG_EPI_RELUGRAD_POOL: prob [rows], dnp [n_titles, ldn] fp32 (ldn % 4 == 0)
+  const uint8_t* cmask;                    // ... and the sign mask of e1: [rows][32 bytes], bit j of the row = (e1[row, j] > 0)
+  float* colsum_out;                       // RELUGRAD / RELUGRAD_POOL: optional [grid * 4][n_total] partial column sums of `out`
   __nv_bfloat16* out; int64_t ldo;
   int ns_a, ns_b, halo;
   int use_tma;                             // A tiles staged by TMA (3-D tile load / gather4) instead of cp.async

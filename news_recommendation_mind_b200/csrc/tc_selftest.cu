@@ -145,3 +145,44 @@ int mr_tc_selftest(const float* a, int64_t ra, int64_t ca, const float* b, int64
 }
 
 }  // extern "C"
+
+// ---- micro-benchmark: cycles per tcgen05.mma (M = 128, K = 16, bf16) as a function of N, operands fixed in smem ----
+namespace mr {
+__global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(int N, int iters, int b_layout, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid * 16; i < 64 * 1024; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_barrier_init(); }
+  tc::fence_proxy_async();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = tc::make_idesc(128, N, 0, 0);
+    const uint32_t a = tc::smem_u32(smem), b = a + 32 * 1024;
+    const uint64_t da = tc::make_desc_sw(a, 16, 1024, 2, 0);
+    const uint64_t db = b_layout == 2 ? tc::make_desc_sw(b, 16, 1024, 2, 0) : tc::make_desc(b, (uint32_t)N * 16, 128);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) tc::umma(tmem, da, db, idesc, 1);
+    tc::umma_commit(&bar);
+    tc::mbar_wait(&bar, 0);
+    out[0] = clock64() - t0;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+}  // namespace mr
+
+extern "C" __attribute__((visibility("default"))) int mr_debug_mma_rate(int N, int iters, int b_layout, long long* out_device, void* stream) {
+  using namespace mr;
+  if (int rc = require_sm100()) return rc;
+  cudaFuncSetAttribute(tc_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  tc_mma_rate_kernel<<<1, 128, 64 * 1024, as_stream(stream)>>>(N, iters, b_layout, out_device);
+  MR_CHECK_LAUNCH("tc_mma_rate_kernel");
+  return MR_OK;
+}

@@ -1,0 +1,55 @@
+"""Per-kernel device time of the bf16 training step (bench config), measured in situ with CUPTI activity records
+(torch.profiler): warm caches, real overlap -- complements the serialised cold-cache ncu launch list.
+
+    python scripts/step_kernels.py [steps] > gpurun_out/step_kernels.txt
+"""
+import os, sys, collections
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+import news_recommendation_mind_b200 as mr
+from news_recommendation_mind_b200 import data, trainer
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+CFG = bench.CFG
+dev = "cuda:0"
+torch.manual_seed(42)
+man = bench.manager_ns(dev, os.environ.get("MINDREC_PRECISION", "bf16"))
+model = mr.TwoTower(man, mr.BERT_Embedding(man, vocab_size=CFG["V"]), mr.CNN_Encoder(man), mr.RNN_User_Encoder(man)).to(dev)
+opt = trainer.FusedAdam(model, lr=1e-4, bert_lr=6e-6)
+ids, mask = data.make_news_table(CFG["n_news"], CFG["L"])
+devb = [{k: v.to(dev) for k, v in data.make_train_batch(ids, mask, CFG["B"], CFG["C"], CFG["S"], seed=i).items()} for i in range(4)]
+for s in range(5):
+    trainer.train_step(model, devb[s % 4], opt)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for s in range(steps):
+    trainer.train_step(model, devb[s % 4], opt)
+e1.record(); torch.cuda.synchronize()
+print("unprofiled: %.3f ms/step" % (e0.elapsed_time(e1) / steps))
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for s in range(steps):
+        trainer.train_step(model, devb[s % 4], opt)
+    torch.cuda.synchronize()
+agg = collections.OrderedDict()
+seq = []
+for ev in prof.events():
+    if ev.device_type == torch.autograd.DeviceType.CUDA:
+        name = ev.name.split("(")[0]
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+        seq.append((ev.time_range.start, name, ev.device_time if hasattr(ev, "device_time") else ev.cuda_time))
+tot = sum(v[1] for v in agg.values())
+print("%-64s %5s %10s %7s %9s" % ("kernel", "n/step", "us/step", "share", "us/launch"))
+for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    print("%-64s %5.1f %10.1f %6.1f%% %9.1f" % (name[:64], n / steps, us / steps, 100 * us / tot, us / n))
+print("sum of kernel time per step: %.1f us, launches per step: %.1f" % (tot / steps, sum(v[0] for v in agg.values()) / steps))
+if os.environ.get("SEQ"):
+    seq.sort()
+    per = len(seq) // steps
+    print("--- launch sequence of the last step ---")
+    for t, name, us in seq[-per:]:
+        print("%8.1f  %s" % (us, name[:90]))

@@ -176,12 +176,16 @@ def cnn_encoder_bf16_backward_emulation(table, ids, mask, conv_w, conv_b, proj_w
     dot = (p * dp).sum(-1, keepdim=True)
     ds = p * (dp - dot) / math.sqrt(H)
     d_q = (ds.unsqueeze(-1) * key).sum((0, 1))
-    dkp = _bf((ds.unsqueeze(-1) * q * (1 - key * key)).float())
-    dcp = _bf((p.unsqueeze(-1) * g).float())
-    dconv = _bf(((c > 0).double() * (dcp + dkp @ wq)).float())
-    d_proj_b = dkp.sum((0, 1))
+    dkp_f = ds.unsqueeze(-1) * q * (1 - key * key)
+    dkp = _bf(dkp_f.float())
+    dcp = p.unsqueeze(-1) * g
+    if L > 32 or H > 160:                      # generic pooling path: p * d_news is stored as bf16 (fast path: formed in fp32
+        dcp = _bf(dcp.float())                 # inside the RELUGRAD_POOL epilogue, never stored)
+    dconv_f = (c > 0).double() * (dcp + dkp @ wq)
+    dconv = _bf(dconv_f.float())
+    d_proj_b = dkp_f.sum((0, 1))               # bias gradients are summed in fp32 before the bf16 rounding of the stored tensor
     d_proj_w = torch.einsum("nlh,nlk->hk", dkp, c)
-    d_conv_b = dconv.sum((0, 1))
+    d_conv_b = dconv_f.sum((0, 1))
     xpad = torch.nn.functional.pad(x, (0, 0, 1, 1))
     d_conv_w = torch.stack([torch.einsum("nlh,nle->he", dconv, xpad[:, tap:tap + L]) for tap in range(3)], dim=-1)
     gpad = torch.nn.functional.pad(dconv, (0, 0, 1, 1))
