@@ -57,7 +57,7 @@ int64_t news_cnn_tc_workspace_bytes(const mr_cnn_shape* s, int backward) {
   b += 2 * arena_bytes(s->N * s->H, 4);                               // dq / dbq partials (generic pooling path)
   b += arena_bytes(s->N * Hp, 4);                                     // d_news padded to the row pitch
   b += arena_bytes(ceil_div(s->N, 8) * 2 * Hp, 4);                    // per-CTA (dq | dbq) partials of the fast pooling backward
-  b += arena_bytes((int64_t)sm_count() * 4 * Hp, 4);                  // per-warp column sums of dconv (conv-bias gradient)
+  b += arena_bytes((int64_t)sm_count() * 8 * Hp, 4);                  // per-warp column sums of dconv (conv-bias gradient)
   b += arena_bytes(T * 32, 1);                                        // relu'(c) as a bit mask, 32 bytes per token
   b += arena_bytes(colsum_chunks(T) * Hp, 4);
   const int64_t pc = tokred_partial_bytes(s->N, (int)s->L, 3, (int)Kp, (int)Hp);
@@ -170,7 +170,7 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
   float* dbp = ar.take<float>(N * H);
   float* dnp = ar.take<float>(N * Hp);
   float* ppart = ar.take<float>(ceil_div(N, 8) * 2 * Hp);
-  float* csum = ar.take<float>((int64_t)sm_count() * 4 * Hp);
+  float* csum = ar.take<float>((int64_t)sm_count() * 8 * Hp);
   uint8_t* cmask = ar.take<uint8_t>(T * 32);
   float* cp = ar.take<float>(colsum_chunks(T) * Hp);
   const int64_t pb_conv = tokred_partial_bytes(N, (int)L, 3, (int)Kp, (int)Hp);
@@ -238,9 +238,9 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
     a.e1 = c; a.lde = Hp; a.out = dcv; a.ldo = Hp;
     a.colsum_out = csum;
     if (int rc = tapgemm_plan(a, &plan)) return rc;
-    MR_REQUIRE(plan.grid <= sm_count(), MR_ERR_LAUNCH, "mr_news_cnn_bwd: tap-GEMM grid %d exceeds the column-sum partials", plan.grid);
+    MR_REQUIRE(plan.colsum_rows <= sm_count() * 8, MR_ERR_LAUNCH, "mr_news_cnn_bwd: tap-GEMM grid %d exceeds the column-sum partials", plan.grid);
     if (int rc = tapgemm_launch(plan, st)) return rc;
-    e = colsum_small(csum, Hp, d_conv_b, (int64_t)plan.grid * 4, H, st);
+    e = colsum_small(csum, Hp, d_conv_b, (int64_t)plan.colsum_rows, H, st);
     MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "colsum dbc: %s", cudaGetErrorString(e));
   }
   // 4. d_conv_w[h,e,tap] = sum_t x[t+tap-1, e] dconv[t, h]

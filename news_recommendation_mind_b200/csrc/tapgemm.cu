@@ -34,9 +34,13 @@ struct Ring {
 };
 
 // POOL = true: the instantiation whose epilogue is TG_EPI_RELUGRAD_POOL (kept apart so that neither epilogue pays for the
-// other's registers and instructions)
-template <bool POOL>
-__global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArgs p, const __grid_constant__ CUtensorMap tmap) {
+// other's registers and instructions).
+// EPI2 = true (dense A staged by TMA, N <= 256): 12 warps, warps 8-11 are a SECOND epilogue group.  Group w owns
+// accumulator stage w, i.e. every other tile of the CTA: an epilogue is a long dependent chain per thread (TMEM load,
+// convert, activation, pack, store), so one warp per scheduler leaves most issue slots empty; two tiles in flight fill them.
+template <bool POOL, bool EPI2>
+__global__ void __launch_bounds__(EPI2 ? TG_THREADS2 : TG_THREADS, 1) tapgemm_kernel(const TapGemmArgs p, const __grid_constant__ CUtensorMap tmap) {
+  constexpr int NT = EPI2 ? TG_THREADS2 : TG_THREADS;
   long long dbg_acc[4] = {0, 0, 0, 0};
   const long long dbg_t0 = clock64();
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -70,11 +74,11 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
   // ---- one-time setup ----------------------------------------------------------------------
   {
     const uint32_t a_bytes = (uint32_t)p.ns_a * p.a_slot_bytes;
-    for (uint32_t i = tid * 16; i < a_bytes; i += TG_THREADS * 16) *reinterpret_cast<uint4*>(sA + i) = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < 512; i += TG_THREADS)
+    for (uint32_t i = tid * 16; i < a_bytes; i += NT * 16) *reinterpret_cast<uint4*>(sA + i) = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 512; i += NT)
       sbias[i] = (p.bias != nullptr && i < p.n_valid) ? p.bias[i] + (p.bias2 != nullptr ? p.bias2[i] : 0.f) : 0.f;
     if (p.ids != nullptr)
-      for (uint32_t i = tid; i < (uint32_t)p.n_hot * (hot_pitch / 16); i += TG_THREADS) {
+      for (uint32_t i = tid; i < (uint32_t)p.n_hot * (hot_pitch / 16); i += NT) {
         const uint32_t h = i / (hot_pitch / 16), q = i % (hot_pitch / 16);
         reinterpret_cast<uint4*>(hot + (size_t)h * hot_pitch)[q] = __ldg(reinterpret_cast<const uint4*>(p.a + p.hot_ids[h] * p.lda) + q);
       }
@@ -99,20 +103,27 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
   }
   const uint32_t tmem = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < 4 || (EPI2 && warp >= 8)) {
     // =================================== epilogue ===========================================
-    const int r = tid;
+    const int wg = EPI2 ? (warp >> 3) : 0;                   // epilogue group (EPI2: group w <-> accumulator stage w)
+    const int r = tid & 127;
     const int g = r % p.G, l = r / p.G;
     const bool row_ok = l < p.L;
     const int64_t row_off = (int64_t)g * p.L + l;            // token offset inside the tile's G titles
     Ring acc(acc_stages);
+    if (EPI2) acc.pos = (uint32_t)wg;
+    auto acc_advance = [&]() {
+      if (EPI2) acc.phase ^= 1u;                              // same stage every time, next use
+      else acc.next();
+    };
+    const int64_t tile_step = (int64_t)gridDim.x * (EPI2 ? 2 : 1);
     float colacc[8];                      // column sums of the stored rows: lane j, slot ci <-> column 32 ci + j
 #pragma unroll
     for (int ci = 0; ci < 8; ++ci) colacc[ci] = 0.f;
     const int lane = tid & 31;
     float* sdn = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(hot) + 15) & ~(uintptr_t)15);     // POOL: [2][G][dn_pitch]
     const int dn_pitch = n_total + 4;        // +16 B per row: the G rows read by one LDS.128 fall into different banks
-    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    for (int64_t tile = blockIdx.x + (int64_t)wg * gridDim.x; tile < p.n_tiles; tile += tile_step) {
       const int64_t t = tile * p.G * p.L + row_off;
       const bool valid = row_ok && (tile * p.G + g < p.n_titles) && t < p.n_rows;
       if constexpr (POOL) {
@@ -130,19 +141,19 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
         float* sd_stage = sdn + (size_t)acc.pos * p.G * dn_pitch;
         {
           const int pieces = n_total >> 2;
-          for (int i = tid; i < p.G * pieces; i += 128) {
+          for (int i = r; i < p.G * pieces; i += 128) {
             const int gg = i / pieces, q = i - gg * pieces;
             const int64_t title = tile * p.G + gg;
             float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (title < p.n_titles) v4 = __ldg(reinterpret_cast<const float4*>(p.dnp + title * p.ldn) + q);
             *reinterpret_cast<float4*>(sd_stage + gg * dn_pitch + 4 * q) = v4;
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
         }
         const float4* dn_row = reinterpret_cast<const float4*>(sd_stage + g * dn_pitch);
         TG_TIMED(0, tc::mbar_wait(&t_full[acc.pos], acc.phase));
         tc::tc_fence_after();
-        const uint32_t tb = tmem + ((uint32_t)(warp * 32) << 16) + acc.pos * 256u;
+        const uint32_t tb = tmem + ((uint32_t)((warp & 3) * 32) << 16) + acc.pos * 256u;
 #pragma unroll
         for (int ci = 0; ci < 5; ++ci) {
           if (ci * 32 < n_total) {
@@ -214,13 +225,13 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
         }
         tc::tc_fence_before();
         tc::mbar_arrive(&t_empty[acc.pos]);
-        acc.next();
+        acc_advance();
         continue;
       }
       if constexpr (!POOL) {
       TG_TIMED(0, tc::mbar_wait(&t_full[acc.pos], acc.phase));
       tc::tc_fence_after();
-      const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + acc.pos * 256u;
+      const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16) + acc.pos * 256u;
       int col0 = 0;
       for (int sub = 0; sub < p.n_sub; ++sub) {
         const int nsub = sub == 0 ? p.nsz[0] : p.nsz[1];
@@ -305,11 +316,11 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
       }
       tc::tc_fence_before();
       tc::mbar_arrive(&t_empty[acc.pos]);
-      acc.next();
+      acc_advance();
       }
     }
     if (p.colsum_out != nullptr) {
-      float* cs = p.colsum_out + ((size_t)blockIdx.x * 4 + warp) * n_total;
+      float* cs = p.colsum_out + ((size_t)blockIdx.x * (EPI2 ? 8 : 4) + wg * 4 + (warp & 3)) * n_total;
 #pragma unroll
       for (int ci = 0; ci < 8; ++ci)
         if (ci * 32 + lane < n_total) cs[ci * 32 + lane] = colacc[ci];
@@ -461,7 +472,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tapgemm_kernel(const TapGemmArg
         }
       }
     }
-  } else {
+  } else if constexpr (!EPI2) {
     // =================================== A producers (cp.async) =============================
     const int ptid = tid - 192;            // 0..127
     const int rgrp = ptid >> 3, j = ptid & 7;
@@ -665,6 +676,9 @@ int tapgemm_plan(TapGemmArgs& a, TapGemmPlan* plan) {
   // (PAD/[CLS]/[SEP] rows hammer a few L2 lines when fetched by every SM; MINDREC_TMA_GATHER=1 selects gather4).
   a.hot_reps = a.ids != nullptr ? hot_replicas() : 0;
   a.use_tma = use_tma_default() && (a.ids == nullptr || use_tma_gather() || a.hot_reps > 0) ? 1 : 0;
+  if (a.epi == TG_EPI_RELUGRAD_POOL) a.use_tma = 1;          // this epilogue only exists in the two-group (TMA) instantiation
+  plan->epi2 = a.use_tma && a.ids == nullptr && n_total <= 256;
+  plan->colsum_rows = 0;
   a.halo = a.taps > 1 ? (int)align_up(G, 8) : 0;      // multiple of 8 rows: tile rows start on a 1024-byte swizzle period
   a.a_ps = 0;
   a.a_slot_bytes = (uint32_t)(align_up(128 + 2 * a.halo, 8) * 128);      // one k-chunk of 64 columns, SWIZZLE_128B rows
@@ -720,6 +734,7 @@ int tapgemm_plan(TapGemmArgs& a, TapGemmPlan* plan) {
   plan->smem_bytes = (size_t)ns_a * a.a_slot_bytes + (size_t)ns_b * a.b_slot_bytes + TG_SMEM_FIXED + hot_bytes;
   int64_t g = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
   plan->grid = (int)(g < 1 ? 1 : g);
+  plan->colsum_rows = plan->grid * (plan->epi2 ? 8 : 4);
   return MR_OK;
 }
 
@@ -727,8 +742,9 @@ int tapgemm_launch(const TapGemmPlan& plan, cudaStream_t stream) {
   if (plan.args.n_titles <= 0) return MR_OK;
   static thread_local size_t attr_set = 0;
   if (plan.smem_bytes > attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM_MAX);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM_MAX);
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM_MAX);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM_MAX);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM_MAX);
     MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "tap gemm: cannot opt in to %zu bytes of shared memory: %s", TG_SMEM_MAX,
                cudaGetErrorString(e));
     attr_set = TG_SMEM_MAX;
@@ -736,8 +752,9 @@ int tapgemm_launch(const TapGemmPlan& plan, cudaStream_t stream) {
   TapGemmArgs args = plan.args;
   args.dbg = g_tapgemm_dbg;
   if (g_tapgemm_dbg != nullptr) g_tapgemm_dbg += 148 * 4 * 5;     // one record block per launch
-  if (args.epi == TG_EPI_RELUGRAD_POOL) tapgemm_kernel<true><<<plan.grid, TG_THREADS, plan.smem_bytes, stream>>>(args, plan.tmap);
-  else tapgemm_kernel<false><<<plan.grid, TG_THREADS, plan.smem_bytes, stream>>>(args, plan.tmap);
+  if (args.epi == TG_EPI_RELUGRAD_POOL) tapgemm_kernel<true, true><<<plan.grid, TG_THREADS2, plan.smem_bytes, stream>>>(args, plan.tmap);
+  else if (plan.epi2) tapgemm_kernel<false, true><<<plan.grid, TG_THREADS2, plan.smem_bytes, stream>>>(args, plan.tmap);
+  else tapgemm_kernel<false, false><<<plan.grid, TG_THREADS, plan.smem_bytes, stream>>>(args, plan.tmap);
   MR_CHECK_LAUNCH("tapgemm_kernel");
   return MR_OK;
 }

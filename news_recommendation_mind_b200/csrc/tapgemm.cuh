@@ -30,6 +30,7 @@ enum { TG_EPI_BIAS_RELU = 0, TG_EPI_BIAS_TANH = 1, TG_EPI_RELUGRAD = 2, TG_EPI_S
        TG_EPI_RELUGRAD_POOL = 5 };
 constexpr int TG_KC = 64;          // k-chunk (elements) = 8 panels
 constexpr int TG_THREADS = 320;
+constexpr int TG_THREADS2 = 384;   // two epilogue groups (dense A by TMA): warps 0-3 / 8-11 epilogue, 4 MMA, 5 weights, 6 TMA
 constexpr int TG_MAX_SLOTS = 8;
 constexpr int TG_W_REPS = 4;       // replicas of the packed weights in global memory (spreads L2 slice load)
 
@@ -65,6 +66,8 @@ struct TapGemmPlan {
   TapGemmArgs args;
   size_t smem_bytes;
   int grid;
+  bool epi2;                               // two-epilogue-group instantiation (384 threads)
+  int colsum_rows;                         // rows of args.colsum_out this launch writes (grid x epilogue warps)
 };
 
 inline int64_t tapgemm_pack_bytes(int taps, int n_total, int K) {      // all replicas
