@@ -130,6 +130,20 @@ MR_API int mr_news_cnn_bwd(const mr_cnn_shape* s,
                     float* d_query, void* d_emb,
                     void* workspace, int64_t workspace_bytes, void* stream);
 
+/* MR_BF16, ids path: the same backward, but the gradient of the token table is produced directly (dense [V,E] fp32,
+ * padding row zero; replaces mr_news_cnn_bwd(d_emb) + mr_embed_grad_segreduce = autograd of BERT.py:39 + CNN.py:41).
+ * The conv-output gradient is first summed per vocabulary row (sorted token positions, fixed-order partial sums, no
+ * atomics), so the table- and filter-gradient GEMMs run over V rows instead of N*L tokens.  `table_bf16` is the padded
+ * bf16 table the forward gathered from, with table_rows >= align_up(V, 32) rows (rows >= V zero).  E % 4 == 0. */
+MR_API int64_t mr_news_cnn_bwd_table_workspace_bytes(const mr_cnn_shape* s);
+MR_API int mr_news_cnn_bwd_table(const mr_cnn_shape* s,
+                    const void* ids, int ids_i64, const void* table_bf16, int64_t table_rows,
+                    const float* conv_w, const float* proj_w, const float* query,
+                    const void* c_save, const void* key_save, const float* prob, const float* d_news,
+                    float* d_conv_w, float* d_conv_b, float* d_proj_w, float* d_proj_b, float* d_query,
+                    float* d_table, int64_t padding_idx,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ----------------------------------------------------------------------------------------------
  * Recurrent user encoders.   models/Encoders/RNN.py:36-73 (RNN_User_Encoder, LSTM / GRU) and
  *                             RNN.py:76-104 (LSTUR: h0 given, no length masking)

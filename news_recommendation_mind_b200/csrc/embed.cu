@@ -14,6 +14,7 @@
 //   reference produces, so that a dense Adam step sees every row).
 #include <cub/cub.cuh>
 #include "common.cuh"
+#include "embed.cuh"
 
 namespace mr {
 
@@ -164,18 +165,24 @@ seg_reduce_l1_kernel(const T* __restrict__ d_emb, int64_t ld, const int32_t* __r
 constexpr int SEG_HEAVY = 8;
 constexpr int SEG_SPLIT = 4;      // CTAs per heavy row
 
+template <class TO> __device__ __forceinline__ TO seg_out(float v);
+template <> __device__ __forceinline__ float seg_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 seg_out<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
+
+// TO = float: the dense table gradient;  TO = bf16: the grouped conv-gradient rows S (row pitch ldo)
+template <class TO>
 __global__ void __launch_bounds__(256)
 seg_reduce_l2_kernel(const int32_t* __restrict__ chunk_off, const int32_t* __restrict__ nchunk,
-                     const float* __restrict__ partial, float* __restrict__ d_table, int64_t V, int64_t E,
+                     const float* __restrict__ partial, TO* __restrict__ d_table, int64_t ldo, int64_t V, int64_t E,
                      int32_t* __restrict__ heavy_count, int32_t* __restrict__ heavy_rows, int32_t max_heavy) {
   const int lane = threadIdx.x & 31;
   const int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (v >= V) return;
   const int32_t n = nchunk[v];
   if (n == 1) return;                                   // written by level 1
-  float* dst = d_table + v * E;
+  TO* dst = d_table + v * ldo;
   if (n == 0) {
-    for (int64_t e = lane; e < E; e += 32) dst[e] = 0.f;
+    for (int64_t e = lane; e < E; e += 32) dst[e] = seg_out<TO>(0.f);
     return;
   }
   if (n > SEG_HEAVY) {
@@ -189,7 +196,7 @@ seg_reduce_l2_kernel(const int32_t* __restrict__ chunk_off, const int32_t* __res
   for (int64_t e = lane; e < E; e += 32) {
     float s = 0.f;
     for (int32_t j = 0; j < n; ++j) s += src[(int64_t)j * E + e];
-    dst[e] = s;
+    dst[e] = seg_out<TO>(s);
   }
 }
 
@@ -221,8 +228,9 @@ seg_reduce_heavy_kernel(const int32_t* __restrict__ chunk_off, const int32_t* __
   }
 }
 
+template <class TO>
 __global__ void __launch_bounds__(256)
-seg_reduce_heavy_final_kernel(const float* __restrict__ partial2, float* __restrict__ d_table,
+seg_reduce_heavy_final_kernel(const float* __restrict__ partial2, TO* __restrict__ d_table, int64_t ldo,
                               const int32_t* __restrict__ heavy_count, const int32_t* __restrict__ heavy_rows, int64_t E) {
   const int h = blockIdx.x;
   if (h >= *heavy_count) return;
@@ -231,7 +239,7 @@ seg_reduce_heavy_final_kernel(const float* __restrict__ partial2, float* __restr
     float s = 0.f;
 #pragma unroll
     for (int sp = 0; sp < SEG_SPLIT; ++sp) s += partial2[((int64_t)h * SEG_SPLIT + sp) * E + e];
-    d_table[(int64_t)v * E + e] = s;
+    d_table[(int64_t)v * ldo + e] = seg_out<TO>(s);
   }
 }
 
@@ -250,6 +258,154 @@ static EmbedGradPlan plan_embed_grad(int64_t T, int64_t E, int64_t V) {
                                   (const int32_t*)nullptr, (int32_t*)nullptr, (int)T, 0, bits);
   cub::DeviceScan::ExclusiveSum(nullptr, p.cub_scan_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, (int)V + 1);
   return p;
+}
+
+// ---- token-grouped conv gradient ("sum before multiply") -------------------------------------------------------------
+// Every use of a vocabulary row v in the conv input contributes  x_v (outer) dconv[t - tap + 1]  to the filter gradient
+// and  dconv[t - tap + 1] W_tap^T  to the gradient of row v.  Both are linear in dconv, so the rows are first summed per
+// vocabulary row:   S[v, tap, :] = sum over tokens t with ids[t] = v of dconv[t + 1 - tap, :]   (same title only),
+// and the two GEMMs then run over V rows instead of T tokens (news_cnn_tc.cu).  Same machinery as the table gradient
+// above (sorted token positions, <= 32-row chunks per warp, fixed-order partial sums, no atomics); a token's "row" is
+// the 3 x Hp concatenation of its right neighbour, itself and its left neighbour in dconv.
+template <int MAXV>     // 16-byte vectors per lane: 3 * Hp / 8 <= 32 * MAXV
+__global__ void __launch_bounds__(256)
+group_taps_l1_kernel(const __nv_bfloat16* __restrict__ dconv, int64_t ld, int L, int pieces, const int32_t* __restrict__ sorted_pos,
+                     const int32_t* __restrict__ seg_start, const int32_t* __restrict__ chunk_off,
+                     const int32_t* __restrict__ chunk_row, const int32_t* __restrict__ nchunk,
+                     __nv_bfloat16* __restrict__ S, int64_t lds, float* __restrict__ partial, int64_t n_chunks, int64_t V) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ch = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (ch >= n_chunks || ch >= chunk_off[V]) return;
+  const int32_t v = chunk_row[ch];
+  const int32_t j = (int32_t)ch - chunk_off[v];
+  const int32_t beg = seg_start[v] + j * SEG_CHUNK;
+  const int32_t end = min(seg_start[v + 1], beg + SEG_CHUNK);
+  const int nvec = 3 * pieces;
+  int shift[MAXV], col[MAXV];             // vector i = lane + 32 a: tap = i / pieces reads row t + 1 - tap, columns 8 (i % pieces)..
+#pragma unroll
+  for (int a = 0; a < MAXV; ++a) {
+    const int i = lane + 32 * a;
+    const int tap = i / pieces;
+    shift[a] = 1 - tap;
+    col[a] = (i - tap * pieces) * 8;
+  }
+  float acc[MAXV][8];
+#pragma unroll
+  for (int a = 0; a < MAXV; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+  // my = this lane's sorted position (one coalesced load per chunk), broadcast per row
+  const int32_t my = (beg + lane < end) ? sorted_pos[beg + lane] : 0;
+#pragma unroll 4
+  for (int32_t r = 0; r < end - beg; ++r) {
+    const int32_t t = __shfl_sync(0xffffffffu, my, r);
+    const int l = t % L;
+#pragma unroll
+    for (int a = 0; a < MAXV; ++a) {
+      const int i = lane + 32 * a;
+      const int ls = l + shift[a];
+      if (i < nvec && ls >= 0 && ls < L) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(dconv + (int64_t)(t + shift[a]) * ld + col[a]));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const float2 f = __bfloat1622float2(h[w]);
+          acc[a][2 * w] += f.x;
+          acc[a][2 * w + 1] += f.y;
+        }
+      }
+    }
+  }
+  const bool direct = nchunk[v] == 1;
+#pragma unroll
+  for (int a = 0; a < MAXV; ++a) {
+    const int i = lane + 32 * a;
+    if (i < nvec) {
+      if (direct) {
+        uint4 o;
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(acc[a][0], acc[a][1]), p1 = __floats2bfloat162_rn(acc[a][2], acc[a][3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(acc[a][4], acc[a][5]), p3 = __floats2bfloat162_rn(acc[a][6], acc[a][7]);
+        o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+        o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+        *reinterpret_cast<uint4*>(S + (int64_t)v * lds + i * 8) = o;
+      } else {
+        float4* d = reinterpret_cast<float4*>(partial + ch * (int64_t)(nvec * 8) + i * 8);
+        d[0] = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+        d[1] = make_float4(acc[a][4], acc[a][5], acc[a][6], acc[a][7]);
+      }
+    }
+  }
+}
+
+int64_t token_group_workspace_bytes(int64_t T, int64_t Hp, int64_t V) {
+  if (T < 0 || V < 1 || T >= (1ll << 31)) return -1;
+  const int64_t E = 3 * Hp;
+  EmbedGradPlan p = plan_embed_grad(T, E, V);
+  int64_t b = 0;
+  b += 4 * arena_bytes(T, 4);
+  b += 3 * arena_bytes(V + 1, 4);
+  b += arena_bytes(p.max_chunks, 4);
+  b += arena_bytes(p.max_chunks * E, 4);
+  b += arena_bytes(p.max_heavy + 1, 4) + arena_bytes(p.max_heavy * SEG_SPLIT * E, 4);
+  b += arena_bytes((int64_t)p.cub_sort_bytes, 1) + arena_bytes((int64_t)p.cub_scan_bytes, 1);
+  return b + 256;
+}
+
+int token_group_taps(const void* ids, int ids_i64, const __nv_bfloat16* dconv, int64_t ld, int L, int64_t T, int64_t V,
+                     __nv_bfloat16* S, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  const int64_t Hp = ld, E = 3 * Hp;
+  MR_REQUIRE(Hp % 8 == 0 && 3 * Hp / 8 <= 64, MR_ERR_UNSUPPORTED, "token grouping: row pitch %lld", (long long)Hp);
+  EmbedGradPlan p = plan_embed_grad(T, E, V);
+  Arena ar(workspace, workspace_bytes);
+  int32_t* keys = ar.take<int32_t>(T);
+  int32_t* vals = ar.take<int32_t>(T);
+  int32_t* skeys = ar.take<int32_t>(T);
+  int32_t* svals = ar.take<int32_t>(T);
+  int32_t* seg_start = ar.take<int32_t>(V + 1);
+  int32_t* nchunk = ar.take<int32_t>(V + 1);
+  int32_t* chunk_off = ar.take<int32_t>(V + 1);
+  int32_t* chunk_row = ar.take<int32_t>(p.max_chunks);
+  float* partial = ar.take<float>(p.max_chunks * E);
+  int32_t* heavy = ar.take<int32_t>(p.max_heavy + 1);
+  float* partial2 = ar.take<float>(p.max_heavy * SEG_SPLIT * E);
+  void* cub_sort = ar.take<char>((int64_t)p.cub_sort_bytes);
+  void* cub_scan = ar.take<char>((int64_t)p.cub_scan_bytes);
+  MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "token grouping: workspace too small (%lld given)", (long long)workspace_bytes);
+  make_keys_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, st>>>(ids, ids_i64, keys, vals, T, V);
+  MR_CHECK_LAUNCH("make_keys_kernel");
+  int bits = 1;
+  while ((1ll << bits) < V) ++bits;
+  size_t sb = p.cub_sort_bytes;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_sort, sb, keys, skeys, vals, svals, (int)T, 0, bits, st);
+  MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "radix sort: %s", cudaGetErrorString(e));
+  count_launch(2 * ((bits + 7) / 8) + 1);
+  seg_bounds_kernel<<<(unsigned)ceil_div(V + 1, 256), 256, 0, st>>>(skeys, seg_start, T, V);
+  MR_CHECK_LAUNCH("seg_bounds_kernel");
+  chunk_count_kernel<<<(unsigned)ceil_div(V + 1, 256), 256, 0, st>>>(seg_start, nchunk, V, -1);     // every row, padding row included
+  MR_CHECK_LAUNCH("chunk_count_kernel");
+  size_t cb = p.cub_scan_bytes;
+  e = cub::DeviceScan::ExclusiveSum(cub_scan, cb, nchunk, chunk_off, (int)V + 1, st);
+  MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "scan: %s", cudaGetErrorString(e));
+  count_launch(2);
+  chunk_fill_kernel<<<(unsigned)ceil_div(V, 256), 256, 0, st>>>(nchunk, chunk_off, chunk_row, V);
+  MR_CHECK_LAUNCH("chunk_fill_kernel");
+  const int pieces = (int)(Hp / 8);
+  if (3 * pieces <= 32)
+    group_taps_l1_kernel<1><<<(unsigned)ceil_div(p.max_chunks, 8), 256, 0, st>>>(dconv, ld, L, pieces, svals, seg_start, chunk_off, chunk_row,
+                                                                               nchunk, S, E, partial, p.max_chunks, V);
+  else
+    group_taps_l1_kernel<2><<<(unsigned)ceil_div(p.max_chunks, 8), 256, 0, st>>>(dconv, ld, L, pieces, svals, seg_start, chunk_off, chunk_row,
+                                                                               nchunk, S, E, partial, p.max_chunks, V);
+  MR_CHECK_LAUNCH("group_taps_l1_kernel");
+  cudaMemsetAsync(heavy, 0, sizeof(int32_t), st);
+  seg_reduce_l2_kernel<__nv_bfloat16><<<(unsigned)ceil_div(V, 8), 256, 0, st>>>(chunk_off, nchunk, partial, S, E, V, E, heavy, heavy + 1,
+                                                                                (int32_t)p.max_heavy);
+  MR_CHECK_LAUNCH("seg_reduce_l2_kernel");
+  seg_reduce_heavy_kernel<<<(unsigned)(p.max_heavy * SEG_SPLIT), 256, 0, st>>>(chunk_off, nchunk, partial, partial2, heavy, heavy + 1, E);
+  MR_CHECK_LAUNCH("seg_reduce_heavy_kernel");
+  seg_reduce_heavy_final_kernel<__nv_bfloat16><<<(unsigned)p.max_heavy, 256, 0, st>>>(partial2, S, E, heavy, heavy + 1, E);
+  MR_CHECK_LAUNCH("seg_reduce_heavy_final_kernel");
+  return MR_OK;
 }
 
 }  // namespace mr
@@ -345,13 +501,13 @@ int mr_embed_grad_segreduce(const void* ids, int ids_i64, const void* d_emb, int
         static_cast<const __nv_bfloat16*>(d_emb), E4, svals, seg_start, chunk_off, chunk_row, nchunk, d_table, partial, p.max_chunks, E, V);
   MR_CHECK_LAUNCH("seg_reduce_l1_kernel");
   cudaMemsetAsync(heavy, 0, sizeof(int32_t), st);
-  seg_reduce_l2_kernel<<<(unsigned)ceil_div(V, 8), 256, 0, st>>>(chunk_off, nchunk, partial, d_table, V, E, heavy, heavy + 1,
-                                                                 (int32_t)p.max_heavy);
+  seg_reduce_l2_kernel<float><<<(unsigned)ceil_div(V, 8), 256, 0, st>>>(chunk_off, nchunk, partial, d_table, E, V, E, heavy, heavy + 1,
+                                                                        (int32_t)p.max_heavy);
   MR_CHECK_LAUNCH("seg_reduce_l2_kernel");
   seg_reduce_heavy_kernel<<<(unsigned)(p.max_heavy * SEG_SPLIT), 256, 0, st>>>(chunk_off, nchunk, partial, partial2, heavy,
                                                                              heavy + 1, E);
   MR_CHECK_LAUNCH("seg_reduce_heavy_kernel");
-  seg_reduce_heavy_final_kernel<<<(unsigned)p.max_heavy, 256, 0, st>>>(partial2, d_table, heavy, heavy + 1, E);
+  seg_reduce_heavy_final_kernel<float><<<(unsigned)p.max_heavy, 256, 0, st>>>(partial2, d_table, E, heavy, heavy + 1, E);
   MR_CHECK_LAUNCH("seg_reduce_heavy_final_kernel");
   return MR_OK;
 }

@@ -217,4 +217,35 @@ int mr_news_cnn_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
                  as_stream(stream));
 }
 
+int64_t mr_news_cnn_bwd_table_workspace_bytes(const mr_cnn_shape* s) {
+  if (!s || s->precision != MR_BF16) return -1;
+  return mr::news_cnn_tc_workspace_bytes(s, 2);
+}
+
+int mr_news_cnn_bwd_table(const mr_cnn_shape* s, const void* ids, int ids_i64, const void* table_bf16, int64_t table_rows,
+                          const float* conv_w, const float* proj_w, const float* query, const void* c_save,
+                          const void* key_save, const float* prob, const float* d_news, float* d_conv_w, float* d_conv_b,
+                          float* d_proj_w, float* d_proj_b, float* d_query, float* d_table, int64_t padding_idx,
+                          void* workspace, int64_t workspace_bytes, void* stream) {
+  using namespace mr;
+  if (int rc = require_sm100()) return rc;
+  if (int rc = check_shape(s, "mr_news_cnn_bwd_table")) return rc;
+  MR_REQUIRE(s->precision == MR_BF16, MR_ERR_UNSUPPORTED, "mr_news_cnn_bwd_table: bf16 path only");
+  MR_REQUIRE(ids && table_bf16 && conv_w && proj_w && query && c_save && key_save && prob && d_news && d_conv_w && d_conv_b &&
+                 d_proj_w && d_proj_b && d_query && d_table, MR_ERR_NULL, "mr_news_cnn_bwd_table: null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (s->N == 0) {
+    cudaMemsetAsync(d_conv_w, 0, sizeof(float) * s->H * s->E * 3, st);
+    cudaMemsetAsync(d_conv_b, 0, sizeof(float) * s->H, st);
+    cudaMemsetAsync(d_proj_w, 0, sizeof(float) * s->H * s->H, st);
+    cudaMemsetAsync(d_proj_b, 0, sizeof(float) * s->H, st);
+    cudaMemsetAsync(d_query, 0, sizeof(float) * s->H, st);
+    cudaMemsetAsync(d_table, 0, sizeof(float) * s->V * s->E, st);
+    return MR_OK;
+  }
+  return news_cnn_tc_bwd(s, ids, ids_i64, nullptr, table_bf16, conv_w, proj_w, query, c_save, key_save, prob, d_news, nullptr,
+                         d_conv_w, d_conv_b, d_proj_w, d_proj_b, d_query, nullptr, workspace, workspace_bytes, st, d_table,
+                         table_rows, padding_idx);
+}
+
 }  // extern "C"

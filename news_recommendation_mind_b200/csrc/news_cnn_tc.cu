@@ -15,6 +15,7 @@
 #include "pool_kernels.cuh"
 #include "tapgemm.cuh"
 #include "tokred.cuh"
+#include "embed.cuh"
 #include "gemm_simt.cuh"
 
 namespace mr {
@@ -53,6 +54,13 @@ int64_t news_cnn_tc_workspace_bytes(const mr_cnn_shape* s, int backward) {
   b += arena_bytes(tapgemm_pack_bytes(1, (int)Hp, (int)Hp), 1);
   b += arena_bytes(T * Kp, 2);
   b += 2 * arena_bytes(T * Hp, 2);                                    // dkp, dc_pool / dconv
+  if (backward == 2) {                                                // token-grouped table / filter gradient
+    const int64_t Vp = align_up(s->V, 128);
+    b += arena_bytes(Vp * 3 * Hp, 2);                                 // S
+    b += arena_bytes(token_group_workspace_bytes(T, Hp, s->V), 1);
+    b += arena_bytes(tapgemm_pack_bytes(1, 256, (int)(3 * Hp)), 1);
+    b += arena_bytes(tokred_partial_bytes(ceil_div(s->V, 32), 32, 1, (int)Kp, (int)Hp), 1);
+  }
   b += arena_bytes(tapgemm_pack_bytes(3, 256, (int)Hp), 1);           // dgrad weights (one block of <= 256 columns)
   b += 2 * arena_bytes(s->N * s->H, 4);                               // dq / dbq partials (generic pooling path)
   b += arena_bytes(s->N * Hp, 4);                                     // d_news padded to the row pitch
@@ -152,7 +160,8 @@ __global__ void add_rows_bf16_kernel(__nv_bfloat16* __restrict__ dst, int64_t ld
 int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const float* emb, const void* table,
                     const float* conv_w, const float* proj_w, const float* query, const void* c_save, const void* key_save,
                     const float* prob, const float* d_news, const float* d_c, float* d_conv_w, float* d_conv_b,
-                    float* d_proj_w, float* d_proj_b, float* d_query, void* d_emb, void* ws, int64_t wsb, cudaStream_t st) {
+                    float* d_proj_w, float* d_proj_b, float* d_query, void* d_emb, void* ws, int64_t wsb, cudaStream_t st,
+                    float* d_table, int64_t table_rows, int64_t padding_idx) {
   if (int rc = check_tc(s, "mr_news_cnn_bwd")) return rc;
   const int64_t N = s->N, L = s->L, E = s->E, H = s->H, T = N * L, Hp = hp_of(s), Kp = kp_of(s);
   const __nv_bfloat16* c = static_cast<const __nv_bfloat16*>(c_save);
@@ -242,6 +251,57 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
     if (int rc = tapgemm_launch(plan, st)) return rc;
     e = colsum_small(csum, Hp, d_conv_b, (int64_t)plan.colsum_rows, H, st);
     MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "colsum dbc: %s", cudaGetErrorString(e));
+  }
+  if (d_table != nullptr) {
+    // 4'/5'. token-grouped form of steps 4 and 5 (embed.cuh): S[v, tap, :] = sum_{t: ids[t]=v} dconv[t+1-tap, :], then
+    //   d_table[v, e]      = sum_{tap,h} S[v,tap,h] conv_w[h,e,tap]        (dense [V,E]: rows of absent tokens come out zero)
+    //   d_conv_w[h,e,tap]  = sum_v table[v,e] S[v,tap,h]
+    // -- the same sums as steps 4/5 with the token sum taken first, so both GEMMs run over V rows instead of T tokens.
+    const int64_t V = s->V, Vp = align_up(V, 128), SH = 3 * Hp;
+    MR_REQUIRE(ids != nullptr && table != nullptr && E % 4 == 0 && table_rows >= align_up(V, 32), MR_ERR_BAD_SHAPE,
+               "mr_news_cnn_bwd_table: needs the ids path, E %% 4 == 0 and a bf16 table with >= %lld (zero padded) rows, got %lld",
+               (long long)align_up(V, 32), (long long)table_rows);
+    __nv_bfloat16* S = ar.take<__nv_bfloat16>(Vp * SH);
+    const int64_t gwb = token_group_workspace_bytes(T, Hp, V);
+    void* gws = ar.take<uint8_t>(gwb);
+    uint8_t* wtab = ar.take<uint8_t>(tapgemm_pack_bytes(1, 256, (int)SH));
+    const int64_t n_rows32 = ceil_div(V, 32);
+    float* partial_v = ar.take<float>(tokred_partial_bytes(n_rows32, 32, 1, (int)Kp, (int)Hp) / 4);
+    MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "mr_news_cnn_bwd_table: workspace too small (%lld given)", (long long)wsb);
+    if (Vp > V) cudaMemsetAsync(S + V * SH, 0, (size_t)(Vp - V) * SH * 2, st);
+    if (int rc = token_group_taps(ids, ids_i64, dcv, Hp, (int)L, T, V, S, gws, gwb, st)) return rc;
+    // d_table = S [V, 3Hp] x W^T, W[e, tap*Hp + h] = conv_w[h, e, tap]; fp32 output rows, <= 256 columns per launch
+    const int64_t nblk2 = ceil_div(Kp, 256);
+    const int64_t nbsz2 = align_up(ceil_div(Kp, nblk2), 16);
+    for (int64_t blk = 0; blk < nblk2; ++blk) {
+      const int64_t n0 = blk * nbsz2;
+      const int64_t nb = (Kp - n0) < nbsz2 ? (Kp - n0) : nbsz2;
+      const int64_t nv = (E - n0) < nb ? (E - n0) : nb;
+      if (nv <= 0) break;
+      if (int rc = tapgemm_pack_blocks(conv_w + n0 * 3, wtab, 1, (int)nb, (int)SH, (int)nv, (int)H, 3, 3 * E, 0, (int)Hp, 1, st)) return rc;
+      TapGemmArgs a{};
+      TapGemmPlan plan;
+      a.n_titles = n_rows32; a.L = 32; a.taps = 1; a.dir = 1; a.K = (int)SH;
+      a.n_sub = 1; a.nsz[0] = (int)nb;
+      a.ids = nullptr; a.a = S; a.lda = SH;
+      a.wpack = wtab; a.epi = TG_EPI_BIAS_F32; a.bias = nullptr; a.n_valid = (int)nv;
+      a.n_rows = V; a.out_f32 = d_table + n0; a.ldo = E; a.n_store = (int)nv;
+      if (int rc = tapgemm_plan(a, &plan)) return rc;
+      if (int rc = tapgemm_launch(plan, st)) return rc;
+    }
+    if (padding_idx >= 0 && padding_idx < V) cudaMemsetAsync(d_table + padding_idx * E, 0, sizeof(float) * E, st);   // BERT.py:16-21
+    // d_conv_w[:, :, tap] = table^T [E, V] x S[:, tap, :] [V, H]   (token-reduction GEMM over vocabulary rows)
+    for (int tap = 0; tap < 3; ++tap) {
+      TokRedArgs a{};
+      TokRedPlan plan;
+      a.n_titles = n_rows32; a.L = 32; a.taps = 1;
+      a.ids = nullptr; a.p = static_cast<const __nv_bfloat16*>(table); a.ldp = table_ld(s); a.KP = (int)Kp;
+      a.q = S + tap * Hp; a.ldq = SH; a.NQ = (int)Hp; a.partial = partial_v;
+      if (int rc = tokred_plan(a, &plan)) return rc;
+      if (int rc = tokred_launch(plan, st)) return rc;
+      if (int rc = tokred_reduce(plan, d_conv_w + tap, (int)E, (int)H, 3 * E, 3, 0, st)) return rc;
+    }
+    return MR_OK;
   }
   // 4. d_conv_w[h,e,tap] = sum_t x[t+tap-1, e] dconv[t, h]
   {

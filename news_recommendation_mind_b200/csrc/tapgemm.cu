@@ -587,9 +587,11 @@ __global__ void __launch_bounds__(EPI2 ? TG_THREADS2 : TG_THREADS, 1) tapgemm_ke
 
 // Packs fp32 weights into the [chunk][tap] panel blocks the kernel streams:
 //   W[tap][n, k] = src[n*sn + k*sk + tap*st]  for n < n_valid, k < k_valid, else 0
+// k_mod > 0: the K index is a concatenation of blocks of k_mod columns, k = b*k_mod + kk, read from
+//   src[n*sn + kk*sk + b*sb + tap*st]  for kk < k_valid  (e.g. the three conv taps side by side, each padded to k_mod)
 __global__ void tapgemm_pack_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int taps, int n_total, int K,
                                     int n_valid, int k_valid, int64_t sn, int64_t sk, int64_t st, uint32_t slot_bytes,
-                                    int reps, int64_t rep_stride) {
+                                    int reps, int64_t rep_stride, int k_mod, int64_t sb) {
   const int n_chunks = (K + TG_KC - 1) / TG_KC;
   const int64_t total = (int64_t)n_chunks * taps * (TG_KC / 8) * n_total;      // 16-byte units
   for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (int64_t)gridDim.x * blockDim.x) {
@@ -606,8 +608,14 @@ __global__ void tapgemm_pack_kernel(const float* __restrict__ src, uint8_t* __re
     for (int e = 0; e < 4; ++e) {
       float lo = 0.f, hi = 0.f;
       const int k = k0 + 2 * e;
-      if (n < n_valid && k < k_valid) lo = src[n * sn + k * sk + tap * st];
-      if (n < n_valid && k + 1 < k_valid) hi = src[n * sn + (k + 1) * sk + tap * st];
+      if (k_mod > 0) {
+        const int b0 = k / k_mod, kk0 = k - b0 * k_mod, b1 = (k + 1) / k_mod, kk1 = k + 1 - b1 * k_mod;
+        if (n < n_valid && kk0 < k_valid) lo = src[n * sn + kk0 * sk + b0 * sb + tap * st];
+        if (n < n_valid && kk1 < k_valid) hi = src[n * sn + kk1 * sk + b1 * sb + tap * st];
+      } else {
+        if (n < n_valid && k < k_valid) lo = src[n * sn + k * sk + tap * st];
+        if (n < n_valid && k + 1 < k_valid) hi = src[n * sn + (k + 1) * sk + tap * st];
+      }
       w[e] = tc::pack_bf16(lo, hi);
     }
     uint8_t* o = dst + (size_t)(c * taps + tap) * slot_bytes + (size_t)panel * n_total * 16 + (size_t)n * 16;
@@ -759,16 +767,21 @@ int tapgemm_launch(const TapGemmPlan& plan, cudaStream_t stream) {
   return MR_OK;
 }
 
-int tapgemm_pack(const float* src, uint8_t* dst, int taps, int n_total, int K, int n_valid, int k_valid, int64_t sn,
-                 int64_t sk, int64_t st, cudaStream_t stream) {
+int tapgemm_pack_blocks(const float* src, uint8_t* dst, int taps, int n_total, int K, int n_valid, int k_valid, int64_t sn,
+                        int64_t sk, int64_t st, int k_mod, int64_t sb, cudaStream_t stream) {
   const int64_t units = tapgemm_pack_bytes(taps, n_total, K) / TG_W_REPS / 16;
   const uint32_t slot = (uint32_t)((TG_KC / 8) * n_total * 16);
   int blocks = (int)ceil_div(units, 256);
   if (blocks > 1024) blocks = 1024;
   tapgemm_pack_kernel<<<blocks, 256, 0, stream>>>(src, dst, taps, n_total, K, n_valid, k_valid, sn, sk, st, slot, TG_W_REPS,
-                                                  tapgemm_pack_bytes(taps, n_total, K) / TG_W_REPS);
+                                                  tapgemm_pack_bytes(taps, n_total, K) / TG_W_REPS, k_mod, sb);
   MR_CHECK_LAUNCH("tapgemm_pack_kernel");
   return MR_OK;
+}
+
+int tapgemm_pack(const float* src, uint8_t* dst, int taps, int n_total, int K, int n_valid, int k_valid, int64_t sn,
+                 int64_t sk, int64_t st, cudaStream_t stream) {
+  return tapgemm_pack_blocks(src, dst, taps, n_total, K, n_valid, k_valid, sn, sk, st, 0, 0, stream);
 }
 
 }  // namespace mr

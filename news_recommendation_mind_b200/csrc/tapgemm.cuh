@@ -76,6 +76,9 @@ inline int64_t tapgemm_pack_bytes(int taps, int n_total, int K) {      // all re
 
 int tapgemm_pack(const float* src, uint8_t* dst, int taps, int n_total, int K, int n_valid, int k_valid, int64_t sn,
                  int64_t sk, int64_t st, cudaStream_t stream);
+// K index = concatenated blocks of k_mod columns: W[n, b*k_mod + kk] = src[n*sn + kk*sk + b*sb] for kk < k_valid (tapgemm.cu)
+int tapgemm_pack_blocks(const float* src, uint8_t* dst, int taps, int n_total, int K, int n_valid, int k_valid, int64_t sn,
+                        int64_t sk, int64_t st, int k_mod, int64_t sb, cudaStream_t stream);
 // fills the derived fields of `a` (G, halo, slots, tiles); returns MR_OK or an error
 int tapgemm_plan(TapGemmArgs& a, TapGemmPlan* plan);
 int tapgemm_launch(const TapGemmPlan& plan, cudaStream_t stream);

@@ -84,7 +84,11 @@ class BERT_Embedding(nn.Module):
         w = self.weight
         key = (w.data_ptr(), w._version, tuple(w.shape))
         if self._shadow is None or self._shadow_key != key:
-            self._shadow = ops.cast_pad_bf16(w.detach(), ops.pad_to(w.shape[1], 64), extra_rows=len(self.hot_ids) * self.hot_reps)
+            # rows: V (+ optional hot-row replicas), then zero rows up to a multiple of 128 -- the token-grouped backward
+            # reads the table in 128-row tiles (mr_news_cnn_bwd_table)
+            extra = len(self.hot_ids) * self.hot_reps
+            extra += ops.pad_to(w.shape[0] + extra, 128) - (w.shape[0] + extra)
+            self._shadow = ops.cast_pad_bf16(w.detach(), ops.pad_to(w.shape[1], 64), extra_rows=extra)
             self._replicate_hot(self._shadow)
             self._shadow_key = key
         return self._shadow

@@ -8,12 +8,18 @@ from __future__ import annotations
 
 from ctypes import byref, c_float, c_int
 
+import os
+
 import torch
 
 from . import _lib
 from ._lib import CnnShape, RnnShape, MR_BF16, MR_F32, check, index_flag, ptr, stream_ptr, workspace
 
 PRECISIONS = {"fp32": MR_F32, "f32": MR_F32, "bf16": MR_BF16}
+
+
+# MINDREC_GROUPED=0 switches the bf16 ids path back to the per-token d_emb + segmented reduction (A/B, tests)
+GROUPED_TABLE_GRAD = os.environ.get("MINDREC_GROUPED", "1") != "0"
 
 
 def pad_to(n: int, m: int) -> int:
@@ -151,6 +157,19 @@ class NewsCNN(torch.autograd.Function):
         d_pb = torch.empty(H, dtype=torch.float32, device=dev)
         d_q = torch.empty(H, dtype=torch.float32, device=dev)
         need_x = ctx.need_table_grad or ctx.need_emb_grad
+        d_table = None
+        d_emb_out = None
+        if (ctx.need_table_grad and s.precision == MR_BF16 and d_c_c is None and E % 4 == 0 and GROUPED_TABLE_GRAD
+                and tab.shape[0] >= pad_to(s.V, 32)):
+            # token-grouped backward: the table gradient comes out of the encoder backward directly
+            V, _ = ctx.table_shape
+            d_table = torch.empty(V, E, dtype=torch.float32, device=dev)
+            ws = workspace(lib.mr_news_cnn_bwd_table_workspace_bytes(byref(s)), dev)
+            check(lib.mr_news_cnn_bwd_table(byref(s), ptr(ids_c), index_flag(ids_c), ptr(tab), tab.shape[0], ptr(cw), ptr(pw),
+                                            ptr(q), ptr(c_save), ptr(key_save), ptr(prob), ptr(d_news_c), ptr(d_cw), ptr(d_cb),
+                                            ptr(d_pw), ptr(d_pb), ptr(d_q), ptr(d_table), ctx.padding_idx, ptr(ws), ws.numel(),
+                                            stream_ptr(dev)), "mr_news_cnn_bwd_table")
+            return (None, None, None, d_table, None, d_cw, d_cb, d_pw, d_pb, d_q.view(1, H), None, None, None)
         d_emb = None
         if need_x:
             if s.precision == MR_BF16:      # row pitch = E rounded up to 16 (16-byte aligned tensor-core epilogue stores)
@@ -162,8 +181,6 @@ class NewsCNN(torch.autograd.Function):
                                   ptr(tab), ptr(cw), ptr(pw), ptr(q), ptr(c_save), ptr(key_save), ptr(prob),
                                   ptr(d_news_c), ptr(d_c_c), ptr(d_cw), ptr(d_cb), ptr(d_pw), ptr(d_pb), ptr(d_q),
                                   ptr(d_emb), ptr(ws), ws.numel(), stream_ptr(dev)), "mr_news_cnn_bwd")
-        d_table = None
-        d_emb_out = None
         if ctx.need_table_grad:
             V, _ = ctx.table_shape
             d_table = embed_grad(ids_c.view(-1), d_emb, V, E, ctx.padding_idx)
@@ -400,6 +417,8 @@ def cast_pad_bf16(src: torch.Tensor, ld: int, extra_rows: int = 0) -> torch.Tens
     sc = _f32c(src)
     rows, cols = sc.shape
     dst = torch.empty(rows + extra_rows, ld, dtype=torch.bfloat16, device=sc.device)
+    if extra_rows:
+        dst[rows:].zero_()
     check(lib.mr_cast_pad_bf16(ptr(sc), ptr(dst), rows, cols, ld, stream_ptr(sc.device)), "mr_cast_pad_bf16")
     return dst
 

@@ -158,7 +158,7 @@ def test_twotower_bf16_training_step_vs_fp32_oracle(B, C, S, L, E, H):
     assert float(model.embedding.weight.grad[0].abs().max()) == 0.0
 
 
-def cnn_encoder_bf16_backward_emulation(table, ids, mask, conv_w, conv_b, proj_w, proj_b, query, g):
+def cnn_encoder_bf16_backward_emulation(table, ids, mask, conv_w, conv_b, proj_w, proj_b, query, g, grouped=False):
     """float64 restatement of the backward of oracle.twotower_oracle.cnn_news_encoder (autograd of CNN.py:30-51,
     softmax backward of Attention.py:77-80) with bf16 rounding at the points where the MR_BF16 kernels store
     bf16: c, key, dkey_pre, p*d_news, dconv, d_emb."""
@@ -186,24 +186,38 @@ def cnn_encoder_bf16_backward_emulation(table, ids, mask, conv_w, conv_b, proj_w
     d_proj_b = dkp_f.sum((0, 1))               # bias gradients are summed in fp32 before the bf16 rounding of the stored tensor
     d_proj_w = torch.einsum("nlh,nlk->hk", dkp, c)
     d_conv_b = dconv_f.sum((0, 1))
-    xpad = torch.nn.functional.pad(x, (0, 0, 1, 1))
-    d_conv_w = torch.stack([torch.einsum("nlh,nle->he", dconv, xpad[:, tap:tap + L]) for tap in range(3)], dim=-1)
     gpad = torch.nn.functional.pad(dconv, (0, 0, 1, 1))
     cw = _bf(conv_w)
-    d_x = sum(gpad[:, 2 - tap:2 - tap + L] @ cw[:, :, tap] for tap in range(3))
-    d_x = _bf(d_x.float())
-    d_table = torch.zeros(table.shape, dtype=torch.float64).index_add_(0, ids.cpu().reshape(-1), d_x.reshape(-1, E))
+    if grouped:
+        # token-grouped backward (mr_news_cnn_bwd_table): S[v, tap] = bf16(sum_{t: ids[t]=v} dconv[t+1-tap]) is the rounding
+        # point; the table and filter gradients are GEMMs over vocabulary rows
+        V = table.shape[0]
+        flat = ids.cpu().reshape(-1)
+        S = [_bf(torch.zeros(V, H, dtype=torch.float64).index_add_(0, flat, gpad[:, 2 - tap:2 - tap + L].reshape(-1, H)).float())
+             for tap in range(3)]
+        tb = _bf(table)
+        d_conv_w = torch.stack([S[tap].t() @ tb for tap in range(3)], dim=-1)
+        d_table = sum(S[tap] @ cw[:, :, tap] for tap in range(3))
+    else:
+        xpad = torch.nn.functional.pad(x, (0, 0, 1, 1))
+        d_conv_w = torch.stack([torch.einsum("nlh,nle->he", dconv, xpad[:, tap:tap + L]) for tap in range(3)], dim=-1)
+        d_x = sum(gpad[:, 2 - tap:2 - tap + L] @ cw[:, :, tap] for tap in range(3))
+        d_x = _bf(d_x.float())
+        d_table = torch.zeros(table.shape, dtype=torch.float64).index_add_(0, ids.cpu().reshape(-1), d_x.reshape(-1, E))
     d_table[0] = 0
     return {"cnn.weight": d_conv_w, "cnn.bias": d_conv_b, "wordQueryProject.weight": d_proj_w,
             "wordQueryProject.bias": d_proj_b, "query_words": d_q.view(1, H), "table": d_table}
 
 
+@pytest.mark.parametrize("grouped", [True, False])
 @pytest.mark.parametrize("N,L,E,H", [(37, 32, 300, 150), (23, 30, 300, 150), (9, 48, 64, 32), (130, 20, 768, 150), (515, 32, 300, 150)])
-def test_news_cnn_bf16_backward(N, L, E, H):
+def test_news_cnn_bf16_backward(N, L, E, H, grouped, monkeypatch):
     import sys, os
     sys.path.insert(0, os.path.dirname(__file__))
     from helpers import manager_for, rel_err
     import news_recommendation_mind_b200 as mr
+    from news_recommendation_mind_b200 import ops
+    monkeypatch.setattr(ops, "GROUPED_TABLE_GRAD", grouped)      # token-grouped table / filter gradient vs per-token d_emb + seg-reduce
     torch.manual_seed(N + L)
     V = 997
     man = manager_for("cnn", "lstm", 5, 50, L, E, H, 10, precision="bf16")
@@ -223,7 +237,7 @@ def test_news_cnn_bf16_backward(N, L, E, H):
     (news * g.cuda()).sum().backward()
     torch.cuda.synchronize()
     exp = cnn_encoder_bf16_backward_emulation(emb.weight, ids, mask, enc.cnn.weight, enc.cnn.bias, enc.wordQueryProject.weight,
-                                              enc.wordQueryProject.bias, enc.query_words, g)
+                                              enc.wordQueryProject.bias, enc.query_words, g, grouped=grouped)
     worst = 0.0
     for k, p in enc.named_parameters():
         e = rel_err(p.grad, exp[k])
