@@ -72,13 +72,18 @@ __global__ void chunk_count_kernel(const int32_t* __restrict__ seg_start, int32_
   nchunk[v] = (v == padding_idx) ? 0 : (cnt + SEG_CHUNK - 1) / SEG_CHUNK;
 }
 
-// expands per-row chunk counts into a chunk -> row table
-__global__ void chunk_fill_kernel(const int32_t* __restrict__ nchunk, const int32_t* __restrict__ chunk_off,
-                                  int32_t* __restrict__ chunk_row, int64_t V) {
-  int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= V) return;
-  int32_t n = nchunk[v], o = chunk_off[v];
-  for (int32_t j = 0; j < n; ++j) chunk_row[o + j] = (int32_t)v;
+// chunk -> row table: chunk ch belongs to the last row v with chunk_off[v] <= ch (binary search; a per-row loop would
+// serialise the thousands of chunks of the PAD token in one thread)
+__global__ void chunk_fill_kernel(const int32_t* __restrict__ chunk_off, int32_t* __restrict__ chunk_row, int64_t V,
+                                  int64_t max_chunks) {
+  const int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= max_chunks || ch >= chunk_off[V]) return;
+  int64_t lo = 0, hi = V;                      // invariant: chunk_off[lo] <= ch < chunk_off[hi]
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (chunk_off[mid] <= ch) lo = mid; else hi = mid;
+  }
+  chunk_row[ch] = (int32_t)lo;
 }
 
 template <class T> struct RowReader;
@@ -163,7 +168,6 @@ seg_reduce_l1_kernel(const T* __restrict__ d_emb, int64_t ld, const int32_t* __r
 // segments; rows with more than SEG_HEAVY chunks (frequent tokens: [CLS], [SEP], the head of the Zipf
 // distribution) are queued for the heavy path below instead of being summed by one warp.
 constexpr int SEG_HEAVY = 8;
-constexpr int SEG_SPLIT = 4;      // CTAs per heavy row
 
 template <class TO> __device__ __forceinline__ TO seg_out(float v);
 template <> __device__ __forceinline__ float seg_out<float>(float v) { return v; }
@@ -174,7 +178,7 @@ template <class TO>
 __global__ void __launch_bounds__(256)
 seg_reduce_l2_kernel(const int32_t* __restrict__ chunk_off, const int32_t* __restrict__ nchunk,
                      const float* __restrict__ partial, TO* __restrict__ d_table, int64_t ldo, int64_t V, int64_t E,
-                     int32_t* __restrict__ heavy_count, int32_t* __restrict__ heavy_rows, int32_t max_heavy) {
+                     int32_t* __restrict__ heavy_count, int32_t* __restrict__ heavy_rows, int32_t max_heavy, int32_t heavy_thr) {
   const int lane = threadIdx.x & 31;
   const int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (v >= V) return;
@@ -185,7 +189,7 @@ seg_reduce_l2_kernel(const int32_t* __restrict__ chunk_off, const int32_t* __res
     for (int64_t e = lane; e < E; e += 32) dst[e] = seg_out<TO>(0.f);
     return;
   }
-  if (n > SEG_HEAVY) {
+  if (n > heavy_thr) {
     if (lane == 0) {
       const int32_t slot = atomicAdd(heavy_count, 1);   // integer bookkeeping only: the order of the list does
       if (slot < max_heavy) heavy_rows[slot] = (int32_t)v;   // not influence any floating-point sum
@@ -200,58 +204,136 @@ seg_reduce_l2_kernel(const int32_t* __restrict__ chunk_off, const int32_t* __res
   }
 }
 
-// heavy rows: CTA (h, sp) sums the sp-th quarter of row heavy_rows[h]'s partial rows, four independent
-// accumulators per column combined in a fixed order; heavy_final adds the SEG_SPLIT results in order.
+// heavy rows (more than SEG_HEAVY chunks: PAD, [CLS], [SEP], the head of the Zipf distribution).  Work item = one
+// slice of <= SEG_SLICE consecutive partial rows of one heavy row; items are numbered by a prefix sum over the heavy
+// list (recomputed per CTA in shared memory -- the list has at most a few hundred entries).  A CTA sums a slice with
+// 2 row groups x 128 column vectors, 4 independent accumulators each, combined in a fixed order; heavy_final adds the
+// slice sums of a row in slice order.  The (atomic) order of the heavy list only decides which CTA does what.
+constexpr int SEG_SLICE = 64;
+constexpr int SEG_MAX_HEAVY_SMEM = 2048;
+
+__device__ __forceinline__ int heavy_prefix(const int32_t* __restrict__ heavy_rows, const int32_t* __restrict__ nchunk, int nh,
+                                            int32_t* off /* smem [nh + 1] */) {
+  // off[h] = first item of heavy row h; computed by one warp with a shuffle scan
+  if (threadIdx.x < 32) {
+    int32_t run = 0;
+    for (int base = 0; base < nh; base += 32) {
+      const int h = base + threadIdx.x;
+      int32_t c = h < nh ? (nchunk[heavy_rows[h]] + SEG_SLICE - 1) / SEG_SLICE : 0;
+      int32_t x = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int32_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if ((int)threadIdx.x >= d) x += y;
+      }
+      if (h < nh) off[h] = run + x - c;
+      run += __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (threadIdx.x == 0) off[nh] = run;
+  }
+  __syncthreads();
+  return off[nh];
+}
+
 __global__ void __launch_bounds__(256)
 seg_reduce_heavy_kernel(const int32_t* __restrict__ chunk_off, const int32_t* __restrict__ nchunk,
                         const float* __restrict__ partial, float* __restrict__ partial2,
-                        const int32_t* __restrict__ heavy_count, const int32_t* __restrict__ heavy_rows, int64_t E) {
-  const int h = blockIdx.x / SEG_SPLIT, sp = blockIdx.x % SEG_SPLIT;
-  if (h >= *heavy_count) return;
-  const int32_t v = heavy_rows[h];
-  const int32_t n = nchunk[v];
-  const int32_t per = (n + SEG_SPLIT - 1) / SEG_SPLIT;
-  const int32_t j0 = sp * per, j1 = min(n, j0 + per);
-  const float* src = partial + (int64_t)chunk_off[v] * E;
-  float* dst = partial2 + (int64_t)blockIdx.x * E;
-  for (int64_t e = threadIdx.x; e < E; e += blockDim.x) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int32_t j = j0;
-    for (; j + 3 < j1; j += 4) {
-      a0 += src[(int64_t)j * E + e];
-      a1 += src[(int64_t)(j + 1) * E + e];
-      a2 += src[(int64_t)(j + 2) * E + e];
-      a3 += src[(int64_t)(j + 3) * E + e];
+                        const int32_t* __restrict__ heavy_count, const int32_t* __restrict__ heavy_rows, int64_t E,
+                        int32_t max_items) {
+  __shared__ int32_t off[SEG_MAX_HEAVY_SMEM + 1];
+  __shared__ float4 red[128];
+  const int nh = min(*heavy_count, SEG_MAX_HEAVY_SMEM);
+  if (nh == 0) return;
+  const int n_items = min(heavy_prefix(heavy_rows, nchunk, nh, off), max_items);
+  const int rg = threadIdx.x >> 7, cv = threadIdx.x & 127;
+  const int64_t nv = E >> 2;                             // E % 4 == 0 (checked on the host)
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    int lo = 0, hi = nh;                                 // off[lo] <= item < off[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (off[mid] <= item) lo = mid; else hi = mid;
     }
-    for (; j < j1; ++j) a0 += src[(int64_t)j * E + e];
-    dst[e] = (a0 + a1) + (a2 + a3);
+    const int32_t v = heavy_rows[lo];
+    const int32_t n = nchunk[v];
+    const int32_t j0 = (item - off[lo]) * SEG_SLICE, j1 = min(n, j0 + SEG_SLICE);
+    const float* src = partial + (int64_t)chunk_off[v] * E;
+    for (int64_t c0 = 0; c0 < nv; c0 += 128) {
+      const int64_t c = c0 + cv;
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+      if (c < nv) {
+        int32_t j = j0 + rg;
+        for (; j + 6 < j1; j += 8) {
+          const float4 x0 = *reinterpret_cast<const float4*>(src + (int64_t)j * E + 4 * c);
+          const float4 x1 = *reinterpret_cast<const float4*>(src + (int64_t)(j + 2) * E + 4 * c);
+          const float4 x2 = *reinterpret_cast<const float4*>(src + (int64_t)(j + 4) * E + 4 * c);
+          const float4 x3 = *reinterpret_cast<const float4*>(src + (int64_t)(j + 6) * E + 4 * c);
+          a0.x += x0.x; a0.y += x0.y; a0.z += x0.z; a0.w += x0.w;
+          a1.x += x1.x; a1.y += x1.y; a1.z += x1.z; a1.w += x1.w;
+          a2.x += x2.x; a2.y += x2.y; a2.z += x2.z; a2.w += x2.w;
+          a3.x += x3.x; a3.y += x3.y; a3.z += x3.z; a3.w += x3.w;
+        }
+        for (; j < j1; j += 2) {
+          const float4 x0 = *reinterpret_cast<const float4*>(src + (int64_t)j * E + 4 * c);
+          a0.x += x0.x; a0.y += x0.y; a0.z += x0.z; a0.w += x0.w;
+        }
+      }
+      const float4 t = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y), (a0.z + a1.z) + (a2.z + a3.z),
+                                   (a0.w + a1.w) + (a2.w + a3.w));
+      if (rg == 1) red[cv] = t;
+      __syncthreads();
+      if (rg == 0 && c < nv) {
+        const float4 u = red[cv];
+        *reinterpret_cast<float4*>(partial2 + (int64_t)item * E + 4 * c) = make_float4(t.x + u.x, t.y + u.y, t.z + u.z, t.w + u.w);
+      }
+      __syncthreads();
+    }
   }
 }
 
 template <class TO>
 __global__ void __launch_bounds__(256)
 seg_reduce_heavy_final_kernel(const float* __restrict__ partial2, TO* __restrict__ d_table, int64_t ldo,
-                              const int32_t* __restrict__ heavy_count, const int32_t* __restrict__ heavy_rows, int64_t E) {
-  const int h = blockIdx.x;
-  if (h >= *heavy_count) return;
-  const int32_t v = heavy_rows[h];
-  for (int64_t e = threadIdx.x; e < E; e += blockDim.x) {
-    float s = 0.f;
-#pragma unroll
-    for (int sp = 0; sp < SEG_SPLIT; ++sp) s += partial2[((int64_t)h * SEG_SPLIT + sp) * E + e];
-    d_table[(int64_t)v * ldo + e] = seg_out<TO>(s);
+                              const int32_t* __restrict__ nchunk, const int32_t* __restrict__ heavy_count,
+                              const int32_t* __restrict__ heavy_rows, int64_t E, int32_t max_items) {
+  __shared__ int32_t off[SEG_MAX_HEAVY_SMEM + 1];
+  const int nh = min(*heavy_count, SEG_MAX_HEAVY_SMEM);
+  if (nh == 0) return;
+  heavy_prefix(heavy_rows, nchunk, nh, off);
+  for (int h = blockIdx.x; h < nh; h += gridDim.x) {
+    const int32_t v = heavy_rows[h];
+    const int i0 = off[h], i1 = min(off[h + 1], max_items);
+    for (int64_t e = threadIdx.x; e < E; e += blockDim.x) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int i = i0;
+      for (; i + 3 < i1; i += 4) {
+        a0 += partial2[(int64_t)i * E + e];
+        a1 += partial2[(int64_t)(i + 1) * E + e];
+        a2 += partial2[(int64_t)(i + 2) * E + e];
+        a3 += partial2[(int64_t)(i + 3) * E + e];
+      }
+      for (; i < i1; ++i) a0 += partial2[(int64_t)i * E + e];
+      d_table[(int64_t)v * ldo + e] = seg_out<TO>((a0 + a1) + (a2 + a3));
+    }
   }
 }
 
 struct EmbedGradPlan {
-  int64_t T, E, V, max_chunks, max_heavy;
+  int64_t T, E, V, max_chunks, max_heavy, max_items;
+  int32_t heavy_thr;             // rows with more chunks than this go to the heavy path
   size_t cub_sort_bytes, cub_scan_bytes;
 };
 
 static EmbedGradPlan plan_embed_grad(int64_t T, int64_t E, int64_t V) {
-  EmbedGradPlan p{T, E, V, 0, 0, 0, 0};
+  EmbedGradPlan p{T, E, V, 0, 0, 0, 0, 0, 0};
   p.max_chunks = ceil_div(T, SEG_CHUNK) + V;
-  p.max_heavy = T / ((int64_t)SEG_CHUNK * SEG_HEAVY) + 1;       // rows with more than SEG_HEAVY chunks
+  // heavy threshold: at least SEG_HEAVY chunks, raised so that at most SEG_MAX_HEAVY_SMEM rows can exceed it; the heavy
+  // kernels read float4 columns, so a row length that is not a multiple of 4 keeps everything on level 2
+  int64_t thr = SEG_HEAVY;
+  while (T / ((int64_t)SEG_CHUNK * thr) + 1 > 2048) thr *= 2;
+  if (E % 4 != 0) thr = 0x7fffffff;
+  p.heavy_thr = (int32_t)thr;
+  p.max_heavy = E % 4 != 0 ? 1 : T / ((int64_t)SEG_CHUNK * thr) + 1;
+  p.max_items = p.max_chunks / 64 + p.max_heavy;                // slices of <= SEG_SLICE partial rows
   int bits = 1;
   while ((1ll << bits) < V) ++bits;
   cub::DeviceRadixSort::SortPairs(nullptr, p.cub_sort_bytes, (const int32_t*)nullptr, (int32_t*)nullptr,
@@ -346,7 +428,7 @@ int64_t token_group_workspace_bytes(int64_t T, int64_t Hp, int64_t V) {
   b += 3 * arena_bytes(V + 1, 4);
   b += arena_bytes(p.max_chunks, 4);
   b += arena_bytes(p.max_chunks * E, 4);
-  b += arena_bytes(p.max_heavy + 1, 4) + arena_bytes(p.max_heavy * SEG_SPLIT * E, 4);
+  b += arena_bytes(p.max_heavy + 1, 4) + arena_bytes(p.max_items * E, 4);
   b += arena_bytes((int64_t)p.cub_sort_bytes, 1) + arena_bytes((int64_t)p.cub_scan_bytes, 1);
   return b + 256;
 }
@@ -367,7 +449,7 @@ int token_group_taps(const void* ids, int ids_i64, const __nv_bfloat16* dconv, i
   int32_t* chunk_row = ar.take<int32_t>(p.max_chunks);
   float* partial = ar.take<float>(p.max_chunks * E);
   int32_t* heavy = ar.take<int32_t>(p.max_heavy + 1);
-  float* partial2 = ar.take<float>(p.max_heavy * SEG_SPLIT * E);
+  float* partial2 = ar.take<float>(p.max_items * E);
   void* cub_sort = ar.take<char>((int64_t)p.cub_sort_bytes);
   void* cub_scan = ar.take<char>((int64_t)p.cub_scan_bytes);
   MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "token grouping: workspace too small (%lld given)", (long long)workspace_bytes);
@@ -387,7 +469,7 @@ int token_group_taps(const void* ids, int ids_i64, const __nv_bfloat16* dconv, i
   e = cub::DeviceScan::ExclusiveSum(cub_scan, cb, nchunk, chunk_off, (int)V + 1, st);
   MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "scan: %s", cudaGetErrorString(e));
   count_launch(2);
-  chunk_fill_kernel<<<(unsigned)ceil_div(V, 256), 256, 0, st>>>(nchunk, chunk_off, chunk_row, V);
+  chunk_fill_kernel<<<(unsigned)ceil_div(p.max_chunks, 256), 256, 0, st>>>(chunk_off, chunk_row, V, p.max_chunks);
   MR_CHECK_LAUNCH("chunk_fill_kernel");
   const int pieces = (int)(Hp / 8);
   if (3 * pieces <= 32)
@@ -399,11 +481,11 @@ int token_group_taps(const void* ids, int ids_i64, const __nv_bfloat16* dconv, i
   MR_CHECK_LAUNCH("group_taps_l1_kernel");
   cudaMemsetAsync(heavy, 0, sizeof(int32_t), st);
   seg_reduce_l2_kernel<__nv_bfloat16><<<(unsigned)ceil_div(V, 8), 256, 0, st>>>(chunk_off, nchunk, partial, S, E, V, E, heavy, heavy + 1,
-                                                                                (int32_t)p.max_heavy);
+                                                                                (int32_t)p.max_heavy, p.heavy_thr);
   MR_CHECK_LAUNCH("seg_reduce_l2_kernel");
-  seg_reduce_heavy_kernel<<<(unsigned)(p.max_heavy * SEG_SPLIT), 256, 0, st>>>(chunk_off, nchunk, partial, partial2, heavy, heavy + 1, E);
+  seg_reduce_heavy_kernel<<<148 * 4, 256, 0, st>>>(chunk_off, nchunk, partial, partial2, heavy, heavy + 1, E, (int32_t)p.max_items);
   MR_CHECK_LAUNCH("seg_reduce_heavy_kernel");
-  seg_reduce_heavy_final_kernel<__nv_bfloat16><<<(unsigned)p.max_heavy, 256, 0, st>>>(partial2, S, E, heavy, heavy + 1, E);
+  seg_reduce_heavy_final_kernel<__nv_bfloat16><<<148 * 2, 256, 0, st>>>(partial2, S, E, nchunk, heavy, heavy + 1, E, (int32_t)p.max_items);
   MR_CHECK_LAUNCH("seg_reduce_heavy_final_kernel");
   return MR_OK;
 }
@@ -435,7 +517,7 @@ int64_t mr_embed_grad_workspace_bytes(int64_t T, int64_t E, int64_t V) {
   b += 2 * arena_bytes(V + 1, 4);             // nchunk, chunk_off
   b += arena_bytes(p.max_chunks, 4);          // chunk_row
   b += arena_bytes(p.max_chunks * E, 4);      // partial rows
-  b += arena_bytes(p.max_heavy + 1, 4) + arena_bytes(p.max_heavy * SEG_SPLIT * E, 4);   // heavy list, heavy partials
+  b += arena_bytes(p.max_heavy + 1, 4) + arena_bytes(p.max_items * E, 4);   // heavy list, heavy partials
   b += arena_bytes((int64_t)p.cub_sort_bytes, 1) + arena_bytes((int64_t)p.cub_scan_bytes, 1);
   return b + 256;
 }
@@ -466,7 +548,7 @@ int mr_embed_grad_segreduce(const void* ids, int ids_i64, const void* d_emb, int
   int32_t* chunk_row = ar.take<int32_t>(p.max_chunks);
   float* partial = ar.take<float>(p.max_chunks * E);
   int32_t* heavy = ar.take<int32_t>(p.max_heavy + 1);            // [0] = count, [1..] = rows
-  float* partial2 = ar.take<float>(p.max_heavy * SEG_SPLIT * E);
+  float* partial2 = ar.take<float>(p.max_items * E);
   void* cub_sort = ar.take<char>((int64_t)p.cub_sort_bytes);
   void* cub_scan = ar.take<char>((int64_t)p.cub_scan_bytes);
   MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "mr_embed_grad_segreduce: workspace too small (%lld given)", (long long)workspace_bytes);
@@ -487,7 +569,7 @@ int mr_embed_grad_segreduce(const void* ids, int ids_i64, const void* d_emb, int
   e = cub::DeviceScan::ExclusiveSum(cub_scan, cb, nchunk, chunk_off, (int)V + 1, st);
   MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "scan: %s", cudaGetErrorString(e));
   count_launch(2);
-  chunk_fill_kernel<<<(unsigned)ceil_div(V, 256), 256, 0, st>>>(nchunk, chunk_off, chunk_row, V);
+  chunk_fill_kernel<<<(unsigned)ceil_div(p.max_chunks, 256), 256, 0, st>>>(chunk_off, chunk_row, V, p.max_chunks);
   MR_CHECK_LAUNCH("chunk_fill_kernel");
   // The true chunk count (chunk_off[V]) is only known on the device; launch level 1 for the bound
   // ceil(T/SEG_CHUNK)+V and let surplus warps exit (no host sync on this path).
@@ -502,12 +584,11 @@ int mr_embed_grad_segreduce(const void* ids, int ids_i64, const void* d_emb, int
   MR_CHECK_LAUNCH("seg_reduce_l1_kernel");
   cudaMemsetAsync(heavy, 0, sizeof(int32_t), st);
   seg_reduce_l2_kernel<float><<<(unsigned)ceil_div(V, 8), 256, 0, st>>>(chunk_off, nchunk, partial, d_table, E, V, E, heavy, heavy + 1,
-                                                                        (int32_t)p.max_heavy);
+                                                                        (int32_t)p.max_heavy, p.heavy_thr);
   MR_CHECK_LAUNCH("seg_reduce_l2_kernel");
-  seg_reduce_heavy_kernel<<<(unsigned)(p.max_heavy * SEG_SPLIT), 256, 0, st>>>(chunk_off, nchunk, partial, partial2, heavy,
-                                                                             heavy + 1, E);
+  seg_reduce_heavy_kernel<<<148 * 4, 256, 0, st>>>(chunk_off, nchunk, partial, partial2, heavy, heavy + 1, E, (int32_t)p.max_items);
   MR_CHECK_LAUNCH("seg_reduce_heavy_kernel");
-  seg_reduce_heavy_final_kernel<float><<<(unsigned)p.max_heavy, 256, 0, st>>>(partial2, d_table, E, heavy, heavy + 1, E);
+  seg_reduce_heavy_final_kernel<float><<<148 * 2, 256, 0, st>>>(partial2, d_table, E, nchunk, heavy, heavy + 1, E, (int32_t)p.max_items);
   MR_CHECK_LAUNCH("seg_reduce_heavy_final_kernel");
   return MR_OK;
 }

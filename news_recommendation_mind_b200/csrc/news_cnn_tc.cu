@@ -199,7 +199,7 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
     else if (Hp <= 128) cnn_pool_bwd_bf16_kernel<2><<<grid, 256, 0, st>>>(c, key, Hp, prob, query, d_news, dkp, dnp, ppart, cmask, N, (int)L, (int)H);
     else cnn_pool_bwd_bf16_kernel<3><<<grid, 256, 0, st>>>(c, key, Hp, prob, query, d_news, dkp, dnp, ppart, cmask, N, (int)L, (int)H);
     MR_CHECK_LAUNCH("cnn_pool_bwd_bf16_kernel");
-    cnn_pool_bwd_final_kernel<<<(unsigned)ceil_div(2 * Hp, 32), 256, 0, st>>>(ppart, (int64_t)grid, (int)Hp, (int)H, d_query, d_proj_b);
+    cnn_pool_bwd_final_kernel<<<(unsigned)ceil_div(2 * Hp, 32), 1024, 0, st>>>(ppart, (int64_t)grid, (int)Hp, (int)H, d_query, d_proj_b);
     MR_CHECK_LAUNCH("cnn_pool_bwd_final_kernel");
     if (d_c) {                                   // gradient arriving at the token representations (stand-alone CNN module)
       cast_rows_bf16_kernel<<<(unsigned)ceil_div(T * Hp, 256), 256, 0, st>>>(d_c, dcv, T, H, Hp);

@@ -357,21 +357,21 @@ cnn_pool_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ c, const __nv_bfloat1
 }
 
 // part [rows][2][ld] -> d_query[h] = sum_rows part[.][0][h],  d_proj_b[h] = sum_rows part[.][1][h]   (h < H), fixed order
-static __global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(1024)
 cnn_pool_bwd_final_kernel(const float* __restrict__ part, int64_t rows, int ld, int H, float* __restrict__ d_query,
                           float* __restrict__ d_proj_b) {
-  __shared__ float sm[8][33];
+  __shared__ float sm[32][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + cx;
   float s = 0.f;
   if (col < 2 * ld)
-    for (int64_t r = ry; r < rows; r += 8) s += part[r * 2 * ld + col];
+    for (int64_t r = ry; r < rows; r += 32) s += part[r * 2 * ld + col];
   sm[ry][cx] = s;
   __syncthreads();
   if (ry == 0 && col < 2 * ld) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += sm[i][cx];
+    for (int i = 0; i < 32; ++i) t += sm[i][cx];
     const int which = col >= ld, h = col - which * ld;
     if (h < H) (which ? d_proj_b : d_query)[h] = t;
   }

@@ -255,9 +255,16 @@ __global__ void tokred_reduce_kernel(const float* __restrict__ partial, float* _
   const int m = i / 128, il = i % 128;
   const float* src = partial + (((size_t)m * S * taps + tap) * 128 + il) * NQ + j;
   const size_t stride = (size_t)taps * 128 * NQ;
-  float acc = 0.f;
-  for (int s = 0; s < S; ++s) acc += src[(size_t)s * stride];
-  dst[j * dj + i * di + tap * dt] = acc;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;       // four independent chains (the loads are the latency), fixed combine order
+  int s = 0;
+  for (; s + 3 < S; s += 4) {
+    a0 += src[(size_t)s * stride];
+    a1 += src[(size_t)(s + 1) * stride];
+    a2 += src[(size_t)(s + 2) * stride];
+    a3 += src[(size_t)(s + 3) * stride];
+  }
+  for (; s < S; ++s) a0 += src[(size_t)s * stride];
+  dst[j * dj + i * di + tap * dt] = (a0 + a1) + (a2 + a3);
 }
 
 static void tokred_geometry(int64_t n_titles, int L, int taps, int KP, int* G, int* n_mtiles, int* S, int64_t* n_tiles) {

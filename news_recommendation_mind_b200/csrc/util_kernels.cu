@@ -55,25 +55,25 @@ static cudaError_t colsum_t(const T* x, int64_t ld, float* out, int64_t R, int64
 }
 // single launch, for a few thousand rows at most (per-CTA partials of a producer kernel): one CTA per 32 columns,
 // 8 row groups, fixed summation order
-__global__ void __launch_bounds__(256) colsum_small_kernel(const float* __restrict__ x, int64_t ld, float* __restrict__ out, int64_t R,
-                                                           int64_t C) {
-  __shared__ float sm[8][33];
+__global__ void __launch_bounds__(1024) colsum_small_kernel(const float* __restrict__ x, int64_t ld, float* __restrict__ out, int64_t R,
+                                                            int64_t C) {
+  __shared__ float sm[32][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int64_t c = (int64_t)blockIdx.x * 32 + cx;
   float s = 0.f;
   if (c < C)
-    for (int64_t r = ry; r < R; r += 8) s += x[r * ld + c];
+    for (int64_t r = ry; r < R; r += 32) s += x[r * ld + c];
   sm[ry][cx] = s;
   __syncthreads();
   if (ry == 0 && c < C) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += sm[i][cx];
+    for (int i = 0; i < 32; ++i) t += sm[i][cx];
     out[c] = t;
   }
 }
 cudaError_t colsum_small(const float* x, int64_t ld, float* out, int64_t R, int64_t C, cudaStream_t st) {
-  colsum_small_kernel<<<(unsigned)ceil_div(C, 32), 256, 0, st>>>(x, ld, out, R, C);
+  colsum_small_kernel<<<(unsigned)ceil_div(C, 32), 1024, 0, st>>>(x, ld, out, R, C);
   count_launch(1);
   return cudaGetLastError();
 }
