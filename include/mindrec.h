@@ -260,6 +260,13 @@ MR_API int mr_adam_step(float* p, const float* g, float* m, float* v, int64_t n,
                  double lr, double beta1, double beta2, double eps, double grad_scale,
                  void* shadow_bf16, int64_t row_len, int64_t shadow_ld, void* stream);
 
+/* The same update for up to 24 parameter tensors in one launch (p/g/m/v/numel/lr are HOST arrays of n_tensors entries;
+ * lr per tensor = the two learning-rate groups of Manager._get_optim).  `shadow_tensor` = index of the tensor whose bf16
+ * shadow is refreshed (-1 or shadow_bf16 == NULL: none). */
+MR_API int mr_adam_step_multi(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v,
+                 const int64_t* numel, const double* lr, int64_t step, double beta1, double beta2, double eps,
+                 double grad_scale, int shadow_tensor, void* shadow_bf16, int64_t row_len, int64_t shadow_ld, void* stream);
+
 /* Mean negative log-likelihood (nn.NLLLoss(), utils/Manager.py:381-382,641) over logp [B,C]:
  *   fwd: loss[0] = -(1/B) sum_b logp[b, label[b]];   bwd: d_logp[b,c] = -(d_loss/B) [c == label[b]] */
 MR_API int mr_nll_loss_fwd(const float* logp, const void* label, int label_i64, float* loss,

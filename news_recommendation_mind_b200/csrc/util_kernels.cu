@@ -105,6 +105,80 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// ---- multi-tensor Adam: every parameter of the model in ONE launch -------------------------------------------
+constexpr int AD_MAX_TENSORS = 24;
+constexpr int AD_CHUNK = 4096;          // elements per CTA (256 threads x 4 float4)
+struct AdamMultiArgs {
+  float* p[AD_MAX_TENSORS];
+  const float* g[AD_MAX_TENSORS];
+  float* m[AD_MAX_TENSORS];
+  float* v[AD_MAX_TENSORS];
+  int64_t n[AD_MAX_TENSORS];
+  float lr_over_bc1[AD_MAX_TENSORS];
+  int32_t blk_off[AD_MAX_TENSORS + 1];  // first CTA of tensor i
+  int n_tensors;
+  float inv_sqrt_bc2, beta1, omb1, beta2, omb2, eps, grad_scale;
+  int shadow_tensor;                    // tensor whose bf16 shadow is refreshed (-1 = none)
+  __nv_bfloat16* shadow; int64_t row_len, shadow_ld;
+};
+
+__device__ __forceinline__ float adam_one(float pi, float gi, float& mi, float& vi, const AdamMultiArgs& a, float lr) {
+  gi *= a.grad_scale;
+  mi = a.beta1 * mi + a.omb1 * gi;
+  vi = a.beta2 * vi + a.omb2 * gi * gi;
+  const float denom = sqrtf(vi) * a.inv_sqrt_bc2 + a.eps;
+  return pi - lr * (mi / denom);
+}
+
+__global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__ AdamMultiArgs a) {
+  int t = 0;
+#pragma unroll 1
+  while (t + 1 < a.n_tensors && (int)blockIdx.x >= a.blk_off[t + 1]) ++t;
+  const int64_t n = a.n[t];
+  float* __restrict__ p = a.p[t];
+  const float* __restrict__ g = a.g[t];
+  float* __restrict__ m = a.m[t];
+  float* __restrict__ v = a.v[t];
+  const float lr = a.lr_over_bc1[t];
+  const bool sh = t == a.shadow_tensor;
+  const int64_t base = (int64_t)(blockIdx.x - a.blk_off[t]) * AD_CHUNK;
+  const bool vec = (n & 3) == 0 && (!sh || (a.row_len & 3) == 0);      // tensors come from the torch allocator: 16-byte aligned
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int64_t i = base + ((int64_t)it * 256 + threadIdx.x) * 4;
+    if (i >= n) break;
+    if (vec) {
+      const float4 g4 = *reinterpret_cast<const float4*>(g + i);
+      float4 p4 = *reinterpret_cast<float4*>(p + i), m4 = *reinterpret_cast<float4*>(m + i), v4 = *reinterpret_cast<float4*>(v + i);
+      p4.x = adam_one(p4.x, g4.x, m4.x, v4.x, a, lr);
+      p4.y = adam_one(p4.y, g4.y, m4.y, v4.y, a, lr);
+      p4.z = adam_one(p4.z, g4.z, m4.z, v4.z, a, lr);
+      p4.w = adam_one(p4.w, g4.w, m4.w, v4.w, a, lr);
+      *reinterpret_cast<float4*>(p + i) = p4;
+      *reinterpret_cast<float4*>(m + i) = m4;
+      *reinterpret_cast<float4*>(v + i) = v4;
+      if (sh) {
+        const int64_t r = i / a.row_len, c = i - r * a.row_len;
+        __nv_bfloat162 lo = __floats2bfloat162_rn(p4.x, p4.y), hi = __floats2bfloat162_rn(p4.z, p4.w);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&lo);
+        o.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(a.shadow + r * a.shadow_ld + c) = o;
+      }
+    } else {
+      for (int e = 0; e < 4 && i + e < n; ++e) {
+        float mi = m[i + e], vi = v[i + e];
+        const float pi = adam_one(p[i + e], g[i + e], mi, vi, a, lr);
+        p[i + e] = pi; m[i + e] = mi; v[i + e] = vi;
+        if (sh) {
+          const int64_t r = (i + e) / a.row_len, c = (i + e) - r * a.row_len;
+          a.shadow[r * a.shadow_ld + c] = __float2bfloat16(pi);
+        }
+      }
+    }
+  }
+}
+
 __global__ void cast_pad_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows,
                                      int64_t cols, int64_t ld) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -138,6 +212,44 @@ int mr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int64_
                                                               (float)(1.0 - beta2), (float)eps, (float)grad_scale,
                                                               static_cast<__nv_bfloat16*>(shadow_bf16), row_len, shadow_ld);
   MR_CHECK_LAUNCH("adam_kernel");
+  return MR_OK;
+}
+
+int mr_adam_step_multi(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v,
+                       const int64_t* numel, const double* lr, int64_t step, double beta1, double beta2, double eps,
+                       double grad_scale, int shadow_tensor, void* shadow_bf16, int64_t row_len, int64_t shadow_ld, void* stream) {
+  using namespace mr;
+  if (int rc = require_sm100()) return rc;
+  MR_REQUIRE(n_tensors >= 0 && n_tensors <= AD_MAX_TENSORS, MR_ERR_BAD_SHAPE, "mr_adam_step_multi: %d tensors (max %d per call)", n_tensors,
+             AD_MAX_TENSORS);
+  MR_REQUIRE(step >= 1, MR_ERR_BAD_SHAPE, "mr_adam_step_multi: step=%lld", (long long)step);
+  if (n_tensors == 0) return MR_OK;
+  MR_REQUIRE(p && g && m && v && numel && lr, MR_ERR_NULL, "mr_adam_step_multi: null pointer");
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  AdamMultiArgs a{};
+  int64_t blocks = 0;
+  for (int i = 0; i < n_tensors; ++i) {
+    MR_REQUIRE(p[i] && g[i] && m[i] && v[i] && numel[i] >= 0, MR_ERR_NULL, "mr_adam_step_multi: tensor %d", i);
+    a.p[i] = p[i]; a.g[i] = g[i]; a.m[i] = m[i]; a.v[i] = v[i]; a.n[i] = numel[i];
+    a.lr_over_bc1[i] = (float)(lr[i] / bc1);
+    a.blk_off[i] = (int32_t)blocks;
+    blocks += ceil_div(numel[i], (int64_t)AD_CHUNK);
+    MR_REQUIRE(blocks < (1ll << 30), MR_ERR_BAD_SHAPE, "mr_adam_step_multi: too many elements");
+  }
+  a.blk_off[n_tensors] = (int32_t)blocks;
+  a.n_tensors = n_tensors;
+  a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  a.beta1 = (float)beta1; a.omb1 = (float)(1.0 - beta1); a.beta2 = (float)beta2; a.omb2 = (float)(1.0 - beta2);
+  a.eps = (float)eps; a.grad_scale = (float)grad_scale;
+  a.shadow_tensor = shadow_bf16 ? shadow_tensor : -1;
+  a.shadow = static_cast<__nv_bfloat16*>(shadow_bf16); a.row_len = row_len; a.shadow_ld = shadow_ld;
+  if (a.shadow_tensor >= 0)
+    MR_REQUIRE(shadow_tensor < n_tensors && row_len > 0 && shadow_ld >= row_len && numel[shadow_tensor] % row_len == 0, MR_ERR_BAD_SHAPE,
+               "mr_adam_step_multi: bad shadow geometry");
+  if (blocks == 0) return MR_OK;
+  adam_multi_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(a);
+  MR_CHECK_LAUNCH("adam_multi_kernel");
   return MR_OK;
 }
 

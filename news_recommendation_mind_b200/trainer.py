@@ -43,7 +43,12 @@ class FusedAdam:
 
     @torch.no_grad()
     def step(self):
+        """One Adam update of every parameter that has a gradient: a single mr_adam_step_multi launch (chunks of 24
+        tensors), which also rewrites the bf16 shadow of the token table."""
+        import ctypes
+        from . import _lib
         self.steps += 1
+        items = []
         for g in self.param_groups:
             for p in g["params"]:
                 if p.grad is None:
@@ -51,13 +56,29 @@ class FusedAdam:
                 st = self.state.get(p)
                 if st is None:
                     st = self.state[p] = (torch.zeros_like(p), torch.zeros_like(p))
-                shadow = None
-                if self._want_shadow and p is self.embedding.weight:
+                grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                if not p.data.is_contiguous() or grad.dtype != torch.float32 or p.dtype != torch.float32:
+                    raise RuntimeError("FusedAdam needs contiguous fp32 parameters and gradients")
+                items.append((p, grad, st[0], st[1], g["lr"]))
+        lib = _lib.load()
+        for c0 in range(0, len(items), 24):
+            chunk = items[c0:c0 + 24]
+            n = len(chunk)
+            PA = ctypes.c_void_p * n
+            shadow, shadow_idx, row_len, shadow_ld = None, -1, 0, 0
+            for i, it in enumerate(chunk):
+                if self._want_shadow and it[0] is self.embedding.weight:
                     shadow = self.embedding.shadow_bf16()
-                ops.adam_step(p.data, p.grad.contiguous(), st[0], st[1], self.steps, g["lr"], self.betas[0], self.betas[1],
-                              self.eps, self.grad_scale, shadow)
-                if shadow is not None:
-                    self.embedding.mark_shadow_fresh(shadow)
+                    shadow_idx, row_len, shadow_ld = i, it[0].shape[-1], shadow.shape[-1]
+            dev = chunk[0][0].device
+            _lib.check(lib.mr_adam_step_multi(
+                n, PA(*[it[0].data_ptr() for it in chunk]), PA(*[it[1].data_ptr() for it in chunk]),
+                PA(*[it[2].data_ptr() for it in chunk]), PA(*[it[3].data_ptr() for it in chunk]),
+                (ctypes.c_int64 * n)(*[it[0].numel() for it in chunk]), (ctypes.c_double * n)(*[float(it[4]) for it in chunk]),
+                self.steps, self.betas[0], self.betas[1], self.eps, self.grad_scale, shadow_idx, _lib.ptr(shadow), row_len, shadow_ld,
+                _lib.stream_ptr(dev)), "mr_adam_step_multi")
+            if shadow is not None:
+                self.embedding.mark_shadow_fresh(shadow)
 
 
 def train_step(model, x, optimizer):

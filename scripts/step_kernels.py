@@ -23,11 +23,23 @@ for s in range(5):
     trainer.train_step(model, devb[s % 4], opt)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+import time
 e0.record()
+t0 = time.perf_counter()
 for s in range(steps):
     trainer.train_step(model, devb[s % 4], opt)
+t_enq = time.perf_counter() - t0
 e1.record(); torch.cuda.synchronize()
-print("unprofiled: %.3f ms/step" % (e0.elapsed_time(e1) / steps))
+print("unprofiled: %.3f ms/step (host enqueue %.3f ms/step)" % (e0.elapsed_time(e1) / steps, 1e3 * t_enq / steps))
+# host cost alone: the same loop with the GPU idle at the start of every step
+t_host = 0.0
+for s in range(steps):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    trainer.train_step(model, devb[s % 4], opt)
+    t_host += time.perf_counter() - t0
+torch.cuda.synchronize()
+print("host time to enqueue one step with an idle GPU: %.3f ms" % (1e3 * t_host / steps))
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for s in range(steps):

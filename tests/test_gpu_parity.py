@@ -174,6 +174,43 @@ def test_adam_matches_oracle():
     assert torch.equal(shadow[:, :30], pc.to(torch.bfloat16)) and float(shadow[:, 30:].abs().max()) == 0.0
 
 
+def test_fused_multi_tensor_adam_matches_oracle():
+    """trainer.FusedAdam.step = one mr_adam_step_multi launch for all parameters, two LR groups (Manager.py:389-413),
+    vector (n % 4 == 0) and scalar tails, bf16 shadow of the table refreshed in the same launch."""
+    import types
+    import torch.nn as nn
+    from news_recommendation_mind_b200 import trainer
+    gen = torch.Generator().manual_seed(11)
+    shapes = {"embedding.bert_word_embedding.weight": (257, 300), "encoderN.cnn.weight": (150, 300, 3), "encoderN.cnn.bias": (150,),
+              "encoderN.odd": (7, 3), "encoderU.w": (601,)}
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ps = nn.ParameterDict({k.replace(".", "_"): nn.Parameter(torch.randn(*sh, generator=gen)) for k, sh in shapes.items()})
+
+        def named_parameters(self, *a, **k):
+            for (name, _), p in zip(shapes.items(), self.ps.values()):
+                yield name, p
+    mod = M().cuda()
+    opt = trainer.FusedAdam(mod, lr=1e-2, bert_lr=3e-3)
+    shadow = torch.zeros(257, 320, dtype=torch.bfloat16, device="cuda")
+    table = dict(mod.named_parameters())["embedding.bert_word_embedding.weight"]
+    opt.embedding = types.SimpleNamespace(weight=table, shadow_bf16=lambda: shadow, mark_shadow_fresh=lambda s: None)
+    opt._want_shadow = True
+    ref = {n: (p.detach().cpu().clone(), torch.zeros(p.shape), torch.zeros(p.shape)) for n, p in mod.named_parameters()}
+    for step in range(1, 4):
+        for n, p in mod.named_parameters():
+            g = torch.randn(p.shape, generator=gen) * 1e-2
+            p.grad = g.cuda()
+            O.adam_step(ref[n][0], g, ref[n][1], ref[n][2], step, 3e-3 if "bert" in n else 1e-2)
+        opt.step()
+    for n, p in mod.named_parameters():
+        assert rel_err(p, ref[n][0]) < 1e-6, n
+        assert rel_err(opt.state[p][0], ref[n][1]) < 1e-6 and rel_err(opt.state[p][1], ref[n][2]) < 1e-6, n
+    assert torch.equal(shadow[:, :300], table.detach().to(torch.bfloat16)) and float(shadow[:, 300:].abs().max()) == 0.0
+
+
 def test_predict_fast_and_news_table():
     g = load_golden("tt_cnn_lstm")
     model = model_from_golden(g, "cnn", "lstm", "fp32").eval()
