@@ -176,8 +176,7 @@ def run_ours(args):
     NB = 8
     host = [data.make_train_batch(ids, mask, CFG["B"], CFG["C"], CFG["S"], seed=100 * rank + i, pin=True) for i in range(NB)]
     devb = [{k: v.to(dev) for k, v in b.items()} for b in host]
-    h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in
-              ("cdd_encoded_index", "cdd_attn_mask", "his_encoded_index", "his_attn_mask", "user_id", "label")) + CFG["B"] * 4
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values() if torch.is_tensor(v))      # every field of the batch dict
 
     def barrier():
         if world > 1:
@@ -189,10 +188,14 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
-        for s in range(steps):
-            loss = trainer.train_step(model, batches[s % NB], opt)
-            if read_loss:
-                loss.item()                                   # device -> host read of the step's result
+        if read_loss:
+            # end to end through the public training loop: pinned host batches, every step copies its inputs to the device
+            # (next batch staged on a side stream) and its loss is read back on the host (one step of lag)
+            losses = loop.run(batches, steps)
+            assert len(losses) == steps
+        else:
+            for s in range(steps):
+                trainer.train_step(model, batches[s % NB], opt)
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -224,7 +227,8 @@ def run_ours(args):
             conv_launches, conv_ms = n_.value, m_.value
         lib.mr_debug_conv_timing(0)
     clocks = sampler.stop() if sampler else None
-    trainer.train_step(model, host[0], opt)
+    loop = trainer.TrainLoop(model, opt)          # the public training loop (staging buffers / pinned loss slots made once)
+    loop.run(host, 3)
     ms_e2e = timed(host, args.steps, True)
 
     # dominant kernel = the conv-forward tap GEMM (gather + 3-tap implicit GEMM + bias + ReLU on tcgen05): its

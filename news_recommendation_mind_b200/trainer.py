@@ -94,3 +94,103 @@ def train_step(model, x, optimizer):
 
 def to_device(x, device):
     return {k: (v.to(device, non_blocking=True) if torch.is_tensor(v) and k != "his_mask" else v) for k, v in x.items()}
+
+
+class BatchPrefetcher:
+    """Host -> device staging of the NEXT batch on a side stream while the current step computes.
+
+    The reference copies every field synchronously inside the model (TwoTower.py:24-27,38-41: ``.to(self.device)``
+    on pageable DataLoader tensors).  Here the int64 id / mask tensors of batch i+1 (7.2 MB at the MIND-small
+    shape) cross PCIe during step i.  ``his_mask`` is staged too: left on the host (as the reference does, RNN.py:65)
+    its lengths would reach the device through a pageable, stream-ordered copy that stalls the host until the
+    previous step has drained."""
+
+    def __init__(self, device, depth=2):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.depth = depth
+        self.bufs = [None] * depth          # static device copies of the batch dict (no allocator traffic per step)
+        self.free = [None] * depth          # event: the step that consumed buffer k has been queued and finished
+        self.count = 0
+
+    def _fits(self, buf, x):
+        return buf is not None and all(torch.is_tensor(v) == (k in buf) and (not torch.is_tensor(v) or (
+            buf[k].shape == v.shape and buf[k].dtype == v.dtype)) for k, v in x.items())
+
+    def stage(self, x):
+        k = self.count % self.depth
+        self.count += 1
+        if not self._fits(self.bufs[k], x):
+            self.bufs[k] = {key: torch.empty(v.shape, dtype=v.dtype, device=self.device) for key, v in x.items() if torch.is_tensor(v)}
+            self.free[k] = None
+        with torch.cuda.stream(self.stream):
+            if self.free[k] is not None:
+                self.stream.wait_event(self.free[k])
+            else:
+                self.stream.wait_stream(torch.cuda.current_stream(self.device))     # fresh buffers: allocated on the compute stream
+            for key, dst in self.bufs[k].items():
+                dst.copy_(x[key], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        extra = {key: v for key, v in x.items() if not torch.is_tensor(v)}
+        return k, ev, extra
+
+    def take(self, staged):
+        k, ev, extra = staged
+        torch.cuda.current_stream(self.device).wait_event(ev)
+        out = dict(self.bufs[k])
+        out.update(extra)
+        return out
+
+    def release(self, staged):
+        """call after the step that consumed `staged` has been queued: its buffer may be overwritten once that step is done"""
+        k = staged[0]
+        self.free[k] = torch.cuda.Event()
+        self.free[k].record(torch.cuda.current_stream(self.device))
+
+
+class TrainLoop:
+    """The training loop over host (pinned) batches: input prefetch + lagged loss read.  The loss of step i is copied
+    to pinned host memory right behind step i on the compute stream (+ an event) and read by the host after step i+1
+    has been queued, so the device never waits for the host; the last loss is read at the end of run().  The staging
+    buffers, the pinned loss slots and the events are created once (cudaHostAlloc is a multi-millisecond, device-
+    synchronising call)."""
+
+    def __init__(self, model, optimizer):
+        self.model, self.optimizer = model, optimizer
+        core = model.module if hasattr(model, "module") else model
+        self.prefetch = BatchPrefetcher(core.device)
+        self.slots = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.events = [torch.cuda.Event() for _ in range(2)]
+
+    def run(self, host_batches, steps, on_loss=None):
+        pf, slots, events = self.prefetch, self.slots, self.events
+        n = len(host_batches)
+        losses = []
+
+        def read(i):
+            events[i % 2].synchronize()
+            losses.append(float(slots[i % 2][0]))
+            if on_loss is not None:
+                on_loss(i, losses[-1])
+
+        staged = pf.stage(host_batches[0]) if steps > 0 else None
+        for s in range(steps):
+            cur = staged
+            x = pf.take(cur)
+            if s + 1 < steps:
+                staged = pf.stage(host_batches[(s + 1) % n])
+            loss = train_step(self.model, x, self.optimizer)
+            pf.release(cur)
+            slots[s % 2].copy_(loss.detach().reshape(1), non_blocking=True)        # device -> host read of the step's result
+            events[s % 2].record()
+            if s >= 1:
+                read(s - 1)
+        if steps >= 1:
+            read(steps - 1)
+        return losses
+
+
+def run_steps(model, host_batches, optimizer, steps, on_loss=None):
+    """One-shot convenience wrapper around TrainLoop (pays its set-up cost on every call)."""
+    return TrainLoop(model, optimizer).run(host_batches, steps, on_loss)

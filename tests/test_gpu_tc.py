@@ -158,6 +158,30 @@ def test_twotower_bf16_training_step_vs_fp32_oracle(B, C, S, L, E, H):
     assert float(model.embedding.weight.grad[0].abs().max()) == 0.0
 
 
+def test_train_loop_prefetch_matches_plain_steps():
+    """trainer.TrainLoop (host batches staged on a side stream into static buffers, losses read with one step of lag)
+    produces bit-identical losses and parameters to calling train_step on device-resident copies of the same batches."""
+    import sys, os, copy
+    sys.path.insert(0, os.path.dirname(__file__))
+    from helpers import build_model, manager_for, random_batch
+    from news_recommendation_mind_b200 import trainer
+    B, C, S, L, E, H, V = 6, 5, 9, 32, 300, 150, 500
+    gen = torch.Generator().manual_seed(3)
+    host = [{k: v.pin_memory() for k, v in random_batch(gen, B, C, S, L, V).items()} for _ in range(3)]
+    torch.manual_seed(5)
+    man = manager_for("cnn", "lstm", C, S, L, E, H, 10, precision="bf16")
+    m1 = build_model(man, V)
+    m2 = copy.deepcopy(m1)
+    o1, o2 = trainer.FusedAdam(m1, lr=1e-3, bert_lr=1e-4), trainer.FusedAdam(m2, lr=1e-3, bert_lr=1e-4)
+    seen = []
+    got = trainer.TrainLoop(m1, o1).run(host, 7, on_loss=lambda i, v: seen.append(i))
+    exp = [float(trainer.train_step(m2, {k: v.cuda() for k, v in host[s % 3].items()}, o2)) for s in range(7)]
+    assert seen == list(range(7))
+    assert got == exp, (got, exp)
+    for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert torch.equal(a, b), k
+
+
 def cnn_encoder_bf16_backward_emulation(table, ids, mask, conv_w, conv_b, proj_w, proj_b, query, g, grouped=False):
     """float64 restatement of the backward of oracle.twotower_oracle.cnn_news_encoder (autograd of CNN.py:30-51,
     softmax backward of Attention.py:77-80) with bf16 rounding at the points where the MR_BF16 kernels store
