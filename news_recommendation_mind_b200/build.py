@@ -46,12 +46,24 @@ def _digest() -> str:
                 h.update(f.encode())
                 with open(os.path.join(root, f), "rb") as fh:
                     h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    # flags without the absolute include path: the tree is built here and shipped to the GPU box under another root
+    h.update(" ".join(f for f in NVCC_FLAGS if f != INCLUDE).encode())
     return h.hexdigest()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Idempotent and safe to call from several processes at once (one rank builds, the others wait on a file lock)."""
+    import fcntl
     os.makedirs(BUILD, exist_ok=True)
+    with open(os.path.join(BUILD, "lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> str:
     stamp = os.path.join(BUILD, "stamp")
     digest = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
@@ -73,10 +85,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    tmp = LIB + ".tmp.%d" % os.getpid()
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    os.replace(tmp, LIB)                      # never expose a half-written library
     with open(stamp, "w") as fh:
         fh.write(digest)
     return LIB

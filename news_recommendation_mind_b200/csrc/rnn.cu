@@ -11,6 +11,7 @@
 // pos(s) = s, or S-1-s when `reverse` (the reference flips the padded history *before* packing).
 #include "gemm_simt.cuh"
 #include "rnn_res.cuh"
+#include <stdlib.h>
 #include "tapgemm.cuh"
 #include "tokred.cuh"
 
@@ -424,7 +425,7 @@ static int64_t rnn_ws(const mr_rnn_shape* s, int backward) {
   int64_t b = 0;
   if (!backward) {
     b += arena_bytes(BS * align_up(GH, 4), 4);   // xp
-    b += arena_bytes(s->H * GH + rnn_res_scratch_bytes(s->kind, (int)s->H) / 4, 4);         // whhT / bf16 image of W_hh
+    b += arena_bytes(s->H * GH + rnn_res_scratch_bytes(s->kind, (int)s->H) / 4 + rnn_mma_scratch_bytes(s->kind, (int)s->H) / 4, 4);   // whhT / bf16 images of W_hh
     if (rnn_tc_ok(s)) b += rnn_tc_ws(s, 0);
     return b + 256;
   }
@@ -436,6 +437,16 @@ static int64_t rnn_ws(const mr_rnn_shape* s, int backward) {
 }
 
 }  // namespace mr
+
+// MINDREC_RNN_MMA=0 keeps the SIMT resident-weights recurrence (A/B)
+static bool rnn_use_mma() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MINDREC_RNN_MMA");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 
 extern "C" {
 
@@ -468,7 +479,7 @@ int mr_rnn_user_fwd(const mr_rnn_shape* s, const float* x, const int32_t* lens, 
   Arena ar(workspace, workspace_bytes);
   const int64_t ldx = rnn_tc_ok(s) ? align_up(GH, 4) : GH;       // pitch of the input projection (16-byte rows for the tensor-core epilogue)
   float* xp = ar.take<float>((int64_t)B * S * ldx);
-  float* whhT = ar.take<float>((int64_t)H * GH + rnn_res_scratch_bytes(s->kind, H) / 4);
+  float* whhT = ar.take<float>((int64_t)H * GH + rnn_res_scratch_bytes(s->kind, H) / 4 + rnn_mma_scratch_bytes(s->kind, H) / 4);
   MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "mr_rnn_user_fwd: workspace too small (%lld given)", (long long)workspace_bytes);
   if (rnn_tc_ok(s)) {
     if (int rc = rnn_tc_input_proj(s, x, w_ih, b_ih, s->kind == MR_RNN_LSTM ? b_hh : nullptr, xp, ar, st)) return rc;
@@ -482,6 +493,8 @@ int mr_rnn_user_fwd(const mr_rnn_shape* s, const float* x, const int32_t* lens, 
   cudaMemsetAsync(gates, 0, sizeof(float) * (int64_t)B * S * GH, st);
   cudaMemsetAsync(hs, 0, sizeof(float) * (int64_t)B * S * H, st);
   cudaMemsetAsync(cs, 0, sizeof(float) * (int64_t)B * S * H, st);
+  if (s->precision == MR_BF16 && rnn_mma_supported(s->kind, H) && rnn_use_mma())
+    return rnn_mma_fwd(s->kind, xp, (int)ldx, w_hh, b_hh, h0, lens, gates, hs, cs, user, B, S, H, whhT, st);
   if (s->precision == MR_BF16 && rnn_res_supported(s->kind, H))
     return rnn_res_fwd(s->kind, xp, (int)ldx, w_hh, b_hh, h0, lens, gates, hs, cs, user, B, S, H, whhT, st);
   dim3 tg((unsigned)ceil_div(H, 32), (unsigned)ceil_div(GH, 32)), tb(32, 8);

@@ -18,4 +18,11 @@ int rnn_res_bwd(int kind, const float* w_hh, const float* h0, const int32_t* len
 // scratch for the bf16 image of W_hh the kernels bulk-copy into shared memory
 int64_t rnn_res_scratch_bytes(int kind, int H);
 
+
+// ---- rnn_mma.cu: the same recurrence on mma.sync tensor-core MMAs, W_hh in registers + shared memory, h as bf16 hi + lo ----
+bool rnn_mma_supported(int kind, int H);               // H <= 160, G*H <= 768
+int64_t rnn_mma_scratch_bytes(int kind, int H);
+int rnn_mma_fwd(int kind, const float* xp, int ldx, const float* w_hh, const float* b_hh, const float* h0, const int32_t* lens,
+                float* gates, float* hs, float* cs, float* user, int B, int S, int H, void* scratch, cudaStream_t st);
+
 }  // namespace mr

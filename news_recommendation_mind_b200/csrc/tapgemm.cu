@@ -154,11 +154,14 @@ __global__ void __launch_bounds__(EPI2 ? TG_THREADS2 : TG_THREADS, 1) tapgemm_ke
         TG_TIMED(0, tc::mbar_wait(&t_full[acc.pos], acc.phase));
         tc::tc_fence_after();
         const uint32_t tb = tmem + ((uint32_t)((warp & 3) * 32) << 16) + acc.pos * 256u;
-#pragma unroll
+        // NOT unrolled: five copies of this body (~2k instructions) overflow the instruction cache, and the epilogue warps
+        // then stall on instruction fetch; the per-chunk mask / column-sum registers are picked with selects instead
+#pragma unroll 1
         for (int ci = 0; ci < 5; ++ci) {
           if (ci * 32 < n_total) {
             const int n0 = ci * 32;
             const bool wide = n_total - n0 >= 32;
+            const uint32_t cmask_c = ci == 0 ? cm[0] : (ci == 1 ? cm[1] : (ci == 2 ? cm[2] : (ci == 3 ? cm[3] : cm[4])));
             uint32_t v[32];
             if (wide) {
               tc::tmem_ld32(tb + n0, v);
@@ -200,8 +203,8 @@ __global__ void __launch_bounds__(EPI2 ? TG_THREADS2 : TG_THREADS, 1) tapgemm_ke
                     const float2 e2 = __bfloat1622float2(h0[w]);
                     a0 += e2.x; a1 += e2.y;
                   }
-                  a0 = ((cm[ci] >> j) & 1u) ? a0 : 0.f;
-                  a1 = ((cm[ci] >> (j + 1)) & 1u) ? a1 : 0.f;
+                  a0 = ((cmask_c >> j) & 1u) ? a0 : 0.f;
+                  a1 = ((cmask_c >> (j + 1)) & 1u) ? a1 : 0.f;
                 }
                 f[j] = a0; f[j + 1] = a1;
               }
@@ -220,7 +223,12 @@ __global__ void __launch_bounds__(EPI2 ? TG_THREADS2 : TG_THREADS, 1) tapgemm_ke
                 }
               }
             }
-            if (p.colsum_out != nullptr) colacc[ci] += tc::warp_colsum32(f, lane);
+            if (p.colsum_out != nullptr) {
+              const float csum = tc::warp_colsum32(f, lane);
+#pragma unroll
+              for (int cj = 0; cj < 5; ++cj)
+                if (cj == ci) colacc[cj] += csum;
+            }
           }
         }
         tc::tc_fence_before();
