@@ -290,30 +290,41 @@ seg_reduce_heavy_kernel(const int32_t* __restrict__ chunk_off, const int32_t* __
   }
 }
 
+// final: CTA (h, column block of 64) adds the slice sums of heavy row h in slice order -- 4 slice groups x 64 columns
+// per CTA (4 independent chains each), combined through shared memory in a fixed order
 template <class TO>
 __global__ void __launch_bounds__(256)
 seg_reduce_heavy_final_kernel(const float* __restrict__ partial2, TO* __restrict__ d_table, int64_t ldo,
                               const int32_t* __restrict__ nchunk, const int32_t* __restrict__ heavy_count,
                               const int32_t* __restrict__ heavy_rows, int64_t E, int32_t max_items) {
   __shared__ int32_t off[SEG_MAX_HEAVY_SMEM + 1];
+  __shared__ float red[4][64];
   const int nh = min(*heavy_count, SEG_MAX_HEAVY_SMEM);
   if (nh == 0) return;
   heavy_prefix(heavy_rows, nchunk, nh, off);
+  const int cx = threadIdx.x & 63, sg = threadIdx.x >> 6;
+  const int64_t e = (int64_t)blockIdx.y * 64 + cx;
   for (int h = blockIdx.x; h < nh; h += gridDim.x) {
     const int32_t v = heavy_rows[h];
     const int i0 = off[h], i1 = min(off[h + 1], max_items);
-    for (int64_t e = threadIdx.x; e < E; e += blockDim.x) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      int i = i0;
-      for (; i + 3 < i1; i += 4) {
+    // slice group sg takes a contiguous quarter of the slices
+    const int per = (i1 - i0 + 3) / 4;
+    const int a = min(i1, i0 + sg * per), b = min(i1, a + per);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (e < E) {
+      int i = a;
+      for (; i + 3 < b; i += 4) {
         a0 += partial2[(int64_t)i * E + e];
         a1 += partial2[(int64_t)(i + 1) * E + e];
         a2 += partial2[(int64_t)(i + 2) * E + e];
         a3 += partial2[(int64_t)(i + 3) * E + e];
       }
-      for (; i < i1; ++i) a0 += partial2[(int64_t)i * E + e];
-      d_table[(int64_t)v * ldo + e] = seg_out<TO>((a0 + a1) + (a2 + a3));
+      for (; i < b; ++i) a0 += partial2[(int64_t)i * E + e];
     }
+    red[sg][cx] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (sg == 0 && e < E) d_table[(int64_t)v * ldo + e] = seg_out<TO>((red[0][cx] + red[1][cx]) + (red[2][cx] + red[3][cx]));
+    __syncthreads();
   }
 }
 
@@ -485,7 +496,7 @@ int token_group_taps(const void* ids, int ids_i64, const __nv_bfloat16* dconv, i
   MR_CHECK_LAUNCH("seg_reduce_l2_kernel");
   seg_reduce_heavy_kernel<<<148 * 4, 256, 0, st>>>(chunk_off, nchunk, partial, partial2, heavy, heavy + 1, E, (int32_t)p.max_items);
   MR_CHECK_LAUNCH("seg_reduce_heavy_kernel");
-  seg_reduce_heavy_final_kernel<__nv_bfloat16><<<148 * 2, 256, 0, st>>>(partial2, S, E, nchunk, heavy, heavy + 1, E, (int32_t)p.max_items);
+  seg_reduce_heavy_final_kernel<__nv_bfloat16><<<dim3(64, (unsigned)ceil_div(E, 64)), 256, 0, st>>>(partial2, S, E, nchunk, heavy, heavy + 1, E, (int32_t)p.max_items);
   MR_CHECK_LAUNCH("seg_reduce_heavy_final_kernel");
   return MR_OK;
 }
@@ -588,7 +599,7 @@ int mr_embed_grad_segreduce(const void* ids, int ids_i64, const void* d_emb, int
   MR_CHECK_LAUNCH("seg_reduce_l2_kernel");
   seg_reduce_heavy_kernel<<<148 * 4, 256, 0, st>>>(chunk_off, nchunk, partial, partial2, heavy, heavy + 1, E, (int32_t)p.max_items);
   MR_CHECK_LAUNCH("seg_reduce_heavy_kernel");
-  seg_reduce_heavy_final_kernel<float><<<148 * 2, 256, 0, st>>>(partial2, d_table, E, nchunk, heavy, heavy + 1, E, (int32_t)p.max_items);
+  seg_reduce_heavy_final_kernel<float><<<dim3(64, (unsigned)ceil_div(E, 64)), 256, 0, st>>>(partial2, d_table, E, nchunk, heavy, heavy + 1, E, (int32_t)p.max_items);
   MR_CHECK_LAUNCH("seg_reduce_heavy_final_kernel");
   return MR_OK;
 }

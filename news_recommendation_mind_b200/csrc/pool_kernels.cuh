@@ -185,9 +185,10 @@ __device__ __forceinline__ uint4 f_to_bf8(const float* f) {
 
 // row scores: out (valid in every lane l < L) = sum_h vec[h] * x[l, h];  vec is given as this lane's slices
 // for the "8 lanes per row" mapping: vr[i][0..7] = vec[(part + 8 i) * 8 ..], part = lane & 7
-template <int MAXP>     // MAXP = ceil(pieces / 8) <= 4
+// MASK: also writes one byte per 8-column piece to mask_out[l * 32 + piece], bit e = (x[l, 8 piece + e] > 0)
+template <int MAXP, bool MASK = false>     // MAXP = ceil(pieces / 8) <= 4
 __device__ __forceinline__ float row_dots_bf16(const __nv_bfloat16* __restrict__ x, int64_t ld, int L, int pieces,
-                                               const float (&vr)[MAXP][8], int lane) {
+                                               const float (&vr)[MAXP][8], int lane, uint8_t* __restrict__ mask_out = nullptr) {
   const int rr = lane >> 3, part = lane & 7;
   float mine = 0.f;
   for (int it = 0; it < 8; ++it) {
@@ -206,6 +207,12 @@ __device__ __forceinline__ float row_dots_bf16(const __nv_bfloat16* __restrict__
           bf8_to_f(v[i], f);
 #pragma unroll
           for (int e = 0; e < 8; ++e) d = fmaf(vr[i][e], f[e], d);
+          if (MASK) {
+            uint32_t bits = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) bits |= (f[e] > 0.f ? 1u : 0u) << e;
+            mask_out[(int64_t)l * 32 + part + 8 * i] = (uint8_t)bits;
+          }
         }
     }
     d += __shfl_xor_sync(0xffffffffu, d, 1);
@@ -297,7 +304,8 @@ cnn_pool_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ c, const __nv_bfloat1
         const int h = ((lane & 7) + 8 * i) * 8 + e;
         dr[i][e] = h < H ? __ldg(dn + h) : 0.f;
       }
-    const float dp = row_dots_bf16<MAXP>(cn, ld, L, pieces, dr, lane);        // <d_news, c[l]>
+    // <d_news, c[l]>; the same pass over c writes its sign mask
+    const float dp = row_dots_bf16<MAXP, true>(cn, ld, L, pieces, dr, lane, cmask + n * L * 32);
     const float p = lane < L ? prob[n * L + lane] : 0.f;
     const float dot = warp_sum(p * dp);
     const float ds = p * (dp - dot) * rsqrtf((float)H);                       // softmax backward (Attention.py:77-80)
@@ -315,20 +323,13 @@ cnn_pool_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ c, const __nv_bfloat1
       o[1] = make_float4(dv[4], dv[5], dv[6], dv[7]);
     }
     const uint4* kp = reinterpret_cast<const uint4*>(kn) + lane;
-    const uint4* cpp = reinterpret_cast<const uint4*>(cn) + lane;
     uint4* dko = reinterpret_cast<uint4*>(dkp + n * L * ld) + lane;
-    uint8_t* cmo = cmask + n * L * 32 + lane;          // byte `piece` of the 32-byte row: (c[l, 8 piece + e] > 0) in bit e
 #pragma unroll 4
     for (int l = 0; l < L; ++l) {
       const float dsl = __shfl_sync(0xffffffffu, ds, l);
       if (lane < pieces) {
-        float k[8], o1[8], cv[8];
+        float k[8], o1[8];
         bf8_to_f(__ldg(kp + (int64_t)l * pieces), k);
-        bf8_to_f(__ldg(cpp + (int64_t)l * pieces), cv);
-        uint32_t bits = 0;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) bits |= (cv[e] > 0.f ? 1u : 0u) << e;
-        cmo[(int64_t)l * 32] = (uint8_t)bits;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           dq[e] = fmaf(dsl, k[e], dq[e]);

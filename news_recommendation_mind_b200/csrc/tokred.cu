@@ -244,27 +244,37 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs 
   if (warp == 4) tc::tmem_dealloc(tmem, 512);
 }
 
-__global__ void tokred_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dst, int S, int taps, int NQ,
-                                     int i_valid, int j_valid, int64_t dj, int64_t di, int64_t dt) {
+// 256 threads = 64 outputs x 4 groups of partials (4 independent chains each); fixed combine order
+__global__ void __launch_bounds__(256) tokred_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dst, int S, int taps, int NQ,
+                                                            int i_valid, int j_valid, int64_t dj, int64_t di, int64_t dt) {
+  __shared__ float red[4][64];
+  const int ox = threadIdx.x & 63, sg = threadIdx.x >> 6;
   const int64_t total = (int64_t)taps * i_valid * j_valid;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int j = (int)(idx % j_valid);
-  const int i = (int)((idx / j_valid) % i_valid);
-  const int tap = (int)(idx / ((int64_t)j_valid * i_valid));
-  const int m = i / 128, il = i % 128;
-  const float* src = partial + (((size_t)m * S * taps + tap) * 128 + il) * NQ + j;
-  const size_t stride = (size_t)taps * 128 * NQ;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;       // four independent chains (the loads are the latency), fixed combine order
-  int s = 0;
-  for (; s + 3 < S; s += 4) {
-    a0 += src[(size_t)s * stride];
-    a1 += src[(size_t)(s + 1) * stride];
-    a2 += src[(size_t)(s + 2) * stride];
-    a3 += src[(size_t)(s + 3) * stride];
+  const int64_t idx = (int64_t)blockIdx.x * 64 + ox;
+  const bool on = idx < total;
+  int j = 0, i = 0, tap = 0;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (on) {
+    j = (int)(idx % j_valid);
+    i = (int)((idx / j_valid) % i_valid);
+    tap = (int)(idx / ((int64_t)j_valid * i_valid));
+    const int m = i / 128, il = i % 128;
+    const float* src = partial + (((size_t)m * S * taps + tap) * 128 + il) * NQ + j;
+    const size_t stride = (size_t)taps * 128 * NQ;
+    const int per = (S + 3) / 4;
+    const int s0 = min(S, sg * per), s1 = min(S, s0 + per);
+    int s = s0;
+    for (; s + 3 < s1; s += 4) {
+      a0 += src[(size_t)s * stride];
+      a1 += src[(size_t)(s + 1) * stride];
+      a2 += src[(size_t)(s + 2) * stride];
+      a3 += src[(size_t)(s + 3) * stride];
+    }
+    for (; s < s1; ++s) a0 += src[(size_t)s * stride];
   }
-  for (; s < S; ++s) a0 += src[(size_t)s * stride];
-  dst[j * dj + i * di + tap * dt] = (a0 + a1) + (a2 + a3);
+  red[sg][ox] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (sg == 0 && on) dst[j * dj + i * di + tap * dt] = (red[0][ox] + red[1][ox]) + (red[2][ox] + red[3][ox]);
 }
 
 static void tokred_geometry(int64_t n_titles, int L, int taps, int KP, int* G, int* n_mtiles, int* S, int64_t* n_tiles) {
@@ -353,7 +363,7 @@ int tokred_reduce(const TokRedPlan& plan, float* dst, int i_valid, int j_valid, 
                   cudaStream_t stream) {
   const TokRedArgs& a = plan.args;
   const int64_t total = (int64_t)a.taps * i_valid * j_valid;
-  tokred_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(a.partial, dst, a.S, a.taps, a.NQ, i_valid, j_valid,
+  tokred_reduce_kernel<<<(unsigned)ceil_div(total, 64), 256, 0, stream>>>(a.partial, dst, a.S, a.taps, a.NQ, i_valid, j_valid,
                                                                           dj, di, dt);
   MR_CHECK_LAUNCH("tokred_reduce_kernel");
   return MR_OK;
