@@ -136,12 +136,19 @@ MR_API int mr_news_cnn_bwd(const mr_cnn_shape* s,
  * atomics), so the table- and filter-gradient GEMMs run over V rows instead of N*L tokens.  `table_bf16` is the padded
  * bf16 table the forward gathered from, with table_rows >= align_up(V, 32) rows (rows >= V zero).  E % 4 == 0. */
 MR_API int64_t mr_news_cnn_bwd_table_workspace_bytes(const mr_cnn_shape* s);
+/* The grouping plan (token positions sorted by id, segment bounds, chunk table) depends on the ids only.  It can be
+ * built ahead of the backward -- e.g. on a second stream while the forward runs -- and passed as `group_plan`
+ * (NULL: mr_news_cnn_bwd_table builds it itself).  n_tokens = N*L. */
+MR_API int64_t mr_token_group_plan_bytes(int64_t n_tokens, int64_t V);
+MR_API int mr_token_group_plan(const void* ids, int ids_i64, int64_t n_tokens, int64_t V,
+                    void* plan, int64_t plan_bytes, void* stream);
 MR_API int mr_news_cnn_bwd_table(const mr_cnn_shape* s,
                     const void* ids, int ids_i64, const void* table_bf16, int64_t table_rows,
                     const float* conv_w, const float* proj_w, const float* query,
                     const void* c_save, const void* key_save, const float* prob, const float* d_news,
                     float* d_conv_w, float* d_conv_b, float* d_proj_w, float* d_proj_b, float* d_query,
                     float* d_table, int64_t padding_idx,
+                    const void* group_plan, int64_t group_plan_bytes,
                     void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ----------------------------------------------------------------------------------------------

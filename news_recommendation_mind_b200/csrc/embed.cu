@@ -363,16 +363,14 @@ static EmbedGradPlan plan_embed_grad(int64_t T, int64_t E, int64_t V) {
 template <int MAXV>     // 16-byte vectors per lane: 3 * Hp / 8 <= 32 * MAXV
 __global__ void __launch_bounds__(256)
 group_taps_l1_kernel(const __nv_bfloat16* __restrict__ dconv, int64_t ld, int L, int pieces, const int32_t* __restrict__ sorted_pos,
-                     const int32_t* __restrict__ seg_start, const int32_t* __restrict__ chunk_off,
-                     const int32_t* __restrict__ chunk_row, const int32_t* __restrict__ nchunk,
-                     __nv_bfloat16* __restrict__ S, int64_t lds, float* __restrict__ partial, int64_t n_chunks, int64_t V) {
+                     const int4* __restrict__ chunk_desc, __nv_bfloat16* __restrict__ S, int64_t lds, float* __restrict__ partial,
+                     int64_t n_chunks) {
   const int lane = threadIdx.x & 31;
   const int64_t ch = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (ch >= n_chunks || ch >= chunk_off[V]) return;
-  const int32_t v = chunk_row[ch];
-  const int32_t j = (int32_t)ch - chunk_off[v];
-  const int32_t beg = seg_start[v] + j * SEG_CHUNK;
-  const int32_t end = min(seg_start[v + 1], beg + SEG_CHUNK);
+  if (ch >= n_chunks) return;
+  const int4 cd = __ldg(chunk_desc + ch);
+  if (cd.x < 0) return;
+  const int32_t v = cd.x, beg = cd.y, end = cd.z;
   const int nvec = 3 * pieces;
   int shift[MAXV], col[MAXV];             // vector i = lane + 32 a: tap = i / pieces reads row t + 1 - tap, columns 8 (i % pieces)..
 #pragma unroll
@@ -409,7 +407,7 @@ group_taps_l1_kernel(const __nv_bfloat16* __restrict__ dconv, int64_t ld, int L,
       }
     }
   }
-  const bool direct = nchunk[v] == 1;
+  const bool direct = cd.w != 0;
 #pragma unroll
   for (int a = 0; a < MAXV; ++a) {
     const int i = lane + 32 * a;
@@ -430,45 +428,75 @@ group_taps_l1_kernel(const __nv_bfloat16* __restrict__ dconv, int64_t ld, int L,
   }
 }
 
-int64_t token_group_workspace_bytes(int64_t T, int64_t Hp, int64_t V) {
-  if (T < 0 || V < 1 || T >= (1ll << 31)) return -1;
-  const int64_t E = 3 * Hp;
-  EmbedGradPlan p = plan_embed_grad(T, E, V);
-  int64_t b = 0;
-  b += 4 * arena_bytes(T, 4);
-  b += 3 * arena_bytes(V + 1, 4);
-  b += arena_bytes(p.max_chunks, 4);
-  b += arena_bytes(p.max_chunks * E, 4);
-  b += arena_bytes(p.max_heavy + 1, 4) + arena_bytes(p.max_items * E, 4);
-  b += arena_bytes((int64_t)p.cub_sort_bytes, 1) + arena_bytes((int64_t)p.cub_scan_bytes, 1);
-  return b + 256;
+// ---- the grouping PLAN depends on the token ids only (not on any gradient): it can be built while the forward pass
+// is still running (ops.py queues it on a side stream) and is consumed by the backward --------------------------
+struct GroupPlanLayout {
+  int64_t svals, seg_start, nchunk, chunk_off, chunk_desc, scratch, total;     // byte offsets into the plan buffer
+  int64_t max_chunks;
+  size_t cub_sort_bytes, cub_scan_bytes;
+};
+static GroupPlanLayout group_plan_layout(int64_t T, int64_t V) {
+  GroupPlanLayout l{};
+  EmbedGradPlan p = plan_embed_grad(T, 4, V);
+  l.max_chunks = p.max_chunks;
+  l.cub_sort_bytes = p.cub_sort_bytes;
+  l.cub_scan_bytes = p.cub_scan_bytes;
+  int64_t o = 0;
+  l.svals = o; o += arena_bytes(T, 4);
+  l.seg_start = o; o += arena_bytes(V + 1, 4);
+  l.nchunk = o; o += arena_bytes(V + 1, 4);
+  l.chunk_off = o; o += arena_bytes(V + 1, 4);
+  l.chunk_desc = o; o += arena_bytes(p.max_chunks * 4, 4);
+  l.scratch = o;                                     // keys, vals, sorted keys, cub temporaries (dead after the build)
+  o += 3 * arena_bytes(T, 4) + arena_bytes((int64_t)p.cub_sort_bytes, 1) + arena_bytes((int64_t)p.cub_scan_bytes, 1);
+  l.total = o + 256;
+  return l;
 }
 
-int token_group_taps(const void* ids, int ids_i64, const __nv_bfloat16* dconv, int64_t ld, int L, int64_t T, int64_t V,
-                     __nv_bfloat16* S, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
-  const int64_t Hp = ld, E = 3 * Hp;
-  MR_REQUIRE(Hp % 8 == 0 && 3 * Hp / 8 <= 64, MR_ERR_UNSUPPORTED, "token grouping: row pitch %lld", (long long)Hp);
-  EmbedGradPlan p = plan_embed_grad(T, E, V);
-  Arena ar(workspace, workspace_bytes);
+// chunk ch -> {vocabulary row, first sorted position, end, 1 if it is the row's only chunk}: one 16-byte load in the
+// reduction kernel instead of a chain of dependent lookups
+__global__ void chunk_desc_kernel(const int32_t* __restrict__ chunk_off, const int32_t* __restrict__ seg_start,
+                                  const int32_t* __restrict__ nchunk, int4* __restrict__ desc, int64_t V, int64_t max_chunks) {
+  const int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= max_chunks) return;
+  if (ch >= chunk_off[V]) { desc[ch] = make_int4(-1, 0, 0, 0); return; }
+  int64_t lo = 0, hi = V;
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (chunk_off[mid] <= ch) lo = mid; else hi = mid;
+  }
+  const int32_t v = (int32_t)lo;
+  const int32_t beg = seg_start[v] + ((int32_t)ch - chunk_off[v]) * SEG_CHUNK;
+  desc[ch] = make_int4(v, beg, min(seg_start[v + 1], beg + SEG_CHUNK), nchunk[v] == 1 ? 1 : 0);
+}
+
+int64_t token_group_plan_bytes(int64_t T, int64_t V) {
+  if (T < 0 || V < 1 || T >= (1ll << 31)) return -1;
+  return group_plan_layout(T, V).total;
+}
+
+int token_group_plan_build(const void* ids, int ids_i64, int64_t T, int64_t V, void* plan, int64_t plan_bytes, cudaStream_t st) {
+  const GroupPlanLayout l = group_plan_layout(T, V);
+  MR_REQUIRE(plan != nullptr && plan_bytes >= l.total, MR_ERR_WORKSPACE, "token grouping plan: buffer too small (%lld given, %lld needed)",
+             (long long)plan_bytes, (long long)l.total);
+  uint8_t* base = static_cast<uint8_t*>(plan);
+  int32_t* svals = reinterpret_cast<int32_t*>(base + l.svals);
+  int32_t* seg_start = reinterpret_cast<int32_t*>(base + l.seg_start);
+  int32_t* nchunk = reinterpret_cast<int32_t*>(base + l.nchunk);
+  int32_t* chunk_off = reinterpret_cast<int32_t*>(base + l.chunk_off);
+  int4* desc = reinterpret_cast<int4*>(base + l.chunk_desc);
+  Arena ar(base + l.scratch, plan_bytes - l.scratch);
   int32_t* keys = ar.take<int32_t>(T);
   int32_t* vals = ar.take<int32_t>(T);
   int32_t* skeys = ar.take<int32_t>(T);
-  int32_t* svals = ar.take<int32_t>(T);
-  int32_t* seg_start = ar.take<int32_t>(V + 1);
-  int32_t* nchunk = ar.take<int32_t>(V + 1);
-  int32_t* chunk_off = ar.take<int32_t>(V + 1);
-  int32_t* chunk_row = ar.take<int32_t>(p.max_chunks);
-  float* partial = ar.take<float>(p.max_chunks * E);
-  int32_t* heavy = ar.take<int32_t>(p.max_heavy + 1);
-  float* partial2 = ar.take<float>(p.max_items * E);
-  void* cub_sort = ar.take<char>((int64_t)p.cub_sort_bytes);
-  void* cub_scan = ar.take<char>((int64_t)p.cub_scan_bytes);
-  MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "token grouping: workspace too small (%lld given)", (long long)workspace_bytes);
+  void* cub_sort = ar.take<char>((int64_t)l.cub_sort_bytes);
+  void* cub_scan = ar.take<char>((int64_t)l.cub_scan_bytes);
+  MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "token grouping plan: buffer too small");
   make_keys_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, st>>>(ids, ids_i64, keys, vals, T, V);
   MR_CHECK_LAUNCH("make_keys_kernel");
   int bits = 1;
   while ((1ll << bits) < V) ++bits;
-  size_t sb = p.cub_sort_bytes;
+  size_t sb = l.cub_sort_bytes;
   cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_sort, sb, keys, skeys, vals, svals, (int)T, 0, bits, st);
   MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "radix sort: %s", cudaGetErrorString(e));
   count_launch(2 * ((bits + 7) / 8) + 1);
@@ -476,19 +504,52 @@ int token_group_taps(const void* ids, int ids_i64, const __nv_bfloat16* dconv, i
   MR_CHECK_LAUNCH("seg_bounds_kernel");
   chunk_count_kernel<<<(unsigned)ceil_div(V + 1, 256), 256, 0, st>>>(seg_start, nchunk, V, -1);     // every row, padding row included
   MR_CHECK_LAUNCH("chunk_count_kernel");
-  size_t cb = p.cub_scan_bytes;
+  size_t cb = l.cub_scan_bytes;
   e = cub::DeviceScan::ExclusiveSum(cub_scan, cb, nchunk, chunk_off, (int)V + 1, st);
   MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "scan: %s", cudaGetErrorString(e));
   count_launch(2);
-  chunk_fill_kernel<<<(unsigned)ceil_div(p.max_chunks, 256), 256, 0, st>>>(chunk_off, chunk_row, V, p.max_chunks);
-  MR_CHECK_LAUNCH("chunk_fill_kernel");
+  chunk_desc_kernel<<<(unsigned)ceil_div(l.max_chunks, 256), 256, 0, st>>>(chunk_off, seg_start, nchunk, desc, V, l.max_chunks);
+  MR_CHECK_LAUNCH("chunk_desc_kernel");
+  return MR_OK;
+}
+
+int64_t token_group_workspace_bytes(int64_t T, int64_t Hp, int64_t V) {
+  if (T < 0 || V < 1 || T >= (1ll << 31)) return -1;
+  const int64_t E = 3 * Hp;
+  EmbedGradPlan p = plan_embed_grad(T, E, V);
+  int64_t b = 0;
+  b += arena_bytes(group_plan_layout(T, V).total, 1);           // plan built in place when the caller brings none
+  b += arena_bytes(p.max_chunks * E, 4);
+  b += arena_bytes(p.max_heavy + 1, 4) + arena_bytes(p.max_items * E, 4);
+  return b + 256;
+}
+
+int token_group_taps(const void* ids, int ids_i64, const void* plan_in, const __nv_bfloat16* dconv, int64_t ld, int L, int64_t T,
+                     int64_t V, __nv_bfloat16* S, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  const int64_t Hp = ld, E = 3 * Hp;
+  MR_REQUIRE(Hp % 8 == 0 && 3 * Hp / 8 <= 64, MR_ERR_UNSUPPORTED, "token grouping: row pitch %lld", (long long)Hp);
+  EmbedGradPlan p = plan_embed_grad(T, E, V);
+  const GroupPlanLayout l = group_plan_layout(T, V);
+  Arena ar(workspace, workspace_bytes);
+  uint8_t* own_plan = ar.take<uint8_t>(l.total);
+  float* partial = ar.take<float>(p.max_chunks * E);
+  int32_t* heavy = ar.take<int32_t>(p.max_heavy + 1);
+  float* partial2 = ar.take<float>(p.max_items * E);
+  MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "token grouping: workspace too small (%lld given)", (long long)workspace_bytes);
+  const uint8_t* base = static_cast<const uint8_t*>(plan_in);
+  if (base == nullptr) {
+    if (int rc = token_group_plan_build(ids, ids_i64, T, V, own_plan, l.total, st)) return rc;
+    base = own_plan;
+  }
+  const int32_t* svals = reinterpret_cast<const int32_t*>(base + l.svals);
+  const int32_t* nchunk = reinterpret_cast<const int32_t*>(base + l.nchunk);
+  const int32_t* chunk_off = reinterpret_cast<const int32_t*>(base + l.chunk_off);
+  const int4* desc = reinterpret_cast<const int4*>(base + l.chunk_desc);
   const int pieces = (int)(Hp / 8);
   if (3 * pieces <= 32)
-    group_taps_l1_kernel<1><<<(unsigned)ceil_div(p.max_chunks, 8), 256, 0, st>>>(dconv, ld, L, pieces, svals, seg_start, chunk_off, chunk_row,
-                                                                               nchunk, S, E, partial, p.max_chunks, V);
+    group_taps_l1_kernel<1><<<(unsigned)ceil_div(p.max_chunks, 8), 256, 0, st>>>(dconv, ld, L, pieces, svals, desc, S, E, partial, p.max_chunks);
   else
-    group_taps_l1_kernel<2><<<(unsigned)ceil_div(p.max_chunks, 8), 256, 0, st>>>(dconv, ld, L, pieces, svals, seg_start, chunk_off, chunk_row,
-                                                                               nchunk, S, E, partial, p.max_chunks, V);
+    group_taps_l1_kernel<2><<<(unsigned)ceil_div(p.max_chunks, 8), 256, 0, st>>>(dconv, ld, L, pieces, svals, desc, S, E, partial, p.max_chunks);
   MR_CHECK_LAUNCH("group_taps_l1_kernel");
   cudaMemsetAsync(heavy, 0, sizeof(int32_t), st);
   seg_reduce_l2_kernel<__nv_bfloat16><<<(unsigned)ceil_div(V, 8), 256, 0, st>>>(chunk_off, nchunk, partial, S, E, V, E, heavy, heavy + 1,

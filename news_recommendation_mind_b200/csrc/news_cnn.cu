@@ -5,6 +5,7 @@
 #include "gemm_simt.cuh"
 #include "pool_kernels.cuh"
 #include "news_cnn_tc.cuh"
+#include "embed.cuh"
 
 namespace mr {
 
@@ -217,6 +218,18 @@ int mr_news_cnn_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
                  as_stream(stream));
 }
 
+int64_t mr_token_group_plan_bytes(int64_t n_tokens, int64_t V) { return mr::token_group_plan_bytes(n_tokens, V); }
+
+int mr_token_group_plan(const void* ids, int ids_i64, int64_t n_tokens, int64_t V, void* plan, int64_t plan_bytes, void* stream) {
+  using namespace mr;
+  if (int rc = require_sm100()) return rc;
+  MR_REQUIRE(ids && plan, MR_ERR_NULL, "mr_token_group_plan: null pointer");
+  MR_REQUIRE(n_tokens >= 0 && V >= 1 && n_tokens < (1ll << 31), MR_ERR_BAD_SHAPE, "mr_token_group_plan: n_tokens=%lld V=%lld",
+             (long long)n_tokens, (long long)V);
+  if (n_tokens == 0) return MR_OK;
+  return token_group_plan_build(ids, ids_i64, n_tokens, V, plan, plan_bytes, as_stream(stream));
+}
+
 int64_t mr_news_cnn_bwd_table_workspace_bytes(const mr_cnn_shape* s) {
   if (!s || s->precision != MR_BF16) return -1;
   return mr::news_cnn_tc_workspace_bytes(s, 2);
@@ -226,13 +239,15 @@ int mr_news_cnn_bwd_table(const mr_cnn_shape* s, const void* ids, int ids_i64, c
                           const float* conv_w, const float* proj_w, const float* query, const void* c_save,
                           const void* key_save, const float* prob, const float* d_news, float* d_conv_w, float* d_conv_b,
                           float* d_proj_w, float* d_proj_b, float* d_query, float* d_table, int64_t padding_idx,
-                          void* workspace, int64_t workspace_bytes, void* stream) {
+                          const void* group_plan, int64_t group_plan_bytes, void* workspace, int64_t workspace_bytes, void* stream) {
   using namespace mr;
   if (int rc = require_sm100()) return rc;
   if (int rc = check_shape(s, "mr_news_cnn_bwd_table")) return rc;
   MR_REQUIRE(s->precision == MR_BF16, MR_ERR_UNSUPPORTED, "mr_news_cnn_bwd_table: bf16 path only");
   MR_REQUIRE(ids && table_bf16 && conv_w && proj_w && query && c_save && key_save && prob && d_news && d_conv_w && d_conv_b &&
                  d_proj_w && d_proj_b && d_query && d_table, MR_ERR_NULL, "mr_news_cnn_bwd_table: null pointer");
+  MR_REQUIRE(group_plan == nullptr || group_plan_bytes >= token_group_plan_bytes(s->N * s->L, s->V), MR_ERR_WORKSPACE,
+             "mr_news_cnn_bwd_table: grouping plan of %lld bytes is too small", (long long)group_plan_bytes);
   cudaStream_t st = as_stream(stream);
   if (s->N == 0) {
     cudaMemsetAsync(d_conv_w, 0, sizeof(float) * s->H * s->E * 3, st);
@@ -245,7 +260,7 @@ int mr_news_cnn_bwd_table(const mr_cnn_shape* s, const void* ids, int ids_i64, c
   }
   return news_cnn_tc_bwd(s, ids, ids_i64, nullptr, table_bf16, conv_w, proj_w, query, c_save, key_save, prob, d_news, nullptr,
                          d_conv_w, d_conv_b, d_proj_w, d_proj_b, d_query, nullptr, workspace, workspace_bytes, st, d_table,
-                         table_rows, padding_idx);
+                         table_rows, padding_idx, group_plan);
 }
 
 }  // extern "C"

@@ -161,7 +161,7 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
                     const float* conv_w, const float* proj_w, const float* query, const void* c_save, const void* key_save,
                     const float* prob, const float* d_news, const float* d_c, float* d_conv_w, float* d_conv_b,
                     float* d_proj_w, float* d_proj_b, float* d_query, void* d_emb, void* ws, int64_t wsb, cudaStream_t st,
-                    float* d_table, int64_t table_rows, int64_t padding_idx) {
+                    float* d_table, int64_t table_rows, int64_t padding_idx, const void* group_plan) {
   if (int rc = check_tc(s, "mr_news_cnn_bwd")) return rc;
   const int64_t N = s->N, L = s->L, E = s->E, H = s->H, T = N * L, Hp = hp_of(s), Kp = kp_of(s);
   const __nv_bfloat16* c = static_cast<const __nv_bfloat16*>(c_save);
@@ -269,7 +269,7 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
     float* partial_v = ar.take<float>(tokred_partial_bytes(n_rows32, 32, 1, (int)Kp, (int)Hp) / 4);
     MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "mr_news_cnn_bwd_table: workspace too small (%lld given)", (long long)wsb);
     if (Vp > V) cudaMemsetAsync(S + V * SH, 0, (size_t)(Vp - V) * SH * 2, st);
-    if (int rc = token_group_taps(ids, ids_i64, dcv, Hp, (int)L, T, V, S, gws, gwb, st)) return rc;
+    if (int rc = token_group_taps(ids, ids_i64, group_plan, dcv, Hp, (int)L, T, V, S, gws, gwb, st)) return rc;
     // d_table = S [V, 3Hp] x W^T, W[e, tap*Hp + h] = conv_w[h, e, tap]; fp32 output rows, <= 256 columns per launch
     const int64_t nblk2 = ceil_div(Kp, 256);
     const int64_t nbsz2 = align_up(ceil_div(Kp, nblk2), 16);

@@ -6,7 +6,7 @@ CPU or eager-PyTorch fallback; a missing library or a non-B200 device raises.
 """
 from __future__ import annotations
 
-from ctypes import byref, c_float, c_int
+from ctypes import byref, c_float, c_int, c_void_p
 
 import os
 
@@ -20,6 +20,21 @@ PRECISIONS = {"fp32": MR_F32, "f32": MR_F32, "bf16": MR_BF16}
 
 # MINDREC_GROUPED=0 switches the bf16 ids path back to the per-token d_emb + segmented reduction (A/B, tests)
 GROUPED_TABLE_GRAD = os.environ.get("MINDREC_GROUPED", "1") != "0"
+
+
+def ctypes_stream(stream: torch.cuda.Stream):
+    return c_void_p(stream.cuda_stream)
+
+
+_SIDE_STREAMS = {}
+
+
+def side_stream(device) -> torch.cuda.Stream:
+    """One auxiliary stream per device for work that only depends on the integer inputs (token-grouping plans)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return _SIDE_STREAMS[key]
 
 
 def pad_to(n: int, m: int) -> int:
@@ -127,6 +142,22 @@ class NewsCNN(torch.autograd.Function):
                                   ptr(mask_c), index_flag(mask_c) if mask_c is not None else 0, ptr(tab), ptr(cw),
                                   ptr(cb), ptr(pw), ptr(pb), ptr(q), ptr(c_save), ptr(key_save), ptr(prob), ptr(news),
                                   ptr(ws), ws.numel(), stream_ptr(dev)), "mr_news_cnn_fwd")
+        # token-grouping plan of the backward (a function of the ids only): queued on a side stream BEHIND this encoder's
+        # forward kernels (they own every SM's shared memory, nothing can run beside them), so that the sort and the
+        # segment bookkeeping overlap the latency-bound user encoder (128 of 148 SMs) instead of sitting on the
+        # backward's critical path
+        ctx.group_plan, ctx.group_event = None, None
+        if (precision == MR_BF16 and ids is not None and table is not None and ctx.needs_input_grad[3]
+                and GROUPED_TABLE_GRAD and E % 4 == 0 and tab.shape[0] >= pad_to(V, 32)):
+            nb = lib.mr_token_group_plan_bytes(N * L, V)
+            plan = torch.empty(nb, dtype=torch.uint8, device=dev)
+            cur, side = torch.cuda.current_stream(dev), side_stream(dev)
+            side.wait_stream(cur)
+            check(lib.mr_token_group_plan(ptr(ids_c), index_flag(ids_c), N * L, V, ptr(plan), nb, ctypes_stream(side)), "mr_token_group_plan")
+            ctx.group_event = torch.cuda.Event()
+            ctx.group_event.record(side)
+            ids_c.record_stream(side)
+            ctx.group_plan = plan
         ctx.save_for_backward(ids_c, emb_c, tab, cw, pw, q, c_save, key_save, prob)
         ctx.shape = shape
         ctx.table_shape = None if table is None else tuple(table.shape)
@@ -165,10 +196,15 @@ class NewsCNN(torch.autograd.Function):
             V, _ = ctx.table_shape
             d_table = torch.empty(V, E, dtype=torch.float32, device=dev)
             ws = workspace(lib.mr_news_cnn_bwd_table_workspace_bytes(byref(s)), dev)
+            plan = ctx.group_plan
+            if plan is not None:
+                torch.cuda.current_stream(dev).wait_event(ctx.group_event)
             check(lib.mr_news_cnn_bwd_table(byref(s), ptr(ids_c), index_flag(ids_c), ptr(tab), tab.shape[0], ptr(cw), ptr(pw),
                                             ptr(q), ptr(c_save), ptr(key_save), ptr(prob), ptr(d_news_c), ptr(d_cw), ptr(d_cb),
-                                            ptr(d_pw), ptr(d_pb), ptr(d_q), ptr(d_table), ctx.padding_idx, ptr(ws), ws.numel(),
+                                            ptr(d_pw), ptr(d_pb), ptr(d_q), ptr(d_table), ctx.padding_idx, ptr(plan),
+                                            plan.numel() if plan is not None else 0, ptr(ws), ws.numel(),
                                             stream_ptr(dev)), "mr_news_cnn_bwd_table")
+            ctx.group_plan = None
             return (None, None, None, d_table, None, d_cw, d_cb, d_pw, d_pb, d_q.view(1, H), None, None, None)
         d_emb = None
         if need_x:
