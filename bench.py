@@ -121,7 +121,7 @@ def run_reference(args):
 def config_dict(args, precision):
     return {"workload": "TwoTower CNN+LSTM training, batch 256/GPU, title 32, his 50, npratio 4, 300d->150 "
                         "(BASELINE configs[1])", "global_batch": CFG["B"] * args.gpus, "per_gpu_batch": CFG["B"],
-            "precision": precision, "parallelism": "dp%d" % args.gpus, "optimizer": "Adam lr 1e-4 / bert_lr 6e-6",
+            "precision": precision, "parallelism": "dp%d" % args.gpus, "grad_sync": ("torch DDP" if getattr(args, "ddp", False) else "trainer.GradSync (in-place NCCL all-reduce)") if args.gpus > 1 else "none", "optimizer": "Adam lr 1e-4 / bert_lr 6e-6",
             "l2": "8 distinct batches cycled; per-step working set (saved activations ~0.5-1 GB) exceeds the 126 MB L2"}
 
 
@@ -168,10 +168,13 @@ def run_ours(args):
     man = manager_ns(dev, args.precision)
     model = mr.TwoTower(man, mr.BERT_Embedding(man, vocab_size=CFG["V"]), mr.CNN_Encoder(man), mr.RNN_User_Encoder(man)).to(dev)
     core = model
-    if world > 1:
+    sync = None
+    if world > 1 and args.ddp:
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], output_device=local,
                                                           find_unused_parameters=False)
     opt = trainer.FusedAdam(model, lr=1e-4, bert_lr=6e-6)
+    if world > 1 and not args.ddp:
+        sync = trainer.GradSync(model, opt)           # in-place NCCL all-reduce, table gradient overlapped with the backward
     ids, mask = data.make_news_table(CFG["n_news"], CFG["L"])
     NB = 8
     host = [data.make_train_batch(ids, mask, CFG["B"], CFG["C"], CFG["S"], seed=100 * rank + i, pin=True) for i in range(NB)]
@@ -195,7 +198,7 @@ def run_ours(args):
             assert len(losses) == steps
         else:
             for s in range(steps):
-                trainer.train_step(model, batches[s % NB], opt)
+                trainer.train_step(model, batches[s % NB], opt, sync)
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -209,7 +212,7 @@ def run_ours(args):
         return float(t)
 
     for s in range(max(args.warmup, 3)):
-        trainer.train_step(model, devb[s % NB], opt)
+        trainer.train_step(model, devb[s % NB], opt, sync)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -227,7 +230,7 @@ def run_ours(args):
             conv_launches, conv_ms = n_.value, m_.value
         lib.mr_debug_conv_timing(0)
     clocks = sampler.stop() if sampler else None
-    loop = trainer.TrainLoop(model, opt)          # the public training loop (staging buffers / pinned loss slots made once)
+    loop = trainer.TrainLoop(model, opt, sync)    # the public training loop (staging buffers / pinned loss slots made once)
     loop.run(host, 3)
     ms_e2e = timed(host, args.steps, True)
 
@@ -255,7 +258,7 @@ def run_ours(args):
     if args.precision == "bf16":
         core.dedup_titles = True
         for s_ in range(3):
-            trainer.train_step(model, devb[s_ % NB], opt)
+            trainer.train_step(model, devb[s_ % NB], opt, sync)
         ms_d = timed(devb, args.steps, False)
         core.dedup_titles = False
         dedup_info = {"value": world * CFG["B"] * args.steps / (ms_d * 1e-3), "unit": "impressions/s", "ms_per_step": ms_d / args.steps,
@@ -303,6 +306,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ddp", action="store_true", help="N > 1: wrap the model in torch DDP (the reference's scheme) instead of trainer.GradSync")
     ap.add_argument("--precision", default=os.environ.get("MINDREC_PRECISION", "bf16"), choices=["bf16", "fp32"])
     args = ap.parse_args()
     if args.impl == "reference":

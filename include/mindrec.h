@@ -149,6 +149,7 @@ MR_API int mr_news_cnn_bwd_table(const mr_cnn_shape* s,
                     float* d_conv_w, float* d_conv_b, float* d_proj_w, float* d_proj_b, float* d_query,
                     float* d_table, int64_t padding_idx,
                     const void* group_plan, int64_t group_plan_bytes,
+                    void* table_ready_event,   /* optional cudaEvent_t recorded on `stream` as soon as d_table is complete */
                     void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ----------------------------------------------------------------------------------------------

@@ -42,7 +42,7 @@ _SIGNATURES = {
     "mr_news_cnn_bwd_table_workspace_bytes": (I64, [POINTER(CnnShape)]),
     "mr_token_group_plan_bytes": (I64, [I64, I64]),
     "mr_token_group_plan": (c_int, [P, c_int, I64, I64, P, I64, P]),
-    "mr_news_cnn_bwd_table": (c_int, [POINTER(CnnShape), P, c_int, P, I64, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P, I64, P, I64, P]),
+    "mr_news_cnn_bwd_table": (c_int, [POINTER(CnnShape), P, c_int, P, I64, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P, I64, P, P, I64, P]),
     "mr_rnn_workspace_bytes": (I64, [POINTER(RnnShape), c_int]),
     "mr_rnn_user_fwd": (c_int, [POINTER(RnnShape), P, P, P, P, P, P, P, P, P, P, P, P, I64, P]),
     "mr_rnn_user_bwd": (c_int, [POINTER(RnnShape), P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, P]),

@@ -239,7 +239,8 @@ int mr_news_cnn_bwd_table(const mr_cnn_shape* s, const void* ids, int ids_i64, c
                           const float* conv_w, const float* proj_w, const float* query, const void* c_save,
                           const void* key_save, const float* prob, const float* d_news, float* d_conv_w, float* d_conv_b,
                           float* d_proj_w, float* d_proj_b, float* d_query, float* d_table, int64_t padding_idx,
-                          const void* group_plan, int64_t group_plan_bytes, void* workspace, int64_t workspace_bytes, void* stream) {
+                          const void* group_plan, int64_t group_plan_bytes, void* table_ready_event, void* workspace, int64_t workspace_bytes,
+                          void* stream) {
   using namespace mr;
   if (int rc = require_sm100()) return rc;
   if (int rc = check_shape(s, "mr_news_cnn_bwd_table")) return rc;
@@ -260,7 +261,7 @@ int mr_news_cnn_bwd_table(const mr_cnn_shape* s, const void* ids, int ids_i64, c
   }
   return news_cnn_tc_bwd(s, ids, ids_i64, nullptr, table_bf16, conv_w, proj_w, query, c_save, key_save, prob, d_news, nullptr,
                          d_conv_w, d_conv_b, d_proj_w, d_proj_b, d_query, nullptr, workspace, workspace_bytes, st, d_table,
-                         table_rows, padding_idx, group_plan);
+                         table_rows, padding_idx, group_plan, table_ready_event);
 }
 
 }  // extern "C"

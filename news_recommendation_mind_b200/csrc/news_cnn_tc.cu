@@ -161,7 +161,7 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
                     const float* conv_w, const float* proj_w, const float* query, const void* c_save, const void* key_save,
                     const float* prob, const float* d_news, const float* d_c, float* d_conv_w, float* d_conv_b,
                     float* d_proj_w, float* d_proj_b, float* d_query, void* d_emb, void* ws, int64_t wsb, cudaStream_t st,
-                    float* d_table, int64_t table_rows, int64_t padding_idx, const void* group_plan) {
+                    float* d_table, int64_t table_rows, int64_t padding_idx, const void* group_plan, void* table_ready_event) {
   if (int rc = check_tc(s, "mr_news_cnn_bwd")) return rc;
   const int64_t N = s->N, L = s->L, E = s->E, H = s->H, T = N * L, Hp = hp_of(s), Kp = kp_of(s);
   const __nv_bfloat16* c = static_cast<const __nv_bfloat16*>(c_save);
@@ -290,6 +290,11 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
       if (int rc = tapgemm_launch(plan, st)) return rc;
     }
     if (padding_idx >= 0 && padding_idx < V) cudaMemsetAsync(d_table + padding_idx * E, 0, sizeof(float) * E, st);   // BERT.py:16-21
+    // the table gradient is complete here: a data-parallel caller can start its all-reduce while the filter gradient runs
+    if (table_ready_event != nullptr) {
+      cudaError_t ee = cudaEventRecord(static_cast<cudaEvent_t>(table_ready_event), st);
+      MR_REQUIRE(ee == cudaSuccess, MR_ERR_LAUNCH, "mr_news_cnn_bwd_table: event record: %s", cudaGetErrorString(ee));
+    }
     // d_conv_w[:, :, tap] = table^T [E, V] x S[:, tap, :] [V, H]   (token-reduction GEMM over vocabulary rows)
     for (int tap = 0; tap < 3; ++tap) {
       TokRedArgs a{};

@@ -13,5 +13,5 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
                     const float* prob, const float* d_news, const float* d_c, float* d_conv_w, float* d_conv_b,
                     float* d_proj_w, float* d_proj_b, float* d_query, void* d_emb, void* ws, int64_t wsb, cudaStream_t st,
                     float* d_table = nullptr, int64_t table_rows = 0, int64_t padding_idx = -1,
-                    const void* group_plan = nullptr);
+                    const void* group_plan = nullptr, void* table_ready_event = nullptr);
 }  // namespace mr

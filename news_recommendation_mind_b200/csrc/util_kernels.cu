@@ -142,7 +142,9 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
   const float lr = a.lr_over_bc1[t];
   const bool sh = t == a.shadow_tensor;
   const int64_t base = (int64_t)(blockIdx.x - a.blk_off[t]) * AD_CHUNK;
-  const bool vec = (n & 3) == 0 && (!sh || (a.row_len & 3) == 0);      // tensors come from the torch allocator: 16-byte aligned
+  const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                         reinterpret_cast<uintptr_t>(v)) & 15) == 0;          // gradients may be views into a flat all-reduce buffer
+  const bool vec = aligned && (n & 3) == 0 && (!sh || (a.row_len & 3) == 0);
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const int64_t i = base + ((int64_t)it * 256 + threadIdx.x) * 4;

@@ -26,6 +26,12 @@ def ctypes_stream(stream: torch.cuda.Stream):
     return c_void_p(stream.cuda_stream)
 
 
+# set by trainer.GradSync: called as hook(d_table, event) inside the encoder backward, `event` (a torch.cuda.Event) having been
+# recorded the moment d_table was complete -- the data-parallel all-reduce of the table gradient starts there.  A hook that
+# returns True owns the gradient: backward then returns None for the table (autograd's AccumulateGrad would otherwise CLONE a
+# tensor somebody else still references, i.e. copy it before the in-place all-reduce has run)
+TABLE_GRAD_HOOK = None
+
 _SIDE_STREAMS = {}
 
 
@@ -199,12 +205,17 @@ class NewsCNN(torch.autograd.Function):
             plan = ctx.group_plan
             if plan is not None:
                 torch.cuda.current_stream(dev).wait_event(ctx.group_event)
+            hook = TABLE_GRAD_HOOK
+            ev = hook.event(dev) if hook is not None else None
             check(lib.mr_news_cnn_bwd_table(byref(s), ptr(ids_c), index_flag(ids_c), ptr(tab), tab.shape[0], ptr(cw), ptr(pw),
                                             ptr(q), ptr(c_save), ptr(key_save), ptr(prob), ptr(d_news_c), ptr(d_cw), ptr(d_cb),
                                             ptr(d_pw), ptr(d_pb), ptr(d_q), ptr(d_table), ctx.padding_idx, ptr(plan),
-                                            plan.numel() if plan is not None else 0, ptr(ws), ws.numel(),
+                                            plan.numel() if plan is not None else 0,
+                                            c_void_p(ev.cuda_event) if ev is not None else None, ptr(ws), ws.numel(),
                                             stream_ptr(dev)), "mr_news_cnn_bwd_table")
             ctx.group_plan = None
+            if hook is not None and hook(d_table, ev):
+                d_table = None               # the hook took the gradient (it assigns table.grad itself, see trainer.GradSync)
             return (None, None, None, d_table, None, d_cw, d_cb, d_pw, d_pb, d_q.view(1, H), None, None, None)
         d_emb = None
         if need_x:

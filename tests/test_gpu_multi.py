@@ -54,6 +54,32 @@ def _worker(rank, world, port, out):
                 a, b = grads[k].double(), p.grad.detach().cpu().double()
                 worst = max(worst, float((a - b).norm() / (b.norm() + 1e-30)))
             out.put(("ddp_grad_rel_err", worst))
+        # trainer.GradSync (in-place all-reduce, table gradient started from inside the encoder backward, 1/world folded
+        # into Adam) == DDP on the bf16 path, gradients and one optimiser step
+        import copy
+        torch.manual_seed(1)
+        mb = build_model(manager_for("cnn", "lstm", C, S, L, E, H, 10, precision="bf16", device="cuda:%d" % rank), V)
+        for p_ in mb.parameters():
+            dist.broadcast(p_.data, src=0)
+        mb2 = copy.deepcopy(mb)
+        dd = torch.nn.parallel.DistributedDataParallel(mb, device_ids=[rank], output_device=rank)
+        o1 = trainer.FusedAdam(dd, lr=1e-3, bert_lr=1e-4)
+        trainer.train_step(dd, mine, o1)
+        g_ddp = {k: p.grad.detach().clone() for k, p in mb.named_parameters()}
+        o2 = trainer.FusedAdam(mb2, lr=1e-3, bert_lr=1e-4)
+        sync = trainer.GradSync(mb2, o2)
+        trainer.train_step(mb2, mine, o2, sync)
+        sync.close()
+        torch.cuda.synchronize()
+        worst_g, worst_p = 0.0, 0.0
+        for (k, p1), (_, p2) in zip(mb.named_parameters(), mb2.named_parameters()):
+            a, b = (p2.grad.detach().double() / world), g_ddp[k].double()
+            e_ = float((a - b).norm() / (b.norm() + 1e-30))
+            if rank == 0:
+                print("gradsync vs ddp %-44s %.3e" % (k, e_), flush=True)
+            worst_g = max(worst_g, e_)
+            worst_p = max(worst_p, float((p1.detach().double() - p2.detach().double()).norm() / (p1.detach().double().norm() + 1e-30)))
+        out.put(("gradsync_rank%d" % rank, (worst_g, worst_p)))
         # sharded evaluation == single-rank evaluation
         news_ids, news_mask = data.make_news_table(300, L, seed=5)
         impr = data.make_eval_impressions(news_ids, news_mask, 41, S, seed=9)
@@ -81,6 +107,8 @@ def test_two_gpu_ddp_and_sharded_eval():
     for p in procs:
         p.join(300)
         assert p.exitcode == 0
-    res = dict(out.get(timeout=5) for _ in range(3))
+    res = dict(out.get(timeout=5) for _ in range(5))
     assert res["ddp_grad_rel_err"] < 2e-4, res
     assert res["eval_rank0"] == (True, True) and res["eval_rank1"] == (True, True), res
+    for r in range(world):
+        assert res["gradsync_rank%d" % r][0] < 1e-5 and res["gradsync_rank%d" % r][1] < 1e-6, res
