@@ -370,13 +370,12 @@ static int rnn_tc_input_proj(const mr_rnn_shape* s, const float* x, const float*
 // d_x, d_w_ih, d_w_hh from the gate gradients
 static int rnn_tc_grad_gemms(const mr_rnn_shape* s, const float* x, const float* h0, const float* w_ih, const float* hs,
                              const float* dgi, const float* dgh, float* d_x, float* d_w_ih, float* d_w_hh, Arena& ar,
-                             cudaStream_t st) {
+                             cudaStream_t st, __nv_bfloat16* gib, __nv_bfloat16* ghb, bool precast) {
+  // gib / ghb: bf16 [Mp, GHp] gate gradients; `precast`: already written by the recurrence kernel (else cast from dgi / dgh here)
   const RnnTcGeom g = rnn_tc_geom(s);
   const int H = (int)s->H, S = (int)s->S;
   __nv_bfloat16* xb = ar.take<__nv_bfloat16>(g.Mp * g.Hp);
   __nv_bfloat16* hb = ar.take<__nv_bfloat16>(g.Mp * g.Hp);
-  __nv_bfloat16* gib = ar.take<__nv_bfloat16>(g.Mp * g.GHp);
-  __nv_bfloat16* ghb = ar.take<__nv_bfloat16>(g.Mp * g.GHp);
   uint8_t* wp = ar.take<uint8_t>(tapgemm_pack_bytes(1, (int)g.Hp, (int)g.GHp));
   float* tmp = ar.take<float>(g.M * g.Hp);
   float* partial = ar.take<float>(tokred_partial_bytes(g.Mp / 128, 128, 1, (int)g.GHp, (int)g.Hp) / 4);
@@ -385,14 +384,15 @@ static int rnn_tc_grad_gemms(const mr_rnn_shape* s, const float* x, const float*
   MR_CHECK_LAUNCH("seq_cast_bf16_kernel");
   hprev_bf16_kernel<<<(unsigned)ceil_div(g.Mp * g.Hp, 256), 256, 0, st>>>(hs, h0, hb, g.M, g.Mp, S, H, (int)g.Hp);
   MR_CHECK_LAUNCH("hprev_bf16_kernel");
-  cast_rows_pad_bf16_kernel<<<(unsigned)ceil_div(g.Mp * g.GHp, 256), 256, 0, st>>>(dgi, gib, g.M, g.Mp, (int)g.GH, (int)g.GHp);
-  MR_CHECK_LAUNCH("cast_rows_pad_bf16_kernel");
-  if (dgh != dgi) {
-    cast_rows_pad_bf16_kernel<<<(unsigned)ceil_div(g.Mp * g.GHp, 256), 256, 0, st>>>(dgh, ghb, g.M, g.Mp, (int)g.GH, (int)g.GHp);
+  if (!precast) {
+    cast_rows_pad_bf16_kernel<<<(unsigned)ceil_div(g.Mp * g.GHp, 256), 256, 0, st>>>(dgi, gib, g.M, g.Mp, (int)g.GH, (int)g.GHp);
     MR_CHECK_LAUNCH("cast_rows_pad_bf16_kernel");
-  } else {
-    ghb = gib;
+    if (dgh != dgi) {
+      cast_rows_pad_bf16_kernel<<<(unsigned)ceil_div(g.Mp * g.GHp, 256), 256, 0, st>>>(dgh, ghb, g.M, g.Mp, (int)g.GH, (int)g.GHp);
+      MR_CHECK_LAUNCH("cast_rows_pad_bf16_kernel");
+    }
   }
+  if (s->kind == MR_RNN_LSTM) ghb = gib;
   if (d_x) {        // d_x_seq[m, k] = sum_n dgi[m, n] W_ih[n, k]
     if (int rc = tapgemm_pack(w_ih, wp, 1, (int)g.Hp, (int)g.GHp, H, (int)g.GH, 1, H, 0, st)) return rc;
     TapGemmArgs a{};
@@ -430,6 +430,7 @@ static int64_t rnn_ws(const mr_rnn_shape* s, int backward) {
     return b + 256;
   }
   b += 2 * arena_bytes(BS * GH, 4);         // dgi, dgh
+  b += arena_bytes((int64_t)s->B * 2 * GH, 4);   // per-CTA bias-gradient partials of the resident recurrence kernel
   b += arena_bytes(64 * GH * s->H, 4);      // split-K partial
   b += arena_bytes(colsum_chunks(BS) * GH, 4);
   if (rnn_tc_ok(s)) b += rnn_tc_ws(s, 1);
@@ -542,8 +543,30 @@ int mr_rnn_user_bwd(const mr_rnn_shape* s, const float* x, const int32_t* lens, 
   if (s->kind == MR_RNN_LSTM) dgh = dgi;
   size_t smem = sizeof(float) * (2 * RNN_BPC * H + RNN_BPC * GH);
   unsigned grid = (unsigned)ceil_div(B, RNN_BPC);
-  if (s->precision == MR_BF16 && rnn_res_supported(s->kind, H)) {
-    if (int rc = rnn_res_bwd(s->kind, w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H, sp, st)) return rc;
+  const bool resident = s->precision == MR_BF16 && rnn_res_supported(s->kind, H);
+  // resident recurrence + tensor-core GEMMs: the kernel writes the gate gradients as bf16 GEMM operands and the bias
+  // partial sums itself (no fp32 dgi / dgh round trip, no cast and column-sum passes)
+  const bool fused_out = resident && rnn_tc_ok(s);
+  __nv_bfloat16* gib = nullptr;
+  __nv_bfloat16* ghb = nullptr;
+  float* bias_part = nullptr;
+  RnnTcGeom tg{};
+  if (rnn_tc_ok(s)) {
+    tg = rnn_tc_geom(s);
+    gib = ar.take<__nv_bfloat16>(tg.Mp * tg.GHp);
+    ghb = ar.take<__nv_bfloat16>(tg.Mp * tg.GHp);
+    bias_part = ar.take<float>((int64_t)B * 2 * GH);
+    MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "mr_rnn_user_bwd: workspace too small (%lld given)", (long long)workspace_bytes);
+  }
+  if (resident) {
+    if (fused_out) {
+      cudaMemsetAsync(gib, 0, (size_t)tg.Mp * tg.GHp * 2, st);
+      if (s->kind != MR_RNN_LSTM) cudaMemsetAsync(ghb, 0, (size_t)tg.Mp * tg.GHp * 2, st);
+    }
+    if (int rc = rnn_res_bwd(s->kind, w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H, sp, st,
+                             fused_out ? gib : nullptr, fused_out ? ghb : nullptr, fused_out ? (int)tg.GHp : 0,
+                             fused_out ? bias_part : nullptr))
+      return rc;
   } else if (s->kind == MR_RNN_LSTM) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(rnn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     rnn_bwd_kernel<0><<<grid, RNN_THREADS, smem, st>>>(w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H);
@@ -551,10 +574,10 @@ int mr_rnn_user_bwd(const mr_rnn_shape* s, const float* x, const int32_t* lens, 
     if (smem > 48 * 1024) cudaFuncSetAttribute(rnn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     rnn_bwd_kernel<1><<<grid, RNN_THREADS, smem, st>>>(w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H);
   }
-  if (!(s->precision == MR_BF16 && rnn_res_supported(s->kind, H))) MR_CHECK_LAUNCH("rnn_bwd_kernel");
+  if (!resident) MR_CHECK_LAUNCH("rnn_bwd_kernel");
   cudaError_t e;
   if (rnn_tc_ok(s)) {
-    if (int rc = rnn_tc_grad_gemms(s, x, h0, w_ih, hs, dgi, dgh, d_x, d_w_ih, d_w_hh, ar, st)) return rc;
+    if (int rc = rnn_tc_grad_gemms(s, x, h0, w_ih, hs, dgi, dgh, d_x, d_w_ih, d_w_hh, ar, st, gib, ghb, fused_out)) return rc;
   } else {
     if (d_x) {
       e = gemm_simt<true, true>(BS, H, GH, RowMajor{dgi, GH}, RowMajor{w_ih, H}, SeqStoreEpi{d_x, S, H, s->reverse}, 1, nullptr, st);
@@ -566,6 +589,15 @@ int mr_rnn_user_bwd(const mr_rnn_shape* s, const float* x, const int32_t* lens, 
     e = gemm_simt<false, true>(GH, H, BS, Transposed{dgh, GH}, PrevHiddenKM{hs, h0, S, H}, StoreEpi{d_w_hh, H},
                                pick_splits(GH, H, BS), sp, st);
     MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "rnn d_w_hh: %s", cudaGetErrorString(e));
+  }
+  if (fused_out) {
+    // bias gradients: fold the per-CTA partials (pitch 2*GH: [0] input side, [1] hidden side) in a fixed order
+    const int64_t rows = ceil_div(B, rnn_res_bpc(s->kind, B, H));
+    e = colsum_small(bias_part, 2 * GH, d_b_ih, rows, GH, st);
+    MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "rnn d_b_ih: %s", cudaGetErrorString(e));
+    e = colsum_small(bias_part + (s->kind == MR_RNN_LSTM ? 0 : GH), 2 * GH, d_b_hh, rows, GH, st);
+    MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "rnn d_b_hh: %s", cudaGetErrorString(e));
+    return MR_OK;
   }
   e = colsum(dgi, d_b_ih, BS, GH, cp, st);
   MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "rnn d_b_ih: %s", cudaGetErrorString(e));

@@ -213,7 +213,11 @@ __global__ void __launch_bounds__(RR_THREADS, 1)
 rnn_res_bwd_kernel(const __nv_bfloat16* __restrict__ w_g, const float* __restrict__ h0, const int32_t* __restrict__ lens,
                    const float* __restrict__ gates, const float* __restrict__ hs, const float* __restrict__ cs,
                    const float* __restrict__ d_user, float* __restrict__ dgi, float* __restrict__ dgh,
-                   float* __restrict__ d_h0, int B, int S, int H) {
+                   float* __restrict__ d_h0, int B, int S, int H, __nv_bfloat16* __restrict__ gib, __nv_bfloat16* __restrict__ ghb,
+                   int GHp16, float* __restrict__ bias_part) {
+  // gib / ghb != nullptr: the gate gradients are written as bf16 rows of pitch GHp16 (the layout the weight-gradient
+  // GEMMs read; pre-zeroed by the host) instead of fp32 dgi / dgh, and the bias gradients (column sums of dgi / dgh over
+  // this CTA's sequences and steps) go to bias_part[blockIdx][2][GH]
   constexpr int G = KIND == 0 ? 4 : 3;
   const int GH = G * H, Hp = (H + 7) / 8 * 8, NTk = Hp / 8, NR = (GH + RR_NS - 1) / RR_NS;
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -235,6 +239,7 @@ rnn_res_bwd_kernel(const __nv_bfloat16* __restrict__ w_g, const float* __restric
 #pragma unroll
   for (int i = 0; i < BPC; ++i) max_len = max(max_len, len_s[i]);
   // steps beyond a sequence's length contribute nothing: zero their gate gradients
+  if (gib == nullptr)
   for (int q = 0; q < BPC; ++q) {
     const int b = b0 + q;
     if (b >= B) continue;
@@ -251,6 +256,9 @@ rnn_res_bwd_kernel(const __nv_bfloat16* __restrict__ w_g, const float* __restric
   const int bl = gt ? tid / H : 0, j = gt ? tid - bl * H : 0, b = b0 + bl;
   const int my_len = gt && b < B ? len_s[bl] : 0;
   float dh_c = 0.f, dc_c = 0.f;      // carried dL/dh and dL/dc (LSTM) / direct z-path term (GRU), private to (b, j)
+  float bsum[G], bsum_hn = 0.f;      // bias-gradient partial sums of this (b, j) over its steps (bsum_hn: GRU hidden-side n gate)
+#pragma unroll
+  for (int g = 0; g < G; ++g) bsum[g] = 0.f;
 
   for (int s = max_len - 1; s >= 0; --s) {
     const bool act = gt && s < my_len;
@@ -274,7 +282,13 @@ rnn_res_bwd_kernel(const __nv_bfloat16* __restrict__ w_g, const float* __restric
         d[2] = dc * gi * (1.f - gg * gg);
         d[3] = dh * tc * go * (1.f - go);
         dc_c = dc * gf;
-        gi_out[0] = d[0]; gi_out[H] = d[1]; gi_out[2 * H] = d[2]; gi_out[3 * H] = d[3];
+        if (gib != nullptr) {
+          __nv_bfloat16* go16 = gib + ((int64_t)b * S + s) * GHp16 + j;
+#pragma unroll
+          for (int g = 0; g < G; ++g) { go16[g * H] = __float2bfloat16(d[g]); bsum[g] += d[g]; }
+        } else {
+          gi_out[0] = d[0]; gi_out[H] = d[1]; gi_out[2 * H] = d[2]; gi_out[3 * H] = d[3];
+        }
       } else {
         const float r = gs[0], z = gs[H], nn = gs[2 * H];
         const float hn = cs[o];
@@ -283,9 +297,17 @@ rnn_res_bwd_kernel(const __nv_bfloat16* __restrict__ w_g, const float* __restric
         const float dz = dh * (hprev - nn) * z * (1.f - z);
         const float dr = dn * hn * r * (1.f - r);
         dc_c = dh * z;
-        gi_out[0] = dr; gi_out[H] = dz; gi_out[2 * H] = dn;
-        float* gh_out = dgh + ((int64_t)b * S + s) * GH + j;
-        gh_out[0] = dr; gh_out[H] = dz; gh_out[2 * H] = dn * r;
+        if (gib != nullptr) {
+          __nv_bfloat16* gi16 = gib + ((int64_t)b * S + s) * GHp16 + j;
+          __nv_bfloat16* gh16 = ghb + ((int64_t)b * S + s) * GHp16 + j;
+          gi16[0] = __float2bfloat16(dr); gi16[H] = __float2bfloat16(dz); gi16[2 * H] = __float2bfloat16(dn);
+          gh16[0] = __float2bfloat16(dr); gh16[H] = __float2bfloat16(dz); gh16[2 * H] = __float2bfloat16(dn * r);
+          bsum[0] += dr; bsum[1] += dz; bsum[2] += dn; bsum_hn += dn * r;
+        } else {
+          gi_out[0] = dr; gi_out[H] = dz; gi_out[2 * H] = dn;
+          float* gh_out = dgh + ((int64_t)b * S + s) * GH + j;
+          gh_out[0] = dr; gh_out[H] = dz; gh_out[2 * H] = dn * r;
+        }
         d[0] = dr; d[1] = dz; d[2] = dn * r;
       }
     }
@@ -328,6 +350,26 @@ rnn_res_bwd_kernel(const __nv_bfloat16* __restrict__ w_g, const float* __restric
     }
   }
   if (d_h0 != nullptr && gt && b < B) d_h0[(int64_t)b * H + j] = dh_c;
+  if (bias_part != nullptr) {
+    // fold the BPC sequences of this CTA (fixed order) through the dp scratch: dp[(g*H + j) * BPC + bl]
+    __syncthreads();
+    float* dp2 = dp;                                   // [2][GH][BPC] would not fit for the hidden-side copy: two passes
+    for (int pass = 0; pass < 2; ++pass) {
+      if (gt) {
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          dp2[(size_t)(g * H + j) * BPC + bl] = (pass == 1 && KIND == 1 && g == 2) ? bsum_hn : bsum[g];
+      }
+      __syncthreads();
+      for (int n = tid; n < GH; n += RR_THREADS) {
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < BPC; ++q) a += dp2[(size_t)n * BPC + q];
+        bias_part[((size_t)blockIdx.x * 2 + pass) * GH + n] = a;
+      }
+      __syncthreads();
+    }
+  }
 }
 
 template <int KIND>
@@ -349,13 +391,13 @@ static int launch_fwd(int bpc, const float* xp, int ldx, const __nv_bfloat16* w_
 template <int KIND>
 static int launch_bwd(int bpc, const __nv_bfloat16* w_hh, const float* h0, const int32_t* lens, const float* gates, const float* hs,
                       const float* cs, const float* d_user, float* dgi, float* dgh, float* d_h0, int B, int S, int H,
-                      cudaStream_t st) {
+                      __nv_bfloat16* gib, __nv_bfloat16* ghb, int GHp16, float* bias_part, cudaStream_t st) {
   const RRGeom g = rr_geom(KIND == 0 ? MR_RNN_LSTM : MR_RNN_GRU, H, bpc);
   const unsigned grid = (unsigned)ceil_div(B, bpc);
 #define RR_LAUNCH_B(BPC)                                                                                               \
   {                                                                                                                    \
     cudaFuncSetAttribute(rnn_res_bwd_kernel<KIND, BPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.bwd_bytes); \
-    rnn_res_bwd_kernel<KIND, BPC><<<grid, RR_THREADS, g.bwd_bytes, st>>>(w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H); \
+    rnn_res_bwd_kernel<KIND, BPC><<<grid, RR_THREADS, g.bwd_bytes, st>>>(w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H, gib, ghb, GHp16, bias_part); \
   }
   if (bpc == 1) RR_LAUNCH_B(1) else if (bpc == 2) RR_LAUNCH_B(2) else RR_LAUNCH_B(4)
 #undef RR_LAUNCH_B
@@ -382,14 +424,14 @@ int rnn_res_fwd(int kind, const float* xp, int ldx, const float* w_hh_f32, const
 
 int rnn_res_bwd(int kind, const float* w_hh_f32, const float* h0, const int32_t* lens, const float* gates, const float* hs,
                 const float* cs, const float* d_user, float* dgi, float* dgh, float* d_h0, int B, int S, int H,
-                void* scratch, cudaStream_t st) {
+                void* scratch, cudaStream_t st, __nv_bfloat16* gib, __nv_bfloat16* ghb, int GHp16, float* bias_part) {
   const int bpc = rnn_res_bpc(kind, B, H);
   const RRGeom g = rr_geom(kind, H, bpc);
   __nv_bfloat16* w_hh = static_cast<__nv_bfloat16*>(scratch);
   rnn_res_prep_kernel<<<(unsigned)ceil_div((int64_t)g.GH * g.Hp, 256), 256, 0, st>>>(w_hh_f32, nullptr, w_hh, g.GH, H, g.GHp, g.Hp);
   MR_CHECK_LAUNCH("rnn_res_prep_kernel");
-  return kind == MR_RNN_LSTM ? launch_bwd<0>(bpc, w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H, st)
-                             : launch_bwd<1>(bpc, w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H, st);
+  return kind == MR_RNN_LSTM ? launch_bwd<0>(bpc, w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H, gib, ghb, GHp16, bias_part, st)
+                             : launch_bwd<1>(bpc, w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H, gib, ghb, GHp16, bias_part, st);
 }
 
 }  // namespace mr

@@ -12,9 +12,13 @@ int rnn_res_bpc(int kind, int B, int H);
 // xp: [B*S, ldx] fp32 input projection (+ biases), ldx >= G*H, indexed by step; w_hh [G*H, H] fp32; the rest as rnn.cu
 int rnn_res_fwd(int kind, const float* xp, int ldx, const float* w_hh, const float* b_hh, const float* h0, const int32_t* lens,
                 float* gates, float* hs, float* cs, float* user, int B, int S, int H, void* scratch, cudaStream_t st);
+// gib / ghb (optional, pre-zeroed bf16 [>= B*S rows, GHp16]): gate gradients written directly in the layout of the
+// weight-gradient GEMMs instead of fp32 dgi / dgh; bias_part (optional, [grid = ceil(B / rnn_res_bpc)][2][G*H]): per-CTA
+// column sums of dgi ([.][0]) and dgh ([.][1])
 int rnn_res_bwd(int kind, const float* w_hh, const float* h0, const int32_t* lens, const float* gates, const float* hs,
                 const float* cs, const float* d_user, float* dgi, float* dgh, float* d_h0, int B, int S, int H,
-                void* scratch, cudaStream_t st);
+                void* scratch, cudaStream_t st, __nv_bfloat16* gib = nullptr, __nv_bfloat16* ghb = nullptr, int GHp16 = 0,
+                float* bias_part = nullptr);
 // scratch for the bf16 image of W_hh the kernels bulk-copy into shared memory
 int64_t rnn_res_scratch_bytes(int kind, int H);
 
