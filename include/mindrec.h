@@ -159,7 +159,8 @@ MR_API int mr_news_cnn_bwd_table(const mr_cnn_shape* s,
  *   user[b,:] = hidden state after step lens[b]-1 (pack_padded_sequence + h_n semantics).
  *   Gate order i,f,g,o (LSTM) / r,z,n (GRU); both bias vectors are added.
  *   `reverse` != 0 runs over the flipped sequence (descend_history / LSTUR).
- *   Saved for backward: gates [B,S,G*H] fp32 (activated gates), hs [B,S,H], cs [B,S,H] (LSTM only).
+ *   Saved for backward: gates [B,S,G*H] fp32 (activated gates), hs [B,S,H], cs [B,S,H] (LSTM only); entries of steps
+ *   >= lens[b] are unspecified in MR_BF16 (never read by mr_rnn_user_bwd), zero in MR_F32.
  * -------------------------------------------------------------------------------------------- */
 typedef struct {
   int64_t B, S, H;

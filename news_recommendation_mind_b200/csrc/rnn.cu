@@ -278,8 +278,9 @@ __global__ void seq_cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
   out[i] = __float2bfloat16(v);
 }
 // h_{s-1} of every step (h0 or 0 at s = 0)
-__global__ void hprev_bf16_kernel(const float* __restrict__ hs, const float* __restrict__ h0, __nv_bfloat16* __restrict__ out,
-                                  int64_t M, int64_t Mp, int S, int H, int Hp) {
+// (steps at or beyond a sequence's length give zero rows: the recurrence kernels never write hs there)
+__global__ void hprev_bf16_kernel(const float* __restrict__ hs, const float* __restrict__ h0, const int32_t* __restrict__ lens,
+                                  __nv_bfloat16* __restrict__ out, int64_t M, int64_t Mp, int S, int H, int Hp) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Mp * Hp) return;
   const int64_t m = i / Hp;
@@ -288,7 +289,8 @@ __global__ void hprev_bf16_kernel(const float* __restrict__ hs, const float* __r
   if (m < M && k < H) {
     const int64_t b = m / S;
     const int s = (int)(m - b * S);
-    v = s > 0 ? hs[(m - 1) * H + k] : (h0 ? h0[b * H + k] : 0.f);
+    const int len = lens ? lens[b] : S;
+    if (s < len) v = s > 0 ? hs[(m - 1) * H + k] : (h0 ? h0[b * H + k] : 0.f);
   }
   out[i] = __float2bfloat16(v);
 }
@@ -368,7 +370,7 @@ static int rnn_tc_input_proj(const mr_rnn_shape* s, const float* x, const float*
 }
 
 // d_x, d_w_ih, d_w_hh from the gate gradients
-static int rnn_tc_grad_gemms(const mr_rnn_shape* s, const float* x, const float* h0, const float* w_ih, const float* hs,
+static int rnn_tc_grad_gemms(const mr_rnn_shape* s, const float* x, const float* h0, const int32_t* lens, const float* w_ih, const float* hs,
                              const float* dgi, const float* dgh, float* d_x, float* d_w_ih, float* d_w_hh, Arena& ar,
                              cudaStream_t st, __nv_bfloat16* gib, __nv_bfloat16* ghb, bool precast) {
   // gib / ghb: bf16 [Mp, GHp] gate gradients; `precast`: already written by the recurrence kernel (else cast from dgi / dgh here)
@@ -382,7 +384,7 @@ static int rnn_tc_grad_gemms(const mr_rnn_shape* s, const float* x, const float*
   MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "mr_rnn_user_bwd: workspace too small");
   seq_cast_bf16_kernel<<<(unsigned)ceil_div(g.Mp * g.Hp, 256), 256, 0, st>>>(x, xb, g.M, g.Mp, S, H, (int)g.Hp, s->reverse);
   MR_CHECK_LAUNCH("seq_cast_bf16_kernel");
-  hprev_bf16_kernel<<<(unsigned)ceil_div(g.Mp * g.Hp, 256), 256, 0, st>>>(hs, h0, hb, g.M, g.Mp, S, H, (int)g.Hp);
+  hprev_bf16_kernel<<<(unsigned)ceil_div(g.Mp * g.Hp, 256), 256, 0, st>>>(hs, h0, lens, hb, g.M, g.Mp, S, H, (int)g.Hp);
   MR_CHECK_LAUNCH("hprev_bf16_kernel");
   if (!precast) {
     cast_rows_pad_bf16_kernel<<<(unsigned)ceil_div(g.Mp * g.GHp, 256), 256, 0, st>>>(dgi, gib, g.M, g.Mp, (int)g.GH, (int)g.GHp);
@@ -490,10 +492,14 @@ int mr_rnn_user_fwd(const mr_rnn_shape* s, const float* x, const int32_t* lens, 
                                            TwoBiasEpi{xp, GH, b_ih, s->kind == MR_RNN_LSTM ? b_hh : nullptr}, 1, nullptr, st);
     MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "rnn input projection: %s", cudaGetErrorString(e));
   }
-  // steps past a sequence's length are never written by the kernel: clear the saved tensors
-  cudaMemsetAsync(gates, 0, sizeof(float) * (int64_t)B * S * GH, st);
-  cudaMemsetAsync(hs, 0, sizeof(float) * (int64_t)B * S * H, st);
-  cudaMemsetAsync(cs, 0, sizeof(float) * (int64_t)B * S * H, st);
+  // steps past a sequence's length are never written by the kernels.  The bf16 path's backward never reads them either
+  // (resident recurrence: s < len only; h_{s-1} operand: zero rows beyond len), so only the other paths clear them.
+  const bool resident_path = s->precision == MR_BF16 && rnn_tc_ok(s) && rnn_res_supported(s->kind, H);
+  if (!resident_path) {
+    cudaMemsetAsync(gates, 0, sizeof(float) * (int64_t)B * S * GH, st);
+    cudaMemsetAsync(hs, 0, sizeof(float) * (int64_t)B * S * H, st);
+    cudaMemsetAsync(cs, 0, sizeof(float) * (int64_t)B * S * H, st);
+  }
   if (s->precision == MR_BF16 && rnn_mma_supported(s->kind, H) && rnn_use_mma())
     return rnn_mma_fwd(s->kind, xp, (int)ldx, w_hh, b_hh, h0, lens, gates, hs, cs, user, B, S, H, whhT, st);
   if (s->precision == MR_BF16 && rnn_res_supported(s->kind, H))
@@ -577,7 +583,7 @@ int mr_rnn_user_bwd(const mr_rnn_shape* s, const float* x, const int32_t* lens, 
   if (!resident) MR_CHECK_LAUNCH("rnn_bwd_kernel");
   cudaError_t e;
   if (rnn_tc_ok(s)) {
-    if (int rc = rnn_tc_grad_gemms(s, x, h0, w_ih, hs, dgi, dgh, d_x, d_w_ih, d_w_hh, ar, st, gib, ghb, fused_out)) return rc;
+    if (int rc = rnn_tc_grad_gemms(s, x, h0, lens, w_ih, hs, dgi, dgh, d_x, d_w_ih, d_w_hh, ar, st, gib, ghb, fused_out)) return rc;
   } else {
     if (d_x) {
       e = gemm_simt<true, true>(BS, H, GH, RowMajor{dgi, GH}, RowMajor{w_ih, H}, SeqStoreEpi{d_x, S, H, s->reverse}, 1, nullptr, st);
