@@ -53,7 +53,30 @@ struct Arena {
 };
 inline int64_t arena_bytes(int64_t count, int64_t elt) { return align_up(count * elt, 256); }
 
+// ---- programmatic dependent launch ------------------------------------------------------------
+// Kernels of the hot chain are launched with the programmatic-stream-serialization attribute: the next kernel's CTAs may
+// become resident (and run their prologue: shared-memory clearing, barrier init, TMEM allocation, descriptor prefetch) as
+// soon as the previous kernel's CTAs have retired from an SM, instead of after the whole grid has drained plus a launch
+// latency.  Every such kernel executes pdl_trigger() at its top and pdl_wait() before its first global-memory access;
+// pdl_wait() returns only when the preceding grid has completed and its writes are visible, so the ordering seen by
+// the data is exactly that of ordinary stream serialization.  MINDREC_PDL=0 launches without the attribute.
+bool pdl_enabled();                    // runtime.cu
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- device helpers -------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ int64_t load_index(const void* p, int is64, int64_t i) {
   return is64 ? static_cast<const int64_t*>(p)[i] : (int64_t) static_cast<const int32_t*>(p)[i];
 }

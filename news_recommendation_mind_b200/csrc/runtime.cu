@@ -1,5 +1,6 @@
 // Library-wide runtime bits: error channel, device gate, launch counter.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace mr {
 
@@ -16,6 +17,15 @@ int set_err(int code, const char* fmt, ...) {
   vsnprintf(err_buf(), 512, fmt, ap);
   va_end(ap);
   return code;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MINDREC_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 int require_sm100() {

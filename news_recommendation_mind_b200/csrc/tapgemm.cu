@@ -72,16 +72,10 @@ __global__ void __launch_bounds__(EPI2 ? TG_THREADS2 : TG_THREADS, 1) tapgemm_ke
   const uint8_t* wrep = p.wpack + (size_t)(blockIdx.x % (unsigned)p.w_reps) * p.w_rep_stride;
 
   // ---- one-time setup ----------------------------------------------------------------------
+  pdl_trigger();
   {
     const uint32_t a_bytes = (uint32_t)p.ns_a * p.a_slot_bytes;
     for (uint32_t i = tid * 16; i < a_bytes; i += NT * 16) *reinterpret_cast<uint4*>(sA + i) = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < 512; i += NT)
-      sbias[i] = (p.bias != nullptr && i < p.n_valid) ? p.bias[i] + (p.bias2 != nullptr ? p.bias2[i] : 0.f) : 0.f;
-    if (p.ids != nullptr)
-      for (uint32_t i = tid; i < (uint32_t)p.n_hot * (hot_pitch / 16); i += NT) {
-        const uint32_t h = i / (hot_pitch / 16), q = i % (hot_pitch / 16);
-        reinterpret_cast<uint4*>(hot + (size_t)h * hot_pitch)[q] = __ldg(reinterpret_cast<const uint4*>(p.a + p.hot_ids[h] * p.lda) + q);
-      }
     if (tid == 0) {
       for (int i = 0; i < TG_MAX_SLOTS; ++i) {
         tc::mbar_init(&a_full[i], p.use_tma ? 1 : 128);
@@ -96,6 +90,14 @@ __global__ void __launch_bounds__(EPI2 ? TG_THREADS2 : TG_THREADS, 1) tapgemm_ke
       tc::fence_barrier_init();
     }
     if (warp == 4) tc::tmem_alloc(tmem_slot, 512);
+    pdl_wait();                        // everything above touched this CTA's shared memory / TMEM only
+    for (int i = tid; i < 512; i += NT)
+      sbias[i] = (p.bias != nullptr && i < p.n_valid) ? p.bias[i] + (p.bias2 != nullptr ? p.bias2[i] : 0.f) : 0.f;
+    if (p.ids != nullptr)
+      for (uint32_t i = tid; i < (uint32_t)p.n_hot * (hot_pitch / 16); i += NT) {
+        const uint32_t h = i / (hot_pitch / 16), q = i % (hot_pitch / 16);
+        reinterpret_cast<uint4*>(hot + (size_t)h * hot_pitch)[q] = __ldg(reinterpret_cast<const uint4*>(p.a + p.hot_ids[h] * p.lda) + q);
+      }
     tc::fence_proxy_async();
     tc::tc_fence_before();
     __syncthreads();
@@ -600,6 +602,8 @@ __global__ void __launch_bounds__(EPI2 ? TG_THREADS2 : TG_THREADS, 1) tapgemm_ke
 __global__ void tapgemm_pack_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int taps, int n_total, int K,
                                     int n_valid, int k_valid, int64_t sn, int64_t sk, int64_t st, uint32_t slot_bytes,
                                     int reps, int64_t rep_stride, int k_mod, int64_t sb) {
+  pdl_trigger();
+  pdl_wait();
   const int n_chunks = (K + TG_KC - 1) / TG_KC;
   const int64_t total = (int64_t)n_chunks * taps * (TG_KC / 8) * n_total;      // 16-byte units
   for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (int64_t)gridDim.x * blockDim.x) {
@@ -768,9 +772,9 @@ int tapgemm_launch(const TapGemmPlan& plan, cudaStream_t stream) {
   TapGemmArgs args = plan.args;
   args.dbg = g_tapgemm_dbg;
   if (g_tapgemm_dbg != nullptr) g_tapgemm_dbg += 148 * 4 * 5;     // one record block per launch
-  if (args.epi == TG_EPI_RELUGRAD_POOL) tapgemm_kernel<true, true><<<plan.grid, TG_THREADS2, plan.smem_bytes, stream>>>(args, plan.tmap);
-  else if (plan.epi2) tapgemm_kernel<false, true><<<plan.grid, TG_THREADS2, plan.smem_bytes, stream>>>(args, plan.tmap);
-  else tapgemm_kernel<false, false><<<plan.grid, TG_THREADS, plan.smem_bytes, stream>>>(args, plan.tmap);
+  if (args.epi == TG_EPI_RELUGRAD_POOL) launch_pdl(tapgemm_kernel<true, true>, dim3(plan.grid), dim3(TG_THREADS2), plan.smem_bytes, stream, args, plan.tmap);
+  else if (plan.epi2) launch_pdl(tapgemm_kernel<false, true>, dim3(plan.grid), dim3(TG_THREADS2), plan.smem_bytes, stream, args, plan.tmap);
+  else launch_pdl(tapgemm_kernel<false, false>, dim3(plan.grid), dim3(TG_THREADS), plan.smem_bytes, stream, args, plan.tmap);
   MR_CHECK_LAUNCH("tapgemm_kernel");
   return MR_OK;
 }
@@ -781,8 +785,8 @@ int tapgemm_pack_blocks(const float* src, uint8_t* dst, int taps, int n_total, i
   const uint32_t slot = (uint32_t)((TG_KC / 8) * n_total * 16);
   int blocks = (int)ceil_div(units, 256);
   if (blocks > 1024) blocks = 1024;
-  tapgemm_pack_kernel<<<blocks, 256, 0, stream>>>(src, dst, taps, n_total, K, n_valid, k_valid, sn, sk, st, slot, TG_W_REPS,
-                                                  tapgemm_pack_bytes(taps, n_total, K) / TG_W_REPS, k_mod, sb);
+  launch_pdl(tapgemm_pack_kernel, dim3(blocks), dim3(256), 0, stream, src, dst, taps, n_total, K, n_valid, k_valid, sn, sk, st, slot, (int)TG_W_REPS,
+             (int64_t)(tapgemm_pack_bytes(taps, n_total, K) / TG_W_REPS), k_mod, sb);
   MR_CHECK_LAUNCH("tapgemm_pack_kernel");
   return MR_OK;
 }

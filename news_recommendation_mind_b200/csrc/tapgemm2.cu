@@ -135,9 +135,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG2_THREADS, 1) tapg
   const int n_chunks = (p.K + TG_KC - 1) / TG_KC;
   const int last_kc = p.K - (n_chunks - 1) * TG_KC;
 
+  pdl_trigger();
   {
     const uint32_t a_bytes = (uint32_t)p.ns_a * p.a_slot_bytes;
     for (uint32_t i = tid * 16; i < a_bytes; i += TG2_THREADS * 16) *reinterpret_cast<uint4*>(sA + i) = make_uint4(0, 0, 0, 0);
+    pdl_wait();                        // first global read below; the stores above are to this CTA's shared memory
     for (int i = tid; i < 512; i += TG2_THREADS) sbias[i] = (p.bias != nullptr && i < p.n_valid) ? p.bias[i] : 0.f;
     for (uint32_t i = tid; i < (uint32_t)p.n_hot * (hot_pitch / 16); i += TG2_THREADS) {
       const uint32_t h = i / (hot_pitch / 16), pc = i % (hot_pitch / 16);
@@ -399,6 +401,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG2_THREADS, 1) tapg
 // W[tap][n, k] packed per CTA rank: [rank][chunk][tap][panel][n % (N/2)][8 x bf16]
 __global__ void tapgemm2_pack_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int taps, int N, int K, int n_valid,
                                      int k_valid, int64_t sn, int64_t sk, int64_t st, uint32_t half_slot, uint32_t half_total) {
+  pdl_trigger();
+  pdl_wait();
   const int n_chunks = (K + TG_KC - 1) / TG_KC;
   const int NH = N / 2;
   const int64_t total = (int64_t)n_chunks * taps * (TG_KC / 8) * N;
@@ -473,7 +477,7 @@ int tapgemm2_pack(const float* src, uint8_t* dst, int taps, int N, int K, int n_
   const int64_t units = (int64_t)n_chunks * taps * (TG_KC / 8) * N;
   int blocks = (int)ceil_div(units, 256);
   if (blocks > 1024) blocks = 1024;
-  tapgemm2_pack_kernel<<<blocks, 256, 0, stream>>>(src, dst, taps, N, K, n_valid, k_valid, sn, sk, st, half_slot, half_total);
+  launch_pdl(tapgemm2_pack_kernel, dim3(blocks), dim3(256), 0, stream, src, dst, taps, N, K, n_valid, k_valid, sn, sk, st, half_slot, half_total);
   MR_CHECK_LAUNCH("tapgemm2_pack_kernel");
   return MR_OK;
 }
@@ -519,7 +523,7 @@ int tapgemm2_run(TapGemmArgs a, const uint8_t* wpack2, cudaStream_t stream) {
   int64_t clusters = sm_count() / 2;
   if (clusters > q.n_pairs) clusters = q.n_pairs;
   if (clusters < 1) clusters = 1;
-  tapgemm2_kernel<<<(unsigned)(2 * clusters), TG2_THREADS, smem, stream>>>(q);
+  launch_pdl(tapgemm2_kernel, dim3((unsigned)(2 * clusters)), dim3(TG2_THREADS), smem, stream, q);
   MR_CHECK_LAUNCH("tapgemm2_kernel");
   return MR_OK;
 }

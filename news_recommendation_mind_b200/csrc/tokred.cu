@@ -33,9 +33,11 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs 
   const int m = blockIdx.x / p.S, s = blockIdx.x % p.S;
   const bool has_tiles = (int64_t)s < p.n_tiles;
 
+  pdl_trigger();
   {
     const uint32_t bytes = (uint32_t)p.n_stages * p.stage_bytes;
     for (uint32_t i = tid * 16; i < bytes; i += TR_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+    pdl_wait();                        // first global read below
     if (p.ids != nullptr)
       for (int i = tid; i < p.n_hot * 16; i += TR_THREADS) {
         const int h = i >> 4, q = i & 15;
@@ -248,6 +250,8 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tokred_kernel(const TokRedArgs 
 __global__ void __launch_bounds__(256) tokred_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dst, int S, int taps, int NQ,
                                                             int i_valid, int j_valid, int64_t dj, int64_t di, int64_t dt) {
   __shared__ float red[4][64];
+  pdl_trigger();
+  pdl_wait();
   const int ox = threadIdx.x & 63, sg = threadIdx.x >> 6;
   const int64_t total = (int64_t)taps * i_valid * j_valid;
   const int64_t idx = (int64_t)blockIdx.x * 64 + ox;
@@ -354,7 +358,7 @@ int tokred_launch(const TokRedPlan& plan, cudaStream_t stream) {
   TokRedArgs args = plan.args;
   args.dbg = g_tapgemm_dbg;
   if (g_tapgemm_dbg != nullptr) g_tapgemm_dbg += 148 * 4 * 5;
-  tokred_kernel<<<plan.grid, TR_THREADS, plan.smem_bytes, stream>>>(args, plan.pmap, plan.qmap);
+  launch_pdl(tokred_kernel, dim3(plan.grid), dim3(TR_THREADS), plan.smem_bytes, stream, args, plan.pmap, plan.qmap);
   MR_CHECK_LAUNCH("tokred_kernel");
   return MR_OK;
 }
@@ -363,8 +367,8 @@ int tokred_reduce(const TokRedPlan& plan, float* dst, int i_valid, int j_valid, 
                   cudaStream_t stream) {
   const TokRedArgs& a = plan.args;
   const int64_t total = (int64_t)a.taps * i_valid * j_valid;
-  tokred_reduce_kernel<<<(unsigned)ceil_div(total, 64), 256, 0, stream>>>(a.partial, dst, a.S, a.taps, a.NQ, i_valid, j_valid,
-                                                                          dj, di, dt);
+  launch_pdl(tokred_reduce_kernel, dim3((unsigned)ceil_div(total, 64)), dim3(256), 0, stream, (const float*)a.partial, dst, a.S, a.taps, a.NQ,
+             i_valid, j_valid, dj, di, dt);
   MR_CHECK_LAUNCH("tokred_reduce_kernel");
   return MR_OK;
 }
