@@ -179,6 +179,8 @@ __global__ void __launch_bounds__(256)
 seg_reduce_l2_kernel(const int32_t* __restrict__ chunk_off, const int32_t* __restrict__ nchunk,
                      const float* __restrict__ partial, TO* __restrict__ d_table, int64_t ldo, int64_t V, int64_t E,
                      int32_t* __restrict__ heavy_count, int32_t* __restrict__ heavy_rows, int32_t max_heavy, int32_t heavy_thr) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (v >= V) return;
@@ -240,6 +242,8 @@ seg_reduce_heavy_kernel(const int32_t* __restrict__ chunk_off, const int32_t* __
                         const float* __restrict__ partial, float* __restrict__ partial2,
                         const int32_t* __restrict__ heavy_count, const int32_t* __restrict__ heavy_rows, int64_t E,
                         int32_t max_items) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ int32_t off[SEG_MAX_HEAVY_SMEM + 1];
   __shared__ float4 red[128];
   const int nh = min(*heavy_count, SEG_MAX_HEAVY_SMEM);
@@ -297,6 +301,8 @@ __global__ void __launch_bounds__(256)
 seg_reduce_heavy_final_kernel(const float* __restrict__ partial2, TO* __restrict__ d_table, int64_t ldo,
                               const int32_t* __restrict__ nchunk, const int32_t* __restrict__ heavy_count,
                               const int32_t* __restrict__ heavy_rows, int64_t E, int32_t max_items) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ int32_t off[SEG_MAX_HEAVY_SMEM + 1];
   __shared__ float red[4][64];
   const int nh = min(*heavy_count, SEG_MAX_HEAVY_SMEM);
@@ -365,6 +371,8 @@ __global__ void __launch_bounds__(256)
 group_taps_l1_kernel(const __nv_bfloat16* __restrict__ dconv, int64_t ld, int L, int pieces, const int32_t* __restrict__ sorted_pos,
                      const int4* __restrict__ chunk_desc, __nv_bfloat16* __restrict__ S, int64_t lds, float* __restrict__ partial,
                      int64_t n_chunks) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t ch = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (ch >= n_chunks) return;
@@ -547,17 +555,17 @@ int token_group_taps(const void* ids, int ids_i64, const void* plan_in, const __
   const int4* desc = reinterpret_cast<const int4*>(base + l.chunk_desc);
   const int pieces = (int)(Hp / 8);
   if (3 * pieces <= 32)
-    group_taps_l1_kernel<1><<<(unsigned)ceil_div(p.max_chunks, 8), 256, 0, st>>>(dconv, ld, L, pieces, svals, desc, S, E, partial, p.max_chunks);
+    launch_pdl(group_taps_l1_kernel<1>, dim3((unsigned)ceil_div(p.max_chunks, 8)), dim3(256), 0, st, dconv, ld, L, pieces, svals, desc, S, E, partial, p.max_chunks);
   else
-    group_taps_l1_kernel<2><<<(unsigned)ceil_div(p.max_chunks, 8), 256, 0, st>>>(dconv, ld, L, pieces, svals, desc, S, E, partial, p.max_chunks);
+    launch_pdl(group_taps_l1_kernel<2>, dim3((unsigned)ceil_div(p.max_chunks, 8)), dim3(256), 0, st, dconv, ld, L, pieces, svals, desc, S, E, partial, p.max_chunks);
   MR_CHECK_LAUNCH("group_taps_l1_kernel");
   cudaMemsetAsync(heavy, 0, sizeof(int32_t), st);
-  seg_reduce_l2_kernel<__nv_bfloat16><<<(unsigned)ceil_div(V, 8), 256, 0, st>>>(chunk_off, nchunk, partial, S, E, V, E, heavy, heavy + 1,
+  launch_pdl(seg_reduce_l2_kernel<__nv_bfloat16>, dim3((unsigned)ceil_div(V, 8)), dim3(256), 0, st, chunk_off, nchunk, partial, S, E, V, E, heavy, heavy + 1,
                                                                                 (int32_t)p.max_heavy, p.heavy_thr);
   MR_CHECK_LAUNCH("seg_reduce_l2_kernel");
-  seg_reduce_heavy_kernel<<<148 * 4, 256, 0, st>>>(chunk_off, nchunk, partial, partial2, heavy, heavy + 1, E, (int32_t)p.max_items);
+  launch_pdl(seg_reduce_heavy_kernel, dim3(148 * 4), dim3(256), 0, st, chunk_off, nchunk, partial, partial2, heavy, heavy + 1, E, (int32_t)p.max_items);
   MR_CHECK_LAUNCH("seg_reduce_heavy_kernel");
-  seg_reduce_heavy_final_kernel<__nv_bfloat16><<<dim3(64, (unsigned)ceil_div(E, 64)), 256, 0, st>>>(partial2, S, E, nchunk, heavy, heavy + 1, E, (int32_t)p.max_items);
+  launch_pdl(seg_reduce_heavy_final_kernel<__nv_bfloat16>, dim3(64, (unsigned)ceil_div(E, 64)), dim3(256), 0, st, partial2, S, E, nchunk, heavy, heavy + 1, E, (int32_t)p.max_items);
   MR_CHECK_LAUNCH("seg_reduce_heavy_final_kernel");
   return MR_OK;
 }
@@ -655,12 +663,12 @@ int mr_embed_grad_segreduce(const void* ids, int ids_i64, const void* d_emb, int
         static_cast<const __nv_bfloat16*>(d_emb), E4, svals, seg_start, chunk_off, chunk_row, nchunk, d_table, partial, p.max_chunks, E, V);
   MR_CHECK_LAUNCH("seg_reduce_l1_kernel");
   cudaMemsetAsync(heavy, 0, sizeof(int32_t), st);
-  seg_reduce_l2_kernel<float><<<(unsigned)ceil_div(V, 8), 256, 0, st>>>(chunk_off, nchunk, partial, d_table, E, V, E, heavy, heavy + 1,
+  launch_pdl(seg_reduce_l2_kernel<float>, dim3((unsigned)ceil_div(V, 8)), dim3(256), 0, st, chunk_off, nchunk, partial, d_table, E, V, E, heavy, heavy + 1,
                                                                         (int32_t)p.max_heavy, p.heavy_thr);
   MR_CHECK_LAUNCH("seg_reduce_l2_kernel");
-  seg_reduce_heavy_kernel<<<148 * 4, 256, 0, st>>>(chunk_off, nchunk, partial, partial2, heavy, heavy + 1, E, (int32_t)p.max_items);
+  launch_pdl(seg_reduce_heavy_kernel, dim3(148 * 4), dim3(256), 0, st, chunk_off, nchunk, partial, partial2, heavy, heavy + 1, E, (int32_t)p.max_items);
   MR_CHECK_LAUNCH("seg_reduce_heavy_kernel");
-  seg_reduce_heavy_final_kernel<float><<<dim3(64, (unsigned)ceil_div(E, 64)), 256, 0, st>>>(partial2, d_table, E, nchunk, heavy, heavy + 1, E, (int32_t)p.max_items);
+  launch_pdl(seg_reduce_heavy_final_kernel<float>, dim3(64, (unsigned)ceil_div(E, 64)), dim3(256), 0, st, partial2, d_table, E, nchunk, heavy, heavy + 1, E, (int32_t)p.max_items);
   MR_CHECK_LAUNCH("seg_reduce_heavy_final_kernel");
   return MR_OK;
 }

@@ -138,10 +138,10 @@ int news_cnn_tc_fwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
   if (int rc = tapgemm_launch(plan, st)) return rc;
   if (L <= 32 && Hp <= 256) {
     const unsigned grid = (unsigned)ceil_div(N, 8);
-    if (Hp <= 64) cnn_pool_fwd_bf16_kernel<1><<<grid, 256, 0, st>>>(c, key, Hp, mask, mask_i64, query, prob, news, N, (int)L, (int)H);
-    else if (Hp <= 128) cnn_pool_fwd_bf16_kernel<2><<<grid, 256, 0, st>>>(c, key, Hp, mask, mask_i64, query, prob, news, N, (int)L, (int)H);
-    else if (Hp <= 192) cnn_pool_fwd_bf16_kernel<3><<<grid, 256, 0, st>>>(c, key, Hp, mask, mask_i64, query, prob, news, N, (int)L, (int)H);
-    else cnn_pool_fwd_bf16_kernel<4><<<grid, 256, 0, st>>>(c, key, Hp, mask, mask_i64, query, prob, news, N, (int)L, (int)H);
+    if (Hp <= 64) launch_pdl(cnn_pool_fwd_bf16_kernel<1>, dim3(grid), dim3(256), 0, st, c, key, Hp, mask, mask_i64, query, prob, news, N, (int)L, (int)H);
+    else if (Hp <= 128) launch_pdl(cnn_pool_fwd_bf16_kernel<2>, dim3(grid), dim3(256), 0, st, c, key, Hp, mask, mask_i64, query, prob, news, N, (int)L, (int)H);
+    else if (Hp <= 192) launch_pdl(cnn_pool_fwd_bf16_kernel<3>, dim3(grid), dim3(256), 0, st, c, key, Hp, mask, mask_i64, query, prob, news, N, (int)L, (int)H);
+    else launch_pdl(cnn_pool_fwd_bf16_kernel<4>, dim3(grid), dim3(256), 0, st, c, key, Hp, mask, mask_i64, query, prob, news, N, (int)L, (int)H);
   } else {
     cnn_pool_fwd_kernel<__nv_bfloat16><<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(c, key, Hp, mask, mask_i64, query, prob, news, N, (int)L, (int)H);
   }
@@ -195,11 +195,11 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
   cudaError_t e;
   if (fast_pool) {
     const unsigned grid = (unsigned)ceil_div(N, 8);
-    if (Hp <= 64) cnn_pool_bwd_bf16_kernel<1><<<grid, 256, 0, st>>>(c, key, Hp, prob, query, d_news, dkp, dnp, ppart, cmask, N, (int)L, (int)H);
-    else if (Hp <= 128) cnn_pool_bwd_bf16_kernel<2><<<grid, 256, 0, st>>>(c, key, Hp, prob, query, d_news, dkp, dnp, ppart, cmask, N, (int)L, (int)H);
-    else cnn_pool_bwd_bf16_kernel<3><<<grid, 256, 0, st>>>(c, key, Hp, prob, query, d_news, dkp, dnp, ppart, cmask, N, (int)L, (int)H);
+    if (Hp <= 64) launch_pdl(cnn_pool_bwd_bf16_kernel<1>, dim3(grid), dim3(256), 0, st, c, key, Hp, prob, query, d_news, dkp, dnp, ppart, cmask, N, (int)L, (int)H);
+    else if (Hp <= 128) launch_pdl(cnn_pool_bwd_bf16_kernel<2>, dim3(grid), dim3(256), 0, st, c, key, Hp, prob, query, d_news, dkp, dnp, ppart, cmask, N, (int)L, (int)H);
+    else launch_pdl(cnn_pool_bwd_bf16_kernel<3>, dim3(grid), dim3(256), 0, st, c, key, Hp, prob, query, d_news, dkp, dnp, ppart, cmask, N, (int)L, (int)H);
     MR_CHECK_LAUNCH("cnn_pool_bwd_bf16_kernel");
-    cnn_pool_bwd_final_kernel<<<(unsigned)ceil_div(2 * Hp, 32), 1024, 0, st>>>(ppart, (int64_t)grid, (int)Hp, (int)H, d_query, d_proj_b);
+    launch_pdl(cnn_pool_bwd_final_kernel, dim3((unsigned)ceil_div(2 * Hp, 32)), dim3(1024), 0, st, ppart, (int64_t)grid, (int)Hp, (int)H, d_query, d_proj_b);
     MR_CHECK_LAUNCH("cnn_pool_bwd_final_kernel");
     if (d_c) {                                   // gradient arriving at the token representations (stand-alone CNN module)
       cast_rows_bf16_kernel<<<(unsigned)ceil_div(T * Hp, 256), 256, 0, st>>>(d_c, dcv, T, H, Hp);

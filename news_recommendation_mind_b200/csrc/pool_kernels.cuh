@@ -229,6 +229,8 @@ __global__ void __launch_bounds__(256)
 cnn_pool_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ c, const __nv_bfloat16* __restrict__ key, int64_t ld,
                          const void* __restrict__ mask, int mask_i64, const float* __restrict__ q, float* __restrict__ prob,
                          float* __restrict__ news, int64_t N, int L, int H) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= N) return;
@@ -285,6 +287,8 @@ cnn_pool_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ c, const __nv_bfloat1
                          const float* __restrict__ prob, const float* __restrict__ q, const float* __restrict__ d_news,
                          __nv_bfloat16* __restrict__ dkp, float* __restrict__ dnp, float* __restrict__ part,
                          uint8_t* __restrict__ cmask, int64_t N, int L, int H) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][2][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -361,6 +365,8 @@ cnn_pool_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ c, const __nv_bfloat1
 static __global__ void __launch_bounds__(1024)
 cnn_pool_bwd_final_kernel(const float* __restrict__ part, int64_t rows, int ld, int H, float* __restrict__ d_query,
                           float* __restrict__ d_proj_b) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sm[32][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + cx;

@@ -265,6 +265,8 @@ struct TwoBiasEpi {
 // rows m = b*S + s (step order: s-th step reads x[b, S-1-s] when `reverse`), padded to a multiple of 128 rows
 __global__ void seq_cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t M, int64_t Mp, int S,
                                      int H, int Hp, int reverse) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Mp * Hp) return;
   const int64_t m = i / Hp;
@@ -281,6 +283,8 @@ __global__ void seq_cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
 // (steps at or beyond a sequence's length give zero rows: the recurrence kernels never write hs there)
 __global__ void hprev_bf16_kernel(const float* __restrict__ hs, const float* __restrict__ h0, const int32_t* __restrict__ lens,
                                   __nv_bfloat16* __restrict__ out, int64_t M, int64_t Mp, int S, int H, int Hp) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Mp * Hp) return;
   const int64_t m = i / Hp;
@@ -304,6 +308,8 @@ __global__ void cast_rows_pad_bf16_kernel(const float* __restrict__ src, __nv_bf
 }
 // d_x[b, pos(s), :] = tmp[(b,s), :H]
 __global__ void unseq_copy_kernel(const float* __restrict__ tmp, float* __restrict__ d_x, int64_t M, int S, int H, int Hp, int reverse) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * H) return;
   const int64_t m = i / H;
@@ -348,7 +354,7 @@ static int rnn_tc_input_proj(const mr_rnn_shape* s, const float* x, const float*
   __nv_bfloat16* xb = ar.take<__nv_bfloat16>(g.Mp * g.Hp);
   uint8_t* wp = ar.take<uint8_t>(tapgemm_pack_bytes(1, (int)g.nbsz, (int)g.Hp));
   MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "mr_rnn_user_fwd: workspace too small");
-  seq_cast_bf16_kernel<<<(unsigned)ceil_div(g.Mp * g.Hp, 256), 256, 0, st>>>(x, xb, g.M, g.Mp, (int)s->S, H, (int)g.Hp, s->reverse);
+  launch_pdl(seq_cast_bf16_kernel, dim3((unsigned)ceil_div(g.Mp * g.Hp, 256)), dim3(256), 0, st, x, xb, g.M, g.Mp, (int)s->S, H, (int)g.Hp, s->reverse);
   MR_CHECK_LAUNCH("seq_cast_bf16_kernel");
   for (int64_t blk = 0; blk < g.nblk; ++blk) {
     const int64_t n0 = blk * g.nbsz;
@@ -382,9 +388,9 @@ static int rnn_tc_grad_gemms(const mr_rnn_shape* s, const float* x, const float*
   float* tmp = ar.take<float>(g.M * g.Hp);
   float* partial = ar.take<float>(tokred_partial_bytes(g.Mp / 128, 128, 1, (int)g.GHp, (int)g.Hp) / 4);
   MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "mr_rnn_user_bwd: workspace too small");
-  seq_cast_bf16_kernel<<<(unsigned)ceil_div(g.Mp * g.Hp, 256), 256, 0, st>>>(x, xb, g.M, g.Mp, S, H, (int)g.Hp, s->reverse);
+  launch_pdl(seq_cast_bf16_kernel, dim3((unsigned)ceil_div(g.Mp * g.Hp, 256)), dim3(256), 0, st, x, xb, g.M, g.Mp, S, H, (int)g.Hp, s->reverse);
   MR_CHECK_LAUNCH("seq_cast_bf16_kernel");
-  hprev_bf16_kernel<<<(unsigned)ceil_div(g.Mp * g.Hp, 256), 256, 0, st>>>(hs, h0, lens, hb, g.M, g.Mp, S, H, (int)g.Hp);
+  launch_pdl(hprev_bf16_kernel, dim3((unsigned)ceil_div(g.Mp * g.Hp, 256)), dim3(256), 0, st, hs, h0, lens, hb, g.M, g.Mp, S, H, (int)g.Hp);
   MR_CHECK_LAUNCH("hprev_bf16_kernel");
   if (!precast) {
     cast_rows_pad_bf16_kernel<<<(unsigned)ceil_div(g.Mp * g.GHp, 256), 256, 0, st>>>(dgi, gib, g.M, g.Mp, (int)g.GH, (int)g.GHp);
@@ -406,7 +412,7 @@ static int rnn_tc_grad_gemms(const mr_rnn_shape* s, const float* x, const float*
     a.n_rows = g.M; a.out_f32 = tmp; a.ldo = g.Hp; a.n_store = (int)g.Hp;
     if (int rc = tapgemm_plan(a, &plan)) return rc;
     if (int rc = tapgemm_launch(plan, st)) return rc;
-    unseq_copy_kernel<<<(unsigned)ceil_div(g.M * H, 256), 256, 0, st>>>(tmp, d_x, g.M, S, H, (int)g.Hp, s->reverse);
+    launch_pdl(unseq_copy_kernel, dim3((unsigned)ceil_div(g.M * H, 256)), dim3(256), 0, st, tmp, d_x, g.M, S, H, (int)g.Hp, s->reverse);
     MR_CHECK_LAUNCH("unseq_copy_kernel");
   }
   for (int which = 0; which < 2; ++which) {   // d_w_ih[n,k] = sum_m dgi[m,n] x[m,k];  d_w_hh[n,k] = sum_m dgh[m,n] h_{s-1}[m,k]

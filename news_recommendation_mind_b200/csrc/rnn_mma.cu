@@ -44,6 +44,8 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t smem_addr
 
 // W_hh [GH, H] fp32 -> bf16 image [MT*16][KT*16], zero padded
 __global__ void rnn_mma_prep_kernel(const float* __restrict__ w_hh, __nv_bfloat16* __restrict__ img, int GH, int H, int rows, int cols) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   const int n = i / cols, k = i - n * cols;
@@ -81,6 +83,8 @@ __global__ void __launch_bounds__(RM_THREADS, 1)
 rnn_mma_fwd_kernel(const float* __restrict__ xp, int ldx, const __nv_bfloat16* __restrict__ w_img, const float* __restrict__ b_hh,
                    const float* __restrict__ h0, const int32_t* __restrict__ lens, float* __restrict__ gates,
                    float* __restrict__ hs, float* __restrict__ cs, float* __restrict__ user, int B, int S, int H, int MT, int KT) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int G = KIND == 0 ? 4 : 3;
   constexpr int PPT = (NSEQ * RM_MAXKT * 16 + RM_THREADS - 1) / RM_THREADS;       // (sequence, unit) pairs per thread
   const int GH = G * H;
@@ -265,7 +269,7 @@ static int rm_launch_fwd(int nseq, const float* xp, int ldx, const __nv_bfloat16
 #define RM_LAUNCH_F(NS)                                                                                              \
   {                                                                                                                  \
     cudaFuncSetAttribute(rnn_mma_fwd_kernel<KIND, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);     \
-    rnn_mma_fwd_kernel<KIND, NS><<<grid, RM_THREADS, g.smem, st>>>(xp, ldx, img, b_hh, h0, lens, gates, hs, cs, user, B, S, H, g.MT, g.KT); \
+    launch_pdl(rnn_mma_fwd_kernel<KIND, NS>, dim3(grid), dim3(RM_THREADS), g.smem, st, xp, ldx, img, b_hh, h0, lens, gates, hs, cs, user, B, S, H, g.MT, g.KT); \
   }
   if (nseq == 2) RM_LAUNCH_F(2) else if (nseq == 4) RM_LAUNCH_F(4) else RM_LAUNCH_F(8)
 #undef RM_LAUNCH_F
@@ -279,7 +283,7 @@ int rnn_mma_fwd(int kind, const float* xp, int ldx, const float* w_hh_f32, const
   const RMGeom g = rm_geom(kind, H, nseq);
   __nv_bfloat16* img = static_cast<__nv_bfloat16*>(scratch);
   const int rows = g.MT * 16, cols = g.KT * 16;
-  rnn_mma_prep_kernel<<<(unsigned)ceil_div((int64_t)rows * cols, 256), 256, 0, st>>>(w_hh_f32, img, g.GH, H, rows, cols);
+  launch_pdl(rnn_mma_prep_kernel, dim3((unsigned)ceil_div((int64_t)rows * cols, 256)), dim3(256), 0, st, w_hh_f32, img, g.GH, H, rows, cols);
   MR_CHECK_LAUNCH("rnn_mma_prep_kernel");
   return kind == MR_RNN_LSTM ? rm_launch_fwd<0>(nseq, xp, ldx, img, b_hh, h0, lens, gates, hs, cs, user, B, S, H, st)
                              : rm_launch_fwd<1>(nseq, xp, ldx, img, b_hh, h0, lens, gates, hs, cs, user, B, S, H, st);

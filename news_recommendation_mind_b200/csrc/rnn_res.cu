@@ -67,6 +67,8 @@ bool rnn_res_supported(int kind, int H) { return rr_fits(kind, H, 1); }
 //   wt [H][GHp]  (forward:  Wt[k][n] = W_hh[n][k], zero padded columns)      w [GH][Hp]  (backward, zero padded)
 __global__ void rnn_res_prep_kernel(const float* __restrict__ w_hh, __nv_bfloat16* __restrict__ wt, __nv_bfloat16* __restrict__ w,
                                     int GH, int H, int GHp, int Hp) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (wt != nullptr && i < H * GHp) {
     const int k = i / GHp, n = i - k * GHp;
@@ -100,6 +102,8 @@ __global__ void __launch_bounds__(RR_THREADS, 1)
 rnn_res_fwd_kernel(const float* __restrict__ xp, int ldx, const __nv_bfloat16* __restrict__ wt_g, const float* __restrict__ b_hh,
                    const float* __restrict__ h0, const int32_t* __restrict__ lens, float* __restrict__ gates,
                    float* __restrict__ hs, float* __restrict__ cs, float* __restrict__ user, int B, int S, int H) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int G = KIND == 0 ? 4 : 3;
   const int GH = G * H, NT = (GH + 7) / 8, GHp = NT * 8, KR = (H + RR_KS - 1) / RR_KS;
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -215,6 +219,8 @@ rnn_res_bwd_kernel(const __nv_bfloat16* __restrict__ w_g, const float* __restric
                    const float* __restrict__ d_user, float* __restrict__ dgi, float* __restrict__ dgh,
                    float* __restrict__ d_h0, int B, int S, int H, __nv_bfloat16* __restrict__ gib, __nv_bfloat16* __restrict__ ghb,
                    int GHp16, float* __restrict__ bias_part) {
+  pdl_trigger();
+  pdl_wait();
   // gib / ghb != nullptr: the gate gradients are written as bf16 rows of pitch GHp16 (the layout the weight-gradient
   // GEMMs read; pre-zeroed by the host) instead of fp32 dgi / dgh, and the bias gradients (column sums of dgi / dgh over
   // this CTA's sequences and steps) go to bias_part[blockIdx][2][GH]
@@ -380,7 +386,7 @@ static int launch_fwd(int bpc, const float* xp, int ldx, const __nv_bfloat16* w_
 #define RR_LAUNCH_F(BPC)                                                                                               \
   {                                                                                                                    \
     cudaFuncSetAttribute(rnn_res_fwd_kernel<KIND, BPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.fwd_bytes); \
-    rnn_res_fwd_kernel<KIND, BPC><<<grid, RR_THREADS, g.fwd_bytes, st>>>(xp, ldx, w_hh, b_hh, h0, lens, gates, hs, cs, user, B, S, H); \
+    launch_pdl(rnn_res_fwd_kernel<KIND, BPC>, dim3(grid), dim3(RR_THREADS), g.fwd_bytes, st, xp, ldx, w_hh, b_hh, h0, lens, gates, hs, cs, user, B, S, H); \
   }
   if (bpc == 1) RR_LAUNCH_F(1) else if (bpc == 2) RR_LAUNCH_F(2) else RR_LAUNCH_F(4)
 #undef RR_LAUNCH_F
@@ -397,7 +403,7 @@ static int launch_bwd(int bpc, const __nv_bfloat16* w_hh, const float* h0, const
 #define RR_LAUNCH_B(BPC)                                                                                               \
   {                                                                                                                    \
     cudaFuncSetAttribute(rnn_res_bwd_kernel<KIND, BPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.bwd_bytes); \
-    rnn_res_bwd_kernel<KIND, BPC><<<grid, RR_THREADS, g.bwd_bytes, st>>>(w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H, gib, ghb, GHp16, bias_part); \
+    launch_pdl(rnn_res_bwd_kernel<KIND, BPC>, dim3(grid), dim3(RR_THREADS), g.bwd_bytes, st, w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H, gib, ghb, GHp16, bias_part); \
   }
   if (bpc == 1) RR_LAUNCH_B(1) else if (bpc == 2) RR_LAUNCH_B(2) else RR_LAUNCH_B(4)
 #undef RR_LAUNCH_B
@@ -416,7 +422,7 @@ int rnn_res_fwd(int kind, const float* xp, int ldx, const float* w_hh_f32, const
   const int bpc = rnn_res_bpc(kind, B, H);
   const RRGeom g = rr_geom(kind, H, bpc);
   __nv_bfloat16* w_hh = static_cast<__nv_bfloat16*>(scratch);
-  rnn_res_prep_kernel<<<(unsigned)ceil_div((int64_t)H * g.GHp, 256), 256, 0, st>>>(w_hh_f32, w_hh, nullptr, g.GH, H, g.GHp, g.Hp);
+  launch_pdl(rnn_res_prep_kernel, dim3((unsigned)ceil_div((int64_t)H * g.GHp, 256)), dim3(256), 0, st, w_hh_f32, w_hh, nullptr, g.GH, H, g.GHp, g.Hp);
   MR_CHECK_LAUNCH("rnn_res_prep_kernel");
   return kind == MR_RNN_LSTM ? launch_fwd<0>(bpc, xp, ldx, w_hh, b_hh, h0, lens, gates, hs, cs, user, B, S, H, st)
                              : launch_fwd<1>(bpc, xp, ldx, w_hh, b_hh, h0, lens, gates, hs, cs, user, B, S, H, st);
@@ -428,7 +434,7 @@ int rnn_res_bwd(int kind, const float* w_hh_f32, const float* h0, const int32_t*
   const int bpc = rnn_res_bpc(kind, B, H);
   const RRGeom g = rr_geom(kind, H, bpc);
   __nv_bfloat16* w_hh = static_cast<__nv_bfloat16*>(scratch);
-  rnn_res_prep_kernel<<<(unsigned)ceil_div((int64_t)g.GH * g.Hp, 256), 256, 0, st>>>(w_hh_f32, nullptr, w_hh, g.GH, H, g.GHp, g.Hp);
+  launch_pdl(rnn_res_prep_kernel, dim3((unsigned)ceil_div((int64_t)g.GH * g.Hp, 256)), dim3(256), 0, st, w_hh_f32, nullptr, w_hh, g.GH, H, g.GHp, g.Hp);
   MR_CHECK_LAUNCH("rnn_res_prep_kernel");
   return kind == MR_RNN_LSTM ? launch_bwd<0>(bpc, w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H, gib, ghb, GHp16, bias_part, st)
                              : launch_bwd<1>(bpc, w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H, gib, ghb, GHp16, bias_part, st);

@@ -12,6 +12,8 @@ namespace mr {
 __global__ void __launch_bounds__(256)
 score_logsoftmax_fwd_kernel(const float* __restrict__ cdd, const float* __restrict__ user, float* __restrict__ logp,
                             int64_t B, int C, int H) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -36,6 +38,8 @@ score_logsoftmax_fwd_kernel(const float* __restrict__ cdd, const float* __restri
 
 __global__ void nll_mean_kernel(const float* __restrict__ logp, const void* __restrict__ label, int label_i64,
                                 float* __restrict__ loss, int64_t B, int C) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sm[32];
   float s = 0.f;
   for (int64_t b = threadIdx.x; b < B; b += blockDim.x) {
@@ -54,6 +58,8 @@ __global__ void nll_mean_kernel(const float* __restrict__ logp, const void* __re
 
 __global__ void nll_bwd_kernel(const void* __restrict__ label, int label_i64, const float* __restrict__ d_loss,
                                float* __restrict__ d_logp, int64_t B, int C) {
+  pdl_trigger();
+  pdl_wait();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   int64_t b = i / C; int c = (int)(i - b * C);
@@ -65,6 +71,8 @@ __global__ void __launch_bounds__(256)
 score_logsoftmax_bwd_kernel(const float* __restrict__ cdd, const float* __restrict__ user, const float* __restrict__ logp,
                             const float* __restrict__ d_logp, float* __restrict__ d_cdd, float* __restrict__ d_user,
                             int64_t B, int C, int H) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -330,11 +338,11 @@ int mr_score_logsoftmax_fwd(const float* cdd, const float* user, float* logp, co
              (long long)C, (long long)H);
   if (B == 0) return MR_OK;
   cudaStream_t st = as_stream(stream);
-  score_logsoftmax_fwd_kernel<<<(unsigned)ceil_div(B, 8), 256, 0, st>>>(cdd, user, logp, B, (int)C, (int)H);
+  launch_pdl(score_logsoftmax_fwd_kernel, dim3((unsigned)ceil_div(B, 8)), dim3(256), 0, st, cdd, user, logp, B, (int)C, (int)H);
   MR_CHECK_LAUNCH("score_logsoftmax_fwd_kernel");
   if (loss_mean) {
     MR_REQUIRE(label != nullptr, MR_ERR_NULL, "mr_score_logsoftmax_fwd: loss requested without labels");
-    nll_mean_kernel<<<1, 256, 0, st>>>(logp, label, label_i64, loss_mean, B, (int)C);
+    launch_pdl(nll_mean_kernel, dim3(1), dim3(256), 0, st, logp, label, label_i64, loss_mean, B, (int)C);
     MR_CHECK_LAUNCH("nll_mean_kernel");
   }
   return MR_OK;
@@ -344,7 +352,7 @@ int mr_nll_loss_fwd(const float* logp, const void* label, int label_i64, float* 
   if (int rc = require_sm100()) return rc;
   MR_REQUIRE(logp && label && loss, MR_ERR_NULL, "mr_nll_loss_fwd: null pointer");
   MR_REQUIRE(B >= 1 && C >= 1, MR_ERR_BAD_SHAPE, "mr_nll_loss_fwd: bad shape");
-  nll_mean_kernel<<<1, 256, 0, as_stream(stream)>>>(logp, label, label_i64, loss, B, (int)C);
+  launch_pdl(nll_mean_kernel, dim3(1), dim3(256), 0, as_stream(stream), logp, label, label_i64, loss, B, (int)C);
   MR_CHECK_LAUNCH("nll_mean_kernel");
   return MR_OK;
 }
@@ -353,7 +361,7 @@ int mr_nll_loss_bwd(const void* label, int label_i64, const float* d_loss, float
   if (int rc = require_sm100()) return rc;
   MR_REQUIRE(label && d_logp, MR_ERR_NULL, "mr_nll_loss_bwd: null pointer");
   MR_REQUIRE(B >= 1 && C >= 1, MR_ERR_BAD_SHAPE, "mr_nll_loss_bwd: bad shape");
-  nll_bwd_kernel<<<(unsigned)ceil_div(B * C, 256), 256, 0, as_stream(stream)>>>(label, label_i64, d_loss, d_logp, B, (int)C);
+  launch_pdl(nll_bwd_kernel, dim3((unsigned)ceil_div(B * C, 256)), dim3(256), 0, as_stream(stream), label, label_i64, d_loss, d_logp, B, (int)C);
   MR_CHECK_LAUNCH("nll_bwd_kernel");
   return MR_OK;
 }
@@ -364,7 +372,7 @@ int mr_score_logsoftmax_bwd(const float* cdd, const float* user, const float* lo
   MR_REQUIRE(cdd && user && logp && d_logp && d_cdd && d_user, MR_ERR_NULL, "mr_score_logsoftmax_bwd: null pointer");
   MR_REQUIRE(B >= 0 && C >= 1 && H >= 1, MR_ERR_BAD_SHAPE, "mr_score_logsoftmax_bwd: bad shape");
   if (B == 0) return MR_OK;
-  score_logsoftmax_bwd_kernel<<<(unsigned)ceil_div(B, 8), 256, 0, as_stream(stream)>>>(cdd, user, logp, d_logp, d_cdd,
+  launch_pdl(score_logsoftmax_bwd_kernel, dim3((unsigned)ceil_div(B, 8)), dim3(256), 0, as_stream(stream), cdd, user, logp, d_logp, d_cdd,
                                                                                        d_user, B, (int)C, (int)H);
   MR_CHECK_LAUNCH("score_logsoftmax_bwd_kernel");
   return MR_OK;

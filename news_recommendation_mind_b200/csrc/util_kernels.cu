@@ -57,6 +57,8 @@ static cudaError_t colsum_t(const T* x, int64_t ld, float* out, int64_t R, int64
 // 8 row groups, fixed summation order
 __global__ void __launch_bounds__(1024) colsum_small_kernel(const float* __restrict__ x, int64_t ld, float* __restrict__ out, int64_t R,
                                                             int64_t C) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sm[32][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int64_t c = (int64_t)blockIdx.x * 32 + cx;
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(1024) colsum_small_kernel(const float* __restr
   }
 }
 cudaError_t colsum_small(const float* x, int64_t ld, float* out, int64_t R, int64_t C, cudaStream_t st) {
-  colsum_small_kernel<<<(unsigned)ceil_div(C, 32), 1024, 0, st>>>(x, ld, out, R, C);
+  launch_pdl(colsum_small_kernel, dim3((unsigned)ceil_div(C, 32)), dim3(1024), 0, st, x, ld, out, R, C);
   count_launch(1);
   return cudaGetLastError();
 }
@@ -131,6 +133,8 @@ __device__ __forceinline__ float adam_one(float pi, float gi, float& mi, float& 
 }
 
 __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__ AdamMultiArgs a) {
+  pdl_trigger();
+  pdl_wait();
   int t = 0;
 #pragma unroll 1
   while (t + 1 < a.n_tensors && (int)blockIdx.x >= a.blk_off[t + 1]) ++t;
@@ -250,7 +254,7 @@ int mr_adam_step_multi(int n_tensors, float* const* p, const float* const* g, fl
     MR_REQUIRE(shadow_tensor < n_tensors && row_len > 0 && shadow_ld >= row_len && numel[shadow_tensor] % row_len == 0, MR_ERR_BAD_SHAPE,
                "mr_adam_step_multi: bad shadow geometry");
   if (blocks == 0) return MR_OK;
-  adam_multi_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(a);
+  launch_pdl(adam_multi_kernel, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream), a);
   MR_CHECK_LAUNCH("adam_multi_kernel");
   return MR_OK;
 }
