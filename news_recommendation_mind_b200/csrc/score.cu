@@ -227,6 +227,18 @@ attnpool_bwd_kernel(const float* __restrict__ r, const float* __restrict__ q, co
   for (int h0 = 0; h0 < H; h0 += 32) {
     int h = h0 + lane;
     float qh = h < H ? __ldg(q + h) : 0.f, gh = h < H ? __ldg(go + h) : 0.f, dq = 0.f;
+    // dq = sum_t ds[t] r[t,h] with sum_t ds[t] = 0: when the rows r[t,:] are nearly equal (the output of a self-attention
+    // layer) the plain sum cancels catastrophically in fp32.  Summing ds[t] (r[t,h] - rbar[h]) with rbar = sum_t p[t] r[t,h]
+    // is the same number with both factors small.
+    float rbar = 0.f;
+#pragma unroll
+    for (int i = 0; i < AP_MAXR; ++i) {
+      if (i * 32 >= S) break;
+      for (int j = 0; j < 32 && i * 32 + j < S; ++j) {
+        float pt = __shfl_sync(0xffffffffu, p[i], j);
+        if (h < H) rbar = fmaf(pt, __ldg(r + (b * S + i * 32 + j) * H + h), rbar);
+      }
+    }
 #pragma unroll
     for (int i = 0; i < AP_MAXR; ++i) {
       if (i * 32 >= S) break;
@@ -236,7 +248,7 @@ attnpool_bwd_kernel(const float* __restrict__ r, const float* __restrict__ q, co
         float pt = __shfl_sync(0xffffffffu, p[i], j);
         if (h < H) {
           int64_t o = (b * S + t) * H + h;
-          dq = fmaf(dst, __ldg(r + o), dq);
+          dq = fmaf(dst, __ldg(r + o) - rbar, dq);
           d_r[o] = pt * gh + dst * qh;
         }
       }

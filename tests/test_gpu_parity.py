@@ -271,3 +271,60 @@ def test_fast_evaluation_metrics_match_oracle(precision):
     else:   # bf16 scores differ in the 3rd significant digit; the rank-based means move by at most a few 1e-3
         for k in got:
             assert abs(got[k] - exp[k]) < 5e-3, (k, got[k], exp[k])
+
+
+@pytest.mark.parametrize("name,encn,encu,B,C,S,L,precision,tol_logit,tol_grad", [
+    # BASELINE configs[2]: CNN news encoder + MHA user encoder, title 32 / his 50 / npratio 4, 300d -> 150, 10 heads
+    ("config3_fp32", "cnn", "mha", 12, 5, 50, 32, "fp32", 1e-5, 5e-4),
+    ("config3_bf16", "cnn", "mha", 12, 5, 50, 32, "bf16", 1e-3, None),
+    # BASELINE configs[4]: MHA news encoder + LSTUR user encoder, title 48 / his 100 / npratio 9
+    ("config5_fp32", "mha", "lstur", 3, 10, 100, 48, "fp32", 1e-5, 5e-4),
+    ("config5_bf16", "mha", "lstur", 3, 10, 100, 48, "bf16", 1e-3, None),
+])
+def test_baseline_config_shapes_vs_oracle(name, encn, encu, B, C, S, L, precision, tol_logit, tol_grad):
+    """The other BASELINE.json configurations at their real title / history / candidate sizes (small batch so that
+    the CPU oracle finishes in seconds): training logits, loss gradients (fp32) and evaluation probabilities against
+    the oracle; north_star bounds 1e-5 (fp32) / 1e-3 (bf16) relative on the logits.  Dropout is switched off
+    (dropout_p = 0) and the LSTUR Bernoulli draw is injected, so the comparison is deterministic."""
+    E, H, V, hn, n_users = 300, 150, 3000, 10, 40
+    gen = torch.Generator().manual_seed(hash(name) % 1000)
+    torch.manual_seed(17)
+    man = manager_for(encn, encu, C, S, L, E, H, hn, precision=precision, n_users=n_users, dropout_p=0.0)
+    model = build_model(man, V)
+    with torch.no_grad():
+        model.embedding.weight.normal_(0, 0.3)
+    x = _random_batch(gen, B, C, S, L, V, n_users=n_users)
+    keep = None
+    if encu == "lstur":
+        keep = torch.bernoulli(torch.full((B,), 0.5), generator=gen)
+        model.encoderU.keep_user = keep
+    params = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    kw = dict(encoder_n=encn, encoder_u=encu, head_num=hn, keep_user=keep, dropout_p=0.0)
+    ref = O.forward(params, x, True, **kw)
+    O.nll_loss(ref, x["label"]).backward()
+    model.train()
+    logp = model(x)[0]
+    torch.nn.NLLLoss()(logp, x["label"].cuda()).backward()
+    e = rel_err(logp, ref)
+    print("%s: train logits rel err %.3e" % (name, e))
+    assert e < tol_logit, e
+    if tol_grad is not None:
+        # gradients: against a float64 run of the oracle; an fp32 implementation is allowed tol_grad, or -- for the
+        # ill-conditioned ones (the pooling queries: softmax backward sums to zero over 50..100 items) -- three times
+        # the error the fp32 oracle itself makes against float64
+        p64 = {k: v.detach().double().requires_grad_(True) for k, v in params.items()}
+        x64 = {k: (v.double() if v.is_floating_point() else v) for k, v in x.items()}
+        O.nll_loss(O.forward(p64, x64, True, **kw), x["label"]).backward()
+        for k, p in model.named_parameters():
+            if p.grad is None or p64[k].grad is None:
+                continue
+            ge = rel_err(p.grad, p64[k].grad)
+            oe = rel_err(params[k].grad, p64[k].grad)
+            print("  %-40s cuda %.2e   fp32 oracle %.2e" % (k, ge, oe))
+            assert ge < max(tol_grad, 3 * oe), (k, ge, oe)
+    assert float(model.embedding.weight.grad[0].abs().max()) == 0.0
+    model.eval()
+    with torch.no_grad():
+        prob = model(x)[0]
+        eref = O.forward(params, x, False, **kw)
+    assert rel_err(prob, eref) < tol_logit
