@@ -45,6 +45,30 @@ def _worker(rank, world, port, n_rows, H, n_impr, out):
         dist.all_reduce(grad)
         grad /= world
         assert torch.allclose(grad, torch.full((5,), (world + 1) / 2))
+        # 4. trainer.GradSync's flat path (every gradient that the encoder-backward hook did not take): SUM over ranks,
+        #    gradients re-pointed at 16-byte aligned views of one flat buffer, 1/world left to the optimiser's grad_scale
+        import types
+        from news_recommendation_mind_b200 import trainer
+        torch.manual_seed(3)
+        net = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3))          # 35 + 5 + 15 + 3 parameters: odd sizes
+        opt = types.SimpleNamespace(grad_scale=1.0)
+        sync = trainer.GradSync(net, opt)
+        assert opt.grad_scale == 1.0 / world
+        for p0 in net.parameters():                                                      # rank 0's weights everywhere
+            ref = p0.detach().clone()
+            dist.broadcast(ref, src=0)
+            assert torch.equal(ref, p0.detach())
+        xs = torch.full((4, 7), float(rank + 1))
+        net(xs).sum().backward()
+        local = [p0.grad.detach().clone() for p0 in net.parameters()]
+        sync.finish()
+        for p0, g0 in zip(net.parameters(), local):
+            tot = g0.clone()
+            dist.all_reduce(tot)
+            assert torch.allclose(p0.grad, tot, rtol=1e-6, atol=1e-6)
+            assert p0.grad.data_ptr() % 16 == 0 and p0.grad.is_contiguous() and p0.grad.shape == p0.shape
+        sync.close()
+        assert opt.grad_scale == 1.0
         out.put((rank, i0, i1, lo, hi))
     finally:
         dist.destroy_process_group()
