@@ -6,12 +6,12 @@
 //   * W_hh as the A operand, converted to bf16 once per launch; k-tiles < KREG live in REGISTERS for the whole
 //     kernel (each of the 16 warps owns up to three 16-row tiles), the remaining k-tiles in shared memory and are
 //     fetched with ldmatrix (conflict-free padded pitch) -- no per-step global or L2 traffic for the weights;
-//   * h as the B operand, split into bf16 high + low parts (two MMAs per A fragment), so the recurrence keeps
-//     ~16 mantissa bits of the fp32 hidden state; cell state, gate math and all saved tensors are fp32.
+//   * h as the B operand, split into bf16 high + low parts (side by side in the 8 MMA columns when a CTA owns <= 4
+//     sequences, two MMAs per A fragment otherwise), so the recurrence keeps ~16 mantissa bits of the fp32 hidden state; cell state, gate math and all saved tensors are fp32.
 // One CTA owns NSEQ (2/4/8) sequences for all S steps: no inter-CTA traffic, no per-step launch.
-// Measured (B200, H=150, 2 sequences per CTA): the MMA phase is ~4000 of the ~4600 cycles of a step -- legacy HMMA issues at
-// ~20 cycles per m16n8k16 per SM sub-partition on sm_100a, so the 800 MMAs of a step (hi + lo, N padded to 8) are
-// throughput bound; the gate phase is ~600 cycles.
+// Measured (B200, H=150, 2 sequences per CTA): with one MMA per part (800 per step) the MMA phase was ~4000 of the ~4600
+// cycles of a step -- legacy HMMA issues at ~20-33 cycles per m16n8k16 per SM sub-partition on sm_100a; packing the two
+// parts into the columns of one MMA (400 per step) brought the step to ~3900 cycles; the gate phase is ~600 cycles.
 // Step = (1) MMA phase -> pre-activations to shared memory, (2) gate phase: one thread per (sequence, unit).
 #include "rnn_res.cuh"
 #include "tapgemm.cuh"   // sm_count()
@@ -172,42 +172,63 @@ rnn_mma_fwd_kernel(const float* __restrict__ xp, int ldx, const __nv_bfloat16* _
       }
     }
     // ---- (1) pre = W_hh . (h_hi + h_lo) ------------------------------------------------------------------------
-    float acc[RM_MAXMT][4], acl[RM_MAXMT][4];      // separate chains for the high and the low part of h (MMA latency, not rate, bounds a step)
+    // NSEQ <= 4: the high and the low part of h sit side by side in the N = 8 columns of ONE MMA (columns [0, NSEQ) high,
+    // [NSEQ, 2 NSEQ) low) -- half the MMAs of the two-pass form, and the MMA count is what bounds a step; NSEQ = 8 needs
+    // all eight columns for the sequences and issues one MMA per part into two independent accumulator chains
+    constexpr bool PACK = NSEQ <= 4;
+    // (splitting the k-tiles over two accumulator chains did not change the step time: the phase is HMMA-throughput bound)
+    float acc[RM_MAXMT][4], acl[RM_MAXMT][4];
 #pragma unroll
     for (int i = 0; i < RM_MAXMT; ++i)
 #pragma unroll
       for (int r = 0; r < 4; ++r) { acc[i][r] = 0.f; acl[i][r] = 0.f; }
+    // B-fragment row of this lane's column gq: PACK -> high part of sequence gq, low part of sequence gq - NSEQ, or a zero row
+    const __nv_bfloat16* hrow = !PACK ? hsm + gq * hp
+                                      : (gq < NSEQ ? hsm + gq * hp : (gq < 2 * NSEQ ? hsm + 8 * hp + (gq - NSEQ) * hp : hsm + 7 * hp));
 #pragma unroll
     for (int kt = 0; kt < RM_MAXKT; ++kt) {
       if (kt < KT) {
-        const __nv_bfloat16* hb = hsm + gq * hp + kt * 16 + 2 * tq;
+        const __nv_bfloat16* hb = hrow + kt * 16 + 2 * tq;
         const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(hb), bh1 = *reinterpret_cast<const uint32_t*>(hb + 8);
-        const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(hb + 8 * hp), bl1 = *reinterpret_cast<const uint32_t*>(hb + 8 * hp + 8);
+        uint32_t bl0 = 0, bl1 = 0;
+        if (!PACK) {
+          bl0 = *reinterpret_cast<const uint32_t*>(hb + 8 * hp);
+          bl1 = *reinterpret_cast<const uint32_t*>(hb + 8 * hp + 8);
+        }
 #pragma unroll
         for (int i = 0; i < RM_MAXMT; ++i) {
           const int mt = warp + RM_WARPS * i;
           if (mt < MT) {
             if (kt < RM_KREG) {
               mma_bf16(acc[i], areg[i][kt < RM_KREG ? kt : 0], bh0, bh1);
-              mma_bf16(acl[i], areg[i][kt < RM_KREG ? kt : 0], bl0, bl1);
+              if (!PACK) mma_bf16(acl[i], areg[i][kt < RM_KREG ? kt : 0], bl0, bl1);
             } else {
               uint32_t a[4];
               ldmatrix_x4(a, wsm_u + (uint32_t)(mt * 16 * wp + (kt - RM_KREG) * 16) * 2u + lm_off);
               mma_bf16(acc[i], a, bh0, bh1);
-              mma_bf16(acl[i], a, bl0, bl1);
+              if (!PACK) mma_bf16(acl[i], a, bl0, bl1);
             }
           }
         }
       }
     }
-    // accumulator (row gq / gq + 8, columns 2 tq, 2 tq + 1 = sequences) -> pre[row][n]
+    // accumulator (row gq / gq + 8, columns 2 tq, 2 tq + 1) -> pre[row][n] = high + low
 #pragma unroll
     for (int i = 0; i < RM_MAXMT; ++i) {
       const int mt = warp + RM_WARPS * i;
+      float v0, v1, v2, v3;
+      v0 = acc[i][0] + acl[i][0]; v1 = acc[i][1] + acl[i][1];
+      v2 = acc[i][2] + acl[i][2]; v3 = acc[i][3] + acl[i][3];
+      if (PACK) {        // the low-part columns live NSEQ / 2 lanes further (same row group)
+        v0 += __shfl_xor_sync(0xffffffffu, v0, NSEQ / 2);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, NSEQ / 2);
+        v2 += __shfl_xor_sync(0xffffffffu, v2, NSEQ / 2);
+        v3 += __shfl_xor_sync(0xffffffffu, v3, NSEQ / 2);
+      }
       if (mt < MT && 2 * tq < NSEQ) {
         float* p0 = pre + (size_t)(mt * 16 + gq) * NSEQ + 2 * tq;
-        *reinterpret_cast<float2*>(p0) = make_float2(acc[i][0] + acl[i][0], acc[i][1] + acl[i][1]);
-        *reinterpret_cast<float2*>(p0 + 8 * NSEQ) = make_float2(acc[i][2] + acl[i][2], acc[i][3] + acl[i][3]);
+        *reinterpret_cast<float2*>(p0) = make_float2(v0, v1);
+        *reinterpret_cast<float2*>(p0 + 8 * NSEQ) = make_float2(v2, v3);
       }
     }
     __syncthreads();
