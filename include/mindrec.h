@@ -276,6 +276,13 @@ MR_API int mr_adam_step_multi(int n_tensors, float* const* p, const float* const
                  const int64_t* numel, const double* lr, int64_t step, double beta1, double beta2, double eps,
                  double grad_scale, int shadow_tensor, void* shadow_bf16, int64_t row_len, int64_t shadow_ld, void* stream);
 
+/* Same, with the two step-dependent factors {1 / (1 - beta1^t), 1 / sqrt(1 - beta2^t)} read from DEVICE memory (`dyn_device`,
+ * 2 floats; `step` is then ignored) -- the form a captured CUDA graph can replay for every step. */
+MR_API int mr_adam_step_multi_dyn(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v,
+                 const int64_t* numel, const double* lr, int64_t step, double beta1, double beta2, double eps,
+                 double grad_scale, int shadow_tensor, void* shadow_bf16, int64_t row_len, int64_t shadow_ld,
+                 const float* dyn_device, void* stream);
+
 /* Mean negative log-likelihood (nn.NLLLoss(), utils/Manager.py:381-382,641) over logp [B,C]:
  *   fwd: loss[0] = -(1/B) sum_b logp[b, label[b]];   bwd: d_logp[b,c] = -(d_loss/B) [c == label[b]] */
 MR_API int mr_nll_loss_fwd(const float* logp, const void* label, int label_i64, float* loss,

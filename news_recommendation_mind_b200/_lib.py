@@ -64,6 +64,7 @@ _SIGNATURES = {
     "mr_rank_metrics": (c_int, [P, P, P, P, P, I64, I64, P]),
     "mr_adam_step": (c_int, [P, P, P, P, I64, I64, c_double, c_double, c_double, c_double, c_double, P, I64, I64, P]),
     "mr_adam_step_multi": (c_int, [c_int, P, P, P, P, P, P, I64, c_double, c_double, c_double, c_double, c_int, P, I64, I64, P]),
+    "mr_adam_step_multi_dyn": (c_int, [c_int, P, P, P, P, P, P, I64, c_double, c_double, c_double, c_double, c_int, P, I64, I64, P, P]),
     "mr_nll_loss_fwd": (c_int, [P, P, c_int, P, I64, I64, P]),
     "mr_nll_loss_bwd": (c_int, [P, c_int, P, P, I64, I64, P]),
     "mr_cast_pad_bf16": (c_int, [P, P, I64, I64, I64, P]),

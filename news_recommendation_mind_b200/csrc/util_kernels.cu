@@ -120,15 +120,17 @@ struct AdamMultiArgs {
   int32_t blk_off[AD_MAX_TENSORS + 1];  // first CTA of tensor i
   int n_tensors;
   float inv_sqrt_bc2, beta1, omb1, beta2, omb2, eps, grad_scale;
+  const float* dyn;                     // optional device scalars {1 / (1 - beta1^t), 1 / sqrt(1 - beta2^t)}: when set, lr_over_bc1 holds the
+                                        // plain learning rates and the step-dependent factors are read here (CUDA-graph replay)
   int shadow_tensor;                    // tensor whose bf16 shadow is refreshed (-1 = none)
   __nv_bfloat16* shadow; int64_t row_len, shadow_ld;
 };
 
-__device__ __forceinline__ float adam_one(float pi, float gi, float& mi, float& vi, const AdamMultiArgs& a, float lr) {
+__device__ __forceinline__ float adam_one(float pi, float gi, float& mi, float& vi, const AdamMultiArgs& a, float lr, float inv_sqrt_bc2) {
   gi *= a.grad_scale;
   mi = a.beta1 * mi + a.omb1 * gi;
   vi = a.beta2 * vi + a.omb2 * gi * gi;
-  const float denom = sqrtf(vi) * a.inv_sqrt_bc2 + a.eps;
+  const float denom = sqrtf(vi) * inv_sqrt_bc2 + a.eps;
   return pi - lr * (mi / denom);
 }
 
@@ -143,7 +145,8 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
   const float* __restrict__ g = a.g[t];
   float* __restrict__ m = a.m[t];
   float* __restrict__ v = a.v[t];
-  const float lr = a.lr_over_bc1[t];
+  const float lr = a.dyn != nullptr ? a.lr_over_bc1[t] * __ldg(a.dyn) : a.lr_over_bc1[t];
+  const float isb2 = a.dyn != nullptr ? __ldg(a.dyn + 1) : a.inv_sqrt_bc2;
   const bool sh = t == a.shadow_tensor;
   const int64_t base = (int64_t)(blockIdx.x - a.blk_off[t]) * AD_CHUNK;
   const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
@@ -156,10 +159,10 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
     if (vec) {
       const float4 g4 = *reinterpret_cast<const float4*>(g + i);
       float4 p4 = *reinterpret_cast<float4*>(p + i), m4 = *reinterpret_cast<float4*>(m + i), v4 = *reinterpret_cast<float4*>(v + i);
-      p4.x = adam_one(p4.x, g4.x, m4.x, v4.x, a, lr);
-      p4.y = adam_one(p4.y, g4.y, m4.y, v4.y, a, lr);
-      p4.z = adam_one(p4.z, g4.z, m4.z, v4.z, a, lr);
-      p4.w = adam_one(p4.w, g4.w, m4.w, v4.w, a, lr);
+      p4.x = adam_one(p4.x, g4.x, m4.x, v4.x, a, lr, isb2);
+      p4.y = adam_one(p4.y, g4.y, m4.y, v4.y, a, lr, isb2);
+      p4.z = adam_one(p4.z, g4.z, m4.z, v4.z, a, lr, isb2);
+      p4.w = adam_one(p4.w, g4.w, m4.w, v4.w, a, lr, isb2);
       *reinterpret_cast<float4*>(p + i) = p4;
       *reinterpret_cast<float4*>(m + i) = m4;
       *reinterpret_cast<float4*>(v + i) = v4;
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
     } else {
       for (int e = 0; e < 4 && i + e < n; ++e) {
         float mi = m[i + e], vi = v[i + e];
-        const float pi = adam_one(p[i + e], g[i + e], mi, vi, a, lr);
+        const float pi = adam_one(p[i + e], g[i + e], mi, vi, a, lr, isb2);
         p[i + e] = pi; m[i + e] = mi; v[i + e] = vi;
         if (sh) {
           const int64_t r = (i + e) / a.row_len, c = (i + e) - r * a.row_len;
@@ -224,6 +227,14 @@ int mr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int64_
 int mr_adam_step_multi(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v,
                        const int64_t* numel, const double* lr, int64_t step, double beta1, double beta2, double eps,
                        double grad_scale, int shadow_tensor, void* shadow_bf16, int64_t row_len, int64_t shadow_ld, void* stream) {
+  return mr_adam_step_multi_dyn(n_tensors, p, g, m, v, numel, lr, step, beta1, beta2, eps, grad_scale, shadow_tensor, shadow_bf16, row_len,
+                                shadow_ld, nullptr, stream);
+}
+
+int mr_adam_step_multi_dyn(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v,
+                           const int64_t* numel, const double* lr, int64_t step, double beta1, double beta2, double eps,
+                           double grad_scale, int shadow_tensor, void* shadow_bf16, int64_t row_len, int64_t shadow_ld,
+                           const float* dyn_device, void* stream) {
   using namespace mr;
   if (int rc = require_sm100()) return rc;
   MR_REQUIRE(n_tensors >= 0 && n_tensors <= AD_MAX_TENSORS, MR_ERR_BAD_SHAPE, "mr_adam_step_multi: %d tensors (max %d per call)", n_tensors,
@@ -238,7 +249,7 @@ int mr_adam_step_multi(int n_tensors, float* const* p, const float* const* g, fl
   for (int i = 0; i < n_tensors; ++i) {
     MR_REQUIRE(p[i] && g[i] && m[i] && v[i] && numel[i] >= 0, MR_ERR_NULL, "mr_adam_step_multi: tensor %d", i);
     a.p[i] = p[i]; a.g[i] = g[i]; a.m[i] = m[i]; a.v[i] = v[i]; a.n[i] = numel[i];
-    a.lr_over_bc1[i] = (float)(lr[i] / bc1);
+    a.lr_over_bc1[i] = dyn_device != nullptr ? (float)lr[i] : (float)(lr[i] / bc1);
     a.blk_off[i] = (int32_t)blocks;
     blocks += ceil_div(numel[i], (int64_t)AD_CHUNK);
     MR_REQUIRE(blocks < (1ll << 30), MR_ERR_BAD_SHAPE, "mr_adam_step_multi: too many elements");
@@ -248,6 +259,7 @@ int mr_adam_step_multi(int n_tensors, float* const* p, const float* const* g, fl
   a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
   a.beta1 = (float)beta1; a.omb1 = (float)(1.0 - beta1); a.beta2 = (float)beta2; a.omb2 = (float)(1.0 - beta2);
   a.eps = (float)eps; a.grad_scale = (float)grad_scale;
+  a.dyn = dyn_device;
   a.shadow_tensor = shadow_bf16 ? shadow_tensor : -1;
   a.shadow = static_cast<__nv_bfloat16*>(shadow_bf16); a.row_len = row_len; a.shadow_ld = shadow_ld;
   if (a.shadow_tensor >= 0)

@@ -395,3 +395,35 @@ def test_full_size_step_is_bit_reproducible_and_paths_agree(monkeypatch):
     cs1, cs3 = g1[tab].double().sum(0), g3[tab].double().sum(0)
     assert float((cs1 - cs3).norm() / cs3.norm()) < 2e-2                                                  # (4)
     assert bool(torch.isfinite(g1[tab]).all())
+
+
+def test_graph_step_matches_eager_steps():
+    """trainer.GraphStep (the training step captured as one CUDA graph, Adam bias corrections read from device memory)
+    replays to bit-identical losses and parameters as eager train_step calls on the same batches."""
+    import sys, os, copy
+    sys.path.insert(0, os.path.dirname(__file__))
+    from helpers import build_model, manager_for, random_batch
+    from news_recommendation_mind_b200 import trainer
+    B, C, S, L, E, H, V = 6, 5, 9, 32, 300, 150, 500
+    gen = torch.Generator().manual_seed(4)
+    batches = [{k: v.cuda() for k, v in random_batch(gen, B, C, S, L, V).items()} for _ in range(3)]
+    torch.manual_seed(6)
+    man = manager_for("cnn", "lstm", C, S, L, E, H, 10, precision="bf16")
+    m1 = build_model(man, V)
+    m2 = copy.deepcopy(m1)
+    o1, o2 = trainer.FusedAdam(m1, lr=1e-3, bert_lr=1e-4), trainer.FusedAdam(m2, lr=1e-3, bert_lr=1e-4)
+    gs = trainer.GraphStep(m1, o1, batches[0])              # runs 3 warm-up steps on batches[0], then records the graph
+    o2.enable_device_step_scalars("cuda:0")                 # same arithmetic for the bias corrections as the graph path
+    for _ in range(gs.warmup_steps):
+        o2.begin_step()
+        trainer.train_step(m2, batches[0], o2)
+    for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert torch.equal(a, b), ("after capture", k)
+    for s in range(6):
+        got = float(gs(batches[s % 3]))
+        o2.begin_step()
+        exp = float(trainer.train_step(m2, batches[s % 3], o2))
+        assert got == exp, (s, got, exp)
+    assert o1.steps == o2.steps == 9
+    for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert torch.equal(a, b), k
