@@ -1,0 +1,116 @@
+"""CPU tests of the host-side pieces that need no GPU: the synthetic MIND-shaped generator (SURVEY.md 8d input
+contract), the optimiser's learning-rate groups (Manager._get_optim, utils/Manager.py:389-413), padding helpers,
+and the staging-buffer compatibility check of the training loop."""
+import re
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from news_recommendation_mind_b200 import data, ops, trainer
+
+
+def test_news_table_follows_the_reference_layout():
+    """MIND.py:103-127: row 0 is the empty article [CLS] [SEP] PAD..., every title starts with [CLS]=101, ends with
+    [SEP]=102 at its last valid position, PAD=0 afterwards; the attention mask marks exactly the valid prefix."""
+    L = 32
+    ids, mask = data.make_news_table(300, L, seed=3)
+    assert ids.dtype == torch.int64 and mask.dtype == torch.int64 and ids.shape == (301, L) and mask.shape == (301, L)
+    assert ids[0, :2].tolist() == [101, 102] and int(ids[0, 2:].abs().sum()) == 0 and mask[0].tolist() == [1, 1] + [0] * (L - 2)
+    ln = mask.sum(1)
+    assert int(ln.min()) >= 2 and int(ln.max()) <= L
+    pos = torch.arange(L)[None, :]
+    assert torch.equal(mask, (pos < ln[:, None]).long())                      # valid prefix
+    assert bool((ids[:, 0] == 101).all())
+    assert bool((ids.gather(1, (ln - 1)[:, None]).squeeze(1) == 102).all())   # [SEP] closes every title
+    assert int((ids * (1 - mask)).abs().sum()) == 0                           # PAD after the title
+    assert int(ids.max()) < 30522 and int(ids.min()) >= 0
+
+
+def test_train_batch_schema_matches_the_reference_collate():
+    """MIND.__getitem__ + default collate (MIND.py:352-363): field names, dtypes and shapes; history right padded
+    with news 0 and his_mask = 1 on the first max(len, 1) slots; label = index of the positive (always 0)."""
+    B, C, S, L = 16, 5, 50, 32
+    ids, mask = data.make_news_table(500, L, seed=1)
+    x = data.make_train_batch(ids, mask, B, C, S, seed=7)
+    assert x["cdd_encoded_index"].shape == (B, C, L) and x["his_encoded_index"].shape == (B, S, L)
+    assert x["cdd_attn_mask"].shape == (B, C, L) and x["his_attn_mask"].shape == (B, S, L)
+    for k in ("cdd_encoded_index", "his_encoded_index", "cdd_attn_mask", "his_attn_mask", "user_id", "cdd_id", "his_id", "label"):
+        assert x[k].dtype == torch.int64, k
+    assert x["his_mask"].dtype == torch.float64 and x["his_mask"].shape == (B, S, 1)
+    assert x["label"].shape == (B,) and int(x["label"].abs().sum()) == 0
+    hm = x["his_mask"].squeeze(-1)
+    ln = hm.sum(1).long()
+    assert int(ln.min()) >= 1
+    assert torch.equal(hm, (torch.arange(S)[None, :] < ln[:, None]).double())  # a prefix of ones
+    his_id = x["his_id"]
+    assert int((his_id * (1 - hm).long()).abs().sum()) == 0                    # padded slots hold news 0
+    assert torch.equal(x["his_encoded_index"], ids[his_id]) and torch.equal(x["cdd_encoded_index"], ids[x["cdd_id"]])
+    assert int(x["cdd_id"].min()) >= 1                                         # candidates are real news
+    y = data.make_train_batch(ids, mask, B, C, S, seed=7)
+    assert all(torch.equal(x[k], y[k]) for k in x)                             # seeded: reproducible
+
+
+def test_eval_impressions_are_well_formed():
+    L, S = 32, 50
+    ids, mask = data.make_news_table(400, L, seed=2)
+    imp = data.make_eval_impressions(ids, mask, 25, S, seed=5)
+    off = imp["offsets"]
+    assert off[0] == 0 and off.numel() == 26 and off[-1] == imp["cdd_id"].numel() == imp["label"].numel()
+    n = np.diff(np.asarray(off))
+    assert n.min() >= 2 and n.max() <= 300
+    lab = np.asarray(imp["label"])
+    for i in range(25):
+        seg = lab[off[i]:off[i + 1]]
+        assert seg.max() == 1 and seg.min() == 0                               # AUC defined: one positive, one negative at least
+        c = np.asarray(imp["cdd_id"][off[i]:off[i + 1]])
+        assert len(set(c.tolist())) == len(c) and c.min() >= 1                 # distinct candidates
+
+
+def test_fused_adam_groups_follow_the_bert_regex():
+    """Manager._get_optim: parameters whose NAME matches the regex `bert` get bert_lr, the others lr."""
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.embedding = torch.nn.Module()
+            self.embedding.bert_word_embedding = torch.nn.Embedding(7, 4)
+            self.encoderN = torch.nn.Linear(4, 3)
+            self.encoderU = torch.nn.Linear(3, 3)
+    m = M()
+    opt = trainer.FusedAdam(m, lr=1e-4, bert_lr=6e-6)
+    base, bert = opt.param_groups
+    names = dict(m.named_parameters())
+    assert base["lr"] == 1e-4 and bert["lr"] == 6e-6
+    assert [id(p) for p in bert["params"]] == [id(p) for n, p in names.items() if re.search("bert", n)]
+    assert len(bert["params"]) == 1 and len(base["params"]) == 4
+    for g in opt.param_groups:
+        for p in g["params"]:
+            p.grad = torch.ones_like(p)
+    opt.zero_grad(set_to_none=False)
+    assert all(float(p.grad.abs().sum()) == 0 for p in m.parameters())
+    opt.zero_grad()
+    assert all(p.grad is None for p in m.parameters())
+
+
+def test_padding_helpers_and_flags():
+    assert ops.pad_to(150, 16) == 160 and ops.pad_to(160, 16) == 160 and ops.pad_to(300, 64) == 320 and ops.pad_to(30522, 128) == 30592
+    assert ops.PRECISIONS["bf16"] != ops.PRECISIONS["fp32"] and ops.PRECISIONS["f32"] == ops.PRECISIONS["fp32"]
+    assert isinstance(ops.GROUPED_TABLE_GRAD, bool)
+
+
+def test_prefetcher_buffer_compatibility_check():
+    pf = types.SimpleNamespace()
+    fits = trainer.BatchPrefetcher._fits
+    a = {"ids": torch.zeros(4, 3, dtype=torch.int64), "mask": torch.zeros(4, 1, dtype=torch.float64), "tag": "x"}
+    buf = {"ids": torch.empty(4, 3, dtype=torch.int64), "mask": torch.empty(4, 1, dtype=torch.float64)}
+    assert fits(pf, buf, a)
+    assert not fits(pf, None, a)
+    assert not fits(pf, buf, dict(a, ids=torch.zeros(5, 3, dtype=torch.int64)))          # another batch size
+    assert not fits(pf, buf, dict(a, mask=torch.zeros(4, 1, dtype=torch.float32)))        # another dtype
+    assert not fits(pf, buf, dict(a, extra=torch.zeros(1)))                               # a tensor the buffers do not hold
+
+
+def test_graph_step_refuses_a_gradient_synchroniser():
+    with pytest.raises(NotImplementedError):
+        trainer.GraphStep(torch.nn.Linear(2, 2), types.SimpleNamespace(), {}, sync=object())
