@@ -126,3 +126,17 @@ def evaluate(model, news_ids, news_mask, impr, metrics=("auc", "mean_mrr", "ndcg
     mean = reduce_metric_sums(m).tolist()
     names = ["auc", "mean_mrr", "ndcg@5", "ndcg@10"]
     return {k: round(v, 4) for k, v in zip(names, mean) if k in metrics}
+
+
+def write_predictions(path: str, ranks, offsets, first_index: int = 1) -> int:
+    """`prediction.txt` of Manager.test (utils/Manager.py:842-850): one line per impression,
+    ``<index> [r1,r2,...]`` with the ordinal ranks of the candidates (1 = highest probability, ties in candidate
+    order = scipy.stats.rankdata(1 - p, method="ordinal")), impressions numbered from 1.  `ranks` is the int32 output
+    of ops.rank_metrics(..., want_rank=True) (CSR over `offsets`); both may live on the device.  Returns the number
+    of lines written."""
+    r = ranks.detach().cpu().tolist() if torch.is_tensor(ranks) else list(ranks)
+    off = offsets.detach().cpu().tolist() if torch.is_tensor(offsets) else list(offsets)
+    with open(path, "w") as f:
+        for i in range(len(off) - 1):
+            f.write(str(first_index + i) + " [" + ",".join(str(int(v)) for v in r[off[i]:off[i + 1]]) + "]" + "\n")
+    return len(off) - 1

@@ -114,3 +114,21 @@ def test_prefetcher_buffer_compatibility_check():
 def test_graph_step_refuses_a_gradient_synchroniser():
     with pytest.raises(NotImplementedError):
         trainer.GraphStep(torch.nn.Linear(2, 2), types.SimpleNamespace(), {}, sync=object())
+
+
+def test_prediction_file_matches_the_reference_writer(tmp_path):
+    """Manager.test (utils/Manager.py:842-850): `index [ranks]` lines, ranks = scipy rankdata(1 - p, 'ordinal')."""
+    import scipy.stats as ss
+    from news_recommendation_mind_b200 import evaluate as ev
+    rng = np.random.RandomState(0)
+    preds = [rng.rand(n).round(2) for n in (5, 2, 17, 1, 9)]                  # rounded: ties occur
+    offsets = np.concatenate([[0], np.cumsum([len(p) for p in preds])])
+    ranks = np.concatenate([ss.rankdata(1 - p, method="ordinal") for p in preds]).astype(np.int32)
+    path = tmp_path / "prediction.txt"
+    n = ev.write_predictions(str(path), torch.from_numpy(ranks), torch.from_numpy(offsets))
+    assert n == 5
+    # (the reference's pinned environment -- scipy of the torch-1.9 era -- returns integer ordinal ranks, printed as `3`; scipy
+    #  >= 1.10 returns float64 and the same code would print `3.0`.  The MIND submission format and this writer use integers.)
+    exp = "".join(str(i + 1) + " [" + ",".join(str(int(r)) for r in ss.rankdata(1 - np.asarray(p), method="ordinal")) + "]\n"
+                  for i, p in enumerate(preds))
+    assert path.read_text() == exp
