@@ -48,6 +48,44 @@ class FusedAdam:
         self._dyn_host[1] = 1.0 / (1.0 - self.betas[1] ** self.steps) ** 0.5
         self.dyn.copy_(self._dyn_host, non_blocking=True)
 
+    # ---- checkpoints: the torch.optim.Adam state-dict layout, so that Manager.save / Manager.load (utils/Manager.py:289-343)
+    # work unchanged and a checkpoint written with the reference's optim.Adam resumes here (and vice versa) ---------------
+    def state_dict(self):
+        state, groups, idx = {}, [], 0
+        for g in self.param_groups:
+            ids = []
+            for p in g["params"]:
+                st = self.state.get(p)
+                if st is not None:
+                    state[idx] = {"step": torch.tensor(float(self.steps)), "exp_avg": st[0], "exp_avg_sq": st[1]}
+                ids.append(idx)
+                idx += 1
+            groups.append({"lr": g["lr"], "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                           "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                           "params": ids})
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        groups = sd["param_groups"]
+        if len(groups) != len(self.param_groups) or any(len(a["params"]) != len(b["params"]) for a, b in zip(groups, self.param_groups)):
+            raise ValueError("loaded state dict has a different number of parameter groups / parameters")
+        params = [p for g in self.param_groups for p in g["params"]]
+        flat_ids = [i for g in groups for i in g["params"]]
+        for g, loaded in zip(self.param_groups, groups):
+            g["lr"] = loaded["lr"]
+        self.betas, self.eps = tuple(groups[0].get("betas", self.betas)), groups[0].get("eps", self.eps)
+        self.state, steps = {}, 0
+        for p, i in zip(params, flat_ids):
+            st = sd["state"].get(i)
+            if st is None:
+                continue
+            if st["exp_avg"].shape != p.shape:
+                raise ValueError("optimizer state of parameter %d has shape %s, expected %s" % (i, tuple(st["exp_avg"].shape), tuple(p.shape)))
+            self.state[p] = (st["exp_avg"].to(device=p.device, dtype=torch.float32).clone().contiguous(),
+                             st["exp_avg_sq"].to(device=p.device, dtype=torch.float32).clone().contiguous())
+            steps = max(steps, int(float(st["step"])))
+        self.steps = steps
+
     def zero_grad(self, set_to_none=True):
         for g in self.param_groups:
             for p in g["params"]:
@@ -95,6 +133,32 @@ class FusedAdam:
                 shadow_ld, _lib.ptr(self.dyn), _lib.stream_ptr(dev)), "mr_adam_step_multi")
             if shadow is not None:
                 self.embedding.mark_shadow_fresh(shadow)
+
+
+class LinearWarmupSchedule:
+    """transformers.get_linear_schedule_with_warmup as Manager._get_optim uses it (utils/Manager.py:414-420): every
+    group's learning rate = its initial value x (step / warmup while step < warmup, else the linear decay to 0 at
+    `total`).  Call step() after every optimiser step."""
+
+    def __init__(self, optimizer, num_warmup_steps, num_training_steps):
+        self.optimizer, self.warmup, self.total = optimizer, int(num_warmup_steps), int(num_training_steps)
+        self.base = [g["lr"] for g in optimizer.param_groups]
+        self.last = 0
+        self._apply()
+
+    def factor(self, step):
+        if step < self.warmup:
+            return float(step) / float(max(1, self.warmup))
+        return max(0.0, float(self.total - step) / float(max(1, self.total - self.warmup)))
+
+    def _apply(self):
+        f = self.factor(self.last)
+        for g, b in zip(self.optimizer.param_groups, self.base):
+            g["lr"] = b * f
+
+    def step(self):
+        self.last += 1
+        self._apply()
 
 
 class GradSync:

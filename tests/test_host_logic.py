@@ -132,3 +132,52 @@ def test_prediction_file_matches_the_reference_writer(tmp_path):
     exp = "".join(str(i + 1) + " [" + ",".join(str(int(r)) for r in ss.rankdata(1 - np.asarray(p), method="ordinal")) + "]\n"
                   for i, p in enumerate(preds))
     assert path.read_text() == exp
+
+
+def test_fused_adam_state_dict_interchanges_with_torch_adam():
+    """Manager.save / load (utils/Manager.py:289-343) go through optimizer.state_dict() / load_state_dict(): the layout
+    is torch.optim.Adam's, so a checkpoint of the reference's optimiser resumes here and the other way round."""
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.embedding = torch.nn.Module()
+            self.embedding.bert_word_embedding = torch.nn.Embedding(7, 4)
+            self.encoderN = torch.nn.Linear(4, 3)
+    torch.manual_seed(0)
+    m = M()
+    base = [p for n, p in m.named_parameters() if not re.search("bert", n)]
+    bert = [p for n, p in m.named_parameters() if re.search("bert", n)]
+    ref = torch.optim.Adam([{"params": base, "lr": 1e-4}, {"params": bert, "lr": 6e-6}])      # Manager._get_optim
+    for _ in range(3):
+        ref.zero_grad()
+        (m.encoderN(m.embedding.bert_word_embedding(torch.tensor([1, 2, 3]))).sum() ** 2).backward()
+        ref.step()
+    ours = trainer.FusedAdam(m, lr=9.0, bert_lr=9.0)
+    ours.load_state_dict(ref.state_dict())
+    assert ours.steps == 3 and [g["lr"] for g in ours.param_groups] == [1e-4, 6e-6]
+    for p in base + bert:
+        assert torch.equal(ours.state[p][0], ref.state[p]["exp_avg"]) and torch.equal(ours.state[p][1], ref.state[p]["exp_avg_sq"])
+    sd = ours.state_dict()
+    assert [g["params"] for g in sd["param_groups"]] == [g["params"] for g in ref.state_dict()["param_groups"]]
+    fresh = torch.optim.Adam([{"params": base, "lr": 1.0}, {"params": bert, "lr": 1.0}])
+    fresh.load_state_dict(sd)                                                                   # torch accepts our layout
+    for p in base + bert:
+        assert torch.equal(fresh.state[p]["exp_avg"], ref.state[p]["exp_avg"])
+        assert float(fresh.state[p]["step"]) == 3.0
+    assert [g["lr"] for g in fresh.param_groups] == [1e-4, 6e-6]
+    with pytest.raises(ValueError):
+        ours.load_state_dict({"state": {}, "param_groups": sd["param_groups"][:1]})
+
+
+def test_linear_warmup_schedule_matches_transformers():
+    from transformers import get_linear_schedule_with_warmup
+    w = [torch.nn.Parameter(torch.zeros(2)), torch.nn.Parameter(torch.zeros(3))]
+    ref_opt = torch.optim.Adam([{"params": [w[0]], "lr": 1e-4}, {"params": [w[1]], "lr": 6e-6}])
+    ref = get_linear_schedule_with_warmup(ref_opt, num_warmup_steps=5, num_training_steps=23)
+    ours_opt = types.SimpleNamespace(param_groups=[{"lr": 1e-4}, {"lr": 6e-6}])
+    ours = trainer.LinearWarmupSchedule(ours_opt, 5, 23)
+    for _ in range(30):
+        assert [g["lr"] for g in ours_opt.param_groups] == pytest.approx([g["lr"] for g in ref_opt.param_groups], rel=1e-12, abs=0)
+        ref_opt.step()
+        ref.step()
+        ours.step()
