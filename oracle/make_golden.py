@@ -293,8 +293,71 @@ def metric_cases():
     assert ka["auc"] == 0.75
 
 
+def np_params(shapes, seed):
+    """Deterministic parameters from numpy alone (independent of torch's RNG stream, so that the test can rebuild them
+    from the (name, shape) list stored in the fixture): N(0, 0.3^2) for the token table, N(0, 0.1^2) for matrices,
+    N(0, 0.05^2) for vectors, the LayerNorm weight around 1."""
+    rng = np.random.RandomState(seed)
+    out = {}
+    for name in sorted(shapes):
+        shp = tuple(int(v) for v in shapes[name])
+        scale = 0.3 if "bert_word_embedding" in name else (0.1 if len(shp) > 1 else 0.05)
+        a = rng.normal(0.0, scale, size=shp).astype(np.float32)
+        if name.endswith("layerNorm.weight"):
+            a = a + 1.0
+        if name.endswith("userEmbedding.weight"):
+            a[0] = 0.0                                   # RNN.py:81-82: row 0 of the user table is zero
+        out[name] = torch.from_numpy(a)
+    return out
+
+
+def grad_stats(t):
+    """what the fixture keeps of a (large) gradient: sum, sum of |.|, L2 norm and the first 8 entries"""
+    f = t.detach().double().reshape(-1)
+    head = torch.zeros(8, dtype=torch.float64)
+    head[: min(8, f.numel())] = f[:8]
+    return torch.cat([torch.stack([f.sum(), f.abs().sum(), f.norm()]), head])
+
+
+def config_case(R, name, encN, encU, B, C, S, L, seed, E=300, H=150, V=300, hn=10):
+    """The BASELINE.json configurations at their real title / history / candidate / embedding / hidden sizes (small
+    batch and vocabulary).  The parameters are rebuilt from numpy in the test, so the fixture holds the inputs, the
+    outputs and per-parameter gradient statistics only (a full copy of the weights and gradients would be megabytes)."""
+    g = torch.Generator().manual_seed(seed)
+    man = fake_manager(encoderN=encN, encoderU=encU, cdd_size=C, his_size=S, signal_length=L, bert_dim=E,
+                       hidden_dim=H, head_num=hn, dropout_p=0.0)
+    model = build_reference_model(R, man, V)
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    model.load_state_dict(np_params(shapes, seed))
+    x = synth_batch(g, B, C, S, L, V, man.n_users)
+    extra = {}
+    if encU == "lstur":
+        keep = torch.randint(0, 2, (B,), generator=g)
+        model.encoderU.keep_user = keep
+        extra["keep_user"] = keep
+    model.train()
+    logp = model(x)[0]
+    loss = nn.NLLLoss()(logp, x["label"])
+    loss.backward()
+    gstats = {k: grad_stats(p.grad) for k, p in model.named_parameters() if p.grad is not None}
+    model.eval()
+    with torch.no_grad():
+        prob = model(x)[0]
+        cdd_repr = model.encode_news(x)
+        user_repr = model.encode_user(x)[0]
+    names = sorted(shapes)
+    dump(name, x=x, extra=extra, train_logp=logp.detach(), loss=loss.detach(), eval_prob=prob, cdd_repr=cdd_repr,
+         user_repr=user_repr, grad_stats=gstats,
+         param_names=np.array(names), param_shapes=np.array([list(shapes[n]) + [0] * (3 - len(shapes[n])) for n in names], dtype=np.int64),
+         param_ndim=np.array([len(shapes[n]) for n in names], dtype=np.int64),
+         meta=np.array([B, C, S, L, E, H, V, hn, seed], dtype=np.int64))
+
+
 def main():
     R = _import_reference()
+    if "--configs-only" in sys.argv:
+        config_cases(R)
+        return
     module_cases(R)
     metric_cases()
     small = dict(B=3, C=4, S=5, L=8, E=24, H=12, V=60, hn=3)
@@ -308,6 +371,15 @@ def main():
     model_case(R, "tt_cnn_lstur", "cnn", "lstur", seed=9, **small)
     # a MIND-small-shaped (but narrow) case: L=32, npratio 4
     model_case(R, "tt_cnn_lstm_L32", "cnn", "lstm", seed=10, B=4, C=5, S=6, L=32, E=40, H=20, V=120, hn=5)
+    config_cases(R)
+
+
+def config_cases(R):
+    # BASELINE.json configs 1-2 (CNN + LSTM, title 32 / his 50 / npratio 4, 300d -> 150), 3 (CNN + MHA user), 5 (MHA news +
+    # LSTUR, title 48 / his 100 / npratio 9)
+    config_case(R, "cfg_cnn_lstm", "cnn", "lstm", B=2, C=5, S=50, L=32, seed=21)
+    config_case(R, "cfg_cnn_mha", "cnn", "mha", B=2, C=5, S=50, L=32, seed=22)
+    config_case(R, "cfg_mha_lstur", "mha", "lstur", B=2, C=10, S=100, L=48, seed=23)
 
 
 if __name__ == "__main__":

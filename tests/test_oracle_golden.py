@@ -1,5 +1,7 @@
 """Pins the oracle (oracle/*.py) to the real reference: every case below was
 produced by oracle/make_golden.py running /root/reference itself."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -51,6 +53,43 @@ def test_forward_and_grads_match_reference(name, encn, encu):
         ukw = {k: v for k, v in kw.items()}
         user = O.encode_user(params, g["x"], **ukw)
         torch.testing.assert_close(user, g["user_repr"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,encn,encu", [("cfg_cnn_lstm", "cnn", "lstm"), ("cfg_cnn_mha", "cnn", "mha"),
+                                            ("cfg_mha_lstur", "mha", "lstur")])
+def test_baseline_config_sizes_match_reference(name, encn, encu):
+    """The oracle against the REAL reference at the sizes of BASELINE.json's configurations (title 32 / his 50 / npratio 4
+    and title 48 / his 100 / npratio 9; 300d -> 150, 10 heads; small batch and vocabulary).  The weights are rebuilt from
+    numpy (oracle/make_golden.py::np_params) from the (name, shape) list in the fixture; the fixture holds the reference's
+    outputs and, per parameter, sum / sum|.| / L2 norm / first 8 entries of its gradient."""
+    from oracle.make_golden import grad_stats, np_params
+    g = load_golden(name)
+    B, C, S, L, E, H, V, hn, seed = [int(v) for v in g["meta"]]
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    shapes = {str(n): tuple(int(v) for v in shp[:nd]) for n, shp, nd in zip(z["param_names"], z["param_shapes"], z["param_ndim"])}
+    params = {k: v.clone().requires_grad_(True) for k, v in np_params(shapes, seed).items()}
+    kw = dict(encoder_n=encn, encoder_u=encu, head_num=hn)
+    if "keep_user" in g.get("extra", {}):
+        kw["keep_user"] = g["extra"]["keep_user"]
+    logp = O.forward(params, g["x"], True, dropout_p=0.0, **kw)
+    torch.testing.assert_close(logp, g["train_logp"], rtol=1e-5, atol=1e-6)
+    loss = O.nll_loss(logp, g["x"]["label"])
+    torch.testing.assert_close(loss, g["loss"], rtol=1e-5, atol=1e-6)
+    loss.backward()
+    assert len(g["grad_stats"]) >= 6
+    for k, ref in g["grad_stats"].items():
+        assert params[k].grad is not None, k
+        got = grad_stats(params[k].grad)
+        scale = float(ref[2])                                     # L2 norm of the reference gradient
+        assert float((got - ref).abs().max()) <= 2e-4 * max(scale, float(ref[1])) + 1e-7, (k, got[:3], ref[:3])
+    for k, p in params.items():
+        if k not in g["grad_stats"]:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+    with torch.no_grad():
+        torch.testing.assert_close(O.forward(params, g["x"], False, **kw), g["eval_prob"], rtol=1e-5, atol=1e-6)
+        cdd = O.encode_news(params, g["x"]["cdd_encoded_index"], g["x"]["cdd_attn_mask"], encn, hn)
+        torch.testing.assert_close(cdd, g["cdd_repr"], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(O.encode_user(params, g["x"], **kw), g["user_repr"], rtol=1e-5, atol=1e-6)
 
 
 def test_padding_row_gets_no_gradient():
