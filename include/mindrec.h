@@ -67,6 +67,19 @@ MR_API int mr_embed_gather_f32(const void* ids, int ids_i64, const float* table,
                         int64_t T, int64_t E, int64_t V, void* stream);
 
 /* ----------------------------------------------------------------------------------------------
+ * Title rows by news id.   utils/MIND.py:347-355 (train) / :389-398 (dev): the dataset looks up
+ * ``encoded_news[cdd_ids][:, :L]`` / ``attn_mask[...]`` per sample on the host and the batch carries the int64
+ * token tensors over PCIe (7.2 MB per 256 impressions).  With the token table resident in HBM (int32
+ * tok_ids / tok_mask [n_rows, L], row 0 = the empty article of MIND.py:125-127) the batch carries news ids only:
+ *   out_ids[r, :]  = tok_ids[nid[r], :],  out_mask[r, :] = tok_mask[nid[r], :]
+ * rows 0..n_a-1 from nid_a (candidates), rows n_a..n_a+n_b-1 from nid_b (clicked history; may be NULL with n_b = 0).
+ * An id outside [0, n_rows) reads row 0.
+ * -------------------------------------------------------------------------------------------- */
+MR_API int mr_gather_titles(const int32_t* tok_ids, const int32_t* tok_mask, int64_t n_rows, int64_t L,
+                     const void* nid_a, int64_t n_a, const void* nid_b, int64_t n_b, int nid_i64,
+                     int32_t* out_ids, int32_t* out_mask, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
  * Embedding-table gradient.   autograd of BERT.py:39 = embedding_dense_backward, padding_idx=0
  *   d_table[v, :] = sum over t with ids[t]==v of d_emb[t, :];  row `padding_idx` (and every id
  *   that does not occur) is written as zeros.  Atomic-free: a stable key sort of the token ids
@@ -276,8 +289,10 @@ MR_API int mr_adam_step_multi(int n_tensors, float* const* p, const float* const
                  const int64_t* numel, const double* lr, int64_t step, double beta1, double beta2, double eps,
                  double grad_scale, int shadow_tensor, void* shadow_bf16, int64_t row_len, int64_t shadow_ld, void* stream);
 
-/* Same, with the two step-dependent factors {1 / (1 - beta1^t), 1 / sqrt(1 - beta2^t)} read from DEVICE memory (`dyn_device`,
- * 2 floats; `step` is then ignored) -- the form a captured CUDA graph can replay for every step. */
+/* Same, with every step-dependent scalar read from DEVICE memory: `dyn_device` = 4 + n_tensors floats
+ *   {1 / (1 - beta1^t), 1 / sqrt(1 - beta2^t), grad_scale, unused, lr[0], ..., lr[n_tensors-1]}
+ * (`step`, the host `lr` array and `grad_scale` are then ignored) -- the form a captured CUDA graph can replay for every
+ * step while a learning-rate schedule (Manager.py:414-420) keeps moving the rates.  dyn_device == NULL: mr_adam_step_multi. */
 MR_API int mr_adam_step_multi_dyn(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v,
                  const int64_t* numel, const double* lr, int64_t step, double beta1, double beta2, double eps,
                  double grad_scale, int shadow_tensor, void* shadow_bf16, int64_t row_len, int64_t shadow_ld,

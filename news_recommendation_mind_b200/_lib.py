@@ -32,6 +32,7 @@ _SIGNATURES = {
     "mr_device_check": (c_int, [c_int]),
     "mr_launch_count": (I64, []),
     "mr_embed_gather_f32": (c_int, [P, c_int, P, P, I64, I64, I64, P]),
+    "mr_gather_titles": (c_int, [P, P, I64, I64, P, I64, P, I64, c_int, P, P, P]),
     "mr_embed_grad_workspace_bytes": (I64, [I64, I64, I64]),
     "mr_embed_grad_segreduce": (c_int, [P, c_int, P, c_int, I64, P, I64, I64, I64, I64, P, I64, P]),
     "mr_news_cnn_set_hot_tokens": (c_int, [POINTER(c_int64), c_int]),

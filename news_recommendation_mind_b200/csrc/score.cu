@@ -274,7 +274,11 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ d_out, float* __res
 
 // ---------------------------------------------------------------------------------------------
 // ranking metrics: block per impression, O(n^2) rank counting in shared memory (n is tens to a
-// few hundred in MIND).  Order: descending score, ties by ascending position.
+// few hundred in MIND).  Two tie rules, both the reference's: prediction.txt ranks are
+// scipy.stats.rankdata(method="ordinal") = descending score, ties by ASCENDING position (Manager.py:846);
+// MRR / nDCG order with np.argsort(score)[::-1] (Manager.py:1216,1269), i.e. a reversed ascending sort = ties by
+// DESCENDING position wherever numpy's sort is stable (numpy 1.x insertion sort for n <= 16; beyond that, and in
+// numpy 2.x with AVX-512, the reference's tie order is an implementation detail no rule can reproduce).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 rank_metrics_kernel(const float* __restrict__ prob, const float* __restrict__ label, const int64_t* __restrict__ offsets,
@@ -296,15 +300,16 @@ rank_metrics_kernel(const float* __restrict__ prob, const float* __restrict__ la
   double a_num = 0.0, a_pos = 0.0, mrr_num = 0.0, dcg5 = 0.0, dcg10 = 0.0, idcg5 = 0.0, idcg10 = 0.0;
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
     const float sj = S_[j], lj = L_[j];
-    int rank = 1, lrank = 1;
+    int rank = 1, lrank = 1, orank = 1;
     double below = 0.0;
     for (int k = 0; k < n; ++k) {
       const float sk = S_[k], lk = L_[k];
-      rank += (sk > sj) || (sk == sj && k < j);
-      lrank += (lk > lj) || (lk == lj && k < j);
+      orank += (sk > sj) || (sk == sj && k < j);      // ordinal rank of prediction.txt
+      rank += (sk > sj) || (sk == sj && k > j);       // position in argsort(score)[::-1]
+      lrank += (lk > lj) || (lk == lj && k > j);      // ideal order (tie order irrelevant: equal labels, equal gains)
       if (lj == 1.f && lk != 1.f) below += (sj > sk) ? 1.0 : (sj == sk ? 0.5 : 0.0);
     }
-    if (rank_out) rank_out[beg + j] = rank;
+    if (rank_out) rank_out[beg + j] = orank;
     const double gain = exp2((double)lj) - 1.0;
     if (lj == 1.f) { a_pos += 1.0; a_num += below; }
     mrr_num += (double)lj / (double)rank;

@@ -120,14 +120,16 @@ struct AdamMultiArgs {
   int32_t blk_off[AD_MAX_TENSORS + 1];  // first CTA of tensor i
   int n_tensors;
   float inv_sqrt_bc2, beta1, omb1, beta2, omb2, eps, grad_scale;
-  const float* dyn;                     // optional device scalars {1 / (1 - beta1^t), 1 / sqrt(1 - beta2^t)}: when set, lr_over_bc1 holds the
-                                        // plain learning rates and the step-dependent factors are read here (CUDA-graph replay)
+  const float* dyn;                     // optional device block {1 / (1 - beta1^t), 1 / sqrt(1 - beta2^t), grad_scale, unused, lr[0..n_tensors)}:
+                                        // when set, every step-dependent scalar (bias corrections, 1/world, the per-tensor learning rates a
+                                        // schedule moves) is read here, so that one captured launch stays valid for every step (CUDA-graph replay)
   int shadow_tensor;                    // tensor whose bf16 shadow is refreshed (-1 = none)
   __nv_bfloat16* shadow; int64_t row_len, shadow_ld;
 };
 
-__device__ __forceinline__ float adam_one(float pi, float gi, float& mi, float& vi, const AdamMultiArgs& a, float lr, float inv_sqrt_bc2) {
-  gi *= a.grad_scale;
+__device__ __forceinline__ float adam_one(float pi, float gi, float& mi, float& vi, const AdamMultiArgs& a, float lr, float inv_sqrt_bc2,
+                                          float grad_scale) {
+  gi *= grad_scale;
   mi = a.beta1 * mi + a.omb1 * gi;
   vi = a.beta2 * vi + a.omb2 * gi * gi;
   const float denom = sqrtf(vi) * inv_sqrt_bc2 + a.eps;
@@ -145,8 +147,9 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
   const float* __restrict__ g = a.g[t];
   float* __restrict__ m = a.m[t];
   float* __restrict__ v = a.v[t];
-  const float lr = a.dyn != nullptr ? a.lr_over_bc1[t] * __ldg(a.dyn) : a.lr_over_bc1[t];
+  const float lr = a.dyn != nullptr ? __ldg(a.dyn + 4 + t) * __ldg(a.dyn) : a.lr_over_bc1[t];
   const float isb2 = a.dyn != nullptr ? __ldg(a.dyn + 1) : a.inv_sqrt_bc2;
+  const float gs = a.dyn != nullptr ? __ldg(a.dyn + 2) : a.grad_scale;
   const bool sh = t == a.shadow_tensor;
   const int64_t base = (int64_t)(blockIdx.x - a.blk_off[t]) * AD_CHUNK;
   const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
@@ -159,10 +162,10 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
     if (vec) {
       const float4 g4 = *reinterpret_cast<const float4*>(g + i);
       float4 p4 = *reinterpret_cast<float4*>(p + i), m4 = *reinterpret_cast<float4*>(m + i), v4 = *reinterpret_cast<float4*>(v + i);
-      p4.x = adam_one(p4.x, g4.x, m4.x, v4.x, a, lr, isb2);
-      p4.y = adam_one(p4.y, g4.y, m4.y, v4.y, a, lr, isb2);
-      p4.z = adam_one(p4.z, g4.z, m4.z, v4.z, a, lr, isb2);
-      p4.w = adam_one(p4.w, g4.w, m4.w, v4.w, a, lr, isb2);
+      p4.x = adam_one(p4.x, g4.x, m4.x, v4.x, a, lr, isb2, gs);
+      p4.y = adam_one(p4.y, g4.y, m4.y, v4.y, a, lr, isb2, gs);
+      p4.z = adam_one(p4.z, g4.z, m4.z, v4.z, a, lr, isb2, gs);
+      p4.w = adam_one(p4.w, g4.w, m4.w, v4.w, a, lr, isb2, gs);
       *reinterpret_cast<float4*>(p + i) = p4;
       *reinterpret_cast<float4*>(m + i) = m4;
       *reinterpret_cast<float4*>(v + i) = v4;
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
     } else {
       for (int e = 0; e < 4 && i + e < n; ++e) {
         float mi = m[i + e], vi = v[i + e];
-        const float pi = adam_one(p[i + e], g[i + e], mi, vi, a, lr, isb2);
+        const float pi = adam_one(p[i + e], g[i + e], mi, vi, a, lr, isb2, gs);
         p[i + e] = pi; m[i + e] = mi; v[i + e] = vi;
         if (sh) {
           const int64_t r = (i + e) / a.row_len, c = (i + e) - r * a.row_len;
@@ -198,9 +201,45 @@ __global__ void cast_pad_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
   }
 }
 
+// ---- title rows by news id (device-resident replacement of the per-sample token assembly of utils/MIND.py:347-355) ----
+// one warp per output row: out_ids[r, :] = tok_ids[nid[r], :], out_mask[r, :] = tok_mask[nid[r], :]; rows 0..n_a-1 come from
+// nid_a (candidates), rows n_a..n_a+n_b-1 from nid_b (clicked history); an id outside [0, n_rows) reads row 0 (the empty article)
+__global__ void __launch_bounds__(256) gather_titles_kernel(const int32_t* __restrict__ tok_ids, const int32_t* __restrict__ tok_mask,
+                                                            int64_t n_rows, int L, const void* __restrict__ nid_a, int64_t n_a,
+                                                            const void* __restrict__ nid_b, int64_t n_b, int nid_i64,
+                                                            int32_t* __restrict__ out_ids, int32_t* __restrict__ out_mask) {
+  pdl_trigger();
+  pdl_wait();
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= n_a + n_b) return;
+  int64_t nid = r < n_a ? load_index(nid_a, nid_i64, r) : load_index(nid_b, nid_i64, r - n_a);
+  if (nid < 0 || nid >= n_rows) nid = 0;
+  const int32_t* si = tok_ids + nid * L;
+  const int32_t* sm_ = tok_mask + nid * L;
+  for (int l = threadIdx.x & 31; l < L; l += 32) {
+    out_ids[r * L + l] = __ldg(si + l);
+    out_mask[r * L + l] = __ldg(sm_ + l);
+  }
+}
+
 }  // namespace mr
 
 extern "C" {
+
+int mr_gather_titles(const int32_t* tok_ids, const int32_t* tok_mask, int64_t n_rows, int64_t L, const void* nid_a, int64_t n_a,
+                     const void* nid_b, int64_t n_b, int nid_i64, int32_t* out_ids, int32_t* out_mask, void* stream) {
+  using namespace mr;
+  if (int rc = require_sm100()) return rc;
+  MR_REQUIRE(tok_ids && tok_mask && out_ids && out_mask, MR_ERR_NULL, "mr_gather_titles: null pointer");
+  MR_REQUIRE(n_rows >= 1 && L >= 1 && L <= 4096 && n_a >= 0 && n_b >= 0, MR_ERR_BAD_SHAPE, "mr_gather_titles: rows=%lld L=%lld n_a=%lld n_b=%lld",
+             (long long)n_rows, (long long)L, (long long)n_a, (long long)n_b);
+  MR_REQUIRE((n_a == 0 || nid_a) && (n_b == 0 || nid_b), MR_ERR_NULL, "mr_gather_titles: null id list");
+  if (n_a + n_b == 0) return MR_OK;
+  launch_pdl(gather_titles_kernel, dim3((unsigned)ceil_div(n_a + n_b, 8)), dim3(256), 0, as_stream(stream), tok_ids, tok_mask, n_rows, (int)L,
+             nid_a, n_a, nid_b, n_b, nid_i64, out_ids, out_mask);
+  MR_CHECK_LAUNCH("gather_titles_kernel");
+  return MR_OK;
+}
 
 int mr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t step, double lr, double beta1,
                  double beta2, double eps, double grad_scale, void* shadow_bf16, int64_t row_len, int64_t shadow_ld,

@@ -37,8 +37,10 @@ def _zipf_ids(rng, a, size, n_news):
 
 
 def make_train_batch(news_ids, news_mask, B: int, C: int, S: int, seed: int, n_users: int = USER_NUM["small"],
-                     pin: bool = False):
-    """One training batch (dict of CPU tensors) in the reference schema."""
+                     pin: bool = False, id_only: bool = False):
+    """One training batch (dict of CPU tensors) in the reference schema.  id_only: the batch of the device-resident
+    input pipeline (TwoTower.attach_news_tokens) -- the same sample, but only news ids (int32), the history mask (uint8),
+    user ids and labels cross PCIe; the token tensors are gathered on the device."""
     rng = np.random.RandomState(seed)
     n_news = news_ids.shape[0] - 1
     cdd_id = _zipf_ids(rng, 1.05, (B, C), n_news)
@@ -57,38 +59,59 @@ def make_train_batch(news_ids, news_mask, B: int, C: int, S: int, seed: int, n_u
         "his_mask": torch.from_numpy(his_mask),
         "label": torch.zeros(B, dtype=torch.int64),
     }
+    if id_only:
+        x = {"user_id": x["user_id"], "cdd_id": cdd_t.to(torch.int32), "his_id": his_t.to(torch.int32),
+             "his_mask": x["his_mask"].to(torch.uint8), "label": x["label"]}
     if pin:
         x = {k: v.pin_memory() for k, v in x.items()}
     return x
 
 
-def make_eval_impressions(news_ids, news_mask, n_impr: int, S: int, seed: int, n_users: int = USER_NUM["small"]):
+def make_eval_impressions(news_ids, news_mask, n_impr: int, S: int, seed: int, n_users: int = USER_NUM["small"],
+                          with_tokens: bool = True, impr_size: int = 0):
     """Dev impressions in CSR form: candidate counts ~ LogNormal(3.3, 0.8) clipped to [2, 300], labels
     Bernoulli(0.04) with at least one positive and one negative, distinct candidates per impression
-    (no score ties).  -> dict with his_* [n_impr, S, ...], cdd_id [n_cand], offsets [n_impr+1], label [n_cand]."""
+    (no score ties).  -> dict with his_* [n_rows, S, ...], cdd_id [n_cand], offsets [n_rows+1], label [n_cand],
+    impr_index [n_rows].  Vectorised (the full-scale dev set is 376 k impressions).
+    with_tokens=False leaves out his_encoded_index / his_attn_mask (history-from-table evaluation needs his_id only).
+    impr_size > 0 cuts impressions with more candidates into chunks of at most impr_size rows that share one
+    impr_index and one history, as utils/MIND.py:225-226 does."""
     rng = np.random.RandomState(seed)
     n_news = news_ids.shape[0] - 1
     n_c = np.clip(np.rint(rng.lognormal(3.3, 0.8, size=n_impr)), 2, min(300, n_news)).astype(np.int64)
     offsets = np.concatenate([[0], np.cumsum(n_c)])
-    cdd = np.empty(offsets[-1], dtype=np.int64)
-    lab = np.zeros(offsets[-1], dtype=np.float32)
-    for i in range(n_impr):
-        a, b = offsets[i], offsets[i + 1]
-        cdd[a:b] = rng.choice(n_news, size=b - a, replace=False) + 1
-        y = (rng.random_sample(b - a) < 0.04)
-        y[rng.randint(0, b - a)] = True
-        if y.all():
-            y[0] = False
-        lab[a:b] = y
+    total = int(offsets[-1])
+    # distinct candidates: an arithmetic progression modulo n_news with a stride coprime to n_news, random start
+    stride = next(p for p in (7919, 7907, 7901, 104729, 3, 5, 7, 11, 13, 1) if np.gcd(p, n_news) == 1)
+    start = rng.randint(0, n_news, size=n_impr).astype(np.int64)
+    k = np.arange(total, dtype=np.int64) - np.repeat(offsets[:-1], n_c)
+    cdd = (np.repeat(start, n_c) + k * stride) % n_news + 1
+    lab = (rng.random_sample(total) < 0.04)
+    lab[offsets[:-1] + (rng.random_sample(n_impr) * n_c).astype(np.int64)] = True
+    all_pos = np.add.reduceat(lab.astype(np.int64), offsets[:-1]) == n_c
+    lab[offsets[:-1][all_pos]] = False
+    lab = lab.astype(np.float32)
     his_len = np.clip(np.rint(rng.lognormal(3.0, 0.9, size=n_impr)), 0, S).astype(np.int64)
     his_id = _zipf_ids(rng, 1.05, (n_impr, S), n_news)
     pos = np.arange(S)[None, :]
     his_id = np.where(pos < his_len[:, None], his_id, 0)
     his_mask = (pos < np.maximum(his_len, 1)[:, None]).astype(np.float64)[:, :, None]
+    user_id = rng.randint(1, n_users + 1, size=n_impr).astype(np.int64)
+    impr_index = np.arange(n_impr, dtype=np.int64)
+    if impr_size and impr_size > 0:
+        n_chunks = (n_c + impr_size - 1) // impr_size
+        row_of = np.repeat(np.arange(n_impr), n_chunks)                      # source impression of every row
+        chunk_no = np.arange(row_of.size) - np.repeat(np.concatenate([[0], np.cumsum(n_chunks)])[:-1], n_chunks)
+        row_cnt = np.minimum(impr_size, n_c[row_of] - chunk_no * impr_size)
+        offsets = np.concatenate([[0], np.cumsum(row_cnt)])                  # candidate order is unchanged
+        his_id, his_mask, user_id, impr_index = his_id[row_of], his_mask[row_of], user_id[row_of], impr_index[row_of]
     his_t = torch.from_numpy(his_id)
-    return {
-        "impr_index": torch.arange(n_impr), "user_id": torch.from_numpy(rng.randint(1, n_users + 1, size=n_impr).astype(np.int64)),
+    out = {
+        "impr_index": torch.from_numpy(impr_index), "user_id": torch.from_numpy(user_id),
         "cdd_id": torch.from_numpy(cdd), "offsets": torch.from_numpy(offsets.astype(np.int64)), "label": torch.from_numpy(lab),
-        "his_id": his_t, "his_encoded_index": news_ids[his_t], "his_attn_mask": news_mask[his_t],
-        "his_mask": torch.from_numpy(his_mask),
+        "his_id": his_t, "his_mask": torch.from_numpy(his_mask),
     }
+    if with_tokens:
+        out["his_encoded_index"] = news_ids[his_t]
+        out["his_attn_mask"] = news_mask[his_t]
+    return out

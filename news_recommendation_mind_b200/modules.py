@@ -100,6 +100,20 @@ class BERT_Embedding(nn.Module):
             if self.hot_reps > 0:
                 shadow[V + h * self.hot_reps: V + (h + 1) * self.hot_reps] = shadow[t]
 
+    def invalidate_shadow(self) -> None:
+        """Forget the bf16 shadow: the next forward rebuilds it from the fp32 master.  For writers that go around the
+        tensor version counter (``weight.data.copy_``, collectives on ``weight.data``)."""
+        self._shadow, self._shadow_key = None, None
+
+    def refresh_shadow_inplace(self) -> None:
+        """Re-cast the fp32 master into the EXISTING shadow buffer (same address: a captured CUDA graph gathers from it)."""
+        if self._shadow is None:
+            return
+        w = self.weight
+        ops.cast_pad_bf16(w.detach(), self._shadow.shape[1], out=self._shadow[: w.shape[0]])
+        self._replicate_hot(self._shadow)
+        self._shadow_key = (w.data_ptr(), w._version, tuple(w.shape))
+
     def mark_shadow_fresh(self, shadow: torch.Tensor) -> None:
         """Called by the fused optimiser, which rewrites the shadow inside the Adam kernel."""
         w = self.weight

@@ -76,6 +76,26 @@ def embed_grad(ids: torch.Tensor, d_emb: torch.Tensor, V: int, E: int, padding_i
     return d_table
 
 
+def gather_titles(tok_ids: torch.Tensor, tok_mask: torch.Tensor, nid_a: torch.Tensor, nid_b: torch.Tensor = None):
+    """Token rows of the news `nid_a` (then `nid_b`) from the device-resident int32 token table -> (ids, mask) int32
+    [n_a + n_b, L].  Integer work, bit-exact (utils/MIND.py:347-355 done on the device)."""
+    lib = _lib.load()
+    if tok_ids.dtype != torch.int32 or tok_mask.dtype != torch.int32 or tok_ids.shape != tok_mask.shape:
+        raise ValueError("gather_titles: token table must be two int32 [n_rows, L] tensors")
+    dev = tok_ids.device
+    a = _idx(nid_a.to(dev, non_blocking=True)).view(-1)
+    b = None if nid_b is None else _idx(nid_b.to(dev, non_blocking=True)).view(-1)
+    if b is not None and b.dtype != a.dtype:
+        b = b.to(a.dtype)
+    n_rows, L = tok_ids.shape
+    n = a.numel() + (0 if b is None else b.numel())
+    out_ids = torch.empty(n, L, dtype=torch.int32, device=dev)
+    out_mask = torch.empty(n, L, dtype=torch.int32, device=dev)
+    check(lib.mr_gather_titles(ptr(tok_ids), ptr(tok_mask), n_rows, L, ptr(a), a.numel(), ptr(b), 0 if b is None else b.numel(),
+                               index_flag(a), ptr(out_ids), ptr(out_mask), stream_ptr(dev)), "mr_gather_titles")
+    return out_ids, out_mask
+
+
 class EmbeddingGather(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ids, table, padding_idx):
@@ -163,7 +183,8 @@ class NewsCNN(torch.autograd.Function):
             ctx.group_event = torch.cuda.Event()
             ctx.group_event.record(side)
             ids_c.record_stream(side)
-            ctx.group_plan = plan
+            plan.record_stream(side)         # allocated on the compute stream, written on the side stream: if the backward never
+            ctx.group_plan = plan            # runs (and so never waits for group_event) the block must not be recycled early
         ctx.save_for_backward(ids_c, emb_c, tab, cw, pw, q, c_save, key_save, prob)
         ctx.shape = shape
         ctx.table_shape = None if table is None else tuple(table.shape)
@@ -459,13 +480,18 @@ def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale
           "mr_adam_step")
 
 
-def cast_pad_bf16(src: torch.Tensor, ld: int, extra_rows: int = 0) -> torch.Tensor:
+def cast_pad_bf16(src: torch.Tensor, ld: int, extra_rows: int = 0, out: torch.Tensor = None) -> torch.Tensor:
     lib = _lib.load()
     sc = _f32c(src)
     rows, cols = sc.shape
-    dst = torch.empty(rows + extra_rows, ld, dtype=torch.bfloat16, device=sc.device)
-    if extra_rows:
-        dst[rows:].zero_()
+    if out is not None:
+        if out.dtype != torch.bfloat16 or tuple(out.shape) != (rows, ld) or not out.is_contiguous():
+            raise ValueError("cast_pad_bf16: out must be a contiguous bf16 [%d, %d] tensor" % (rows, ld))
+        dst = out
+    else:
+        dst = torch.empty(rows + extra_rows, ld, dtype=torch.bfloat16, device=sc.device)
+        if extra_rows:
+            dst[rows:].zero_()
     check(lib.mr_cast_pad_bf16(ptr(sc), ptr(dst), rows, cols, ld, stream_ptr(sc.device)), "mr_cast_pad_bf16")
     return dst
 

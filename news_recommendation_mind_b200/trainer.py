@@ -36,17 +36,40 @@ class FusedAdam:
         # begin_step() before every replay, so that the captured launch stays valid for every step
         self.dyn = None
         self._dyn_host = None
+        self._dyn_ids = None             # ids of the parameters the (captured) launch updates, in launch order
+
+    DYN_BLOCK = 4 + 24                   # floats per launch: {1/bc1, 1/sqrt(bc2), grad_scale, -, lr[24]} (mr_adam_step_multi_dyn)
 
     def enable_device_step_scalars(self, device):
-        self.dyn = torch.zeros(2, dtype=torch.float32, device=device)
-        self._dyn_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        n_params = sum(len(g["params"]) for g in self.param_groups)
+        n_blocks = max(1, (n_params + 23) // 24)
+        self.dyn = torch.zeros(n_blocks * self.DYN_BLOCK, dtype=torch.float32, device=device)
+        self._dyn_host = torch.zeros(n_blocks * self.DYN_BLOCK, dtype=torch.float32).pin_memory()
+
+    def _dyn_items(self):
+        """the (parameter, lr) list in group order"""
+        return [(p, g["lr"]) for g in self.param_groups for p in g["params"]]
+
+    def _write_dyn(self):
+        """upload the step-dependent scalars: bias corrections, grad_scale and the CURRENT learning rate of every tensor of the
+        launch (a schedule or load_state_dict may have moved them since the capture); stream ordered, asynchronous"""
+        h = self._dyn_host
+        ids = self._dyn_ids
+        lrs = [lr for p, lr in self._dyn_items() if (ids is None and p.requires_grad) or (ids is not None and id(p) in ids)]
+        for b in range(h.numel() // self.DYN_BLOCK):
+            o = b * self.DYN_BLOCK
+            h[o] = 1.0 / (1.0 - self.betas[0] ** max(self.steps, 1))
+            h[o + 1] = 1.0 / (1.0 - self.betas[1] ** max(self.steps, 1)) ** 0.5
+            h[o + 2] = self.grad_scale
+            chunk = lrs[b * 24:(b + 1) * 24]
+            if chunk:
+                h[o + 4:o + 4 + len(chunk)] = torch.tensor(chunk, dtype=torch.float32)
+        self.dyn.copy_(h, non_blocking=True)
 
     def begin_step(self):
-        """graph mode: advance the step counter and upload {1/(1-beta1^t), 1/sqrt(1-beta2^t)} (stream ordered, async)"""
+        """graph mode: advance the step counter and refresh the device block before the (captured) step runs"""
         self.steps += 1
-        self._dyn_host[0] = 1.0 / (1.0 - self.betas[0] ** self.steps)
-        self._dyn_host[1] = 1.0 / (1.0 - self.betas[1] ** self.steps) ** 0.5
-        self.dyn.copy_(self._dyn_host, non_blocking=True)
+        self._write_dyn()
 
     # ---- checkpoints: the torch.optim.Adam state-dict layout, so that Manager.save / Manager.load (utils/Manager.py:289-343)
     # work unchanged and a checkpoint written with the reference's optim.Adam resumes here (and vice versa) ---------------
@@ -103,17 +126,23 @@ class FusedAdam:
         if self.dyn is None:
             self.steps += 1
         items = []
-        for g in self.param_groups:
-            for p in g["params"]:
-                if p.grad is None:
-                    continue
-                st = self.state.get(p)
-                if st is None:
-                    st = self.state[p] = (torch.zeros_like(p), torch.zeros_like(p))
-                grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                if not p.data.is_contiguous() or grad.dtype != torch.float32 or p.dtype != torch.float32:
-                    raise RuntimeError("FusedAdam needs contiguous fp32 parameters and gradients")
-                items.append((p, grad, st[0], st[1], g["lr"]))
+        for idx, (p, lr) in enumerate(self._dyn_items()):
+            if p.grad is None:
+                continue
+            st = self.state.get(p)
+            if st is None:
+                st = self.state[p] = (torch.zeros_like(p), torch.zeros_like(p))
+            grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+            if not p.data.is_contiguous() or grad.dtype != torch.float32 or p.dtype != torch.float32:
+                raise RuntimeError("FusedAdam needs contiguous fp32 parameters and gradients")
+            items.append((p, grad, st[0], st[1], lr))
+        if self.dyn is not None:
+            ids = {id(it[0]) for it in items}
+            if ids != self._dyn_ids:     # first step in graph mode (eager warm-up): the launch's tensor list is known now
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("FusedAdam: the set of parameters with gradients changed between warm-up and capture")
+                self._dyn_ids = ids
+                self._write_dyn()
         lib = _lib.load()
         for c0 in range(0, len(items), 24):
             chunk = items[c0:c0 + 24]
@@ -125,12 +154,13 @@ class FusedAdam:
                     shadow = self.embedding.shadow_bf16()
                     shadow_idx, row_len, shadow_ld = i, it[0].shape[-1], shadow.shape[-1]
             dev = chunk[0][0].device
+            dyn = None if self.dyn is None else self.dyn[(c0 // 24) * self.DYN_BLOCK:(c0 // 24 + 1) * self.DYN_BLOCK]
             _lib.check(lib.mr_adam_step_multi_dyn(
                 n, PA(*[it[0].data_ptr() for it in chunk]), PA(*[it[1].data_ptr() for it in chunk]),
                 PA(*[it[2].data_ptr() for it in chunk]), PA(*[it[3].data_ptr() for it in chunk]),
                 (ctypes.c_int64 * n)(*[it[0].numel() for it in chunk]), (ctypes.c_double * n)(*[float(it[4]) for it in chunk]),
                 max(self.steps, 1), self.betas[0], self.betas[1], self.eps, self.grad_scale, shadow_idx, _lib.ptr(shadow), row_len,
-                shadow_ld, _lib.ptr(self.dyn), _lib.stream_ptr(dev)), "mr_adam_step_multi")
+                shadow_ld, _lib.ptr(dyn), _lib.stream_ptr(dev)), "mr_adam_step_multi")
             if shadow is not None:
                 self.embedding.mark_shadow_fresh(shadow)
 
@@ -165,24 +195,52 @@ class GradSync:
     """Data-parallel gradient averaging for the package's own training loop (the reference wraps the model in DDP,
     twotower.py:49-50, which also works with these modules; this does the same mean with less traffic on the step's
     critical path):
-      * the 36.6 MB table gradient is all-reduced (SUM) IN PLACE, on a side stream, from the moment the encoder
-        backward has produced it -- i.e. while the filter-gradient GEMMs still run -- instead of being copied into
-        and out of a bucket after the whole backward;
-      * the small dense gradients go through ONE flat buffer and one all-reduce;
-      * the 1/world factor is folded into the Adam kernel (optimizer.grad_scale)."""
+      * the 36.6 MB table gradient is all-reduced (SUM) IN PLACE from the moment the encoder backward has produced it
+        -- i.e. while the filter-gradient GEMMs still run -- instead of being copied into and out of a bucket after the
+        whole backward;
+      * the small dense gradients go through ONE static flat buffer and one all-reduce;
+      * the 1/world factor is folded into the Adam kernel (optimizer.grad_scale).
+    Every collective is issued with async_op=True: ProcessGroupNCCL then runs all of them on its ONE internal stream, in
+    issue order, which is the same on every rank (table gradient(s) first, flat buffer last).  Two collectives of one
+    communicator are therefore never in flight on two streams (NCCL gives no ordering guarantee across streams; with one
+    of them issued synchronously on the compute stream the two kernels were independent, which is unsafe in eager mode and
+    dead-locks as two unordered branches of a captured CUDA graph)."""
 
-    def __init__(self, model, optimizer, group=None):
+    def __init__(self, model, optimizer, group=None, prewarm=8):
         self.model, self.optimizer, self.group = model, optimizer, group
         self.world = dist.get_world_size(group)
         optimizer.grad_scale = 1.0 / self.world
         self.params = [p for p in model.parameters() if p.requires_grad]
-        self._events, self._table_work, self._table = {}, None, None
+        self._events, self._pending, self._extra = {}, [], []
+        self._flat, self._flat_key = None, None
         emb = getattr(model, "embedding", None)
         self.table_param = emb.weight if emb is not None and hasattr(emb, "weight") else None
         ops.TABLE_GRAD_HOOK = self
         # same initial weights on every rank, as DDP's constructor does
-        for p in model.parameters():
-            dist.broadcast(p.data, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        with torch.no_grad():
+            for p in model.parameters():
+                dist.broadcast(p.detach(), src=src, group=group)
+        if emb is not None and hasattr(emb, "invalidate_shadow"):
+            emb.invalidate_shadow()          # the bf16 shadow may have been built from the pre-broadcast table
+        if prewarm:
+            self.prewarm(prewarm)
+
+    def prewarm(self, rounds=8):
+        """Set-up, not training: runs the step's two collectives `rounds` times on scratch buffers of the real sizes so that
+        NCCL's lazily created channels / connections / algorithm choices for these message sizes exist before the first
+        timed step (a training loop otherwise pays for them during its first ~10 steps)."""
+        dev = self.params[0].device
+        big = torch.zeros(self.table_param.numel() if self.table_param is not None else 1 << 20, dtype=torch.float32, device=dev)
+        small = torch.zeros(sum((p.numel() + 3) // 4 * 4 for p in self.params if p is not self.table_param) or 4,
+                            dtype=torch.float32, device=dev)
+        for _ in range(rounds):
+            w1 = dist.all_reduce(big, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            w2 = dist.all_reduce(small, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            w1.wait()
+            w2.wait()
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
 
     # -- hook protocol used by ops.NewsCNN.backward -------------------------------------------------------------
     def event(self, device):
@@ -195,37 +253,48 @@ class GradSync:
 
     def __call__(self, d_table, ev):
         tp = self.table_param
-        if tp is None or tp.grad is not None or d_table.shape != tp.shape:
-            return False                     # not ours (or a second backward into the same .grad): leave it to autograd
+        if tp is None or d_table.shape != tp.shape:
+            return False                     # not ours: leave it to autograd
         side = ops.side_stream(d_table.device)
-        side.wait_event(ev)
+        side.wait_event(ev)                  # d_table is complete at `ev`; the rest of the backward keeps running
         with torch.cuda.stream(side):
-            self._table_work = dist.all_reduce(d_table, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        d_table.record_stream(side)
-        self._table = d_table
-        tp.grad = d_table                    # assigned here, not through AccumulateGrad (which would clone it, see ops.TABLE_GRAD_HOOK)
+            work = dist.all_reduce(d_table, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._pending.append(work)
+        if tp.grad is None:
+            tp.grad = d_table                # assigned here, not through AccumulateGrad (which would clone it, see ops.TABLE_GRAD_HOOK)
+        else:
+            # a second encoder backward in the same step (encode_news and encode_user called separately, as the reference's
+            # forward does): this contribution gets its own all-reduce and is added to .grad in finish(), after both are done
+            self._extra.append(d_table)
         return True
 
     # -- after loss.backward() ----------------------------------------------------------------------------------
     def finish(self):
-        done = self._table.data_ptr() if self._table is not None else None
-        rest = [p for p in self.params if p.grad is not None and p.grad.data_ptr() != done]
+        own = {t.data_ptr() for t in self._extra}
+        if self.table_param is not None and self.table_param.grad is not None and self._pending:
+            own.add(self.table_param.grad.data_ptr())
+        rest = [p for p in self.params if p.grad is not None and p.grad.data_ptr() not in own]
         if rest:
-            # one flat buffer, every segment starting on a 16-byte boundary (the Adam kernel reads float4)
-            sizes = [p.grad.numel() for p in rest]
-            offs, total = [], 0
-            for n in sizes:
-                offs.append(total)
-                total += (n + 3) // 4 * 4
-            flat = torch.zeros(total, dtype=torch.float32, device=rest[0].grad.device)
-            views = [flat[o:o + n] for o, n in zip(offs, sizes)]
+            # one static flat buffer, every segment starting on a 16-byte boundary (the Adam kernel reads float4)
+            key = tuple((id(p), p.grad.numel()) for p in rest)
+            if self._flat_key != key:
+                total = sum((n + 3) // 4 * 4 for _, n in key)
+                self._flat = torch.zeros(total, dtype=torch.float32, device=rest[0].grad.device)
+                self._flat_key = key
+            views, o = [], 0
+            for p in rest:
+                n = p.grad.numel()
+                views.append(self._flat[o:o + n])
+                o += (n + 3) // 4 * 4
             torch._foreach_copy_(views, [p.grad.reshape(-1) for p in rest])
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            self._pending.append(dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
             for p, v in zip(rest, views):
                 p.grad = v.view_as(p.grad)
-        if self._table_work is not None:
-            self._table_work.wait()          # the compute stream waits for the side-stream all-reduce
-            self._table_work, self._table = None, None
+        for work in self._pending:
+            work.wait()                      # the compute stream waits for the collective (no host synchronisation)
+        for t in self._extra:
+            self.table_param.grad.add_(t)
+        self._pending, self._extra = [], []
 
     def close(self):
         if ops.TABLE_GRAD_HOOK is self:
@@ -305,37 +374,61 @@ class BatchPrefetcher:
 
 
 class GraphStep:
-    """The whole training step (zero_grad, forward, NLLLoss, backward, Adam) captured ONCE as a CUDA graph and replayed:
-    the host then issues one graph launch per step instead of ~75 kernel launches through Python / ctypes (1.2-1.5 ms of
-    host work against 1.5 ms of device work).  Inputs are copied into static device tensors, the Adam bias corrections
-    come from device memory (FusedAdam.begin_step), the loss is a static device scalar.  Measured on one B200 at the
-    bench shape: 1.458 ms/step with 0.07 ms of host time per step, against 1.490 ms / 1.18 ms for the eager step.
-    Single-process training only: capturing the step together with GradSync's NCCL all-reduces (the one started from
-    inside the encoder backward on the side stream) dead-locked at 2 GPUs and is refused here.
-    Every call must bring tensors of the captured shapes."""
+    """The whole training step (zero_grad, forward, NLLLoss, backward, gradient all-reduce, Adam) captured ONCE as a CUDA
+    graph and replayed: the host then issues one graph launch per step instead of ~75 kernel launches through Python /
+    ctypes (1.2-1.5 ms of host work against 1.5 ms of device work).  Inputs are copied into static device tensors; every
+    step-dependent optimiser scalar (Adam bias corrections, the learning rates a schedule moves, grad_scale) comes from a
+    device block that FusedAdam.begin_step() refreshes before each replay, so LinearWarmupSchedule / load_state_dict keep
+    working; the loss is a static device scalar.  Parameters, Adam moments and the step counter are snapshotted before the
+    three warm-up steps the capture needs and restored afterwards: constructing a GraphStep does not train.
 
-    def __init__(self, model, optimizer, example, sync=None):
-        if sync is not None:
-            raise NotImplementedError("GraphStep cannot capture a GradSync (NCCL inside the captured step dead-locks); "
-                                      "use the eager train_step(model, x, optimizer, sync) for data-parallel training")
+    With a GradSync the NCCL all-reduces are captured too (thread-local capture mode; all of them on ProcessGroupNCCL's one
+    internal stream, i.e. ONE dependency chain inside the graph -- see GradSync).  Every rank must construct the GraphStep
+    at the same point.  Every call must bring tensors of the captured shapes."""
+
+    def __init__(self, model, optimizer, example, sync=None, warmup_steps=3):
         core = model.module if hasattr(model, "module") else model
         self.model, self.optimizer, self.device, self.sync = model, optimizer, torch.device(core.device), sync
         self.static_x = {k: (v.to(self.device).clone() if torch.is_tensor(v) else v) for k, v in example.items()}
-        optimizer.enable_device_step_scalars(self.device)
+        if optimizer.dyn is None:
+            optimizer.enable_device_step_scalars(self.device)
+        # ---- snapshot: the warm-up steps below are real optimiser steps on the example batch
+        params = [p for g in optimizer.param_groups for p in g["params"]]
+        snap_p = [p.detach().clone() for p in params]
+        snap_state = {p: (st[0].clone(), st[1].clone()) for p, st in optimizer.state.items()}
+        snap_steps = optimizer.steps
         # warm-up on a side stream (allocator state, lazy initialisation), as torch.cuda.graphs requires
         s = torch.cuda.Stream(self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
-            for _ in range(3):
+            for _ in range(warmup_steps):
                 optimizer.begin_step()
                 train_step(model, self.static_x, optimizer, sync)
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):                  # recorded, not executed: the step counter is not advanced here
+        mode = {"capture_error_mode": "thread_local"} if sync is not None else {}
+        with torch.cuda.graph(self.graph, **mode):          # recorded, not executed: the step counter is not advanced here
             self.loss = train_step(model, self.static_x, optimizer, sync)
         torch.cuda.synchronize(self.device)
-        self.warmup_steps = 3
+        # ---- restore IN PLACE (the graph holds the addresses of the parameters and of the moment tensors)
+        with torch.no_grad():
+            for p, old in zip(params, snap_p):
+                p.copy_(old)
+            for p, st in optimizer.state.items():
+                old = snap_state.get(p)
+                if old is None:
+                    st[0].zero_()
+                    st[1].zero_()
+                else:
+                    st[0].copy_(old[0])
+                    st[1].copy_(old[1])
+        optimizer.steps = snap_steps
+        emb = getattr(core, "embedding", None)
+        if emb is not None and hasattr(emb, "refresh_shadow_inplace"):
+            emb.refresh_shadow_inplace()                     # the captured forward gathers from this very buffer
+        torch.cuda.synchronize(self.device)
+        self.warmup_steps = warmup_steps
 
     def __call__(self, x):
         for k, dst in self.static_x.items():

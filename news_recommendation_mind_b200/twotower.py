@@ -52,6 +52,30 @@ class TwoTowerBaseModel(nn.Module):
         self.news_reprs = None
         del self.news_reprs
 
+    # ---- device-resident token table ------------------------------------------
+    def attach_news_tokens(self, encoded_news: torch.Tensor, attn_mask: torch.Tensor):
+        """Keep the tokenised news set ([N+1, L] ids and attention masks, row 0 = the empty article; utils/MIND.py:103-127)
+        in HBM as int32.  Batches may then carry ``cdd_id`` / ``his_id`` only: the ``*_encoded_index`` / ``*_attn_mask``
+        tensors the reference's dataset assembles per sample on the host (MIND.py:347-355) are gathered on the device."""
+        L = self.signal_length
+        self.news_tok_ids = encoded_news[:, :L].to(device=self.device, dtype=torch.int32).contiguous()
+        self.news_tok_mask = attn_mask[:, :L].to(device=self.device, dtype=torch.int32).contiguous()
+
+    def detach_news_tokens(self):
+        self.news_tok_ids = self.news_tok_mask = None
+
+    def _titles_of(self, x, which):
+        """(ids, mask) of the `which` ("cdd" | "his") titles of a batch: from the batch when it carries tokens (the
+        reference's contract), else from the resident token table by news id."""
+        key = which + "_encoded_index"
+        if key in x:
+            return x[key].to(self.device, non_blocking=True), x[which + "_attn_mask"].to(self.device, non_blocking=True)
+        if getattr(self, "news_tok_ids", None) is None:
+            raise KeyError("batch has no %r and no token table is attached (TwoTower.attach_news_tokens)" % key)
+        nid = x[which + "_id"]
+        ids, mask = ops.gather_titles(self.news_tok_ids, self.news_tok_mask, nid)
+        return ids.view(*nid.shape, -1), mask.view(*nid.shape, -1)
+
     def compute_score(self, cdd_news_repr, user_repr):
         """[B,C,H] x [B,1,H] -> raw scores [B,C] = <cdd, user>/sqrt(H) (TwoTowerBaseModel.py:51-62).
         Kept for API parity (no autograd); forward() uses the fused score+log-softmax / sigmoid kernels."""
@@ -69,7 +93,10 @@ class TwoTowerBaseModel(nn.Module):
 
     def predict_fast(self, x):
         cdd_id = x["cdd_id"].to(self.device)
-        user_repr, _ = self.encode_user(x)
+        if getattr(self, "history_from_table", False) and "his_id" in x:
+            user_repr = self.encode_user_from_table(self.news_reprs.weight, x["his_id"], x)
+        else:
+            user_repr, _ = self.encode_user(x)
         B, n = cdd_id.shape
         offsets = torch.arange(0, (B + 1) * n, n, dtype=torch.int64, device=cdd_id.device)
         prob = ops.score_sigmoid_gather(self.news_reprs.weight, cdd_id, offsets, user_repr)
@@ -92,6 +119,12 @@ class TwoTower(TwoTowerBaseModel):
         # the (candidate | history) slots -- identical outputs, the backward sums the slot gradients per news with
         # the deterministic segmented reduction.  Needs cdd_id / his_id in the batch (utils/MIND.py:354-355).
         self.dedup_titles = bool(getattr(manager, "dedup_titles", False))
+        # opt-in (manager.history_from_table): predict_fast looks the clicked-news vectors up in the news table built by
+        # init_embedding instead of re-encoding them from tokens (what models/PLM.py:112-113 does).
+        # Same bits: the table rows come from the same batch-invariant encoder, row 0 must be the encoded empty article
+        # (evaluate.encode_all_news encodes it; the reference's own table leaves row 0 at zero, Manager.py:496).
+        self.history_from_table = bool(getattr(manager, "history_from_table", False))
+        self.news_tok_ids = self.news_tok_mask = None
 
     # ---- news side ---------------------------------------------------------------------------
     def _encode_titles(self, ids, mask):
@@ -100,8 +133,7 @@ class TwoTower(TwoTowerBaseModel):
         return self.encoderN(self.embedding(ids), mask)[1]
 
     def encode_news(self, x):
-        cdd_news = x["cdd_encoded_index"].to(self.device, non_blocking=True)
-        cdd_attn_mask = x["cdd_attn_mask"].to(self.device, non_blocking=True)
+        cdd_news, cdd_attn_mask = self._titles_of(x, "cdd")
         return self._encode_titles(cdd_news, cdd_attn_mask)
 
     # ---- user side ---------------------------------------------------------------------------
@@ -109,10 +141,15 @@ class TwoTower(TwoTowerBaseModel):
         return self.encoderU(his_news_repr, his_mask=x["his_mask"], user_id=x["user_id"].to(self.device, non_blocking=True))
 
     def encode_user(self, x):
-        his_news = x["his_encoded_index"].to(self.device, non_blocking=True)
-        his_attn_mask = x["his_attn_mask"].to(self.device, non_blocking=True)
+        his_news, his_attn_mask = self._titles_of(x, "his")
         his_news_repr = self._encode_titles(his_news, his_attn_mask)
         return self._encode_user_from(his_news_repr, x), None
+
+    def encode_user_from_table(self, table, his_id, x):
+        """User vectors from already encoded news: ``his_news_repr = table[his_id]`` (models/PLM.py:112-113), then the
+        user encoder.  `table` [N+1, H] fp32 with row 0 = the encoded empty article; eval only (no gradient to the table)."""
+        his_news_repr = ops.EmbeddingGather.apply(his_id.to(self.device, non_blocking=True), table, None)
+        return self._encode_user_from(his_news_repr, x)
 
     # ---- whole model ---------------------------------------------------------------------------
     def forward(self, x):
@@ -121,21 +158,36 @@ class TwoTower(TwoTowerBaseModel):
         kernels see B*(C+S) titles per launch instead of two launches."""
         if not self._fused:
             return super().forward(x)
-        cdd = x["cdd_encoded_index"].to(self.device, non_blocking=True)
-        his = x["his_encoded_index"].to(self.device, non_blocking=True)
-        cm = x["cdd_attn_mask"].to(self.device, non_blocking=True)
-        hm = x["his_attn_mask"].to(self.device, non_blocking=True)
-        B, C, L = cdd.shape
-        S = his.shape[1]
-        ids = torch.cat([cdd.reshape(B * C, L), his.reshape(B * S, L)], dim=0)
-        mask = torch.cat([cm.reshape(B * C, L), hm.reshape(B * S, L)], dim=0)
-        if self.dedup_titles and "cdd_id" in x and "his_id" in x:
+        dedup = self.dedup_titles and "cdd_id" in x and "his_id" in x
+        if "cdd_encoded_index" in x:
+            cdd = x["cdd_encoded_index"].to(self.device, non_blocking=True)
+            his = x["his_encoded_index"].to(self.device, non_blocking=True)
+            cm = x["cdd_attn_mask"].to(self.device, non_blocking=True)
+            hm = x["his_attn_mask"].to(self.device, non_blocking=True)
+            B, C, L = cdd.shape
+            S = his.shape[1]
+            ids = torch.cat([cdd.reshape(B * C, L), his.reshape(B * S, L)], dim=0)
+            mask = torch.cat([cm.reshape(B * C, L), hm.reshape(B * S, L)], dim=0)
+        else:
+            # id-only batch: the token rows come from the resident table, candidates and history in ONE gather launch
+            if self.news_tok_ids is None:
+                raise KeyError("batch has no 'cdd_encoded_index' and no token table is attached (TwoTower.attach_news_tokens)")
+            (B, C), S = x["cdd_id"].shape, x["his_id"].shape[1]
+            ids = mask = None
+            if not dedup:
+                ids, mask = ops.gather_titles(self.news_tok_ids, self.news_tok_mask, x["cdd_id"], x["his_id"])
+        if dedup:
             nid = torch.cat([x["cdd_id"].reshape(-1), x["his_id"].reshape(-1)])           # integer bookkeeping only
             uniq, inverse = torch.unique(nid, return_inverse=True)
-            first = torch.full((uniq.numel(),), nid.numel(), dtype=torch.int64, device=nid.device)
-            first.scatter_reduce_(0, inverse, torch.arange(nid.numel(), device=nid.device), reduce="amin")
-            first, inverse = first.to(self.device, non_blocking=True), inverse.to(self.device, non_blocking=True)
-            news_u = self._encode_titles(ids.index_select(0, first), mask.index_select(0, first))
+            if ids is None:
+                u_ids, u_mask = ops.gather_titles(self.news_tok_ids, self.news_tok_mask, uniq)
+            else:
+                first = torch.full((uniq.numel(),), nid.numel(), dtype=torch.int64, device=nid.device)
+                first.scatter_reduce_(0, inverse, torch.arange(nid.numel(), device=nid.device), reduce="amin")
+                first = first.to(self.device, non_blocking=True)
+                u_ids, u_mask = ids.index_select(0, first), mask.index_select(0, first)
+            inverse = inverse.to(self.device, non_blocking=True)
+            news_u = self._encode_titles(u_ids, u_mask)
             news = ops.EmbeddingGather.apply(inverse, news_u, None)
             self.last_unique_titles = int(uniq.numel())
         else:

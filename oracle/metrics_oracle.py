@@ -5,11 +5,17 @@ numpy restatement of the functions the reference evaluates with
 Pinned against the reference's own `cal_metric` by `oracle/make_golden.py`
 (-> tests/golden/metrics.npz) and `tests/test_oracle_golden.py`.
 
-Tie rule.  The reference orders candidates with ``np.argsort(score)[::-1]``
-(Manager.py:1216,1269) which is not a stable sort, so the order of equal scores is
-a numpy implementation detail.  This oracle -- and the CUDA
-ranking kernel -- define the order as *descending score, ties by ascending
-candidate position*; the golden vectors are tie-free so both agree bit for bit.
+Tie rules.  prediction.txt ranks are ``scipy.stats.rankdata(1 - p, "ordinal")``
+(Manager.py:846): descending score, ties by ASCENDING candidate position -- exact.
+MRR / nDCG order candidates with ``np.argsort(score)[::-1]`` (Manager.py:1216,1269):
+a reversed ascending sort, i.e. ties by DESCENDING position wherever numpy's sort
+is stable (numpy 1.x, the reference's era: insertion sort for n <= 16).  For longer
+arrays, and in numpy 2.x with AVX-512 for n >= 4 (measured in this container), the
+default sort is not stable and the reference's tie order is an implementation
+detail no rule reproduces.  This oracle and the CUDA ranking kernel define the
+MRR / nDCG order as *stable ascending sort, reversed*; the golden vectors from the
+reference's cal_metric are tie-free, so all three agree to the last bit there, and
+AUC is tie-order independent.
 """
 from __future__ import annotations
 
@@ -49,9 +55,15 @@ def auc(label: np.ndarray, score: np.ndarray) -> float:
     return float((gt + 0.5 * eq) / (len(pos) * len(neg)))
 
 
+def metric_order(score: np.ndarray) -> np.ndarray:
+    """``np.argsort(score)[::-1]`` with a stable sort: descending score, ties by DESCENDING position
+    (Manager.py:1216,1269)."""
+    return np.argsort(np.asarray(score), kind="stable")[::-1]
+
+
 def mrr(label: np.ndarray, score: np.ndarray) -> float:
     """mrr_score (Manager.py:1205-1221): sum of label/rank over sum of labels."""
-    y = np.asarray(label, dtype=np.float64)[descending_order(score)]
+    y = np.asarray(label, dtype=np.float64)[metric_order(score)]
     return float(np.sum(y / (np.arange(len(y)) + 1.0)) / np.sum(y))
 
 
@@ -59,7 +71,7 @@ def dcg(label: np.ndarray, score: np.ndarray, k: int) -> float:
     """dcg_score (Manager.py:1257-1273): gains 2^y - 1, discounts log2(pos + 2),
     first min(k, n) positions."""
     k = min(len(label), k)
-    y = np.asarray(label, dtype=np.float64)[descending_order(score)[:k]]
+    y = np.asarray(label, dtype=np.float64)[metric_order(score)[:k]]
     return float(np.sum((2.0 ** y - 1.0) / np.log2(np.arange(len(y)) + 2.0)))
 
 

@@ -47,6 +47,16 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
+def max_err(a: torch.Tensor, b: torch.Tensor):
+    """element-wise bounds beside the norm ratio of rel_err: (max |a-b|, max |a-b| / max(|b|, floor)) with the floor at 1e-3 of
+    the largest |b| -- a single bad row shows up here even when the Frobenius ratio hides it"""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    d = (a - b).abs()
+    floor = 1e-3 * float(b.abs().max()) + 1e-30
+    return float(d.max()), float((d / b.abs().clamp_min(floor)).max())
+
+
 def random_batch(gen, B, C, S, L, V, n_users=40):
     def titles(n):
         ln = torch.randint(2, L + 1, (n,), generator=gen)

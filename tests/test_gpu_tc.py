@@ -398,8 +398,10 @@ def test_full_size_step_is_bit_reproducible_and_paths_agree(monkeypatch):
 
 
 def test_graph_step_matches_eager_steps():
-    """trainer.GraphStep (the training step captured as one CUDA graph, Adam bias corrections read from device memory)
-    replays to bit-identical losses and parameters as eager train_step calls on the same batches."""
+    """trainer.GraphStep (the training step captured as one CUDA graph; Adam bias corrections, learning rates and grad_scale
+    read from device memory) replays to bit-identical losses and parameters as eager train_step calls on the same batches,
+    WITH a LinearWarmupSchedule moving the learning rates every step (the captured launch must not freeze them), and
+    constructing it does not train: parameters, moments and step counter are as before."""
     import sys, os, copy
     sys.path.insert(0, os.path.dirname(__file__))
     from helpers import build_model, manager_for, random_batch
@@ -412,18 +414,43 @@ def test_graph_step_matches_eager_steps():
     m1 = build_model(man, V)
     m2 = copy.deepcopy(m1)
     o1, o2 = trainer.FusedAdam(m1, lr=1e-3, bert_lr=1e-4), trainer.FusedAdam(m2, lr=1e-3, bert_lr=1e-4)
-    gs = trainer.GraphStep(m1, o1, batches[0])              # runs 3 warm-up steps on batches[0], then records the graph
-    o2.enable_device_step_scalars("cuda:0")                 # same arithmetic for the bias corrections as the graph path
-    for _ in range(gs.warmup_steps):
-        o2.begin_step()
-        trainer.train_step(m2, batches[0], o2)
+    s1 = trainer.LinearWarmupSchedule(o1, 3, 10)            # built FIRST: lr = 0 at capture time (the ADVICE r1 failure mode)
+    s2 = trainer.LinearWarmupSchedule(o2, 3, 10)
+    gs = trainer.GraphStep(m1, o1, batches[0])              # warm-up steps + capture, then everything restored
+    assert o1.steps == 0
     for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
-        assert torch.equal(a, b), ("after capture", k)
+        assert torch.equal(a, b), ("constructing a GraphStep must not train", k)
+    o2.enable_device_step_scalars("cuda:0")                 # same arithmetic for the step scalars as the graph path
     for s in range(6):
         got = float(gs(batches[s % 3]))
+        s1.step()
         o2.begin_step()
         exp = float(trainer.train_step(m2, batches[s % 3], o2))
+        s2.step()
         assert got == exp, (s, got, exp)
-    assert o1.steps == o2.steps == 9
+    assert o1.steps == o2.steps == 6
     for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
         assert torch.equal(a, b), k
+    assert o1.param_groups[0]["lr"] != 1e-3                 # the schedule is live (6th step of a 3-warm-up / 10-total ramp)
+
+
+def test_graph_step_learns_under_warmup_schedule():
+    """With the schedule built before the capture the captured learning rate used to be 0 for ever: the parameters must
+    change once the ramp has left 0."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from helpers import build_model, manager_for, random_batch
+    from news_recommendation_mind_b200 import trainer
+    B, C, S, L, E, H, V = 4, 5, 6, 32, 300, 150, 300
+    gen = torch.Generator().manual_seed(1)
+    x = {k: v.cuda() for k, v in random_batch(gen, B, C, S, L, V).items()}
+    torch.manual_seed(2)
+    m = build_model(manager_for("cnn", "lstm", C, S, L, E, H, 10, precision="bf16"), V)
+    o = trainer.FusedAdam(m, lr=1e-2, bert_lr=1e-3)
+    sched = trainer.LinearWarmupSchedule(o, 2, 8)
+    gs = trainer.GraphStep(m, o, x)
+    before = m.encoderN.cnn.weight.detach().clone()
+    gs(x); sched.step()                                     # lr factor 0: nothing moves
+    assert torch.equal(before, m.encoderN.cnn.weight)
+    gs(x); sched.step()                                     # factor 1/2
+    assert not torch.equal(before, m.encoderN.cnn.weight)

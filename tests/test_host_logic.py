@@ -9,6 +9,7 @@ import pytest
 import torch
 
 from news_recommendation_mind_b200 import data, ops, trainer
+from oracle import metrics_oracle as MO
 
 
 def test_news_table_follows_the_reference_layout():
@@ -111,9 +112,77 @@ def test_prefetcher_buffer_compatibility_check():
     assert not fits(pf, buf, dict(a, extra=torch.zeros(1)))                               # a tensor the buffers do not hold
 
 
-def test_graph_step_refuses_a_gradient_synchroniser():
-    with pytest.raises(NotImplementedError):
-        trainer.GraphStep(torch.nn.Linear(2, 2), types.SimpleNamespace(), {}, sync=object())
+def test_adam_device_block_follows_the_schedule():
+    """FusedAdam's CUDA-graph mode keeps every step-dependent scalar in one device block per launch
+    {1/bc1, 1/sqrt(bc2), grad_scale, -, lr[...]}: the host mirror must follow a LinearWarmupSchedule and grad_scale
+    (the captured launch froze lr at capture time)."""
+    m = torch.nn.Sequential(torch.nn.Linear(3, 2), torch.nn.Linear(2, 1))
+    opt = trainer.FusedAdam(m, lr=1e-2, bert_lr=1e-3)
+    opt.dyn = torch.zeros(trainer.FusedAdam.DYN_BLOCK)             # CPU stand-ins for the device block and its pinned mirror
+    opt._dyn_host = torch.zeros(trainer.FusedAdam.DYN_BLOCK)
+    sched = trainer.LinearWarmupSchedule(opt, 2, 6)
+    opt.grad_scale = 0.25
+    opt.begin_step()
+    assert opt.steps == 1 and opt.dyn[2] == 0.25 and torch.all(opt.dyn[4:8] == 0)          # factor 0 at step 0
+    assert abs(float(opt.dyn[0]) - 1.0 / (1 - 0.9)) < 1e-5 and abs(float(opt.dyn[1]) - 1.0 / (1 - 0.999) ** 0.5) < 1e-3
+    sched.step()
+    opt.begin_step()
+    assert torch.allclose(opt.dyn[4:8], torch.full((4,), 5e-3)) and opt.steps == 2
+    opt.param_groups[0]["lr"] = 7e-3                               # e.g. load_state_dict
+    opt.begin_step()
+    assert torch.allclose(opt.dyn[4:8], torch.full((4,), 7e-3))
+
+
+def test_group_rows_matches_group_lists():
+    """evaluate.group_rows / reorder_rows == utils/utils.py:60-80 (_group_lists): rows with one impr_index are concatenated in
+    arrival order, groups in first-appearance order."""
+    from news_recommendation_mind_b200 import evaluate as ev
+    idx = [3, 5, 3, 7, 5, 3]
+    cols = [[1., 0.], [0.], [0., 1., 1.], [1.], [1., 0.], [0.]]
+    exp = MO.group_by_impression(idx, cols)[0]
+    order, g_off = ev.group_rows(torch.tensor(idx))
+    assert order is not None and order.tolist() == [0, 2, 5, 1, 4, 3] and g_off.tolist() == [0, 3, 5, 6]
+    cnt = torch.tensor([len(c) for c in cols])
+    impr = {"offsets": torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(cnt, 0)]),
+            "label": torch.tensor([v for c in cols for v in c]), "cdd_id": torch.arange(int(cnt.sum())),
+            "impr_index": torch.tensor(idx), "user_id": torch.arange(6)}
+    r = ev.reorder_rows(impr, order)
+    off = r["offsets"][g_off]
+    got = [r["label"][a:b].tolist() for a, b in zip(off[:-1].tolist(), off[1:].tolist())]
+    assert got == exp and r["user_id"].tolist() == [0, 2, 5, 1, 4, 3]
+    # adjacent chunks (the usual case): no permutation needed
+    order, g_off = ev.group_rows(torch.tensor([4, 4, 9, 2, 2, 2]))
+    assert order is None and g_off.tolist() == [0, 2, 3, 6]
+    order, g_off = ev.group_rows(torch.arange(5))
+    assert order is None and g_off.tolist() == [0, 1, 2, 3, 4, 5]
+    # partition: no group is cut; rank spans tile the rows
+    g_off = torch.tensor([0, 2, 3, 6, 7, 11])
+    spans = [ev.group_partition_bounds(g_off, 3, r) for r in range(3)]
+    assert spans[0][0] == 0 and spans[-1][1] == 11 and all(spans[i][1] == spans[i + 1][0] for i in range(2))
+    assert all(s[0] in g_off.tolist() and s[1] in g_off.tolist() for s in spans)
+
+
+def test_mrr_ndcg_tie_rule_is_reversed_stable_argsort():
+    """Manager.py:1216,1269: order = np.argsort(score)[::-1]; with a stable sort equal scores come out in DESCENDING position."""
+    assert MO.mrr(np.array([1, 0]), np.array([.5, .5])) == 0.5
+    assert MO.mrr(np.array([0, 1]), np.array([.5, .5])) == 1.0
+    y, s = np.array([1., 0., 0., 1.]), np.array([.2, .7, .7, .2])
+    order = np.argsort(s, kind="stable")[::-1]
+    assert order.tolist() == [2, 1, 3, 0]
+    exp = np.sum((2 ** y[order[:2]] - 1) / np.log2(np.arange(2) + 2)) / 1.0
+    assert abs(MO.dcg(y, s, 2) - exp) < 1e-15
+    assert MO.ordinal_rank(s).tolist() == [3, 1, 2, 4]             # prediction.txt keeps scipy's ordinal rule (ascending position)
+
+
+def test_id_only_batch_is_the_same_sample():
+    ids, mask = data.make_news_table(300, 32, seed=3)
+    a = data.make_train_batch(ids, mask, 8, 5, 12, seed=7)
+    b = data.make_train_batch(ids, mask, 8, 5, 12, seed=7, id_only=True)
+    assert torch.equal(a["cdd_id"], b["cdd_id"].long()) and torch.equal(a["his_id"], b["his_id"].long())
+    assert torch.equal(a["his_mask"], b["his_mask"].double()) and torch.equal(a["user_id"], b["user_id"])
+    assert torch.equal(ids[b["his_id"].long()], a["his_encoded_index"])
+    nbytes = sum(v.numel() * v.element_size() for v in b.values())
+    assert nbytes < sum(v.numel() * v.element_size() for v in a.values()) // 50
 
 
 def test_prediction_file_matches_the_reference_writer(tmp_path):
