@@ -76,6 +76,17 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 // ---- device helpers -------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// ptxas treats ld.global.nc (what `const T* __restrict__` loads compile to) as movable across griddepcontrol.wait -- the "memory"
+// clobber above does not order non-coherent loads -- and did hoist the first W_hh loads of rnn_mma_fwd_kernel above the wait,
+// i.e. above the completion of the kernel that WRITES that buffer (seen as an intermittent wrong LSTM at >= 4 sequences per
+// CTA).  Laundering the pointer through an asm volatile placed after the wait makes every address derived from it, and so
+// every load, depend on an instruction that cannot move above the wait.  Use it for every buffer the preceding kernel wrote
+// and this kernel reads through a `const __restrict__` pointer early in its prologue.
+template <class T>
+__device__ __forceinline__ T* pdl_acquire(T* p) {
+  asm volatile("" : "+l"(p)::"memory");
+  return p;
+}
 
 __device__ __forceinline__ int64_t load_index(const void* p, int is64, int64_t i) {
   return is64 ? static_cast<const int64_t*>(p)[i] : (int64_t) static_cast<const int32_t*>(p)[i];

@@ -85,6 +85,10 @@ rnn_mma_fwd_kernel(const float* __restrict__ xp, int ldx, const __nv_bfloat16* _
                    float* __restrict__ hs, float* __restrict__ cs, float* __restrict__ user, int B, int S, int H, int MT, int KT) {
   pdl_trigger();
   pdl_wait();
+  w_img = pdl_acquire(w_img);      // written by rnn_mma_prep_kernel, the grid this one programmatically depends on (see common.cuh)
+  xp = pdl_acquire(xp);
+  h0 = pdl_acquire(h0);
+  lens = pdl_acquire(lens);
   constexpr int G = KIND == 0 ? 4 : 3;
   constexpr int PPT = (NSEQ * RM_MAXKT * 16 + RM_THREADS - 1) / RM_THREADS;       // (sequence, unit) pairs per thread
   const int GH = G * H;

@@ -36,8 +36,25 @@ def _zipf_ids(rng, a, size, n_news):
     return (rng.zipf(a, size=size) - 1) % n_news + 1
 
 
+def dedup_plan(cdd_id, his_id, capacity: int = 0):
+    """Host-side bookkeeping of the in-batch unique-news dedup (part of batch assembly, like the reference's collate):
+    -> (uniq_id [capacity] int32, inverse [B*(C+S)] int32, n_unique).  ``uniq_id`` lists the distinct news of the batch in
+    ascending id order, padded with news 0 up to a FIXED `capacity` (fixed shapes: the step can be replayed as one CUDA
+    graph); slot k of the flat (candidates | history) list is title ``uniq_id[inverse[k]]``.  capacity = 0: exact size.
+    Returns None when the batch has more distinct news than `capacity` (the caller then sends the plain batch)."""
+    nid = np.concatenate([np.asarray(cdd_id).reshape(-1), np.asarray(his_id).reshape(-1)]).astype(np.int64)
+    uniq, inverse = np.unique(nid, return_inverse=True)
+    n = int(uniq.size)
+    cap = capacity or n
+    if n > cap:
+        return None
+    out = np.zeros(cap, dtype=np.int32)
+    out[:n] = uniq
+    return torch.from_numpy(out), torch.from_numpy(inverse.astype(np.int32)), n
+
+
 def make_train_batch(news_ids, news_mask, B: int, C: int, S: int, seed: int, n_users: int = USER_NUM["small"],
-                     pin: bool = False, id_only: bool = False):
+                     pin: bool = False, id_only: bool = False, dedup_capacity: int = None):
     """One training batch (dict of CPU tensors) in the reference schema.  id_only: the batch of the device-resident
     input pipeline (TwoTower.attach_news_tokens) -- the same sample, but only news ids (int32), the history mask (uint8),
     user ids and labels cross PCIe; the token tensors are gathered on the device."""
@@ -62,6 +79,10 @@ def make_train_batch(news_ids, news_mask, B: int, C: int, S: int, seed: int, n_u
     if id_only:
         x = {"user_id": x["user_id"], "cdd_id": cdd_t.to(torch.int32), "his_id": his_t.to(torch.int32),
              "his_mask": x["his_mask"].to(torch.uint8), "label": x["label"]}
+        if dedup_capacity is not None:
+            plan = dedup_plan(cdd_id, his_id, dedup_capacity)
+            if plan is not None:
+                x["uniq_id"], x["uniq_inverse"] = plan[0], plan[1]
     if pin:
         x = {k: v.pin_memory() for k, v in x.items()}
     return x

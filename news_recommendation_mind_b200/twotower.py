@@ -158,6 +158,16 @@ class TwoTower(TwoTowerBaseModel):
         kernels see B*(C+S) titles per launch instead of two launches."""
         if not self._fused:
             return super().forward(x)
+        if "uniq_id" in x and self.news_tok_ids is not None:
+            # id-only batch with a host-made dedup plan (data.dedup_plan): every distinct news of the batch is encoded ONCE (fixed
+            # capacity, padded with news 0) and its vector gathered to the (candidate | history) slots -- identical outputs,
+            # the backward sums the slot gradients per news with the deterministic segmented reduction
+            (B, C), S = x["cdd_id"].shape, x["his_id"].shape[1]
+            u_ids, u_mask = ops.gather_titles(self.news_tok_ids, self.news_tok_mask, x["uniq_id"])
+            news_u = self._encode_titles(u_ids, u_mask)
+            news = ops.EmbeddingGather.apply(x["uniq_inverse"].to(self.device, non_blocking=True), news_u, None)
+            self.last_unique_titles = int(x["uniq_id"].numel())
+            return self._finish(news, x, B, C, S)
         dedup = self.dedup_titles and "cdd_id" in x and "his_id" in x
         if "cdd_encoded_index" in x:
             cdd = x["cdd_encoded_index"].to(self.device, non_blocking=True)
@@ -192,6 +202,9 @@ class TwoTower(TwoTowerBaseModel):
             self.last_unique_titles = int(uniq.numel())
         else:
             news = self._encode_titles(ids, mask)
+        return self._finish(news, x, B, C, S)
+
+    def _finish(self, news, x, B, C, S):
         cdd_repr = news[: B * C].view(B, C, -1)
         his_repr = news[B * C:].view(B, S, -1)
         user_repr = self._encode_user_from(his_repr, x)

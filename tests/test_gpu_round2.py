@@ -69,6 +69,35 @@ def test_id_only_batches_equal_token_batches(precision):
         model(x_id)
 
 
+@pytest.mark.parametrize("precision,gtol", [("fp32", 1e-4), ("bf16", 0.15)])
+def test_dedup_plan_batches_are_exact_in_forward(precision, gtol):
+    """Host-made dedup plan (data.dedup_plan: distinct news ids padded to a fixed capacity + slot -> distinct index): the
+    log-probabilities are bit-identical to the plain id-only batch, the gradients equal up to summation order (same bounds as
+    the device-side dedup test: bf16 rounds the per-token gradients after the slot sum instead of before it)."""
+    from news_recommendation_mind_b200 import data
+    C, S, L, E, H, V = 5, 20, 32, 300, 150, 30522
+    news_ids, news_mask = data.make_news_table(500, L, seed=2)
+    x_plain = data.make_train_batch(news_ids, news_mask, 16, C, S, seed=4, id_only=True)
+    x_dedup = data.make_train_batch(news_ids, news_mask, 16, C, S, seed=4, id_only=True, dedup_capacity=256)
+    assert "uniq_id" in x_dedup and x_dedup["uniq_id"].numel() == 256
+    assert "uniq_id" not in data.make_train_batch(news_ids, news_mask, 16, C, S, seed=4, id_only=True, dedup_capacity=8)
+    outs = []
+    for x in (x_plain, x_dedup):
+        torch.manual_seed(5)
+        model = build_model(manager_for("cnn", "lstm", C, S, L, E, H, 10, precision=precision), V)
+        with torch.no_grad():
+            model.embedding.weight.normal_(0, 0.3)
+        model.attach_news_tokens(news_ids, news_mask)
+        model.train()
+        logp = model(x)[0]
+        torch.nn.NLLLoss()(logp, x["label"].cuda()).backward()
+        outs.append((logp.detach().clone(), {k: p.grad.detach().clone() for k, p in model.named_parameters()}))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for k in outs[0][1]:
+        assert rel_err(outs[1][1][k], outs[0][1][k]) < gtol, (k, rel_err(outs[1][1][k], outs[0][1][k]))
+    assert float(outs[1][1]["embedding.bert_word_embedding.weight"][0].abs().max()) == 0.0
+
+
 def _eval_setup(precision, n_news, n_impr, S, seed_model=11, impr_size=0, encu="lstm"):
     from news_recommendation_mind_b200 import data
     torch.manual_seed(seed_model)

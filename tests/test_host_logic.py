@@ -250,3 +250,13 @@ def test_linear_warmup_schedule_matches_transformers():
         ref_opt.step()
         ref.step()
         ours.step()
+
+
+def test_dedup_plan_reconstructs_the_slots():
+    ids, mask = data.make_news_table(300, 32, seed=3)
+    b = data.make_train_batch(ids, mask, 8, 5, 12, seed=7, id_only=True, dedup_capacity=128)
+    flat = torch.cat([b["cdd_id"].reshape(-1), b["his_id"].reshape(-1)]).long()
+    assert torch.equal(b["uniq_id"].long()[b["uniq_inverse"].long()], flat)
+    n = int(torch.unique(flat).numel())
+    assert b["uniq_id"].numel() == 128 and torch.all(b["uniq_id"][n:] == 0) and torch.all(b["uniq_id"][1:n] > b["uniq_id"][:n - 1])
+    assert data.dedup_plan(b["cdd_id"], b["his_id"], n - 1) is None and data.dedup_plan(b["cdd_id"], b["his_id"])[2] == n
