@@ -284,10 +284,21 @@ class Env:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t)
 
-    def close(self):
+    def close(self, graphs=()):
+        """orderly teardown: captured graphs first (a live graph with captured NCCL kernels makes the communicator teardown
+        hang), then the process group; a watchdog ends the process if the teardown itself stalls -- the JSON line is out"""
+        sys.stdout.flush()
+        for g in graphs:
+            if g is not None:
+                g.close()
+        torch.cuda.synchronize()
         if self.world > 1:
+            t = threading.Timer(30.0, lambda: os._exit(0))
+            t.daemon = True
+            t.start()
             self.dist.barrier()
             self.dist.destroy_process_group()
+            t.cancel()
 
 
 def run_train(args):
@@ -380,7 +391,7 @@ def run_train(args):
             conv_launches, conv_ms = n_.value, m_.value
         lib.mr_debug_conv_timing(0)
     tok_info = None
-    if fused:
+    if fused and not args.quick:
         for s in range(2):
             eager(devb_tok[s % NB])
         ms_tok, _ = timed(loop_dev(devb_tok, eager), args.steps)
@@ -401,7 +412,7 @@ def run_train(args):
     d_ms, w_ms = timed(loop_e2e(host), args.steps)
     ms_e2e = max(d_ms, w_ms)
     e2e_tok = None
-    if fused and gstep is None:
+    if fused and gstep is None and not args.quick:
         loop.run(host_tok, 2)
         d_ms, w_ms = timed(loop_e2e(host_tok), args.steps)
         e2e_tok = {"value": world * cfg["B"] * args.steps / (max(d_ms, w_ms) * 1e-3), "unit": "impressions/s",
@@ -434,7 +445,7 @@ def run_train(args):
     # slot -> distinct-news index) is made on the host with the batch (data.dedup_plan), so the step keeps fixed shapes and is
     # replayed as one CUDA graph like the headline step
     dedup_info = None
-    if args.precision == "bf16" and fused and not args.ddp:
+    if args.precision == "bf16" and fused and not args.ddp and not args.quick:
         n_titles = cfg["B"] * (cfg["C"] + cfg["S"])
         cap = (n_titles * 7 // 16 + 255) // 256 * 256
         while True:
@@ -474,7 +485,7 @@ def run_train(args):
 
     # ---------------- second half of the BASELINE metric: evaluation news-encoded/s over the whole news set
     eval_info = None
-    if fused:
+    if fused and not args.quick:
         eval_info = time_news_encoding(env, core, ids, mask, "%s-train news set" % cfg["scale"])
     if rank == 0:
         per_step = ms / args.steps
@@ -505,7 +516,7 @@ def run_train(args):
             v, ms_c, cores, kind, sample = cpu_train_baseline(cfg, 1, 6, Bs=cfg["B"] if args.config in (2, 3) else 32, budget_s=25)
             line["cpu_baseline"] = {"value": v, "unit": "impressions/s", "cores": cores, "kind": kind, "sample": sample}
         print(json.dumps(line))
-    env.close()
+    env.close([gstep, locals().get("gstep_d")])
 
 
 def time_news_encoding(env, core, ids, mask, what):
@@ -638,6 +649,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json configuration (1-based)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="time eager steps only (no trainer.GraphStep)")
+    ap.add_argument("--quick", action="store_true", help="headline + e2e only (no eager / token-batch / dedup / eval extras): stability loops")
     ap.add_argument("--ddp", action="store_true", help="N > 1: wrap the model in torch DDP (the reference's scheme) instead of trainer.GradSync")
     ap.add_argument("--precision", default=os.environ.get("MINDREC_PRECISION", "bf16"), choices=["bf16", "fp32"])
     args = ap.parse_args()

@@ -438,6 +438,14 @@ class GraphStep:
         self.graph.replay()
         return self.loss
 
+    def close(self):
+        """Release the captured graph.  REQUIRED before torch.distributed.destroy_process_group() when a GradSync was captured:
+        a live CUDA graph keeps the communicator's captured kernels referenced and the communicator teardown then hangs."""
+        if self.graph is not None:
+            torch.cuda.synchronize(self.device)
+            self.graph.reset()
+            self.graph = None
+
 
 class TrainLoop:
     """The training loop over host (pinned) batches: input prefetch + lagged loss read.  The loss of step i is copied

@@ -112,7 +112,8 @@ def _worker(rank, world, port, out):
         sync5 = trainer.GradSync(mb5, o5, prewarm=0)
         mine_d = {k: v.cuda() for k, v in mine.items()}
         gs = trainer.GraphStep(mb5, o5, mine_d, sync5)
-        l5 = [float(gs(mine_d)) for _ in range(3)]
+        l5 = [float(gs(mine_d).detach()) for _ in range(3)]
+        gs.close()                                                        # before any communicator teardown (GraphStep.close)
         sync5.close()
         sync6 = trainer.GradSync(mb6, o6, prewarm=0)
         o6.enable_device_step_scalars("cuda:%d" % rank)
