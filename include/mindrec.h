@@ -232,6 +232,22 @@ MR_API int mr_linear_bwd(const float* x, const float* w, const float* d_y, float
                   int64_t M, int64_t N, int64_t K, int precision,
                   void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The same dense layer on the tcgen05 tensor cores (MR_BF16 path of the attention projections keyProject / valueProject,
+ * Attention.py:101-102,125-127): bf16 operands, fp32 accumulation and fp32 output y [M, ldy] (ldy % 4 == 0, ldy >= N rounded up
+ * to 4; columns N..ldy-1 are padding).  The input is EITHER a dense fp32 matrix x [M, K] OR (x == NULL) rows of the padded bf16
+ * token table gathered by ids [M] inside the GEMM (BERT.py:39 fused in, the [M, K] embedding tensor is never materialised).
+ * bwd: dense -> d_x [M, K] (NULL to skip), d_w [N, K], d_b [N] (NULL to skip); gather -> d_table [V, K] instead of d_x (row
+ * `padding_idx` zero; the gradient rows are first summed per token id, so both GEMMs run over V rows), K % 4 == 0, and the bf16
+ * table must have table_rows >= V rounded up to 32 (zero padded).  d_y [M, ldy] fp32. */
+MR_API int64_t mr_linear_tc_workspace_bytes(int64_t M, int64_t N, int64_t K, int64_t V /* 0 = dense */, int backward);
+MR_API int mr_linear_tc_fwd(const float* x, const void* ids, int ids_i64, const void* table_bf16, int64_t table_ld, int64_t V,
+                     const float* w, const float* b, float* y, int64_t ldy, int64_t M, int64_t N, int64_t K,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+MR_API int mr_linear_tc_bwd(const float* x, const void* ids, int ids_i64, const void* table_bf16, int64_t table_ld,
+                     int64_t table_rows, int64_t V, int64_t padding_idx, const float* w, const float* d_y, int64_t ldy,
+                     float* d_x, float* d_table, float* d_w, float* d_b, int64_t M, int64_t N, int64_t K,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
 /* LayerNorm over the last axis, eps 1e-5 (MHA.py:18,37), with optional fused inverted-dropout keep
  * mask (uint8, NULL = none).  mean/rstd [M] saved. */
 MR_API int mr_layernorm_fwd(const float* x, const float* gamma, const float* beta, const uint8_t* keep, float keep_scale,

@@ -56,6 +56,9 @@ _SIGNATURES = {
     "mr_linear_workspace_bytes": (I64, [I64, I64, I64]),
     "mr_linear_fwd": (c_int, [P, P, P, P, I64, I64, I64, c_int, c_int, P]),
     "mr_linear_bwd": (c_int, [P, P, P, P, P, P, I64, I64, I64, c_int, P, I64, P]),
+    "mr_linear_tc_workspace_bytes": (I64, [I64, I64, I64, I64, c_int]),
+    "mr_linear_tc_fwd": (c_int, [P, P, c_int, P, I64, I64, P, P, P, I64, I64, I64, I64, P, I64, P]),
+    "mr_linear_tc_bwd": (c_int, [P, P, c_int, P, I64, I64, I64, I64, P, P, I64, P, P, P, P, I64, I64, I64, P, I64, P]),
     "mr_layernorm_fwd": (c_int, [P, P, P, P, c_float, P, P, P, I64, I64, P]),
     "mr_layernorm_bwd": (c_int, [P, P, P, c_float, P, P, P, P, P, P, I64, I64, I64, P]),
     "mr_score_logsoftmax_fwd": (c_int, [P, P, P, P, c_int, P, I64, I64, I64, P]),

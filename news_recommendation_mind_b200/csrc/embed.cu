@@ -655,7 +655,10 @@ int mr_embed_grad_segreduce(const void* ids, int ids_i64, const void* d_emb, int
   // ceil(T/SEG_CHUNK)+V and let surplus warps exit (no host sync on this path).
   const int64_t E4 = d_emb_ld > 0 ? d_emb_ld : E;
   MR_REQUIRE(E4 >= E, MR_ERR_BAD_SHAPE, "mr_embed_grad_segreduce: row pitch %lld < E=%lld", (long long)E4, (long long)E);
-  if (d_emb_dtype == MR_F32)
+  if (d_emb_dtype == MR_F32 && E > 384)          // up to 512 fp32 columns on the vector path (MHA projection gradients: 450)
+    seg_reduce_l1_kernel<float, 4><<<(unsigned)ceil_div(p.max_chunks, 8), 256, 0, st>>>(
+        static_cast<const float*>(d_emb), E4, svals, seg_start, chunk_off, chunk_row, nchunk, d_table, partial, p.max_chunks, E, V);
+  else if (d_emb_dtype == MR_F32)
     seg_reduce_l1_kernel<float, 3><<<(unsigned)ceil_div(p.max_chunks, 8), 256, 0, st>>>(
         static_cast<const float*>(d_emb), E4, svals, seg_start, chunk_off, chunk_row, nchunk, d_table, partial, p.max_chunks, E, V);
   else

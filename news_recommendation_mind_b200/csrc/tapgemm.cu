@@ -444,7 +444,8 @@ __global__ void __launch_bounds__(EPI2 ? TG_THREADS2 : TG_THREADS, 1) tapgemm_ke
         row_off[k] = l < p.L ? (int64_t)g * p.L + l : -1;
       }
       auto row_id = [&](int64_t tile, int k) -> int {
-        if (p.ids == nullptr || row_off[k] < 0 || tile >= p.n_tiles || tile * p.G + row_g[k] >= p.n_titles)
+        if (p.ids == nullptr || row_off[k] < 0 || tile >= p.n_tiles || tile * p.G + row_g[k] >= p.n_titles ||
+            tile * p.G * p.L + row_off[k] >= p.n_rows)
           return (int)(p.V + (int64_t)p.n_hot * p.hot_reps);      // out of bounds -> zero filled
         int64_t id = load_index(p.ids, p.ids_i64, tile * p.G * p.L + row_off[k]);
         id = id < 0 ? 0 : (id >= p.V ? p.V - 1 : id);
@@ -506,7 +507,8 @@ __global__ void __launch_bounds__(EPI2 ? TG_THREADS2 : TG_THREADS, 1) tapgemm_ke
     // top of the next iteration, so its latency overlaps the staging of the current tile
     auto row_token = [&](int64_t tile, int s) -> int64_t {
       if (row_off[s] < 0 || tile >= p.n_tiles || tile * p.G + row_g[s] >= p.n_titles) return -1;
-      return tile * p.G * p.L + row_off[s];
+      const int64_t t_ = tile * p.G * p.L + row_off[s];
+      return t_ < p.n_rows ? t_ : -1;                 // rows past the problem (flat row lists padded to whole tiles): zero rows, no id read
     };
     auto raw_of = [&](int64_t t) -> int64_t { return (t < 0 || p.ids == nullptr) ? t : load_index(p.ids, p.ids_i64, t); };
     // -> source row (token id in gather mode, token index otherwise); -1 = zero row; -2-h = hot row h (smem copy)

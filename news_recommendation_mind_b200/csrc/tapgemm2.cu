@@ -315,7 +315,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG2_THREADS, 1) tapg
     }
     auto row_token = [&](int64_t tile, int s) -> int64_t {
       if (row_off[s] < 0 || tile >= p.n_tiles || tile * p.G + row_g[s] >= p.n_titles) return -1;
-      return tile * p.G * p.L + row_off[s];
+      const int64_t t_ = tile * p.G * p.L + row_off[s];
+      return t_ < p.n_rows ? t_ : -1;                 // rows past the problem (flat row lists padded to whole tiles): zero rows, no id read
     };
     auto raw_of = [&](int64_t t) -> int64_t { return (t < 0 || p.ids == nullptr) ? t : load_index(p.ids, p.ids_i64, t); };
     auto classify = [&](int64_t t, int64_t raw) -> int64_t {

@@ -257,9 +257,10 @@ class Average_Pooling(nn.Module):
 class MultiheadAttention(nn.Module):
     """models/Modules/Attention.py:83-147: q and k share keyProject, no output projection."""
 
-    def __init__(self, hidden_dim, head_num, key_dim=None, value_dim=None):
+    def __init__(self, hidden_dim, head_num, key_dim=None, value_dim=None, precision=MR_F32):
         super().__init__()
         self.head_num = head_num
+        self.precision = precision
         if not (key_dim and value_dim):
             assert hidden_dim % head_num == 0, "hidden_dim {} must divide head_num {}".format(hidden_dim, head_num)
             head_dim = hidden_dim // head_num
@@ -274,8 +275,26 @@ class MultiheadAttention(nn.Module):
     def forward(self, hidden_states, token_mask=None):
         """hidden_states [n,len,in]; token_mask [n,len] 0/1 (the pair mask m_i*m_j of get_attn_mask is
         formed inside the kernel) -> [n,len,value_dim*head_num]."""
+        if self.precision == MR_BF16:
+            return self._forward_tc(hidden_states, None, None, token_mask)
         qk = ops.Linear.apply(hidden_states, self.keyProject.weight, self.keyProject.bias, 0)
         v = ops.Linear.apply(hidden_states, self.valueProject.weight, self.valueProject.bias, 0)
+        return ops.MHACore.apply(qk, v, token_mask, self.head_num)
+
+    def _forward_tc(self, hidden_states, ids, embedding, token_mask):
+        """MR_BF16: both projections as ONE tensor-core GEMM over the concatenated [keyProject; valueProject] weights (bf16
+        operands, fp32 output); with `ids` the token rows are gathered from the bf16 table inside the GEMM."""
+        w = torch.cat([self.keyProject.weight, self.valueProject.weight], dim=0)
+        b = torch.cat([self.keyProject.bias, self.valueProject.bias], dim=0)
+        nk, nv = self.key_dim * self.head_num, self.value_dim * self.head_num
+        if ids is None:
+            n, length = hidden_states.shape[0], hidden_states.shape[1]
+            y = ops.LinearTC.apply(hidden_states, None, None, None, w, b)
+        else:
+            n, length = ids.shape
+            y = ops.LinearTC.apply(None, ids, embedding.weight, embedding.shadow_bf16(), w, b)
+        qk = y[:, :nk].reshape(n, length, nk)
+        v = y[:, nk:nk + nv].reshape(n, length, nv)
         return ops.MHACore.apply(qk, v, token_mask, self.head_num)
 
 
@@ -289,18 +308,30 @@ class MHA_Encoder(nn.Module):
         self.head_num = manager.head_num
         value_dim, x = divmod(self.hidden_dim, self.head_num)
         assert x == 0, "hidden_dim {} must divide head_num {}".format(self.hidden_dim, self.head_num)
-        self.mha = MultiheadAttention(self.embedding_dim, self.head_num, value_dim=value_dim)
+        self.precision = precision_of(manager)
+        self.mha = MultiheadAttention(self.embedding_dim, self.head_num, value_dim=value_dim, precision=self.precision)
         self.query_words = nn.Parameter(torch.randn(1, self.hidden_dim))
         self.layerNorm = nn.LayerNorm(self.hidden_dim)
         self.dropOut = nn.Dropout(p=manager.dropout_p)
         self.keep_override = None      # parity tests inject the dropout keep mask here
 
     def forward(self, news_embedding, attn_mask=None):
-        batch_size = news_embedding.size(0)
         L = news_embedding.size(-2)
         flat = news_embedding.reshape(-1, L, self.embedding_dim)
         m = None if attn_mask is None else attn_mask.reshape(-1, L).to(device=flat.device, dtype=torch.float32)
         h = self.mha(flat, m)
+        return self._finish(h, m, news_embedding.shape[:-2], L)
+
+    def encode_ids(self, embedding: BERT_Embedding, ids, attn_mask=None):
+        """MR_BF16 fused path: token ids straight into the projection GEMM (rows gathered from the bf16 table shadow), the
+        [B,*,L,E] embedding tensor is never materialised.  Returns the news vectors only."""
+        L = ids.shape[-1]
+        flat_ids = ids.reshape(-1, L)
+        m = None if attn_mask is None else attn_mask.reshape(-1, L).to(device=flat_ids.device, dtype=torch.float32)
+        h = self.mha._forward_tc(None, flat_ids, embedding, m)
+        return self._finish(h, m, ids.shape[:-1], L)[1]
+
+    def _finish(self, h, m, lead, L):
         keep, scale = None, 1.0
         p = self.dropOut.p
         if self.training and p > 0:
@@ -311,7 +342,6 @@ class MHA_Encoder(nn.Module):
             scale = 1.0 / (1.0 - p)
         h = ops.LayerNorm.apply(h, self.layerNorm.weight, self.layerNorm.bias, keep, scale)
         news = ops.AttnPool.apply(h, m, self.query_words).squeeze(1)
-        lead = news_embedding.shape[:-2]
         return h.view(*lead, L, self.hidden_dim), news.view(*lead, self.hidden_dim)
 
 
@@ -327,7 +357,8 @@ class MHA_User_Encoder(nn.Module):
         head_num = manager.head_num
         value_dim, x = divmod(self.hidden_dim, head_num)
         assert x == 0, "hidden_dim {} must divide head_num {}".format(self.hidden_dim, head_num)
-        self.mha = MultiheadAttention(self.hidden_dim, manager.head_num, value_dim=value_dim)
+        self.precision = precision_of(manager)
+        self.mha = MultiheadAttention(self.hidden_dim, manager.head_num, value_dim=value_dim, precision=self.precision)
         self.query_news = nn.Parameter(torch.randn(1, self.hidden_dim))
         self.layerNorm = nn.LayerNorm(self.hidden_dim)
         self.dropOut = nn.Dropout(p=manager.dropout_p)

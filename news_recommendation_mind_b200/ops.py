@@ -534,6 +534,63 @@ class Linear(torch.autograd.Function):
         return d_x, d_w, d_b, None
 
 
+class LinearTC(torch.autograd.Function):
+    """y = x W^T + b on the tcgen05 tensor cores (bf16 operands, fp32 accumulate / output) -- the MR_BF16 path of the attention
+    projections.  Input: dense ``x`` [M, K] fp32, or (``x`` None) token ``ids`` [M] whose rows of the bf16 table shadow are gathered
+    inside the GEMM (then ``table`` is the fp32 master [V, K] that receives the gradient, ``table_bf16`` its padded shadow).
+    Returns the PADDED output [M, ldy], ldy = N rounded up to 4 (16-byte rows for the vector epilogue); slice what you need."""
+
+    @staticmethod
+    def forward(ctx, x, ids, table, table_bf16, w, b):
+        lib = _lib.load()
+        wc = _f32c(w)
+        bc = None if b is None else _f32c(b)
+        N, K = wc.shape
+        dev = wc.device
+        if x is not None:
+            xc = _f32c(x).reshape(-1, K)
+            M, V, ids_c, tab = xc.shape[0], 0, None, None
+        else:
+            ids_c = _idx(ids).reshape(-1)
+            xc, tab = None, table_bf16
+            M, V = ids_c.numel(), table.shape[0]
+            if table.shape[1] != K or tab.dtype != torch.bfloat16:
+                raise ValueError("LinearTC: table width %d != K %d or shadow not bf16" % (table.shape[1], K))
+        ldy = pad_to(N, 4)
+        y = torch.empty(M, ldy, dtype=torch.float32, device=dev)
+        ws = workspace(lib.mr_linear_tc_workspace_bytes(M, N, K, V, 0), dev)
+        check(lib.mr_linear_tc_fwd(ptr(xc), ptr(ids_c), index_flag(ids_c) if ids_c is not None else 0, ptr(tab),
+                                   tab.shape[1] if tab is not None else 0, V, ptr(wc), ptr(bc), ptr(y), ldy, M, N, K, ptr(ws), ws.numel(),
+                                   stream_ptr(dev)), "mr_linear_tc_fwd")
+        ctx.save_for_backward(xc, ids_c, tab, wc)
+        ctx.dims = (M, N, K, V, ldy)
+        ctx.has_bias = b is not None
+        ctx.x_shape = None if x is None else tuple(x.shape)
+        ctx.need_x = x is not None and x.requires_grad
+        ctx.need_table = table is not None and table.requires_grad
+        return y
+
+    @staticmethod
+    def backward(ctx, d_y):
+        lib = _lib.load()
+        xc, ids_c, tab, wc = ctx.saved_tensors
+        M, N, K, V, ldy = ctx.dims
+        dev = wc.device
+        g = _f32c(d_y)
+        d_w = torch.empty(N, K, dtype=torch.float32, device=dev)
+        d_b = torch.empty(N, dtype=torch.float32, device=dev) if ctx.has_bias else None
+        d_x = torch.empty(M, K, dtype=torch.float32, device=dev) if ctx.need_x else None
+        d_table = torch.empty(V, K, dtype=torch.float32, device=dev) if xc is None else None
+        ws = workspace(lib.mr_linear_tc_workspace_bytes(M, N, K, V, 1), dev)
+        check(lib.mr_linear_tc_bwd(ptr(xc), ptr(ids_c), index_flag(ids_c) if ids_c is not None else 0, ptr(tab),
+                                   tab.shape[1] if tab is not None else 0, tab.shape[0] if tab is not None else 0, V, 0, ptr(wc), ptr(g), ldy,
+                                   ptr(d_x), ptr(d_table), ptr(d_w), ptr(d_b), M, N, K, ptr(ws), ws.numel(), stream_ptr(dev)),
+              "mr_linear_tc_bwd")
+        if d_x is not None:
+            d_x = d_x.view(ctx.x_shape)
+        return d_x, None, (d_table if ctx.need_table else None), None, d_w, d_b
+
+
 class MHACore(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qk, v, mask, head_num):

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .modules import BERT_Embedding, CNN_Encoder
+from .modules import BERT_Embedding, CNN_Encoder, MHA_Encoder
 
 
 class TwoTowerBaseModel(nn.Module):
@@ -115,6 +115,10 @@ class TwoTower(TwoTowerBaseModel):
         manager.name = "__".join(["twotower", manager.encoderN, manager.encoderU])
         self.name = manager.name
         self._fused = isinstance(embedding, BERT_Embedding) and isinstance(encoderN, CNN_Encoder)
+        # MHA news encoder in bf16 mode: the token gather is fused into the projection GEMM (candidates and history stay two
+        # calls, as in the reference, so that the dropout draws keep their order)
+        self._fused_mha = isinstance(embedding, BERT_Embedding) and isinstance(encoderN, MHA_Encoder) and \
+            getattr(encoderN, "precision", None) == ops.PRECISIONS["bf16"]
         # opt-in (manager.dedup_titles): encode every distinct news of a batch once and gather the vectors back to
         # the (candidate | history) slots -- identical outputs, the backward sums the slot gradients per news with
         # the deterministic segmented reduction.  Needs cdd_id / his_id in the batch (utils/MIND.py:354-355).
@@ -128,7 +132,7 @@ class TwoTower(TwoTowerBaseModel):
 
     # ---- news side ---------------------------------------------------------------------------
     def _encode_titles(self, ids, mask):
-        if self._fused:
+        if self._fused or self._fused_mha:
             return self.encoderN.encode_ids(self.embedding, ids, mask)
         return self.encoderN(self.embedding(ids), mask)[1]
 

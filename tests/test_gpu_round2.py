@@ -242,3 +242,53 @@ def test_logits_elementwise_bounds(name, encn, encu):
         mabs, mrel = max_err(logp, g["train_logp"])
         print(name, precision, "train logp max abs %.2e max rel %.2e" % (mabs, mrel))
         assert mrel < tol * 3, (precision, mabs, mrel)
+
+
+@pytest.mark.parametrize("M,N,K", [(12800, 300, 150), (1000, 450, 300), (37, 150, 150), (130, 30, 16)])
+def test_linear_tc_dense_matches_bf16_operand_reference(M, N, K):
+    """ops.LinearTC (the MHA projections on tcgen05): y = x W^T + b and its three gradients against float64 matmuls on the
+    bf16-rounded operands the kernels use (x, W; backward additionally d_y) -- fp32 accumulation only, so 2e-5."""
+    from news_recommendation_mind_b200 import ops
+    g_ = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=g_)
+    w = torch.randn(N, K, generator=g_) * 0.1
+    b = torch.randn(N, generator=g_)
+    go = torch.randn(M, N, generator=g_)
+    xc, wc, bc = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    y = ops.LinearTC.apply(xc, None, None, None, wc, bc)
+    assert y.shape == (M, (N + 3) // 4 * 4)
+    (y[:, :N] * go.cuda()).sum().backward()
+    r = lambda t: t.bfloat16().double()                                                        # noqa: E731
+    assert rel_err(y[:, :N], r(x) @ r(w).t() + b.double()) < 2e-5
+    assert rel_err(xc.grad, r(go) @ r(w)) < 2e-5
+    assert rel_err(wc.grad, r(go).t() @ r(x)) < 2e-5
+    assert rel_err(bc.grad, go.double().sum(0)) < 1e-5
+
+
+def test_linear_tc_gather_matches_token_grouped_reference():
+    """Gather mode: rows of the bf16 table shadow by token id inside the GEMM; backward = per-token-id sums of d_y first
+    (fp32, then rounded to bf16), then d_table = S W and d_w = S^T table over vocabulary rows; padding row gets no gradient."""
+    from news_recommendation_mind_b200 import ops
+    V, K, N, n, L = 2000, 300, 450, 41, 48
+    g_ = torch.Generator().manual_seed(7)
+    table = torch.randn(V, K, generator=g_) * 0.3
+    ids = torch.randint(0, V, (n, L), generator=g_)
+    ids[:, 40:] = 0                                                                            # padded tails
+    ids[0, :5] = 7                                                                             # a repeated token
+    w = torch.randn(N, K, generator=g_) * 0.1
+    b = torch.randn(N, generator=g_)
+    go = torch.randn(n * L, N, generator=g_)
+    tc_, wc, bc = table.cuda().requires_grad_(True), w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    shadow = ops.cast_pad_bf16(tc_.detach(), ops.pad_to(K, 64), extra_rows=ops.pad_to(V, 128) - V)
+    y = ops.LinearTC.apply(None, ids.cuda(), tc_, shadow, wc, bc)
+    (y[:, :N] * go.cuda()).sum().backward()
+    r = lambda t: t.bfloat16().double()                                                        # noqa: E731
+    flat = ids.reshape(-1)
+    assert rel_err(y[:, :N], r(table)[flat] @ r(w).t() + b.double()) < 2e-5
+    S = torch.zeros(V, N, dtype=torch.float64).index_add_(0, flat, go.double())
+    Sb = S.float().bfloat16().double()
+    d_table = Sb @ r(w)
+    d_table[0] = 0
+    assert rel_err(tc_.grad, d_table) < 2e-5 and float(tc_.grad[0].abs().max()) == 0.0
+    assert rel_err(wc.grad, Sb.t() @ r(table)) < 2e-5
+    assert rel_err(bc.grad, go.double().sum(0)) < 1e-5
