@@ -75,9 +75,11 @@ struct LtGeom {
 };
 static LtGeom lt_geom(int64_t M, int64_t N, int64_t K, int64_t V) {
   LtGeom g;
-  g.M = M; g.Mp = align_up(M > 0 ? M : 1, 128); g.N = N; g.Np = align_up(N, 16); g.K = K; g.Kp = align_up(K, 16);
+  // N is padded to 32 and cut into blocks that are multiples of 32 columns: the token-reduction GEMM then stages its Q operand
+  // in 64- or 32-column swizzled blocks (the layouts the conv backward exercises), never the 16-column one
+  g.M = M; g.Mp = align_up(M > 0 ? M : 1, 128); g.N = N; g.Np = align_up(N, 32); g.K = K; g.Kp = align_up(K, 16);
   g.V = V; g.Vp = align_up(V > 0 ? V : 1, 128);
-  g.nblk_n = ceil_div(g.Np, 256); g.nbsz_n = align_up(ceil_div(g.Np, g.nblk_n), 16);
+  g.nblk_n = ceil_div(g.Np, 256); g.nbsz_n = align_up(ceil_div(g.Np, g.nblk_n), 32);
   g.nblk_k = ceil_div(g.Kp, 256); g.nbsz_k = align_up(ceil_div(g.Kp, g.nblk_k), 16);
   return g;
 }
@@ -95,12 +97,12 @@ static int64_t lt_ws(int64_t M, int64_t N, int64_t K, int64_t V, int backward) {
   if (V <= 0) {
     b += arena_bytes(g.Mp * g.Kp, 2) + arena_bytes(g.Mp * g.Np, 2);                 // x, d_y as bf16
     b += arena_bytes(M * align_up(K, 4), 4);                                        // d_x with 16-byte rows (K % 4 != 0)
-    b += arena_bytes(tokred_partial_bytes(g.Mp / 128, 128, 1, (int)g.Np, (int)g.Kp), 1);
+    b += arena_bytes(tokred_partial_bytes(g.Mp / 128, 128, 1, (int)g.Kp, (int)g.nbsz_n), 1);
   } else {
     b += arena_bytes(V * N, 4);                                                     // S fp32
     b += arena_bytes(g.Vp * g.Np, 2);                                               // S bf16
     b += arena_bytes(mr_embed_grad_workspace_bytes(M, N, V), 1);
-    b += arena_bytes(tokred_partial_bytes(ceil_div(V, 32), 32, 1, (int)g.Np, (int)g.Kp), 1);
+    b += arena_bytes(tokred_partial_bytes(ceil_div(V, 32), 32, 1, (int)g.Kp, (int)g.nbsz_n), 1);
   }
   return b;
 }
@@ -126,6 +128,27 @@ static int lt_gemm(const __nv_bfloat16* a_dense, int64_t lda, const void* ids, i
     a.n_rows = rows; a.out_f32 = out + n0; a.ldo = ldo; a.n_store = (int)align_up(nv, 4);
     if (int rc = tapgemm_plan(a, &plan)) return rc;
     if (int rc = tapgemm_launch(plan, st)) return rc;
+  }
+  return MR_OK;
+}
+
+// d_w[n, k] = sum_r Q[r, n] P[r, k]:  P (the layer input, KP = K rounded up to 16 columns) is the 128-wide-slice operand of the
+// token-reduction GEMM, Q (the output gradient) its N <= 256 operand -- blocks of the output columns, one launch each
+static int lt_wgrad(const __nv_bfloat16* p, int64_t ldp, const __nv_bfloat16* q, int64_t ldq, int64_t row_tiles, int tile_rows, const LtGeom& g,
+                    float* partial, float* d_w, cudaStream_t st) {
+  for (int64_t blk = 0; blk < g.nblk_n; ++blk) {
+    const int64_t n0 = blk * g.nbsz_n;
+    const int64_t nb = (g.Np - n0) < g.nbsz_n ? (g.Np - n0) : g.nbsz_n;
+    const int64_t nv = (g.N - n0) < nb ? (g.N - n0) : nb;
+    if (nv <= 0 || nb <= 0) break;
+    TokRedArgs a{};
+    TokRedPlan plan;
+    a.n_titles = row_tiles; a.L = tile_rows; a.taps = 1;
+    a.ids = nullptr; a.p = p; a.ldp = ldp; a.KP = (int)g.Kp;
+    a.q = q + n0; a.ldq = ldq; a.NQ = (int)nb; a.partial = partial;
+    if (int rc = tokred_plan(a, &plan)) return rc;
+    if (int rc = tokred_launch(plan, st)) return rc;
+    if (int rc = tokred_reduce(plan, d_w + n0 * g.K, (int)g.K, (int)nv, g.K, 1, 0, st)) return rc;
   }
   return MR_OK;
 }
@@ -201,7 +224,7 @@ int mr_linear_tc_bwd(const float* x, const void* ids, int ids_i64, const void* t
     __nv_bfloat16* gb = ar.take<__nv_bfloat16>(g.Mp * g.Np);
     const int64_t K4 = align_up(K, 4);
     float* dx_tmp = ar.take<float>(M * K4);
-    float* partial = ar.take<float>(tokred_partial_bytes(g.Mp / 128, 128, 1, (int)g.Np, (int)g.Kp) / 4);
+    float* partial = ar.take<float>(tokred_partial_bytes(g.Mp / 128, 128, 1, (int)g.Kp, (int)g.nbsz_n) / 4);
     MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "mr_linear_tc_bwd: workspace too small (%lld given)", (long long)workspace_bytes);
     launch_pdl(lt_cast_kernel, dim3((unsigned)ceil_div(g.Mp * g.Kp, 256)), dim3(256), 0, st, x, K, xb, M, g.Mp, (int)K, (int)g.Kp);
     MR_CHECK_LAUNCH("lt_cast_kernel");
@@ -218,14 +241,7 @@ int mr_linear_tc_bwd(const float* x, const void* ids, int ids_i64, const void* t
       }
     }
     // d_w[n, k] = sum_m d_y[m, n] x[m, k]
-    TokRedArgs a{};
-    TokRedPlan plan;
-    a.n_titles = g.Mp / 128; a.L = 128; a.taps = 1;
-    a.ids = nullptr; a.p = gb; a.ldp = g.Np; a.KP = (int)g.Np;
-    a.q = xb; a.ldq = g.Kp; a.NQ = (int)g.Kp; a.partial = partial;
-    if (int rc = tokred_plan(a, &plan)) return rc;
-    if (int rc = tokred_launch(plan, st)) return rc;
-    return tokred_reduce(plan, d_w, (int)N, (int)K, 1, K, 0, st);
+    return lt_wgrad(xb, g.Kp, gb, g.Np, g.Mp / 128, 128, g, partial, d_w, st);
   }
   // ---- gather mode: token-grouped ------------------------------------------------------------------------------------
   MR_REQUIRE(d_table != nullptr && K % 4 == 0 && table_rows >= align_up(V, 32) && table_ld >= g.Kp, MR_ERR_BAD_SHAPE,
@@ -235,7 +251,7 @@ int mr_linear_tc_bwd(const float* x, const void* ids, int ids_i64, const void* t
   __nv_bfloat16* Sb = ar.take<__nv_bfloat16>(g.Vp * g.Np);
   const int64_t ewb = mr_embed_grad_workspace_bytes(M, N, V);
   void* ews = ar.take<uint8_t>(ewb);
-  float* partial = ar.take<float>(tokred_partial_bytes(ceil_div(V, 32), 32, 1, (int)g.Np, (int)g.Kp) / 4);
+  float* partial = ar.take<float>(tokred_partial_bytes(ceil_div(V, 32), 32, 1, (int)g.Kp, (int)g.nbsz_n) / 4);
   MR_REQUIRE(ar.ok() && ewb >= 0, MR_ERR_WORKSPACE, "mr_linear_tc_bwd: workspace too small (%lld given)", (long long)workspace_bytes);
   // S[v, :] = sum over tokens with id v of d_y[t, :]  (every token counts here, the padding row too: it is an INPUT of the layer)
   if (int rc = mr_embed_grad_segreduce(ids, ids_i64, d_y, MR_F32, ldy, S, M, N, V, -1, ews, ewb, stream)) return rc;
@@ -247,14 +263,7 @@ int mr_linear_tc_bwd(const float* x, const void* ids, int ids_i64, const void* t
     return rc;
   if (padding_idx >= 0 && padding_idx < V) cudaMemsetAsync(d_table + padding_idx * K, 0, sizeof(float) * K, st);
   // d_w[n, k] = sum_v S[v, n] table[v, k]
-  TokRedArgs a{};
-  TokRedPlan plan;
-  a.n_titles = ceil_div(V, 32); a.L = 32; a.taps = 1;
-  a.ids = nullptr; a.p = Sb; a.ldp = g.Np; a.KP = (int)g.Np;
-  a.q = static_cast<const __nv_bfloat16*>(table_bf16); a.ldq = table_ld; a.NQ = (int)g.Kp; a.partial = partial;
-  if (int rc = tokred_plan(a, &plan)) return rc;
-  if (int rc = tokred_launch(plan, st)) return rc;
-  return tokred_reduce(plan, d_w, (int)N, (int)K, 1, K, 0, st);
+  return lt_wgrad(static_cast<const __nv_bfloat16*>(table_bf16), table_ld, Sb, g.Np, ceil_div(V, 32), 32, g, partial, d_w, st);
 }
 
 }  // extern "C"
