@@ -221,6 +221,16 @@ MR_API int mr_mha_core_bwd(const float* qk, const float* v, const float* prob, c
                     float* d_qk, float* d_v,
                     int64_t n, int64_t len, int64_t hn, int64_t dk, int64_t dv, void* stream);
 
+/* The same attention core with explicit row pitches, register-tiled (csrc/mha_attn.cu); limits len <= 64, dk, dv <= 32 (what
+ * the news / user encoders use).  q|k rows at qk + row * ldq (+ h * dk), v rows at v + row * ldv (+ h * dv): both may be column
+ * slices of one projection output.  ctx [n, len, hn*dv] and d_ctx are dense; the backward writes d_qk with pitch ldo_q and d_v
+ * with pitch ldo_v (slices of the projection's gradient buffer).  mr_mha_core_* use these kernels whenever the shape fits. */
+MR_API int mr_mha_attn_fwd(const float* qk, int64_t ldq, const float* v, int64_t ldv, const float* mask, float* prob, float* ctx,
+                    int64_t n, int64_t len, int64_t hn, int64_t dk, int64_t dv, void* stream);
+MR_API int mr_mha_attn_bwd(const float* qk, int64_t ldq, const float* v, int64_t ldv, const float* prob, const float* d_ctx,
+                    float* d_qk, int64_t ldo_q, float* d_v, int64_t ldo_v,
+                    int64_t n, int64_t len, int64_t hn, int64_t dk, int64_t dv, void* stream);
+
 /* Dense layer y = act(x W^T + b) and its gradients (nn.Linear, Attention.py:101-102; CNN.py:22).
  *   x [M,K], w [N,K], b [N] (may be NULL), y [M,N];  act: 0 none, 1 relu, 2 tanh.
  *   bwd: d_x = d_y W  (NULL to skip), d_w = d_y^T x, d_b = colsum(d_y); d_y is the gradient wrt

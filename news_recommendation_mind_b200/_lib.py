@@ -53,6 +53,8 @@ _SIGNATURES = {
     "mr_avgpool_bwd": (c_int, [P, P, I64, I64, I64, P]),
     "mr_mha_core_fwd": (c_int, [P, P, P, P, P, I64, I64, I64, I64, I64, P]),
     "mr_mha_core_bwd": (c_int, [P, P, P, P, P, P, I64, I64, I64, I64, I64, P]),
+    "mr_mha_attn_fwd": (c_int, [P, I64, P, I64, P, P, P, I64, I64, I64, I64, I64, P]),
+    "mr_mha_attn_bwd": (c_int, [P, I64, P, I64, P, P, P, I64, P, I64, I64, I64, I64, I64, I64, P]),
     "mr_linear_workspace_bytes": (I64, [I64, I64, I64]),
     "mr_linear_fwd": (c_int, [P, P, P, P, I64, I64, I64, c_int, c_int, P]),
     "mr_linear_bwd": (c_int, [P, P, P, P, P, P, I64, I64, I64, c_int, P, I64, P]),

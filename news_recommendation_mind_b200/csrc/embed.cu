@@ -113,6 +113,8 @@ seg_reduce_l1_kernel(const T* __restrict__ d_emb, int64_t ld, const int32_t* __r
                      const int32_t* __restrict__ seg_start, const int32_t* __restrict__ chunk_off,
                      const int32_t* __restrict__ chunk_row, const int32_t* __restrict__ nchunk,
                      float* __restrict__ d_table, float* __restrict__ partial, int64_t n_chunks, int64_t E, int64_t V) {
+  // partial rows have pitch Ep = E rounded up to 4 (16-byte rows: the heavy-row kernels read float4 whatever E is)
+  const int64_t Ep = (E + 3) & ~(int64_t)3;
   using R = RowReader<T>;
   constexpr int VEC = R::VEC;
   const int lane = threadIdx.x & 31;
@@ -122,7 +124,7 @@ seg_reduce_l1_kernel(const T* __restrict__ d_emb, int64_t ld, const int32_t* __r
   const int32_t j = (int32_t)ch - chunk_off[v];
   const int32_t beg = seg_start[v] + j * SEG_CHUNK;
   const int32_t end = min(seg_start[v + 1], beg + SEG_CHUNK);
-  float* dst = (nchunk[v] == 1) ? d_table + (int64_t)v * E : partial + ch * E;
+  float* dst = (nchunk[v] == 1) ? d_table + (int64_t)v * E : partial + ch * Ep;
   // vector path: rows are read in VEC-wide pieces up to the row pitch (columns in [E, ld) are padding the
   // producer keeps at zero); only the first E sums are written back.
   const int64_t nv = (E + VEC - 1) / VEC;
@@ -198,10 +200,11 @@ seg_reduce_l2_kernel(const int32_t* __restrict__ chunk_off, const int32_t* __res
     }
     return;
   }
-  const float* src = partial + (int64_t)chunk_off[v] * E;
+  const int64_t Ep = (E + 3) & ~(int64_t)3;
+  const float* src = partial + (int64_t)chunk_off[v] * Ep;
   for (int64_t e = lane; e < E; e += 32) {
     float s = 0.f;
-    for (int32_t j = 0; j < n; ++j) s += src[(int64_t)j * E + e];
+    for (int32_t j = 0; j < n; ++j) s += src[(int64_t)j * Ep + e];
     dst[e] = seg_out<TO>(s);
   }
 }
@@ -250,7 +253,8 @@ seg_reduce_heavy_kernel(const int32_t* __restrict__ chunk_off, const int32_t* __
   if (nh == 0) return;
   const int n_items = min(heavy_prefix(heavy_rows, nchunk, nh, off), max_items);
   const int rg = threadIdx.x >> 7, cv = threadIdx.x & 127;
-  const int64_t nv = E >> 2;                             // E % 4 == 0 (checked on the host)
+  const int64_t Ep = (E + 3) & ~(int64_t)3;              // pitch of the partial rows (columns E..Ep-1 are never read back)
+  const int64_t nv = Ep >> 2;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     int lo = 0, hi = nh;                                 // off[lo] <= item < off[hi]
     while (hi - lo > 1) {
@@ -260,24 +264,24 @@ seg_reduce_heavy_kernel(const int32_t* __restrict__ chunk_off, const int32_t* __
     const int32_t v = heavy_rows[lo];
     const int32_t n = nchunk[v];
     const int32_t j0 = (item - off[lo]) * SEG_SLICE, j1 = min(n, j0 + SEG_SLICE);
-    const float* src = partial + (int64_t)chunk_off[v] * E;
+    const float* src = partial + (int64_t)chunk_off[v] * Ep;
     for (int64_t c0 = 0; c0 < nv; c0 += 128) {
       const int64_t c = c0 + cv;
       float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
       if (c < nv) {
         int32_t j = j0 + rg;
         for (; j + 6 < j1; j += 8) {
-          const float4 x0 = *reinterpret_cast<const float4*>(src + (int64_t)j * E + 4 * c);
-          const float4 x1 = *reinterpret_cast<const float4*>(src + (int64_t)(j + 2) * E + 4 * c);
-          const float4 x2 = *reinterpret_cast<const float4*>(src + (int64_t)(j + 4) * E + 4 * c);
-          const float4 x3 = *reinterpret_cast<const float4*>(src + (int64_t)(j + 6) * E + 4 * c);
+          const float4 x0 = *reinterpret_cast<const float4*>(src + (int64_t)j * Ep + 4 * c);
+          const float4 x1 = *reinterpret_cast<const float4*>(src + (int64_t)(j + 2) * Ep + 4 * c);
+          const float4 x2 = *reinterpret_cast<const float4*>(src + (int64_t)(j + 4) * Ep + 4 * c);
+          const float4 x3 = *reinterpret_cast<const float4*>(src + (int64_t)(j + 6) * Ep + 4 * c);
           a0.x += x0.x; a0.y += x0.y; a0.z += x0.z; a0.w += x0.w;
           a1.x += x1.x; a1.y += x1.y; a1.z += x1.z; a1.w += x1.w;
           a2.x += x2.x; a2.y += x2.y; a2.z += x2.z; a2.w += x2.w;
           a3.x += x3.x; a3.y += x3.y; a3.z += x3.z; a3.w += x3.w;
         }
         for (; j < j1; j += 2) {
-          const float4 x0 = *reinterpret_cast<const float4*>(src + (int64_t)j * E + 4 * c);
+          const float4 x0 = *reinterpret_cast<const float4*>(src + (int64_t)j * Ep + 4 * c);
           a0.x += x0.x; a0.y += x0.y; a0.z += x0.z; a0.w += x0.w;
         }
       }
@@ -287,7 +291,7 @@ seg_reduce_heavy_kernel(const int32_t* __restrict__ chunk_off, const int32_t* __
       __syncthreads();
       if (rg == 0 && c < nv) {
         const float4 u = red[cv];
-        *reinterpret_cast<float4*>(partial2 + (int64_t)item * E + 4 * c) = make_float4(t.x + u.x, t.y + u.y, t.z + u.z, t.w + u.w);
+        *reinterpret_cast<float4*>(partial2 + (int64_t)item * Ep + 4 * c) = make_float4(t.x + u.x, t.y + u.y, t.z + u.z, t.w + u.w);
       }
       __syncthreads();
     }
@@ -308,6 +312,7 @@ seg_reduce_heavy_final_kernel(const float* __restrict__ partial2, TO* __restrict
   const int nh = min(*heavy_count, SEG_MAX_HEAVY_SMEM);
   if (nh == 0) return;
   heavy_prefix(heavy_rows, nchunk, nh, off);
+  const int64_t Ep = (E + 3) & ~(int64_t)3;
   const int cx = threadIdx.x & 63, sg = threadIdx.x >> 6;
   const int64_t e = (int64_t)blockIdx.y * 64 + cx;
   for (int h = blockIdx.x; h < nh; h += gridDim.x) {
@@ -320,12 +325,12 @@ seg_reduce_heavy_final_kernel(const float* __restrict__ partial2, TO* __restrict
     if (e < E) {
       int i = a;
       for (; i + 3 < b; i += 4) {
-        a0 += partial2[(int64_t)i * E + e];
-        a1 += partial2[(int64_t)(i + 1) * E + e];
-        a2 += partial2[(int64_t)(i + 2) * E + e];
-        a3 += partial2[(int64_t)(i + 3) * E + e];
+        a0 += partial2[(int64_t)i * Ep + e];
+        a1 += partial2[(int64_t)(i + 1) * Ep + e];
+        a2 += partial2[(int64_t)(i + 2) * Ep + e];
+        a3 += partial2[(int64_t)(i + 3) * Ep + e];
       }
-      for (; i < b; ++i) a0 += partial2[(int64_t)i * E + e];
+      for (; i < b; ++i) a0 += partial2[(int64_t)i * Ep + e];
     }
     red[sg][cx] = (a0 + a1) + (a2 + a3);
     __syncthreads();
@@ -347,9 +352,8 @@ static EmbedGradPlan plan_embed_grad(int64_t T, int64_t E, int64_t V) {
   // kernels read float4 columns, so a row length that is not a multiple of 4 keeps everything on level 2
   int64_t thr = SEG_HEAVY;
   while (T / ((int64_t)SEG_CHUNK * thr) + 1 > 2048) thr *= 2;
-  if (E % 4 != 0) thr = 0x7fffffff;
   p.heavy_thr = (int32_t)thr;
-  p.max_heavy = E % 4 != 0 ? 1 : T / ((int64_t)SEG_CHUNK * thr) + 1;
+  p.max_heavy = T / ((int64_t)SEG_CHUNK * thr) + 1;
   p.max_items = p.max_chunks / 64 + p.max_heavy;                // slices of <= SEG_SLICE partial rows
   int bits = 1;
   while ((1ll << bits) < V) ++bits;
@@ -596,8 +600,8 @@ int64_t mr_embed_grad_workspace_bytes(int64_t T, int64_t E, int64_t V) {
   b += arena_bytes(V + 1, 4);                 // seg_start
   b += 2 * arena_bytes(V + 1, 4);             // nchunk, chunk_off
   b += arena_bytes(p.max_chunks, 4);          // chunk_row
-  b += arena_bytes(p.max_chunks * E, 4);      // partial rows
-  b += arena_bytes(p.max_heavy + 1, 4) + arena_bytes(p.max_items * E, 4);   // heavy list, heavy partials
+  b += arena_bytes(p.max_chunks * align_up(E, 4), 4);      // partial rows (16-byte pitch)
+  b += arena_bytes(p.max_heavy + 1, 4) + arena_bytes(p.max_items * align_up(E, 4), 4);   // heavy list, heavy partials
   b += arena_bytes((int64_t)p.cub_sort_bytes, 1) + arena_bytes((int64_t)p.cub_scan_bytes, 1);
   return b + 256;
 }
@@ -626,9 +630,9 @@ int mr_embed_grad_segreduce(const void* ids, int ids_i64, const void* d_emb, int
   int32_t* nchunk = ar.take<int32_t>(V + 1);
   int32_t* chunk_off = ar.take<int32_t>(V + 1);
   int32_t* chunk_row = ar.take<int32_t>(p.max_chunks);
-  float* partial = ar.take<float>(p.max_chunks * E);
+  float* partial = ar.take<float>(p.max_chunks * align_up(E, 4));
   int32_t* heavy = ar.take<int32_t>(p.max_heavy + 1);            // [0] = count, [1..] = rows
-  float* partial2 = ar.take<float>(p.max_items * E);
+  float* partial2 = ar.take<float>(p.max_items * align_up(E, 4));
   void* cub_sort = ar.take<char>((int64_t)p.cub_sort_bytes);
   void* cub_scan = ar.take<char>((int64_t)p.cub_scan_bytes);
   MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "mr_embed_grad_segreduce: workspace too small (%lld given)", (long long)workspace_bytes);

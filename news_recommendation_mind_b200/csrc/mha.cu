@@ -4,6 +4,13 @@
 #include "gemm_simt.cuh"
 
 namespace mr {
+// register-tiled kernels for len <= 64, dk, dv <= 32 (mha_attn.cu); the kernels below remain for larger shapes
+bool mha_attn_supported(int64_t len, int64_t dk, int64_t dv);
+int mha_attn_fwd(const float* qk, int64_t ldq, const float* v, int64_t ldv, const float* mask, float* prob, float* ctx, int64_t ldc,
+                 int64_t n, int64_t len, int64_t hn, int64_t dk, int64_t dv, cudaStream_t st);
+int mha_attn_bwd(const float* qk, int64_t ldq, const float* v, int64_t ldv, const float* prob, const float* d_ctx, int64_t ldg,
+                 float* d_qk, int64_t ldo_q, float* d_v, int64_t ldo_v, int64_t n, int64_t len, int64_t hn, int64_t dk, int64_t dv,
+                 cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
 // attention core: one CTA per (sequence, head).  qk/v rows are staged in shared memory, each
@@ -251,6 +258,8 @@ int mr_mha_core_fwd(const float* qk, const float* v, const float* mask, float* p
   MR_REQUIRE(qk && v && prob && ctx, MR_ERR_NULL, "mr_mha_core_fwd: null pointer");
   MR_REQUIRE(n >= 0 && len >= 1 && hn >= 1 && dk >= 1 && dv >= 1, MR_ERR_BAD_SHAPE, "mr_mha_core_fwd: bad shape");
   if (n == 0) return MR_OK;
+  if (mha_attn_supported(len, dk, dv) && n * hn < (1ll << 31))
+    return mha_attn_fwd(qk, hn * dk, v, hn * dv, mask, prob, ctx, hn * dv, n, len, hn, dk, dv, as_stream(stream));
   size_t smem = mha_smem_fwd(len, dk, dv);
   MR_REQUIRE(smem <= 200 * 1024, MR_ERR_UNSUPPORTED, "mr_mha_core_fwd: len=%lld too long", (long long)len);
   if (smem > 48 * 1024) cudaFuncSetAttribute(mha_core_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -266,6 +275,8 @@ int mr_mha_core_bwd(const float* qk, const float* v, const float* prob, const fl
   MR_REQUIRE(qk && v && prob && d_ctx && d_qk && d_v, MR_ERR_NULL, "mr_mha_core_bwd: null pointer");
   MR_REQUIRE(n >= 0 && len >= 1 && hn >= 1 && dk >= 1 && dv >= 1, MR_ERR_BAD_SHAPE, "mr_mha_core_bwd: bad shape");
   if (n == 0) return MR_OK;
+  if (mha_attn_supported(len, dk, dv) && n * hn < (1ll << 31))
+    return mha_attn_bwd(qk, hn * dk, v, hn * dv, prob, d_ctx, hn * dv, d_qk, hn * dk, d_v, hn * dv, n, len, hn, dk, dv, as_stream(stream));
   size_t smem = mha_smem_bwd(len, dk, dv);
   MR_REQUIRE(smem <= 200 * 1024, MR_ERR_UNSUPPORTED, "mr_mha_core_bwd: len=%lld too long", (long long)len);
   if (smem > 48 * 1024) cudaFuncSetAttribute(mha_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

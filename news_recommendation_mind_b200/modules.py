@@ -288,14 +288,8 @@ class MultiheadAttention(nn.Module):
         b = torch.cat([self.keyProject.bias, self.valueProject.bias], dim=0)
         nk, nv = self.key_dim * self.head_num, self.value_dim * self.head_num
         if ids is None:
-            n, length = hidden_states.shape[0], hidden_states.shape[1]
-            y = ops.LinearTC.apply(hidden_states, None, None, None, w, b)
-        else:
-            n, length = ids.shape
-            y = ops.LinearTC.apply(None, ids, embedding.weight, embedding.shadow_bf16(), w, b)
-        qk = y[:, :nk].reshape(n, length, nk)
-        v = y[:, nk:nk + nv].reshape(n, length, nv)
-        return ops.MHACore.apply(qk, v, token_mask, self.head_num)
+            return ops.MHABlock.apply(hidden_states, None, None, None, w, b, token_mask, self.head_num, nk, nv)
+        return ops.MHABlock.apply(None, ids, embedding.weight, embedding.shadow_bf16(), w, b, token_mask, self.head_num, nk, nv)
 
 
 class MHA_Encoder(nn.Module):

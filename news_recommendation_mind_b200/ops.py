@@ -534,6 +534,49 @@ class Linear(torch.autograd.Function):
         return d_x, d_w, d_b, None
 
 
+def _linear_tc_fwd(x, ids, table, table_bf16, w, b):
+    """-> (y [M, ldy] fp32 padded, saved state) -- mr_linear_tc_fwd"""
+    lib = _lib.load()
+    wc = _f32c(w)
+    bc = None if b is None else _f32c(b)
+    N, K = wc.shape
+    dev = wc.device
+    if x is not None:
+        xc = _f32c(x).reshape(-1, K)
+        M, V, ids_c, tab = xc.shape[0], 0, None, None
+    else:
+        ids_c = _idx(ids).reshape(-1)
+        xc, tab = None, table_bf16
+        M, V = ids_c.numel(), table.shape[0]
+        if table.shape[1] != K or tab.dtype != torch.bfloat16:
+            raise ValueError("LinearTC: table width %d != K %d or shadow not bf16" % (table.shape[1], K))
+    ldy = pad_to(N, 4)
+    y = torch.empty(M, ldy, dtype=torch.float32, device=dev)
+    ws = workspace(lib.mr_linear_tc_workspace_bytes(M, N, K, V, 0), dev)
+    check(lib.mr_linear_tc_fwd(ptr(xc), ptr(ids_c), index_flag(ids_c) if ids_c is not None else 0, ptr(tab),
+                               tab.shape[1] if tab is not None else 0, V, ptr(wc), ptr(bc), ptr(y), ldy, M, N, K, ptr(ws), ws.numel(),
+                               stream_ptr(dev)), "mr_linear_tc_fwd")
+    return y, (xc, ids_c, tab, wc), (M, N, K, V, ldy)
+
+
+def _linear_tc_bwd(saved, dims, d_y, has_bias, need_x):
+    """-> (d_x | None, d_table | None, d_w, d_b | None) -- mr_linear_tc_bwd; d_y [M, ldy] fp32 contiguous"""
+    lib = _lib.load()
+    xc, ids_c, tab, wc = saved
+    M, N, K, V, ldy = dims
+    dev = wc.device
+    d_w = torch.empty(N, K, dtype=torch.float32, device=dev)
+    d_b = torch.empty(N, dtype=torch.float32, device=dev) if has_bias else None
+    d_x = torch.empty(M, K, dtype=torch.float32, device=dev) if (need_x and xc is not None) else None
+    d_table = torch.empty(V, K, dtype=torch.float32, device=dev) if xc is None else None
+    ws = workspace(lib.mr_linear_tc_workspace_bytes(M, N, K, V, 1), dev)
+    check(lib.mr_linear_tc_bwd(ptr(xc), ptr(ids_c), index_flag(ids_c) if ids_c is not None else 0, ptr(tab),
+                               tab.shape[1] if tab is not None else 0, tab.shape[0] if tab is not None else 0, V, 0, ptr(wc), ptr(d_y), ldy,
+                               ptr(d_x), ptr(d_table), ptr(d_w), ptr(d_b), M, N, K, ptr(ws), ws.numel(), stream_ptr(dev)),
+          "mr_linear_tc_bwd")
+    return d_x, d_table, d_w, d_b
+
+
 class LinearTC(torch.autograd.Function):
     """y = x W^T + b on the tcgen05 tensor cores (bf16 operands, fp32 accumulate / output) -- the MR_BF16 path of the attention
     projections.  Input: dense ``x`` [M, K] fp32, or (``x`` None) token ``ids`` [M] whose rows of the bf16 table shadow are gathered
@@ -542,28 +585,9 @@ class LinearTC(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, ids, table, table_bf16, w, b):
-        lib = _lib.load()
-        wc = _f32c(w)
-        bc = None if b is None else _f32c(b)
-        N, K = wc.shape
-        dev = wc.device
-        if x is not None:
-            xc = _f32c(x).reshape(-1, K)
-            M, V, ids_c, tab = xc.shape[0], 0, None, None
-        else:
-            ids_c = _idx(ids).reshape(-1)
-            xc, tab = None, table_bf16
-            M, V = ids_c.numel(), table.shape[0]
-            if table.shape[1] != K or tab.dtype != torch.bfloat16:
-                raise ValueError("LinearTC: table width %d != K %d or shadow not bf16" % (table.shape[1], K))
-        ldy = pad_to(N, 4)
-        y = torch.empty(M, ldy, dtype=torch.float32, device=dev)
-        ws = workspace(lib.mr_linear_tc_workspace_bytes(M, N, K, V, 0), dev)
-        check(lib.mr_linear_tc_fwd(ptr(xc), ptr(ids_c), index_flag(ids_c) if ids_c is not None else 0, ptr(tab),
-                                   tab.shape[1] if tab is not None else 0, V, ptr(wc), ptr(bc), ptr(y), ldy, M, N, K, ptr(ws), ws.numel(),
-                                   stream_ptr(dev)), "mr_linear_tc_fwd")
-        ctx.save_for_backward(xc, ids_c, tab, wc)
-        ctx.dims = (M, N, K, V, ldy)
+        y, saved, dims = _linear_tc_fwd(x, ids, table, table_bf16, w, b)
+        ctx.save_for_backward(*saved)
+        ctx.dims = dims
         ctx.has_bias = b is not None
         ctx.x_shape = None if x is None else tuple(x.shape)
         ctx.need_x = x is not None and x.requires_grad
@@ -572,23 +596,52 @@ class LinearTC(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_y):
-        lib = _lib.load()
-        xc, ids_c, tab, wc = ctx.saved_tensors
-        M, N, K, V, ldy = ctx.dims
-        dev = wc.device
-        g = _f32c(d_y)
-        d_w = torch.empty(N, K, dtype=torch.float32, device=dev)
-        d_b = torch.empty(N, dtype=torch.float32, device=dev) if ctx.has_bias else None
-        d_x = torch.empty(M, K, dtype=torch.float32, device=dev) if ctx.need_x else None
-        d_table = torch.empty(V, K, dtype=torch.float32, device=dev) if xc is None else None
-        ws = workspace(lib.mr_linear_tc_workspace_bytes(M, N, K, V, 1), dev)
-        check(lib.mr_linear_tc_bwd(ptr(xc), ptr(ids_c), index_flag(ids_c) if ids_c is not None else 0, ptr(tab),
-                                   tab.shape[1] if tab is not None else 0, tab.shape[0] if tab is not None else 0, V, 0, ptr(wc), ptr(g), ldy,
-                                   ptr(d_x), ptr(d_table), ptr(d_w), ptr(d_b), M, N, K, ptr(ws), ws.numel(), stream_ptr(dev)),
-              "mr_linear_tc_bwd")
+        d_x, d_table, d_w, d_b = _linear_tc_bwd(ctx.saved_tensors, ctx.dims, _f32c(d_y), ctx.has_bias, ctx.need_x)
         if d_x is not None:
             d_x = d_x.view(ctx.x_shape)
         return d_x, None, (d_table if ctx.need_table else None), None, d_w, d_b
+
+
+class MHABlock(torch.autograd.Function):
+    """MR_BF16 multi-head self-attention block (Attention.py:115-147): [keyProject; valueProject] as ONE tcgen05 GEMM
+    (mr_linear_tc_*) followed by the register-tiled attention core (mr_mha_attn_*).  The q|k and v slices of the projection
+    output are read in place (row pitch), and the backward writes d_qk / d_v straight into the projection gradient: no slice
+    copies, no concatenation.  Input: dense x [n, len, K], or token ids [n, len] (rows gathered from the bf16 table)."""
+
+    @staticmethod
+    def forward(ctx, x, ids, table, table_bf16, w, b, mask, head_num, nk, nv):
+        lib = _lib.load()
+        n, length = (x.shape[0], x.shape[1]) if x is not None else tuple(ids.shape)
+        y, saved, dims = _linear_tc_fwd(x, ids, table, table_bf16, w, b)
+        dev, ldy = y.device, dims[4]
+        dk, dv = nk // head_num, nv // head_num
+        mc = None if mask is None else mask.to(device=dev, dtype=torch.float32).reshape(n, length).contiguous()
+        prob = torch.empty(n, head_num, length, length, dtype=torch.float32, device=dev)
+        out = torch.empty(n, length, nv, dtype=torch.float32, device=dev)
+        check(lib.mr_mha_attn_fwd(ptr(y), ldy, c_void_p(y.data_ptr() + 4 * nk), ldy, ptr(mc), ptr(prob), ptr(out), n, length, head_num,
+                                  dk, dv, stream_ptr(dev)), "mr_mha_attn_fwd")
+        ctx.save_for_backward(*saved, y, prob)
+        ctx.dims, ctx.geom = dims, (n, length, head_num, dk, dv, nk, nv)
+        ctx.has_bias = b is not None
+        ctx.x_shape = None if x is None else tuple(x.shape)
+        ctx.need_x = x is not None and x.requires_grad
+        ctx.need_table = table is not None and table.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        *saved, y, prob = ctx.saved_tensors
+        n, length, hn, dk, dv, nk, nv = ctx.geom
+        ldy = ctx.dims[4]
+        g = _f32c(d_out)
+        d_y = torch.empty_like(y)                       # columns >= nk + nv are padding: never read by mr_linear_tc_bwd
+        check(lib.mr_mha_attn_bwd(ptr(y), ldy, c_void_p(y.data_ptr() + 4 * nk), ldy, ptr(prob), ptr(g), ptr(d_y), ldy,
+                                  c_void_p(d_y.data_ptr() + 4 * nk), ldy, n, length, hn, dk, dv, stream_ptr(y.device)), "mr_mha_attn_bwd")
+        d_x, d_table, d_w, d_b = _linear_tc_bwd(tuple(saved), ctx.dims, d_y, ctx.has_bias, ctx.need_x)
+        if d_x is not None:
+            d_x = d_x.view(ctx.x_shape)
+        return d_x, None, (d_table if ctx.need_table else None), None, d_w, d_b, None, None, None, None
 
 
 class MHACore(torch.autograd.Function):

@@ -2,6 +2,7 @@
 (torch.profiler): warm caches, real overlap -- complements the serialised cold-cache ncu launch list.
 
     python scripts/step_kernels.py [steps] > gpurun_out/step_kernels.txt
+    CONFIG=2|3|5 (BASELINE configuration, default 2)   BATCH=tokens|ids|dedup (batch contract, default tokens)
 """
 import os, sys, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -11,14 +12,18 @@ import news_recommendation_mind_b200 as mr
 from news_recommendation_mind_b200 import data, trainer
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-CFG = bench.CFG
+CFG = bench.CONFIGS[int(os.environ.get("CONFIG", "2"))]
 dev = "cuda:0"
 torch.manual_seed(42)
-man = bench.manager_ns(dev, os.environ.get("MINDREC_PRECISION", "bf16"))
-model = mr.TwoTower(man, mr.BERT_Embedding(man, vocab_size=CFG["V"]), mr.CNN_Encoder(man), mr.RNN_User_Encoder(man)).to(dev)
+model = bench.build_model(CFG, dev, os.environ.get("MINDREC_PRECISION", "bf16"))
 opt = trainer.FusedAdam(model, lr=1e-4, bert_lr=6e-6)
 ids, mask = data.make_news_table(CFG["n_news"], CFG["L"])
-devb = [{k: v.to(dev) for k, v in data.make_train_batch(ids, mask, CFG["B"], CFG["C"], CFG["S"], seed=i).items()} for i in range(4)]
+mode = os.environ.get("BATCH", "tokens")
+kw = {} if mode == "tokens" else ({"id_only": True} if mode == "ids" else {"id_only": True, "dedup_capacity": (CFG["B"] * (CFG["C"] + CFG["S"]) * 7 // 16 + 255) // 256 * 256})
+if mode != "tokens":
+    model.attach_news_tokens(ids, mask)
+devb = [{k: v.to(dev) for k, v in data.make_train_batch(ids, mask, CFG["B"], CFG["C"], CFG["S"], seed=i, n_users=CFG["n_users"], **kw).items()} for i in range(4)]
+print("config", os.environ.get("CONFIG", "2"), "batch", mode, {k: tuple(v.shape) for k, v in devb[0].items()})
 for s in range(5):
     trainer.train_step(model, devb[s % 4], opt)
 torch.cuda.synchronize()
