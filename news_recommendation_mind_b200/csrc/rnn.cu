@@ -433,7 +433,8 @@ static int64_t rnn_ws(const mr_rnn_shape* s, int backward) {
   int64_t b = 0;
   if (!backward) {
     b += arena_bytes(BS * align_up(GH, 4), 4);   // xp
-    b += arena_bytes(s->H * GH + rnn_res_scratch_bytes(s->kind, (int)s->H) / 4 + rnn_mma_scratch_bytes(s->kind, (int)s->H) / 4, 4);   // whhT / bf16 images of W_hh
+    b += arena_bytes(s->H * GH + rnn_res_scratch_bytes(s->kind, (int)s->H) / 4 + rnn_mma_scratch_bytes(s->kind, (int)s->H) / 4 +
+                     rnn_tc_scratch_bytes(s->kind, (int)s->H) / 4, 4);   // whhT / bf16 images of W_hh
     if (rnn_tc_ok(s)) b += rnn_tc_ws(s, 0);
     return b + 256;
   }
@@ -488,7 +489,8 @@ int mr_rnn_user_fwd(const mr_rnn_shape* s, const float* x, const int32_t* lens, 
   Arena ar(workspace, workspace_bytes);
   const int64_t ldx = rnn_tc_ok(s) ? align_up(GH, 4) : GH;       // pitch of the input projection (16-byte rows for the tensor-core epilogue)
   float* xp = ar.take<float>((int64_t)B * S * ldx);
-  float* whhT = ar.take<float>((int64_t)H * GH + rnn_res_scratch_bytes(s->kind, H) / 4 + rnn_mma_scratch_bytes(s->kind, H) / 4);
+  float* whhT = ar.take<float>((int64_t)H * GH + rnn_res_scratch_bytes(s->kind, H) / 4 + rnn_mma_scratch_bytes(s->kind, H) / 4 +
+                               rnn_tc_scratch_bytes(s->kind, H) / 4);
   MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "mr_rnn_user_fwd: workspace too small (%lld given)", (long long)workspace_bytes);
   if (rnn_tc_ok(s)) {
     if (int rc = rnn_tc_input_proj(s, x, w_ih, b_ih, s->kind == MR_RNN_LSTM ? b_hh : nullptr, xp, ar, st)) return rc;
@@ -506,6 +508,8 @@ int mr_rnn_user_fwd(const mr_rnn_shape* s, const float* x, const int32_t* lens, 
     cudaMemsetAsync(hs, 0, sizeof(float) * (int64_t)B * S * H, st);
     cudaMemsetAsync(cs, 0, sizeof(float) * (int64_t)B * S * H, st);
   }
+  if (s->precision == MR_BF16 && resident_path && rnn_tc_supported(s->kind, H))
+    return rnn_tc_fwd(s->kind, xp, (int)ldx, w_hh, h0, lens, gates, hs, cs, user, B, S, H, whhT, st);
   if (s->precision == MR_BF16 && rnn_mma_supported(s->kind, H) && rnn_use_mma())
     return rnn_mma_fwd(s->kind, xp, (int)ldx, w_hh, b_hh, h0, lens, gates, hs, cs, user, B, S, H, whhT, st);
   if (s->precision == MR_BF16 && rnn_res_supported(s->kind, H))

@@ -29,4 +29,10 @@ int64_t rnn_mma_scratch_bytes(int kind, int H);
 int rnn_mma_fwd(int kind, const float* xp, int ldx, const float* w_hh, const float* b_hh, const float* h0, const int32_t* lens,
                 float* gates, float* hs, float* cs, float* user, int B, int S, int H, void* scratch, cudaStream_t st);
 
+// ---- rnn_tc.cu: the LSTM recurrence as tcgen05.mma batches, W_hh resident in shared memory (A operand), h as bf16 hi + lo (B operand) ----
+bool rnn_tc_supported(int kind, int H);                // LSTM, H <= 160 (MINDREC_RNN_TC=0 disables)
+int64_t rnn_tc_scratch_bytes(int kind, int H);
+int rnn_tc_fwd(int kind, const float* xp, int ldx, const float* w_hh, const float* h0, const int32_t* lens, float* gates, float* hs,
+               float* cs, float* user, int B, int S, int H, void* scratch, cudaStream_t st);
+
 }  // namespace mr
