@@ -12,6 +12,7 @@
 // Shapes: Hp = H rounded up to 16 (<= 256), Kp = E rounded up to 16; the bf16 token table has row
 // pitch align_up(E, 64) (the shadow kept by the Python BERT_Embedding / written by mr_adam_step).
 #include "news_cnn_tc.cuh"
+#include "cnn_tail.cuh"
 #include "pool_kernels.cuh"
 #include "tapgemm.cuh"
 #include "tokred.cuh"
@@ -71,6 +72,7 @@ int64_t news_cnn_tc_workspace_bytes(const mr_cnn_shape* s, int backward) {
   const int64_t pc = tokred_partial_bytes(s->N, (int)s->L, 3, (int)Kp, (int)Hp);
   const int64_t pp = tokred_partial_bytes(s->N, (int)s->L, 1, (int)Hp, (int)Hp);
   b += arena_bytes(pc > pp ? pc : pp, 1);
+  if (cnn_tail_supported(s->L, Hp)) b += arena_bytes(cnn_tail_bwd_workspace_bytes(s->N, s->L, Hp), 1);
   return b;
 }
 
@@ -127,6 +129,9 @@ int news_cnn_tc_fwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
     cudaEventRecord(g_conv_timing.end[slot], st);
     ++g_conv_timing.count;
   }
+  // projection + tanh + pooling in one kernel (cnn_tail.cu) for titles of 16..32 tokens
+  if (cnn_tail_supported(L, Hp))
+    return cnn_tail_fwd(N, L, H, c, mask, mask_i64, query, proj_b, wproj, key, prob, news, st);
   // projection: key = tanh(c Wq^T + bq)
   TapGemmArgs b{};
   b.n_titles = N; b.L = (int)L; b.taps = 1; b.dir = 1; b.K = (int)Hp;
@@ -185,6 +190,10 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
   const int64_t pb_conv = tokred_partial_bytes(N, (int)L, 3, (int)Kp, (int)Hp);
   const int64_t pb_proj = tokred_partial_bytes(N, (int)L, 1, (int)Hp, (int)Hp);
   float* partial = ar.take<float>((pb_conv > pb_proj ? pb_conv : pb_proj) / 4);
+  // projection + pooling backward as ONE kernel (cnn_tail.cu) unless a gradient arrives at the token representations too
+  const bool fused_tail = cnn_tail_supported(L, Hp) && d_c == nullptr;
+  const int64_t tail_wsb = cnn_tail_supported(L, Hp) ? cnn_tail_bwd_workspace_bytes(N, L, Hp) : 0;
+  uint8_t* tail_ws = tail_wsb ? ar.take<uint8_t>(tail_wsb) : nullptr;
   MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "mr_news_cnn_bwd: workspace too small (%lld given)", (long long)wsb);
   MR_REQUIRE(3 * Hp <= 512, MR_ERR_UNSUPPORTED, "mr_news_cnn_bwd: hidden_dim %lld > 160 is not supported by the bf16 backward", (long long)H);
 
@@ -193,7 +202,10 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
   //    it from prob and the padded copy of d_news; generic path: dcv = p * d_news.
   const bool fast_pool = L <= 32 && Hp <= 160;
   cudaError_t e;
-  if (fast_pool) {
+  if (fused_tail) {
+    if (int rc = tapgemm_pack(proj_w, wpb, 1, (int)Hp, (int)Hp, (int)H, (int)H, 1, H, 0, st)) return rc;
+    if (int rc = cnn_tail_bwd(N, L, H, c, key, prob, d_news, query, wpb, dcv, d_proj_w, d_proj_b, d_query, d_conv_b, tail_ws, tail_wsb, st)) return rc;
+  } else if (fast_pool) {
     const unsigned grid = (unsigned)ceil_div(N, 8);
     if (Hp <= 64) launch_pdl(cnn_pool_bwd_bf16_kernel<1>, dim3(grid), dim3(256), 0, st, c, key, Hp, prob, query, d_news, dkp, dnp, ppart, cmask, N, (int)L, (int)H);
     else if (Hp <= 128) launch_pdl(cnn_pool_bwd_bf16_kernel<2>, dim3(grid), dim3(256), 0, st, c, key, Hp, prob, query, d_news, dkp, dnp, ppart, cmask, N, (int)L, (int)H);
@@ -219,7 +231,7 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
   }
 
   // 2. d_proj_w[n,k] = sum_t dkp[t,n] c[t,k]
-  {
+  if (!fused_tail) {
     TokRedArgs a{};
     TokRedPlan plan;
     a.n_titles = N; a.L = (int)L; a.taps = 1;
@@ -231,7 +243,7 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
   }
   // 3. dconv = relu'(c) * (p * d_news + dkp Wq)   -> dcv;  the conv-bias gradient (column sums of dconv) comes out of
   //    the same epilogue as per-warp partials
-  {
+  if (!fused_tail) {
     if (int rc = tapgemm_pack(proj_w, wpb, 1, (int)Hp, (int)Hp, (int)H, (int)H, 1, H, 0, st)) return rc;
     TapGemmArgs a{};
     TapGemmPlan plan;

@@ -15,7 +15,8 @@ struct SelfTestArgs {
   int N, K;                     // MMA N (multiple of 16, <= 256) and total K (multiple of 16)
   int a_shift, halo;            // A operand starts `a_shift` rows later (|a_shift| <= halo)
   int swap;                     // debug: swap the LBO / SBO fields
-  int a_layout, b_layout;       // 0 = SWIZZLE_NONE panel layout; 2/4/6 = row-linear SWIZZLE_128B/64B/32B (tc05.cuh)
+  int a_layout, b_layout;       // 0 = SWIZZLE_NONE panel layout; 2/4/6 = row-linear SWIZZLE_128B/64B/32B (tc05.cuh);
+                                // a_layout 8: the A operand is read from TENSOR MEMORY (K-major, bf16 pairs per 32-bit column)
   int base_off_mode;            // swizzled operands: 0 = base_offset field 0, 1 = (start >> 7) & 7
 };
 
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(SelfTestArgs p) {
     tc::fence_barrier_init();
   }
   __syncthreads();
-  for (int i = tid; i < p.ra * p.ca; i += 128) {
+  for (int i = tid; p.a_layout != 8 && i < p.ra * p.ca; i += 128) {
     int r = i / p.ca, c = i % p.ca;
     const size_t off = p.a_layout ? sw_off(p.a_layout, a_ps, r + p.halo, c)
                                   : (size_t)(c / 8) * a_ps + (size_t)(r + p.halo) * 16 + (c % 8) * 2;
@@ -61,12 +62,34 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(SelfTestArgs p) {
     const size_t off = p.b_layout ? sw_off(p.b_layout, b_ps, r, c) : (size_t)(c / 8) * b_ps + (size_t)r * 16 + (c % 8) * 2;
     *reinterpret_cast<__nv_bfloat16*>(sb + off) = __float2bfloat16(p.b[i]);
   }
+  if (p.a_layout == 8) {
+    // A -> TMEM columns [256 - K/2 .. 256): thread tid owns row tid
+    const uint32_t tm = tmem_slot;
+    for (int c0 = 0; c0 < p.K / 2; c0 += 8) {
+      uint32_t v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = tc::pack_bf16(p.a[(size_t)tid * p.ca + 2 * (c0 + j)], p.a[(size_t)tid * p.ca + 2 * (c0 + j) + 1]);
+      tc::tmem_st8(tm + ((uint32_t)(warp * 32) << 16) + (uint32_t)(256 - p.K / 2 + c0), v);
+    }
+    tc::tmem_st_wait();
+  }
   tc::fence_proxy_async();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (tid == 0) {
+  if (tid == 0 && p.a_layout == 8) {
+    const uint32_t idesc = tc::make_idesc(128, p.N, 0, p.b_mn);
+    const uint32_t bbase = tc::smem_u32(sb);
+    for (int ks = 0; ks < p.K / 16; ++ks) {
+      uint32_t b_addr, b_lbo, b_sbo;
+      if (!p.b_mn) { b_addr = bbase + 2 * ks * b_ps; b_lbo = b_ps; b_sbo = 128; }
+      else { b_addr = bbase + ks * 256; b_lbo = 128; b_sbo = b_ps; }
+      const uint64_t db = tc::make_desc(b_addr, b_lbo, b_sbo);
+      tc::umma_ts(tmem, tmem + (uint32_t)(256 - p.K / 2 + 8 * ks), (uint32_t)db, (uint32_t)(db >> 32), idesc, ks > 0);
+    }
+    tc::umma_commit(&bar);
+  } else if (tid == 0) {
     const uint32_t idesc = tc::make_idesc(128, p.N, p.a_mn, p.b_mn);
     const uint32_t abase = tc::smem_u32(sa) + (uint32_t)(p.halo + p.a_shift) * 16, bbase = tc::smem_u32(sb);
     for (int ks = 0; ks < p.K / 16; ++ks) {
@@ -130,13 +153,14 @@ int mr_tc_selftest(const float* a, int64_t ra, int64_t ca, const float* b, int64
   SelfTestArgs p{a, (int)ra, (int)ca, b, (int)rb, (int)cb, d, a_mn, b_mn, (int)N, (int)K, (int)a_shift, (int)halo, swap,
                  a_layout, b_layout, base_off_mode};
   auto okl = [](int l) { return l == 0 || l == 2 || l == 4 || l == 6; };
-  MR_REQUIRE(okl(a_layout) && okl(b_layout), MR_ERR_BAD_SHAPE, "mr_tc_selftest: layouts must be 0, 2, 4 or 6");
+  MR_REQUIRE((okl(a_layout) || a_layout == 8) && okl(b_layout), MR_ERR_BAD_SHAPE, "mr_tc_selftest: layouts must be 0, 2, 4 or 6 (A: or 8 = tensor memory)");
+  if (a_layout == 8) MR_REQUIRE(!a_mn && b_layout == 0 && a_shift == 0 && N + K / 2 <= 256 && K % 16 == 0, MR_ERR_BAD_SHAPE, "mr_tc_selftest: A from tensor memory needs a K-major A, N + K/2 <= 256");
   auto opbytes = [](int layout, int64_t rows, int64_t cols) -> size_t {
     if (!layout) return (size_t)(cols / 8) * ((rows | 1) * 16);
     const int64_t rbytes = layout == 2 ? 128 : (layout == 4 ? 64 : 32);
     return (size_t)((cols * 2 + rbytes - 1) / rbytes) * (size_t)((rows + 7) / 8 * 8) * rbytes;
   };
-  size_t smem = (opbytes(a_layout, ra + 2 * halo, ca) + 1023) / 1024 * 1024 + opbytes(b_layout, rb, cb) + 1024;
+  size_t smem = (opbytes(a_layout == 8 ? 0 : a_layout, ra + 2 * halo, ca) + 1023) / 1024 * 1024 + opbytes(b_layout, rb, cb) + 1024;
   MR_REQUIRE(smem <= 220 * 1024, MR_ERR_BAD_SHAPE, "mr_tc_selftest: operands need %zu bytes of shared memory", smem);
   cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   tc_selftest_kernel<<<1, 128, smem, as_stream(stream)>>>(p);

@@ -49,6 +49,25 @@ def test_umma_tile(a_mn, b_mn, N, K, shift):
     assert err < 1e-5, err
 
 
+@pytest.mark.parametrize("a_mn,b_mn,a_layout,b_layout,N,K", [
+    (0, 0, 4, 0, 160, 160),      # cnn_tail D1: A = dkp, K-major rows of 64 B (SWIZZLE_64B blocks of 32 columns); B = Wq panels
+    (1, 1, 4, 4, 160, 128),      # cnn_tail D2: both operands MN-major views of SWIZZLE_64B tiles (K = token rows)
+    (0, 0, 2, 0, 160, 128),      # tap GEMM: A K-major SWIZZLE_128B
+    (1, 1, 2, 4, 160, 128),      # token-reduction GEMM: P SWIZZLE_128B, Q SWIZZLE_64B, both MN-major
+    (1, 1, 4, 4, 32, 64),
+    (0, 0, 8, 0, 16, 160),       # rnn_tc: A (W_hh) read from tensor memory, B = hidden states (16 rows), panel layout
+    (0, 1, 8, 0, 64, 160),
+])
+def test_umma_tile_swizzled_layouts(a_mn, b_mn, a_layout, b_layout, N, K):
+    g = torch.Generator(device="cuda").manual_seed(N + 31 * K + a_layout + 5 * b_layout)
+    a = torch.randn((K, 128) if a_mn else (128, K), generator=g, device="cuda")
+    b = torch.randn((K, N) if b_mn else (N, K), generator=g, device="cuda")
+    d = run_tile(a, b, a_mn, b_mn, N, K, 0, 0, 0, a_layout, b_layout)
+    ref = expected(a, b, a_mn, b_mn, N, K, 0)
+    err = float((d.double() - ref).norm() / ref.norm())
+    assert err < 1e-5, err
+
+
 # ------------------------------------------------------------------------------------------------
 # bf16 (tcgen05) news encoder against the oracle
 # ------------------------------------------------------------------------------------------------
