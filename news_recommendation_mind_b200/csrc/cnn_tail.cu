@@ -291,14 +291,17 @@ cnn_tail_bwd_kernel(const CnnTailBwdArgs p, const __grid_constant__ CUtensorMap 
         if (valid) {
           uint4* dst = reinterpret_cast<uint4*>(p.dconv + t * Hp + n0);
 #pragma unroll
-          for (int w = 0; w < 4; ++w) {
+          for (int w = 0; w < 4; w += 2) {
             if (w < 2 || wide) {
-              uint4 o;
-              o.x = tc::pack_bf16(f[w * 8 + 0], f[w * 8 + 1]);
-              o.y = tc::pack_bf16(f[w * 8 + 2], f[w * 8 + 3]);
-              o.z = tc::pack_bf16(f[w * 8 + 4], f[w * 8 + 5]);
-              o.w = tc::pack_bf16(f[w * 8 + 6], f[w * 8 + 7]);
-              dst[w] = o;
+              uint4 o[2];
+#pragma unroll
+              for (int x = 0; x < 2; ++x) {
+                o[x].x = tc::pack_bf16(f[(w + x) * 8 + 0], f[(w + x) * 8 + 1]);
+                o[x].y = tc::pack_bf16(f[(w + x) * 8 + 2], f[(w + x) * 8 + 3]);
+                o[x].z = tc::pack_bf16(f[(w + x) * 8 + 4], f[(w + x) * 8 + 5]);
+                o[x].w = tc::pack_bf16(f[(w + x) * 8 + 6], f[(w + x) * 8 + 7]);
+              }
+              tc::st_global_256(dst + w, o[0], o[1]);
             }
           }
         }
@@ -640,8 +643,10 @@ cnn_tail_fwd_kernel(const CnnTailFwdArgs p, const __grid_constant__ CUtensorMap 
         if (valid) {
           uint4* dst = reinterpret_cast<uint4*>(p.key + t * Hp + n0);
 #pragma unroll
-          for (int w = 0; w < 4; ++w)
-            if (w < 2 || wide) dst[w] = make_uint4(pk[4 * w], pk[4 * w + 1], pk[4 * w + 2], pk[4 * w + 3]);
+          for (int w = 0; w < 4; w += 2)
+            if (w < 2 || wide)
+              tc::st_global_256(dst + w, make_uint4(pk[4 * w], pk[4 * w + 1], pk[4 * w + 2], pk[4 * w + 3]),
+                                make_uint4(pk[4 * w + 4], pk[4 * w + 5], pk[4 * w + 6], pk[4 * w + 7]));
         }
         // the score uses the bf16-rounded key (what the backward and the stand-alone pooling kernels read)
 #pragma unroll
@@ -659,19 +664,21 @@ cnn_tail_fwd_kernel(const CnnTailFwdArgs p, const __grid_constant__ CUtensorMap 
       if (p.dbg != nullptr) dbg_acc[1] += clock64() - tE0;
       if (half == 0) {
         // ---- masked softmax over the title's rows r' = l' * G + g ----------------------------------------------
+        // rows of title g inside this warp: the lanes with lane % G == g (G is a power of two); the four warps' partial
+        // results meet in shared memory
         const float s_me = score_s[r] + score_s[128 + r];
-        float* e_s = sE + as * 128;
-        // scores of masked rows must not enter the maximum: every thread publishes (keep ? s : -inf) first
-        e_s[r] = keep ? s_me : -INFINITY;
+        float* e_s = sE + as * 128;                                   // [0, 4G): partial maxima, [64, 64 + 4G): partial sums
+        float mx = keep ? s_me : -INFINITY;
+        for (int o = G; o < 32; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane < G) e_s[q4 * G + lane] = mx;
         asm volatile("bar.sync 2, 128;" ::: "memory");
-        float mx = -INFINITY;
-        for (int l2 = 0; l2 < L; ++l2) mx = fmaxf(mx, e_s[l2 * G + g]);
+        mx = fmaxf(fmaxf(e_s[g], e_s[G + g]), fmaxf(e_s[2 * G + g], e_s[3 * G + g]));
         const float ex = keep ? expf(s_me - mx) : 0.f;
+        float sum = ex;
+        for (int o = G; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane < G) e_s[64 + q4 * G + lane] = sum;
         asm volatile("bar.sync 2, 128;" ::: "memory");
-        e_s[r] = ex;
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        float sum = 0.f;
-        for (int l2 = 0; l2 < L; ++l2) sum += e_s[l2 * G + g];
+        sum = (e_s[64 + g] + e_s[64 + G + g]) + (e_s[64 + 2 * G + g] + e_s[64 + 3 * G + g]);
         const float pr = (valid && sum > 0.f) ? ex / sum : 0.f;       // all-masked title -> zeros (XSoftmax, Attention.py:66-74)
         if (valid) p.prob[t] = pr;
         // P operand: bf16 high part in row g, low part in row G + g, column (K index) r

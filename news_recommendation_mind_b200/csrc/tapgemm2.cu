@@ -200,15 +200,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG2_THREADS, 1) tapg
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(__uint_as_float(v[j]) + sbias[c0 + j], 0.f);      // bias + ReLU
           uint4* dst = reinterpret_cast<uint4*>(p.out + t * p.ldo + c0);
+          const bool al32 = ((reinterpret_cast<uintptr_t>(dst) & 31) == 0);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 4; u += 2) {
             if (u < 2 || wide) {
-              uint4 o;
-              o.x = tc::pack_bf16(f[u * 8 + 0], f[u * 8 + 1]);
-              o.y = tc::pack_bf16(f[u * 8 + 2], f[u * 8 + 3]);
-              o.z = tc::pack_bf16(f[u * 8 + 4], f[u * 8 + 5]);
-              o.w = tc::pack_bf16(f[u * 8 + 6], f[u * 8 + 7]);
-              dst[u] = o;
+              uint4 o[2];
+#pragma unroll
+              for (int x = 0; x < 2; ++x) {
+                o[x].x = tc::pack_bf16(f[(u + x) * 8 + 0], f[(u + x) * 8 + 1]);
+                o[x].y = tc::pack_bf16(f[(u + x) * 8 + 2], f[(u + x) * 8 + 3]);
+                o[x].z = tc::pack_bf16(f[(u + x) * 8 + 4], f[(u + x) * 8 + 5]);
+                o[x].w = tc::pack_bf16(f[(u + x) * 8 + 6], f[(u + x) * 8 + 7]);
+              }
+              if (al32) tc::st_global_256(dst + u, o[0], o[1]);      // one 32-byte store per row piece: half the LSU wavefronts
+              else { dst[u] = o[0]; dst[u + 1] = o[1]; }
             }
           }
         }
