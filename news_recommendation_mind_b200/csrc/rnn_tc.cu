@@ -3,11 +3,14 @@
 // Per step every sequence needs  pre[4H] = W_hh[4H, H] . h[H].  Round 1 ran this as mma.sync m16n8k16 with W_hh in registers +
 // shared memory; legacy HMMA issues at ~20 cycles per instruction on sm_100a, 400 instructions per step, so the MMA phase
 // was ~3300 of the ~3900 cycles of a step (99 us for 50 steps).  Here the same product is ONE batch of tcgen05.mma per step:
-//   A = W_hh, bf16, RESIDENT in shared memory for the whole kernel in the K-major panel layout of tc05.cuh
-//       ([H/8 panels][rows][16 B], rows = 4H rounded up to 128; H = 150: 640 x 160 x 2 B = 200 KB), MT = rows/128 tiles of M = 128;
+//   A = W_hh, bf16, RESIDENT IN TENSOR MEMORY for the whole kernel (rows = 4H rounded up to 128 -> MT = rows/128 tiles of M = 128
+//       lanes; a row's K elements are packed two per 32-bit column, KT * 8 columns per tile; H = 150: 5 x 80 = 400 of the 512
+//       columns).  The first version kept W_hh in shared memory: every step then re-read 200 KB through the 128 B/clk
+//       shared-memory port (32 cycles per MMA against the 8-cycle floor of M128 N16 K16) -- with the A operand in TMEM the
+//       tensor core only fetches the 512-byte B tile per MMA;
 //   B = the hidden states of the CTA's NSEQ sequences, 16 rows x H (panel layout, 5 KB): rows [0, NSEQ) the bf16 high parts,
 //       rows [NSEQ, 2 NSEQ) the low parts (h = hi + lo keeps ~16 mantissa bits through the recurrence), remaining rows zero;
-//   D = MT accumulators of 128 lanes x 16 columns in TMEM (fp32).
+//   D = MT accumulators of 128 lanes x 16 columns in TMEM (fp32), behind the A columns.
 // MT x KT = 5 x 10 MMAs of M128 N16 K16 per step: 8 cycles each at the tensor pipe's floor against ~3300 cycles before.
 // A step:  (1) one elected lane issues the MMAs + tcgen05.commit;  (2) all 16 warps wait on the mbarrier, read their TMEM
 // quadrant (tcgen05.ld 32x32b), add the high and low columns and park the pre-activations in shared memory;  (3) gate phase as
@@ -60,7 +63,7 @@ static inline RTGeom rt_geom(int H, int nseq) {
   g.w_ps = (uint32_t)g.rows * 16u;
   g.w_bytes = (uint32_t)g.KT * 2u * g.w_ps;
   g.h_bytes = (uint32_t)g.KT * 2u * 256u;
-  g.smem = (size_t)g.w_bytes + g.h_bytes + (size_t)g.rows * nseq * 4 + 128;
+  g.smem = (size_t)g.h_bytes + (size_t)g.rows * nseq * 4 + 128;
   return g;
 }
 
@@ -76,7 +79,7 @@ static bool rnn_use_tc() {
 bool rnn_tc_supported(int kind, int H) {
   if (kind != MR_RNN_LSTM || H < 8 || H > RT_MAXH || !rnn_use_tc()) return false;
   const RTGeom g = rt_geom(H, 8);
-  return g.MT <= RT_MAXMT && g.smem <= 227 * 1024;
+  return g.MT <= RT_MAXMT && g.MT * (g.KT * 8 + 16) <= 512 && g.smem <= 227 * 1024;
 }
 
 int64_t rnn_tc_scratch_bytes(int kind, int H) {
@@ -103,10 +106,9 @@ rnn_tc_fwd_kernel(const float* __restrict__ xp, int ldx, const uint8_t* __restri
   constexpr int G = 4;
   constexpr int PPT = (NSEQ * RT_MAXH + RT_THREADS - 1) / RT_THREADS;        // (sequence, unit) pairs per thread
   const int GH = G * H, rows = MT * 128;
-  const uint32_t w_ps = (uint32_t)rows * 16u, w_bytes = (uint32_t)KT * 2u * w_ps, h_ps = 256u, h_bytes = (uint32_t)KT * 2u * h_ps;
+  const uint32_t w_ps = (uint32_t)rows * 16u, h_ps = 256u, h_bytes = (uint32_t)KT * 2u * h_ps;
   extern __shared__ __align__(1024) uint8_t rt_smem[];
-  uint8_t* Wsm = rt_smem;                                           // A operand: [KT*2 panels][rows][16 B]
-  uint8_t* Hsm = rt_smem + w_bytes;                                 // B operand: [KT*2 panels][16 rows][16 B]
+  uint8_t* Hsm = rt_smem;                                           // B operand: [KT*2 panels][16 rows][16 B]
   float* pre = reinterpret_cast<float*>(Hsm + h_bytes);             // [rows][NSEQ]
   uint64_t* bars = reinterpret_cast<uint64_t*>(pre + (size_t)rows * NSEQ);      // [0] weights landed, [1] MMAs of the step done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
@@ -120,20 +122,13 @@ rnn_tc_fwd_kernel(const float* __restrict__ xp, int ldx, const uint8_t* __restri
     tc::mbar_init(&bars[1], 1);
     tc::fence_barrier_init();
   }
-  if (warp == 0) tc::tmem_alloc(tmem_slot, 128);
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
   pdl_wait();                                  // everything above touched this CTA's shared memory / TMEM only
   w_img = pdl_acquire(w_img);
   xp = pdl_acquire(xp);
   h0 = pdl_acquire(h0);
   lens = pdl_acquire(lens);
   __syncthreads();
-  if (tid == 0) {
-    tc::mbar_arrive_expect_tx(&bars[0], w_bytes);
-    for (uint32_t off = 0; off < w_bytes; off += 32768) {
-      const uint32_t nb = w_bytes - off < 32768 ? w_bytes - off : 32768;
-      tc::bulk_g2s(tc::smem_u32(Wsm) + off, w_img + off, nb, &bars[0]);
-    }
-  }
   if (tid < NSEQ) {
     const int b = b0 + tid;
     const int l = b < B ? (lens ? lens[b] : S) : 0;
@@ -143,6 +138,19 @@ rnn_tc_fwd_kernel(const float* __restrict__ xp, int ldx, const uint8_t* __restri
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const uint32_t d_col = (uint32_t)(MT * KT * 8);                    // accumulators behind the A columns
+  // W_hh -> tensor memory: warp w fills lanes 32 (w % 4) .. + 31 of tiles w / 4, w / 4 + 4; a lane reads its row's 16-byte
+  // pieces from the panel image (consecutive lanes = consecutive rows: coalesced) and stores 8 columns (K = 16) at a time
+  for (int t = warp >> 2; t < MT; t += 4) {
+    const int row = t * 128 + (warp & 3) * 32 + lane;
+    const uint4* src = reinterpret_cast<const uint4*>(w_img + (size_t)row * 16);
+    for (int ks = 0; ks < KT; ++ks) {
+      const uint4 p0 = __ldg(src + (size_t)(2 * ks) * rows), p1 = __ldg(src + (size_t)(2 * ks + 1) * rows);
+      const uint32_t v[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+      tc::tmem_st8(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t * KT * 8 + ks * 8), v);
+    }
+  }
+  tc::tmem_st_wait();
   int max_len = 0;
 #pragma unroll
   for (int i = 0; i < NSEQ; ++i) max_len = max(max_len, len_s[i]);
@@ -168,13 +176,14 @@ rnn_tc_fwd_kernel(const float* __restrict__ xp, int ldx, const uint8_t* __restri
     }
   }
   tc::fence_proxy_async();                     // the generic-proxy writes of the B tile, before the tensor core reads it
-  tc::mbar_wait(&bars[0], 0);                  // W_hh is resident
+  tc::tc_fence_before();                       // ... and the tcgen05.st of W_hh before the MMAs of another warp
   __syncthreads();
 
   const uint32_t idesc = tc::make_idesc(128, 16, 0, 0);
-  const uint64_t a_tmpl = tc::make_desc(tc::smem_u32(Wsm), w_ps, 128), b_tmpl = tc::make_desc(tc::smem_u32(Hsm), h_ps, 128);
-  const uint32_t a_lo0 = (uint32_t)a_tmpl, a_hi = (uint32_t)(a_tmpl >> 32), b_lo0 = (uint32_t)b_tmpl, b_hi = (uint32_t)(b_tmpl >> 32);
-  const uint32_t a_kstep = (2u * w_ps) >> 4, b_kstep = (2u * h_ps) >> 4, a_tstep = (128u * 16u) >> 4;
+  const uint64_t b_tmpl = tc::make_desc(tc::smem_u32(Hsm), h_ps, 128);
+  const uint32_t b_lo0 = (uint32_t)b_tmpl, b_hi = (uint32_t)(b_tmpl >> 32);
+  const uint32_t b_kstep = (2u * h_ps) >> 4;
+  (void)w_ps;
   const int quad = warp & 3;
   uint32_t phase = 0;
 
@@ -194,10 +203,10 @@ rnn_tc_fwd_kernel(const float* __restrict__ xp, int ldx, const uint8_t* __restri
       if (tc::elect_one()) {
 #pragma unroll 1
         for (int t = 0; t < MT; ++t) {
-          const uint32_t a_lo = a_lo0 + (uint32_t)t * a_tstep;
+          const uint32_t a_col = tmem + (uint32_t)(t * KT * 8);
 #pragma unroll
           for (int ks = 0; ks < RT_MAXH / 16; ++ks)
-            if (ks < KT) tc::umma_lh(tmem + (uint32_t)t * 16u, a_lo + (uint32_t)ks * a_kstep, a_hi, b_lo0 + (uint32_t)ks * b_kstep, b_hi, idesc, (uint32_t)ks);
+            if (ks < KT) tc::umma_ts(tmem + d_col + (uint32_t)t * 16u, a_col + (uint32_t)ks * 8u, b_lo0 + (uint32_t)ks * b_kstep, b_hi, idesc, (uint32_t)ks);
         }
         tc::umma_commit(&bars[1]);
       }
@@ -208,7 +217,7 @@ rnn_tc_fwd_kernel(const float* __restrict__ xp, int ldx, const uint8_t* __restri
     phase ^= 1u;
     tc::tc_fence_after();
     for (int t = warp >> 2; t < MT; t += 4) {
-      const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)t * 16u;
+      const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + d_col + (uint32_t)t * 16u;
       float* prow = pre + (size_t)(t * 128 + quad * 32 + lane) * NSEQ;
       if constexpr (NSEQ == 2) {
         uint32_t v[4];
@@ -267,7 +276,7 @@ rnn_tc_fwd_kernel(const float* __restrict__ xp, int ldx, const uint8_t* __restri
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 128);
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
 static int rt_nseq(int B) {
