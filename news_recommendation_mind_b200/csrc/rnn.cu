@@ -574,14 +574,18 @@ int mr_rnn_user_bwd(const mr_rnn_shape* s, const float* x, const int32_t* lens, 
     bias_part = ar.take<float>((int64_t)B * 2 * GH);
     MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "mr_rnn_user_bwd: workspace too small (%lld given)", (long long)workspace_bytes);
   }
+  // LSTM: the reverse recurrence as tcgen05 batches with W_hh^T resident in tensor memory (rnn_tc.cu)
+  const bool tc_bwd = fused_out && rnn_tc_bwd_supported(s->kind, H, B);
   if (resident) {
     if (fused_out) {
       cudaMemsetAsync(gib, 0, (size_t)tg.Mp * tg.GHp * 2, st);
       if (s->kind != MR_RNN_LSTM) cudaMemsetAsync(ghb, 0, (size_t)tg.Mp * tg.GHp * 2, st);
     }
-    if (int rc = rnn_res_bwd(s->kind, w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H, sp, st,
-                             fused_out ? gib : nullptr, fused_out ? ghb : nullptr, fused_out ? (int)tg.GHp : 0,
-                             fused_out ? bias_part : nullptr))
+    if (tc_bwd) {
+      if (int rc = rnn_tc_bwd(s->kind, w_hh, lens, gates, cs, d_user, gib, (int)tg.GHp, d_h0, bias_part, B, S, H, sp, st)) return rc;
+    } else if (int rc = rnn_res_bwd(s->kind, w_hh, h0, lens, gates, hs, cs, d_user, dgi, dgh, d_h0, B, S, H, sp, st,
+                                    fused_out ? gib : nullptr, fused_out ? ghb : nullptr, fused_out ? (int)tg.GHp : 0,
+                                    fused_out ? bias_part : nullptr))
       return rc;
   } else if (s->kind == MR_RNN_LSTM) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(rnn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -608,7 +612,7 @@ int mr_rnn_user_bwd(const mr_rnn_shape* s, const float* x, const int32_t* lens, 
   }
   if (fused_out) {
     // bias gradients: fold the per-CTA partials (pitch 2*GH: [0] input side, [1] hidden side) in a fixed order
-    const int64_t rows = ceil_div(B, rnn_res_bpc(s->kind, B, H));
+    const int64_t rows = tc_bwd ? rnn_tc_bwd_rows(B) : ceil_div(B, rnn_res_bpc(s->kind, B, H));
     e = colsum_small(bias_part, 2 * GH, d_b_ih, rows, GH, st);
     MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "rnn d_b_ih: %s", cudaGetErrorString(e));
     e = colsum_small(bias_part + (s->kind == MR_RNN_LSTM ? 0 : GH), 2 * GH, d_b_hh, rows, GH, st);

@@ -35,4 +35,12 @@ int64_t rnn_tc_scratch_bytes(int kind, int H);
 int rnn_tc_fwd(int kind, const float* xp, int ldx, const float* w_hh, const float* h0, const int32_t* lens, float* gates, float* hs,
                float* cs, float* user, int B, int S, int H, void* scratch, cudaStream_t st);
 
+// backward recurrence (LSTM): W_hh^T resident in tensor memory; writes the bf16 gate-gradient rows (pitch GHp16, pre-zeroed),
+// d_h0 (optional) and bias_part [rnn_tc_bwd_rows(B)][2][4H]
+bool rnn_tc_bwd_supported(int kind, int H, int B);
+int rnn_tc_bwd_rows(int B);
+int64_t rnn_tc_bwd_scratch_bytes(int kind, int H);
+int rnn_tc_bwd(int kind, const float* w_hh, const int32_t* lens, const float* gates, const float* cs, const float* d_user,
+               __nv_bfloat16* gib, int GHp16, float* d_h0, float* bias_part, int B, int S, int H, void* scratch, cudaStream_t st);
+
 }  // namespace mr
