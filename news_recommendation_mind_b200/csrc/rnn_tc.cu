@@ -62,7 +62,7 @@ static inline RTGeom rt_geom(int H, int nseq) {
   g.rows = g.MT * 128;
   g.w_ps = (uint32_t)g.rows * 16u;
   g.w_bytes = (uint32_t)g.KT * 2u * g.w_ps;
-  g.h_bytes = (uint32_t)g.KT * 2u * 256u;
+  g.h_bytes = (uint32_t)g.KT * 2u * 272u;      // panel stride 256 + 16: consecutive panels in different banks
   g.smem = (size_t)g.h_bytes + (size_t)g.rows * nseq * 4 + 128;
   return g;
 }
@@ -106,7 +106,7 @@ rnn_tc_fwd_kernel(const float* __restrict__ xp, int ldx, const uint8_t* __restri
   constexpr int G = 4;
   constexpr int PPT = (NSEQ * RT_MAXH + RT_THREADS - 1) / RT_THREADS;        // (sequence, unit) pairs per thread
   const int GH = G * H, rows = MT * 128;
-  const uint32_t w_ps = (uint32_t)rows * 16u, h_ps = 256u, h_bytes = (uint32_t)KT * 2u * h_ps;
+  const uint32_t w_ps = (uint32_t)rows * 16u, h_ps = 272u, h_bytes = (uint32_t)KT * 2u * h_ps;
   extern __shared__ __align__(1024) uint8_t rt_smem[];
   uint8_t* Hsm = rt_smem;                                           // B operand: [KT*2 panels][16 rows][16 B]
   float* pre = reinterpret_cast<float*>(Hsm + h_bytes);             // [rows][NSEQ]
@@ -119,7 +119,7 @@ rnn_tc_fwd_kernel(const float* __restrict__ xp, int ldx, const uint8_t* __restri
   for (uint32_t i = tid * 16; i < h_bytes; i += RT_THREADS * 16) *reinterpret_cast<uint4*>(Hsm + i) = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     tc::mbar_init(&bars[0], 1);
-    tc::mbar_init(&bars[1], 1);
+    tc::mbar_init(&bars[1], (uint32_t)MT);
     tc::fence_barrier_init();
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
@@ -198,16 +198,15 @@ rnn_tc_fwd_kernel(const float* __restrict__ xp, int ldx, const uint8_t* __restri
       }
     }
     // ---- (1) D[t] = W_hh[tile t] . [h_hi | h_lo]^T ------------------------------------------------------------------
-    if (warp == 0) {
+    // one issuing warp per M tile (MT arrivals per step on the barrier): the tensor core takes ~22 cycles per M128 N16 K16 MMA
+    // whoever issues it, but the issue loops of the MT independent accumulators overlap
+    if (warp < MT) {
       tc::tc_fence_after();
       if (tc::elect_one()) {
-#pragma unroll 1
-        for (int t = 0; t < MT; ++t) {
-          const uint32_t a_col = tmem + (uint32_t)(t * KT * 8);
+        const uint32_t a_col = tmem + (uint32_t)(warp * KT * 8);
 #pragma unroll
-          for (int ks = 0; ks < RT_MAXH / 16; ++ks)
-            if (ks < KT) tc::umma_ts(tmem + d_col + (uint32_t)t * 16u, a_col + (uint32_t)ks * 8u, b_lo0 + (uint32_t)ks * b_kstep, b_hi, idesc, (uint32_t)ks);
-        }
+        for (int ks = 0; ks < RT_MAXH / 16; ++ks)
+          if (ks < KT) tc::umma_ts(tmem + d_col + (uint32_t)warp * 16u, a_col + (uint32_t)ks * 8u, b_lo0 + (uint32_t)ks * b_kstep, b_hi, idesc, (uint32_t)ks);
         tc::umma_commit(&bars[1]);
       }
       __syncwarp();
@@ -340,8 +339,8 @@ static inline RBGeom rb_geom(int H, int nseq) {
   g.d0_col = g.a1_col + g.KT1 * 8;
   g.d1_col = g.d0_col + 16;
   g.cols = g.d1_col + (g.KT1 ? g.NB1 : 0);
-  g.b0_bytes = (uint32_t)g.KT0 * 2u * 256u;
-  g.b1_bytes = (uint32_t)g.KT1 * 2u * (uint32_t)g.NB1 * 16u;
+  g.b0_bytes = (uint32_t)g.KT0 * 2u * 272u;                        // panel strides + 16 bytes: consecutive panels in different banks
+  g.b1_bytes = (uint32_t)g.KT1 * 2u * ((uint32_t)g.NB1 * 16u + 16u);
   g.smem = (size_t)g.b0_bytes + g.b1_bytes + (size_t)nseq * 128 * 4 + (size_t)4 * nseq * 32 * 4 + 256;
   return g;
 }
@@ -384,7 +383,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1)
 rnn_tc_bwd_kernel(const uint8_t* __restrict__ img0, const uint8_t* __restrict__ img1, const int32_t* __restrict__ lens,
                   const float* __restrict__ gates, const float* __restrict__ cs, const float* __restrict__ d_user,
                   __nv_bfloat16* __restrict__ gib, int GHp16, float* __restrict__ d_h0, float* __restrict__ bias_part, int B, int S, int H,
-                  const RBGeom g) {
+                  const RBGeom g, long long* dbg) {
+  long long dbg_acc[4] = {0, 0, 0, 0}, dbg_t = 0;
+  const long long dbg_t0 = clock64();
   constexpr int G = 4;
   constexpr int PPT = (NSEQ * RT_MAXH + RT_THREADS - 1) / RT_THREADS;
   constexpr int NB1 = 8 * NSEQ;
@@ -443,6 +444,7 @@ rnn_tc_bwd_kernel(const uint8_t* __restrict__ img0, const uint8_t* __restrict__ 
   int pn[PPT], pj[PPT], plen[PPT];
   bool pon[PPT];
   float dh_c[PPT], dc_c[PPT], bsum[PPT][G];
+  uint32_t off0[PPT][G], off1[PPT][G];
 #pragma unroll
   for (int q = 0; q < PPT; ++q) {
     const int p = tid + q * RT_THREADS;
@@ -452,15 +454,21 @@ rnn_tc_bwd_kernel(const uint8_t* __restrict__ img0, const uint8_t* __restrict__ 
     plen[q] = (pon[q] && b0 + pn[q] < B) ? len_s[pn[q]] : 0;
     dh_c[q] = 0.f; dc_c[q] = 0.f;
 #pragma unroll
-    for (int gg = 0; gg < G; ++gg) bsum[q][gg] = 0.f;
+    for (int gg = 0; gg < G; ++gg) {
+      bsum[q][gg] = 0.f;
+      // where this pair's gate gradients go in the two B tiles (high part; the low part is NSEQ rows further)
+      const int gn = gg * H + pj[q], c = gn / g.CL, kk = gn - c * g.CL;
+      off0[q][gg] = (uint32_t)((gn >> 3) * 272 + (gn & 7) * 2 + pn[q] * 16);
+      off1[q][gg] = (uint32_t)((kk >> 3) * (NB1 * 16 + 16) + (2 * NSEQ * c + pn[q]) * 16 + (kk & 7) * 2);
+    }
   }
   tc::tc_fence_before();
   __syncthreads();
 
   const uint32_t idesc0 = tc::make_idesc(128, 16, 0, 0), idesc1 = tc::make_idesc(128, NB1, 0, 0);
-  const uint64_t b0_tmpl = tc::make_desc(tc::smem_u32(B0), 256, 128), b1_tmpl = tc::make_desc(tc::smem_u32(B1), NB1 * 16, 128);
+  const uint64_t b0_tmpl = tc::make_desc(tc::smem_u32(B0), 272, 128), b1_tmpl = tc::make_desc(tc::smem_u32(B1), NB1 * 16 + 16, 128);
   const uint32_t b0_lo = (uint32_t)b0_tmpl, b0_hi = (uint32_t)(b0_tmpl >> 32), b1_lo = (uint32_t)b1_tmpl, b1_hi = (uint32_t)(b1_tmpl >> 32);
-  const uint32_t b0_kstep = (2u * 256u) >> 4, b1_kstep = (2u * NB1 * 16u) >> 4;
+  const uint32_t b0_kstep = (2u * 272u) >> 4, b1_kstep = (2u * (NB1 * 16u + 16u)) >> 4;
   uint32_t phase = 0;
 
   // saved tensors of the step, loaded one step ahead (they do not depend on the carried gradients)
@@ -481,6 +489,7 @@ rnn_tc_bwd_kernel(const uint8_t* __restrict__ img0, const uint8_t* __restrict__ 
   load_step(max_len - 1);
 
   for (int t = max_len - 1; t >= 0; --t) {
+    if (dbg != nullptr) dbg_t = clock64();
     // ---- (1) gate gradients --------------------------------------------------------------------------------------------
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
@@ -502,24 +511,24 @@ rnn_tc_bwd_kernel(const uint8_t* __restrict__ img0, const uint8_t* __restrict__ 
 #pragma unroll
         for (int x = 0; x < G; ++x) { go16[x * H] = __float2bfloat16(d[x]); bsum[q][x] += d[x]; }
       }
+      if (dbg != nullptr && q == 0) { const long long c = clock64(); dbg_acc[0] += c - dbg_t; dbg_t = c; }
 #pragma unroll
       for (int x = 0; x < G; ++x) {
-        const int gn = x * H + j;
         const __nv_bfloat16 hi = __float2bfloat16(d[x]);
         const __nv_bfloat16 lo = __float2bfloat16(d[x] - __bfloat162float(hi));
-        uint8_t* p0 = B0 + (size_t)(gn >> 3) * 256 + (gn & 7) * 2;
-        *reinterpret_cast<__nv_bfloat16*>(p0 + n * 16) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(p0 + (NSEQ + n) * 16) = lo;
+        *reinterpret_cast<__nv_bfloat16*>(B0 + off0[q][x]) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(B0 + off0[q][x] + NSEQ * 16) = lo;
         if (g.KT1) {
-          const int c = gn / g.CL, kk = gn - c * g.CL;
-          uint8_t* p1 = B1 + (size_t)(kk >> 3) * (NB1 * 16) + (size_t)(2 * NSEQ * c) * 16 + (kk & 7) * 2;
-          *reinterpret_cast<__nv_bfloat16*>(p1 + n * 16) = hi;
-          *reinterpret_cast<__nv_bfloat16*>(p1 + (NSEQ + n) * 16) = lo;
+          *reinterpret_cast<__nv_bfloat16*>(B1 + off1[q][x]) = hi;
+          *reinterpret_cast<__nv_bfloat16*>(B1 + off1[q][x] + NSEQ * 16) = lo;
         }
       }
     }
+    if (dbg != nullptr) { const long long c = clock64(); dbg_acc[1] += c - dbg_t; dbg_t = c; }
     tc::fence_proxy_async();
+    if (dbg != nullptr) { const long long c = clock64(); dbg_acc[2] += c - dbg_t; dbg_t = c; }
     __syncthreads();
+    if (dbg != nullptr) { const long long c = clock64(); dbg_acc[3] += c - dbg_t; dbg_t = c; }
     // ---- (2) dh_prev = W_hh^T d ----------------------------------------------------------------------------------------
     if (warp == 0) {
       tc::tc_fence_after();
@@ -566,6 +575,11 @@ rnn_tc_bwd_kernel(const uint8_t* __restrict__ img0, const uint8_t* __restrict__ 
       }
     }
   }
+  if (dbg != nullptr && tid == 0) {
+    // warp 0, whole kernel: {gate math, B-tile stores, fence.proxy.async, __syncthreads} of step (1)
+    long long* d = dbg + (size_t)blockIdx.x * 4 * 5;
+    d[0] = dbg_acc[0]; d[1] = dbg_acc[1]; d[2] = dbg_acc[2]; d[3] = dbg_acc[3]; d[4] = clock64() - dbg_t0;
+  }
 #pragma unroll
   for (int q = 0; q < PPT; ++q)
     if (d_h0 != nullptr && pon[q] && b0 + pn[q] < B) d_h0[(int64_t)(b0 + pn[q]) * H + pj[q]] = dh_c[q];
@@ -604,11 +618,13 @@ int rnn_tc_bwd(int kind, const float* w_hh_f32, const int32_t* lens, const float
   const unsigned grid = (unsigned)ceil_div(B, nseq);
   const uint8_t* i0 = reinterpret_cast<const uint8_t*>(img0);
   const uint8_t* i1 = reinterpret_cast<const uint8_t*>(img1);
+  long long* dbg = g_tapgemm_dbg;                       // mr_debug_tapgemm_counters: [grid][4][5] cycle counters of this launch
+  if (g_tapgemm_dbg != nullptr) g_tapgemm_dbg += 148 * 4 * 5;
 #define RB_LAUNCH(NS)                                                                                                    \
   {                                                                                                                      \
     cudaError_t e = cudaFuncSetAttribute(rnn_tc_bwd_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem); \
     MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "rnn_tc_bwd: shared-memory opt-in failed: %s", cudaGetErrorString(e));    \
-    launch_pdl(rnn_tc_bwd_kernel<NS>, dim3(grid), dim3(RT_THREADS), g.smem, st, i0, i1, lens, gates, cs, d_user, gib, GHp16, d_h0, bias_part, B, S, H, g); \
+    launch_pdl(rnn_tc_bwd_kernel<NS>, dim3(grid), dim3(RT_THREADS), g.smem, st, i0, i1, lens, gates, cs, d_user, gib, GHp16, d_h0, bias_part, B, S, H, g, dbg); \
   }
   if (nseq == 2) RB_LAUNCH(2) else RB_LAUNCH(4)
 #undef RB_LAUNCH
