@@ -74,7 +74,8 @@ cnn_tail_bwd_kernel(const CnnTailBwdArgs p, const __grid_constant__ CUtensorMap 
   uint8_t* sW = sK + 2 * tile_bytes;
   uint8_t* sMask = sW + w_bytes;
   float* sDn = reinterpret_cast<float*>(sMask + p.n_side * 128 * CT_MASK_PITCH);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDn + p.n_side * p.G * dnp);
+  float* sDs = sDn + p.n_side * p.G * dnp;                  // [2 phase-A groups][128]: softmax-backward factor of every tile row
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDs + 2 * 128);
   uint64_t* full = bars;               // [2] TMA: c + key tile landed
   uint64_t* slot_free = bars + 2;      // [2] MMAs that read the stage have completed
   uint64_t* dkp_ready = bars + 4;      // [2] phase A wrote dkp / mask / d_news rows of the stage (128 arrivals)
@@ -121,13 +122,20 @@ cnn_tail_bwd_kernel(const CnnTailBwdArgs p, const __grid_constant__ CUtensorMap 
     const float inv = rsqrtf((float)H);
     const float* prob = pdl_acquire(p.prob);
     const float* d_news = pdl_acquire(p.d_news);
+    // second pass (dkp over key): the group's 128 lanes own (row group, piece) units -- lane gl works on the 16-byte piece
+    // gl % pieces of the rows rg, rg + RG, ...  (RG = 128 / pieces row groups; 120 of 128 lanes busy for 20 pieces, where
+    // one title per warp with one piece per lane kept only 20 of 32)
+    const int gl = wq * 32 + lane, RG = 128 / pieces;
+    const bool unit_on = gl < RG * pieces;
+    const int upiece = gl % pieces, urg = gl / pieces;
     float dq[8], db[8], qv[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int h = lane * 8 + e;
+      const int h = upiece * 8 + e;
       dq[e] = 0.f; db[e] = 0.f;
-      qv[e] = (lane < pieces && h < H) ? __ldg(p.query + h) : 0.f;
+      qv[e] = (unit_on && h < H) ? __ldg(p.query + h) : 0.f;
     }
+    float* ds_s = sDs + a * 128;
     const int rr = lane >> 3, part = lane & 7;
     const uint8_t* cT = sC + (size_t)a * tile_bytes;
     uint8_t* kT = sK + (size_t)a * tile_bytes;
@@ -144,6 +152,7 @@ cnn_tail_bwd_kernel(const CnnTailBwdArgs p, const __grid_constant__ CUtensorMap 
       }
       __syncwarp();
       CT_TIMED(1, tc::mbar_wait(&full[a], ph));
+      asm volatile("bar.sync %0, 128;" ::"r"(3 + (int)a) : "memory");         // nobody of the group still reads the previous tile's ds_s
       const long long tA0 = clock64();
       for (int g = wq; g < G; g += 4) {
         const int64_t n = tile * G + g;
@@ -187,25 +196,33 @@ cnn_tail_bwd_kernel(const CnnTailBwdArgs p, const __grid_constant__ CUtensorMap 
         const float dot = warp_sum(pl * mine);
         if (p.dbg != nullptr) dbg_acc[2] += clock64() - tA0;
         const float ds = pl * (mine - dot) * inv;                              // softmax backward (Attention.py:77-80) and 1/sqrt(H)
-        // dkp over key, same bytes; four rows per pass, loads first (see above)
+        ds_s[lane * G + g] = ds;                                               // row r = l * G + g (lanes past L hold 0)
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(3 + (int)a) : "memory");         // the four warps of this group: every row's factor is there
+      // dkp over key, same bytes; four rows per pass, loads first (see above)
+      if (unit_on) {
 #pragma unroll 1
-        for (int l0 = 0; l0 < L; l0 += 4) {
+        for (int r0 = urg; r0 < 128; r0 += 4 * RG) {
           uint4 kraw[4];
-#pragma unroll
-          for (int w = 0; w < 4; ++w)
-            kraw[w] = (lane < pieces && l0 + w < L) ? *reinterpret_cast<const uint4*>(kT + ct_off((l0 + w) * G + g, lane)) : make_uint4(0, 0, 0, 0);
+          float dsr[4];
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
-            const float dsl = __shfl_sync(0xffffffffu, ds, (l0 + w) & 31);
+            const int r = r0 + w * RG;
+            kraw[w] = r < 128 ? *reinterpret_cast<const uint4*>(kT + ct_off(r, upiece)) : make_uint4(0, 0, 0, 0);
+            dsr[w] = r < 128 ? ds_s[r] : 0.f;
+          }
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int r = r0 + w * RG;
             float k[8], o1[8];
             bf8_to_f(kraw[w], k);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              dq[e] = fmaf(dsl, k[e], dq[e]);
-              o1[e] = dsl * (qv[e] - qv[e] * k[e] * k[e]);
+              dq[e] = fmaf(dsr[w], k[e], dq[e]);
+              o1[e] = dsr[w] * (qv[e] - qv[e] * k[e] * k[e]);
               db[e] += o1[e];
             }
-            if (lane < pieces && l0 + w < L) *reinterpret_cast<uint4*>(kT + ct_off((l0 + w) * G + g, lane)) = f_to_bf8(o1);
+            if (r < 128) *reinterpret_cast<uint4*>(kT + ct_off(r, upiece)) = f_to_bf8(o1);
           }
         }
       }
@@ -215,19 +232,18 @@ cnn_tail_bwd_kernel(const CnnTailBwdArgs p, const __grid_constant__ CUtensorMap 
     }
     // d_query / d_proj_b partials of this CTA: combined below (after every role is done with shared memory)
     __syncthreads();
-    float* red = reinterpret_cast<float*>(sC);                                 // [8][2][Hp]
-    if (lane < pieces) {
+    float* red = reinterpret_cast<float*>(sC);                                 // [256 lanes][16]: (dq | db) of each lane's piece
+    {
+      float* mine = red + (size_t)(a * 128 + gl) * 16;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        red[(warp * 2 + 0) * Hp + lane * 8 + e] = dq[e];
-        red[(warp * 2 + 1) * Hp + lane * 8 + e] = db[e];
-      }
+      for (int e = 0; e < 8; ++e) { mine[e] = dq[e]; mine[8 + e] = db[e]; }
     }
     __syncthreads();
     for (int c = tid; c < 2 * Hp; c += 256) {
+      const int which = c >= Hp, col = c - which * Hp, pc = col >> 3, e = col & 7;
       float v = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) v += red[w * 2 * Hp + c];
+      for (int grp = 0; grp < 2; ++grp)
+        for (int rg = 0; rg < RG; ++rg) v += red[(size_t)(grp * 128 + rg * pieces + pc) * 16 + which * 8 + e];
       p.part_qb[(size_t)blockIdx.x * 2 * Hp + c] = v;
     }
   } else if (warp < 16) {
@@ -468,8 +484,8 @@ int cnn_tail_bwd(int64_t n_titles, int64_t L, int64_t H, const __nv_bfloat16* c,
   a.prob = prob; a.d_news = d_news; a.query = query; a.wq_img = wq_img; a.dconv = dconv;
   const size_t tile_bytes = (size_t)a.nblk * CT_BLK, w_bytes = (size_t)(Hp / 8) * Hp * 16;
   const size_t side = (size_t)128 * CT_MASK_PITCH + (size_t)a.G * (Hp + 4) * 4;
-  a.n_side = 4 * tile_bytes + w_bytes + 3 * side + 13 * 8 + 16 <= 227 * 1024 ? 3 : 2;
-  size_t smem = 4 * tile_bytes + w_bytes + a.n_side * side + 13 * 8 + 16;
+  a.n_side = 4 * tile_bytes + w_bytes + 3 * side + 2 * 128 * 4 + 13 * 8 + 16 <= 227 * 1024 ? 3 : 2;
+  size_t smem = 4 * tile_bytes + w_bytes + a.n_side * side + 2 * 128 * 4 + 13 * 8 + 16;
   const size_t a_reach = 3 * tile_bytes + (size_t)a.n_mt * 4 * CT_BLK;       // the MN-major A operand reads whole 128-column groups
   if (smem < a_reach) smem = a_reach;
   MR_REQUIRE(smem <= 227 * 1024, MR_ERR_UNSUPPORTED, "cnn_tail_bwd: %zu bytes of shared memory", smem);
