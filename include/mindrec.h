@@ -103,7 +103,8 @@ MR_API int mr_embed_grad_segreduce(const void* ids, int ids_i64, const void* d_e
  * [V,E] fp32 in MR_F32 or the bf16 shadow [V, align_up(E,64)] (zero padded) in MR_BF16) OR a dense
  * embedding tensor (ids == NULL, emb [N*L, E] fp32).
  * Saved for backward (caller allocated): c_save, key_save ([N*L,H] fp32, or bf16 [N*L, align_up(H,16)]
- * in MR_BF16), prob [N,L] fp32.  MR_BF16 limits: H <= 256, L <= 128.  c_out (optional, may be NULL) receives the fp32 token-level output
+ * in MR_BF16; there c_save needs 32 more bytes per token BEHIND its N*L rows: the forward leaves the sign mask of c,
+ * one bit per column, for the backward), prob [N,L] fp32.  MR_BF16 limits: H <= 256, L <= 128.  c_out (optional, may be NULL) receives the fp32 token-level output
  * the module interface returns as its first value.
  * -------------------------------------------------------------------------------------------- */
 typedef struct {

@@ -27,7 +27,6 @@ namespace mr {
 
 constexpr int CT_THREADS = 576;     // warps 0-7 phase A (two groups), 8-15 epilogue, 16 MMA issuer, 17 TMA / weights
 constexpr uint32_t CT_BLK = 8192;   // one 32-column block of a tile: 128 rows x 64 B, SWIZZLE_64B
-constexpr int CT_MASK_PITCH = 20;   // sign mask: 160 bits per row
 
 struct CnnTailBwdArgs {
   int64_t n_titles, n_tiles;
@@ -36,6 +35,7 @@ struct CnnTailBwdArgs {
   const float* d_news;
   const float* query;
   const uint8_t* wq_img;
+  const uint8_t* cmask;    // [T][32]: sign bits of c, written by the forward
   __nv_bfloat16* dconv;
   float* part_qb;      // [grid][2][Hp]
   float* part_w;       // [n_mt][grid][128][Hp]
@@ -72,8 +72,7 @@ cnn_tail_bwd_kernel(const CnnTailBwdArgs p, const __grid_constant__ CUtensorMap 
   uint8_t* sC = smem;
   uint8_t* sK = sC + 2 * tile_bytes;
   uint8_t* sW = sK + 2 * tile_bytes;
-  uint8_t* sMask = sW + w_bytes;
-  float* sDn = reinterpret_cast<float*>(sMask + p.n_side * 128 * CT_MASK_PITCH);
+  float* sDn = reinterpret_cast<float*>(sW + w_bytes);
   float* sDs = sDn + p.n_side * p.G * dnp;                  // [2 phase-A groups][128]: softmax-backward factor of every tile row
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDs + 2 * 128);
   uint64_t* full = bars;               // [2] TMA: c + key tile landed
@@ -144,7 +143,6 @@ cnn_tail_bwd_kernel(const CnnTailBwdArgs p, const __grid_constant__ CUtensorMap 
       const uint32_t ph = u & 1u, i = 2u * u + a;
       const uint32_t ss = i % (uint32_t)p.n_side, su = i / (uint32_t)p.n_side;          // side stage and its use count
       float* dn_s = sDn + (size_t)ss * G * dnp;
-      uint8_t* mask_s = sMask + (size_t)ss * 128 * CT_MASK_PITCH;
       CT_TIMED(0, tc::mbar_wait(&e_done[ss], (su & 1u) ^ 1u));   // the epilogue of the side stage's previous tile no longer reads it
       for (int g = wq; g < G; g += 4) {
         const int64_t n = tile * G + g;
@@ -181,11 +179,6 @@ cnn_tail_bwd_kernel(const CnnTailBwdArgs p, const __grid_constant__ CUtensorMap 
             bf8_to_f(raw[v], f);
 #pragma unroll
             for (int e = 0; e < 8; ++e) d = fmaf(dr[v][e], f[e], d);
-            // c = relu(.) >= +0: "c > 0" is "the bf16 bits are not zero"; h + 0x7fff carries into bit 15 exactly for h >= 1
-            const uint32_t m0 = (raw[v].x + 0x7FFF7FFFu) & 0x80008000u, m1 = (raw[v].y + 0x7FFF7FFFu) & 0x80008000u;
-            const uint32_t m2 = (raw[v].z + 0x7FFF7FFFu) & 0x80008000u, m3 = (raw[v].w + 0x7FFF7FFFu) & 0x80008000u;
-            const uint32_t x = (m0 >> 15) | (m1 >> 13) | (m2 >> 11) | (m3 >> 9);
-            if (l < L && part + 8 * v < pieces) mask_s[r * CT_MASK_PITCH + part + 8 * v] = (uint8_t)(x | (x >> 15));
           }
           d += __shfl_xor_sync(0xffffffffu, d, 1);
           d += __shfl_xor_sync(0xffffffffu, d, 2);
@@ -255,6 +248,7 @@ cnn_tail_bwd_kernel(const CnnTailBwdArgs p, const __grid_constant__ CUtensorMap 
     const int nc = (Hp + 31) >> 5;
     const int c_begin = half ? (nc + 1) / 2 : 0, c_end = half ? nc : (nc + 1) / 2;
     const float* prob = pdl_acquire(p.prob);
+    const uint8_t* cmask_g = pdl_acquire(p.cmask);
     float colacc[3] = {0.f, 0.f, 0.f};
     const uint32_t tb = tmem + ((uint32_t)(q4 * 32) << 16);
     uint32_t i = 0;
@@ -263,12 +257,14 @@ cnn_tail_bwd_kernel(const CnnTailBwdArgs p, const __grid_constant__ CUtensorMap 
       const int64_t n = tile * G + g, t = n * L + l;
       const bool valid = row_ok && n < p.n_titles;
       const float pt = valid ? __ldg(prob + t) : 0.f;
+      uint32_t cm[3];
+      {
+        const uint32_t* mrow = reinterpret_cast<const uint32_t*>(cmask_g + t * 32);     // requested before the waits below
+#pragma unroll
+        for (int cj = 0; cj < 3; ++cj) cm[cj] = (valid && c_begin + cj < c_end) ? __ldg(mrow + c_begin + cj) : 0u;
+      }
       CT_TIMED(0, tc::mbar_wait(&dkp_ready[s], ph));
       const uint32_t ss = i % (uint32_t)p.n_side;
-      const uint32_t* mrow = reinterpret_cast<const uint32_t*>(sMask + (size_t)ss * 128 * CT_MASK_PITCH + r * CT_MASK_PITCH);
-      uint32_t cm[3];
-#pragma unroll
-      for (int cj = 0; cj < 3; ++cj) cm[cj] = (valid && c_begin + cj < c_end) ? mrow[c_begin + cj] : 0u;
       const float4* dn_row = reinterpret_cast<const float4*>(sDn + (size_t)ss * G * dnp + g * dnp);
       CT_TIMED(1, tc::mbar_wait(d1_full, i & 1u));
       tc::tc_fence_after();
@@ -464,7 +460,7 @@ int64_t cnn_tail_bwd_workspace_bytes(int64_t n_titles, int64_t L, int64_t Hp) {
   return arena_bytes(grid * 2 * Hp, 4) + arena_bytes(2 * grid * 128 * Hp, 4) + arena_bytes(grid * 4 * Hp, 4) + 256;
 }
 
-int cnn_tail_bwd(int64_t n_titles, int64_t L, int64_t H, const __nv_bfloat16* c, const __nv_bfloat16* key, const float* prob,
+int cnn_tail_bwd(int64_t n_titles, int64_t L, int64_t H, const __nv_bfloat16* c, const __nv_bfloat16* key, const uint8_t* cmask, const float* prob,
                  const float* d_news, const float* query, const uint8_t* wq_img, __nv_bfloat16* dconv, float* d_proj_w,
                  float* d_proj_b, float* d_query, float* d_conv_b, void* ws, int64_t wsb, cudaStream_t st) {
   const int64_t Hp = align_up(H, 16);
@@ -481,9 +477,9 @@ int cnn_tail_bwd(int64_t n_titles, int64_t L, int64_t H, const __nv_bfloat16* c,
   a.part_w = ar.take<float>((int64_t)a.n_mt * grid * 128 * Hp);
   a.csum = ar.take<float>((int64_t)grid * 4 * Hp);
   MR_REQUIRE(ar.ok(), MR_ERR_WORKSPACE, "cnn_tail_bwd: workspace too small (%lld given)", (long long)wsb);
-  a.prob = prob; a.d_news = d_news; a.query = query; a.wq_img = wq_img; a.dconv = dconv;
+  a.prob = prob; a.d_news = d_news; a.query = query; a.wq_img = wq_img; a.dconv = dconv; a.cmask = cmask;
   const size_t tile_bytes = (size_t)a.nblk * CT_BLK, w_bytes = (size_t)(Hp / 8) * Hp * 16;
-  const size_t side = (size_t)128 * CT_MASK_PITCH + (size_t)a.G * (Hp + 4) * 4;
+  const size_t side = (size_t)a.G * (Hp + 4) * 4;
   a.n_side = 4 * tile_bytes + w_bytes + 3 * side + 2 * 128 * 4 + 13 * 8 + 16 <= 227 * 1024 ? 3 : 2;
   size_t smem = 4 * tile_bytes + w_bytes + a.n_side * side + 2 * 128 * 4 + 13 * 8 + 16;
   const size_t a_reach = 3 * tile_bytes + (size_t)a.n_mt * 4 * CT_BLK;       // the MN-major A operand reads whole 128-column groups

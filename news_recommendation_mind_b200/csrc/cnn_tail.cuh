@@ -14,7 +14,8 @@ int64_t cnn_tail_bwd_workspace_bytes(int64_t n_titles, int64_t L, int64_t Hp);
 //   d_proj_w   = dkp^T c,  d_proj_b = sum_t dkp,  d_query = sum_t ds key,  d_conv_b = sum_t dconv
 // with dkp = ds q (1 - key^2), ds = softmax backward of <d_news, c> (Attention.py:77-80).
 // wq_img: bf16 panel image of Wq as the K-major B operand [k][n] (tapgemm_pack(proj_w, ., 1, Hp, Hp, H, H, 1, H, 0), replica 0).
-int cnn_tail_bwd(int64_t n_titles, int64_t L, int64_t H, const __nv_bfloat16* c, const __nv_bfloat16* key, const float* prob,
+// cmask: [T][32 bytes], bit j of a row = (c[row, j] > 0), written by the forward (conv epilogue / cmask_from_c_kernel).
+int cnn_tail_bwd(int64_t n_titles, int64_t L, int64_t H, const __nv_bfloat16* c, const __nv_bfloat16* key, const uint8_t* cmask, const float* prob,
                  const float* d_news, const float* query, const uint8_t* wq_img, __nv_bfloat16* dconv, float* d_proj_w,
                  float* d_proj_b, float* d_query, float* d_conv_b, void* ws, int64_t wsb, cudaStream_t st);
 

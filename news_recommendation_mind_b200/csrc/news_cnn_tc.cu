@@ -39,6 +39,26 @@ static struct ConvTiming {
   int64_t count = 0;
 } g_conv_timing;
 
+// sign mask of c (one bit per column, 32 bytes per token) for conv launches that do not write it themselves
+__global__ void cmask_from_c_kernel(const __nv_bfloat16* __restrict__ c, int64_t T, int Hp, uint8_t* __restrict__ cmask) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one 8-column piece per thread
+  const int pieces = Hp / 8;
+  if (i >= T * 32) return;
+  const int64_t t = i >> 5;
+  const int pc = (int)(i & 31);
+  uint32_t bits = 0;
+  if (pc < pieces) {
+    const uint4 v = *reinterpret_cast<const uint4*>(c + t * Hp + pc * 8);
+    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t m = ((w4[e] + 0x7FFF7FFFu) & 0x80008000u) >> 15;
+      bits |= ((m | (m >> 15)) & 3u) << (2 * e);
+    }
+  }
+  cmask[i] = (uint8_t)bits;
+}
+
 static inline int64_t hp_of(const mr_cnn_shape* s) { return align_up(s->H, 16); }
 static inline int64_t kp_of(const mr_cnn_shape* s) { return align_up(s->E, 16); }
 static inline int64_t table_ld(const mr_cnn_shape* s) { return align_up(s->E, 64); }
@@ -110,6 +130,11 @@ int news_cnn_tc_fwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
   else { a.ids = nullptr; a.a = xa; a.lda = Kp; a.V = 0; }
   a.wpack = wconv; a.epi = TG_EPI_BIAS_RELU; a.bias = conv_b; a.n_valid = (int)H;
   a.out = c; a.ldo = Hp;
+  // fused-tail path: the sign mask of c (what relu' needs in the backward) is written by the conv epilogue behind the rows of
+  // c_save, so that the backward neither recomputes it nor keeps it in shared memory
+  const bool tail = cnn_tail_supported(L, Hp);
+  uint8_t* cmask = tail ? reinterpret_cast<uint8_t*>(c + T * Hp) : nullptr;
+  a.cmask_out = cmask;
   const bool two_cta = tapgemm2_supported(a);       // CTA pairs with the conv weights resident in shared memory
   if (two_cta) {
     if (int rc = tapgemm2_pack(conv_w, wconv, 3, (int)Hp, (int)Kp, (int)H, (int)E, 3 * E, 3, 1, st)) return rc;
@@ -129,8 +154,12 @@ int news_cnn_tc_fwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
     cudaEventRecord(g_conv_timing.end[slot], st);
     ++g_conv_timing.count;
   }
+  if (tail && !two_cta) {
+    cmask_from_c_kernel<<<(unsigned)ceil_div(T * 32, 256), 256, 0, st>>>(c, T, (int)Hp, cmask);
+    MR_CHECK_LAUNCH("cmask_from_c_kernel");
+  }
   // projection + tanh + pooling in one kernel (cnn_tail.cu) for titles of 16..32 tokens
-  if (cnn_tail_supported(L, Hp))
+  if (tail)
     return cnn_tail_fwd(N, L, H, c, mask, mask_i64, query, proj_b, wproj, key, prob, news, st);
   // projection: key = tanh(c Wq^T + bq)
   TapGemmArgs b{};
@@ -204,7 +233,9 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
   cudaError_t e;
   if (fused_tail) {
     if (int rc = tapgemm_pack(proj_w, wpb, 1, (int)Hp, (int)Hp, (int)H, (int)H, 1, H, 0, st)) return rc;
-    if (int rc = cnn_tail_bwd(N, L, H, c, key, prob, d_news, query, wpb, dcv, d_proj_w, d_proj_b, d_query, d_conv_b, tail_ws, tail_wsb, st)) return rc;
+    if (int rc = cnn_tail_bwd(N, L, H, c, key, reinterpret_cast<const uint8_t*>(c + T * Hp), prob, d_news, query, wpb, dcv, d_proj_w, d_proj_b,
+                              d_query, d_conv_b, tail_ws, tail_wsb, st))
+      return rc;
   } else if (fast_pool) {
     const unsigned grid = (unsigned)ceil_div(N, 8);
     if (Hp <= 64) launch_pdl(cnn_pool_bwd_bf16_kernel<1>, dim3(grid), dim3(256), 0, st, c, key, Hp, prob, query, d_news, dkp, dnp, ppart, cmask, N, (int)L, (int)H);

@@ -53,6 +53,7 @@ struct TapGemmArgs {
   const float* prob; const float* dnp; int64_t ldn;   // TG_EPI_RELUGRAD_POOL: prob [rows], dnp [n_titles, ldn] fp32 (ldn % 4 == 0)
   const uint8_t* cmask;                    // ... and the sign mask of e1: [rows][32 bytes], bit j of the row = (e1[row, j] > 0)
   float* colsum_out;                       // RELUGRAD / RELUGRAD_POOL: optional [grid * 4][n_total] partial column sums of `out`
+  uint8_t* cmask_out;                      // two-CTA BIAS_RELU epilogue: optional [rows][32 bytes] sign mask of the stored rows (bit j = out[row, j] > 0)
   __nv_bfloat16* out; int64_t ldo;
   int ns_a, ns_b, halo;
   int use_tma;                             // A tiles staged by TMA (3-D tile load / gather4) instead of cp.async

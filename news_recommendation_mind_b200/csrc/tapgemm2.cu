@@ -183,6 +183,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG2_THREADS, 1) tapg
       const int64_t t = tile * p.G * p.L + row_off;
       const bool valid = row_ok && tile < p.n_tiles && (tile * p.G + g < p.n_titles) && t < p.n_rows;
       const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + acc.pos * 256u;
+      uint32_t cm0 = 0, cm1 = 0, cm2 = 0, cm3 = 0, cm4 = 0;        // sign bits of the row's (<= 160) stored columns
       for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t v[32];
         const bool wide = N - c0 >= 32;
@@ -214,9 +215,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG2_THREADS, 1) tapg
               }
               if (al32) tc::st_global_256(dst + u, o[0], o[1]);      // one 32-byte store per row piece: half the LSU wavefronts
               else { dst[u] = o[0]; dst[u + 1] = o[1]; }
+              if (p.cmask_out != nullptr) {
+                // relu output >= +0: "stored value > 0" is "its bf16 bits are not zero" (h + 0x7fff carries into bit 15 for h >= 1)
+                const uint32_t w8[8] = {o[0].x, o[0].y, o[0].z, o[0].w, o[1].x, o[1].y, o[1].z, o[1].w};
+                uint32_t bits = 0;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const uint32_t m = ((w8[e] + 0x7FFF7FFFu) & 0x80008000u) >> 15;      // bit 0: low half, bit 16: high half
+                  bits |= ((m | (m >> 15)) & 3u) << (2 * e);
+                }
+                const uint32_t sh = bits << (16 * (u >> 1));
+                const int ci = c0 >> 5;
+                cm0 |= ci == 0 ? sh : 0u; cm1 |= ci == 1 ? sh : 0u; cm2 |= ci == 2 ? sh : 0u; cm3 |= ci == 3 ? sh : 0u; cm4 |= ci == 4 ? sh : 0u;
+              }
             }
           }
         }
+      }
+      if (p.cmask_out != nullptr && valid) {
+        uint8_t* mrow = p.cmask_out + t * 32;
+        *reinterpret_cast<uint4*>(mrow) = make_uint4(cm0, cm1, cm2, cm3);
+        *reinterpret_cast<uint32_t*>(mrow + 16) = cm4;
       }
       tc::tc_fence_before();
       asm volatile("bar.sync 1, 128;" ::: "memory");               // the four epilogue warps of this CTA
@@ -467,7 +486,7 @@ int64_t tapgemm2_pack_bytes(int taps, int N, int K) {
 // true when this problem can run on the two-CTA kernel (token-table gather, one N block, weights resident)
 bool tapgemm2_supported(const TapGemmArgs& a) {
   if (!use_2cta() || a.ids == nullptr || a.n_sub != 1 || a.L < 1 || a.L > 128 || a.nsz[0] % 32 != 0 || a.nsz[0] > 256) return false;
-  if (a.epi != TG_EPI_BIAS_RELU) return false;
+  if (a.epi != TG_EPI_BIAS_RELU || (a.cmask_out != nullptr && a.nsz[0] > 160)) return false;
   int G, halo;
   uint32_t a_slot, half_slot, half_total;
   geom2(a, &G, &halo, &a_slot, &half_slot, &half_total);

@@ -153,7 +153,8 @@ class NewsCNN(torch.autograd.Function):
         shape = CnnShape(N, L, E, H, V, precision)
         if precision == MR_BF16:
             Hp = pad_to(H, 16)
-            c_save = torch.empty(N * L, Hp, dtype=torch.bfloat16, device=dev)
+            # rows [0, N*L): c; behind them 32 bytes per token: the sign mask of c the conv epilogue writes for the backward
+            c_save = torch.empty(N * L + (N * L * 32 + 2 * Hp - 1) // (2 * Hp), Hp, dtype=torch.bfloat16, device=dev)
             key_save = torch.empty(N * L, Hp, dtype=torch.bfloat16, device=dev)
             tab = table_bf16 if ids is not None else None
         else:
@@ -194,7 +195,7 @@ class NewsCNN(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         news_out = news.view(*lead, H)
         if want_c:
-            c_out = c_save if precision == MR_F32 else c_save[:, :H].float()
+            c_out = c_save if precision == MR_F32 else c_save[:N * L, :H].float()
             c_out = c_out.view(*lead, L, H)
         else:
             c_out = None
