@@ -385,10 +385,14 @@ def run_train(args):
     ms_eager, _ = timed(loop_dev(devb, eager), args.steps)
     launches_eager = lib.mr_launch_count() - l0
     conv_launches, conv_ms = 0, 0.0
+    ktimes = {}                                                # which -> (launches, mean ms): 0 conv forward, 1 tail forward, 2 tail backward
     if timing_on:
-        n_, m_ = ctypes.c_int64(0), ctypes.c_float(0)
-        if lib.mr_debug_conv_timing_read(ctypes.byref(n_), ctypes.byref(m_)) == 0:
-            conv_launches, conv_ms = n_.value, m_.value
+        lib.mr_debug_kernel_timing_read.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_float)]
+        for which in range(3):
+            n_, m_ = ctypes.c_int64(0), ctypes.c_float(0)
+            if lib.mr_debug_kernel_timing_read(which, ctypes.byref(n_), ctypes.byref(m_)) == 0 and n_.value > 0:
+                ktimes[which] = (n_.value, m_.value)
+        conv_launches, conv_ms = ktimes.get(0, (0, 0.0))
         lib.mr_debug_conv_timing(0)
     tok_info = None
     if fused and not args.quick:
@@ -436,6 +440,27 @@ def run_train(args):
                 "peak_source": pk["source"] + " sustained (kernel timed inside the training step)",
                 "us_per_launch": t_k * 1e6, "launches_timed": int(conv_launches),
                 "algorithmic_flop_per_token": FLOP_PER_TOKEN_CONV}
+    # the other two big kernels of the encoder (HBM bound: the fused projection / pooling tail, csrc/cnn_tail.cu); `roofline` is the
+    # line of whichever launch is the longest of the step, `roofline_kernels` lists all three
+    roof_all = []
+    if roof is not None:
+        roof_all.append(roof)
+        T_tok = cfg["B"] * (cfg["C"] + cfg["S"]) * cfg["L"]
+        Hp = (cfg["H"] + 15) // 16 * 16
+        tj = json.load(open(tp)) if os.path.exists(tp) else {}
+        for which, name, nbytes_tok, key in (
+                (1, "fused tail forward (c tile -> projection MMA -> tanh -> key; softmax; pooled sum as a second MMA)",
+                 2 * Hp * 2 + 4, "cnn_tail_fwd_dram_bytes_per_launch"),
+                (2, "fused tail backward (pooling backward in place over the key tile, dkp Wq and dkp^T c MMAs, relu' epilogue -> dconv)",
+                 3 * Hp * 2 + 32 + 4, "cnn_tail_bwd_dram_bytes_per_launch")):
+            if which in ktimes:
+                t_k = ktimes[which][1] * 1e-3
+                alg = nbytes_tok * T_tok
+                roof_all.append({"kernel": name, "bound": "hbm", "achieved": alg / t_k / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                 "frac": alg / t_k / 1e9 / pk["hbm"], "traffic": tj.get(key), "us_per_launch": t_k * 1e6,
+                                 "launches_timed": int(ktimes[which][0]), "algorithmic_bytes_per_token": nbytes_tok,
+                                 "peak_source": pk["source"] + " copy bandwidth"})
+        roof = max(roof_all, key=lambda r: r["us_per_launch"])
     fpi = flop_per_impression(cfg)
     step_roof = {"bound": "tensor", "algorithmic_gflop_per_impression": fpi / 1e9,
                  "achieved": cfg["B"] * fpi / (ms / args.steps * 1e-3) / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s"}
@@ -496,7 +521,7 @@ def run_train(args):
                 "config": config_dict(args, args.precision, cfg), "clocks": clocks,
                 "e2e": {"value": world * cfg["B"] * args.steps / (ms_e2e * 1e-3), "unit": "impressions/s",
                         "h2d_bytes_per_step": nbytes(host[0]), "d2h_bytes_per_step": 4},
-                "gpu_launches": int(launches_eager), "roofline": roof, "step_roofline": step_roof,
+                "gpu_launches": int(launches_eager), "roofline": roof, "roofline_kernels": roof_all, "step_roofline": step_roof,
                 "windows": {"ms_per_step": [round(w, 5) for w in windows], "median_ms_per_step": sorted(windows)[len(windows) // 2],
                             "note": "four more timed windows of `steps` steps behind the headline region"},
                 "eager": {"ms_per_step": ms_eager / args.steps, "value": world * cfg["B"] * args.steps / (ms_eager * 1e-3),

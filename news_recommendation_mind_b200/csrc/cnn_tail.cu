@@ -18,6 +18,7 @@
 // (dkp and dconv bf16, everything else fp32), so the emulation in tests/test_gpu_tc.py holds for both.
 #include "cnn_tail.cuh"
 #include "gemm_simt.cuh"
+#include "ktiming.cuh"
 #include "pool_kernels.cuh"
 #include "tapgemm.cuh"
 #include "tma.cuh"
@@ -501,7 +502,10 @@ int cnn_tail_bwd(int64_t n_titles, int64_t L, int64_t H, const __nv_bfloat16* c,
     MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "cnn_tail_bwd: shared-memory opt-in failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  launch_pdl(cnn_tail_bwd_kernel, dim3((unsigned)grid), dim3(CT_THREADS), smem, st, a, cmap, kmap);
+  {
+    TimedLaunch tl(2, st);
+    launch_pdl(cnn_tail_bwd_kernel, dim3((unsigned)grid), dim3(CT_THREADS), smem, st, a, cmap, kmap);
+  }
   MR_CHECK_LAUNCH("cnn_tail_bwd_kernel");
   // fixed-order reductions of the per-CTA partials
   launch_pdl(cnn_pool_bwd_final_kernel, dim3((unsigned)ceil_div(2 * Hp, 32)), dim3(1024), 0, st, (const float*)a.part_qb, (int64_t)grid, (int)Hp,

@@ -13,6 +13,7 @@
 // pitch align_up(E, 64) (the shadow kept by the Python BERT_Embedding / written by mr_adam_step).
 #include "news_cnn_tc.cuh"
 #include "cnn_tail.cuh"
+#include "ktiming.cuh"
 #include "pool_kernels.cuh"
 #include "tapgemm.cuh"
 #include "tokred.cuh"
@@ -29,15 +30,10 @@ __global__ void cast_rows_bf16_kernel(const float* __restrict__ src, __nv_bfloat
   dst[i] = __float2bfloat16(c < cols ? src[r * cols + c] : 0.f);
 }
 
-// ---- optional per-launch timing of the dominant kernel (conv forward tap GEMM) with CUDA events on the
-// launching stream; bench.py switches it on for the timed region and reads the average afterwards -------------
-constexpr int CONV_EVT_SLOTS = 256;
-static struct ConvTiming {
-  bool enabled = false;
-  cudaEvent_t beg[CONV_EVT_SLOTS], end[CONV_EVT_SLOTS];
-  bool created = false;
-  int64_t count = 0;
-} g_conv_timing;
+// ---- optional per-launch timing of the big kernels of the encoder (0 conv forward tap GEMM, 1 fused tail forward, 2 fused
+// tail backward) with CUDA events on the launching stream; bench.py switches it on for the eager timed region and reads the
+// averages afterwards -------------
+KernelTiming g_kt;
 
 // sign mask of c (one bit per column, 32 bytes per token) for conv launches that do not write it themselves
 __global__ void cmask_from_c_kernel(const __nv_bfloat16* __restrict__ c, int64_t T, int Hp, uint8_t* __restrict__ cmask) {
@@ -142,25 +138,23 @@ int news_cnn_tc_fwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
     if (int rc = tapgemm_pack(conv_w, wconv, 3, (int)Hp, (int)Kp, (int)H, (int)E, 3 * E, 3, 1, st)) return rc;
     if (int rc = tapgemm_plan(a, &plan)) return rc;
   }
-  const bool timed = g_conv_timing.enabled;
-  const int slot = (int)(g_conv_timing.count % CONV_EVT_SLOTS);
-  if (timed) cudaEventRecord(g_conv_timing.beg[slot], st);
-  if (two_cta) {
-    if (int rc = tapgemm2_run(a, wconv, st)) return rc;
-  } else {
-    if (int rc = tapgemm_launch(plan, st)) return rc;
-  }
-  if (timed) {
-    cudaEventRecord(g_conv_timing.end[slot], st);
-    ++g_conv_timing.count;
+  {
+    TimedLaunch tl(0, st);
+    if (two_cta) {
+      if (int rc = tapgemm2_run(a, wconv, st)) return rc;
+    } else {
+      if (int rc = tapgemm_launch(plan, st)) return rc;
+    }
   }
   if (tail && !two_cta) {
     cmask_from_c_kernel<<<(unsigned)ceil_div(T * 32, 256), 256, 0, st>>>(c, T, (int)Hp, cmask);
     MR_CHECK_LAUNCH("cmask_from_c_kernel");
   }
   // projection + tanh + pooling in one kernel (cnn_tail.cu) for titles of 16..32 tokens
-  if (tail)
+  if (tail) {
+    TimedLaunch tl(1, st);
     return cnn_tail_fwd(N, L, H, c, mask, mask_i64, query, proj_b, wproj, key, prob, news, st);
+  }
   // projection: key = tanh(c Wq^T + bq)
   TapGemmArgs b{};
   b.n_titles = N; b.L = (int)L; b.taps = 1; b.dir = 1; b.K = (int)Hp;
@@ -387,35 +381,42 @@ int news_cnn_tc_bwd(const mr_cnn_shape* s, const void* ids, int ids_i64, const f
 }  // namespace mr
 
 extern "C" {
-/* bench hooks: time every conv-forward tap-GEMM launch with CUDA events on its own stream */
+/* bench hooks: time the launches of the encoder's big kernels with CUDA events on their own stream */
 __attribute__((visibility("default"))) int mr_debug_conv_timing(int enable) {
   using namespace mr;
-  if (enable && !g_conv_timing.created) {
-    for (int i = 0; i < CONV_EVT_SLOTS; ++i) {
-      if (cudaEventCreate(&g_conv_timing.beg[i]) != cudaSuccess || cudaEventCreate(&g_conv_timing.end[i]) != cudaSuccess)
-        return set_err(MR_ERR_LAUNCH, "mr_debug_conv_timing: cannot create events");
-    }
-    g_conv_timing.created = true;
+  if (enable && !g_kt.created) {
+    for (int k = 0; k < KT_KERNELS; ++k)
+      for (int i = 0; i < CONV_EVT_SLOTS; ++i) {
+        if (cudaEventCreate(&g_kt.beg[k][i]) != cudaSuccess || cudaEventCreate(&g_kt.end[k][i]) != cudaSuccess)
+          return set_err(MR_ERR_LAUNCH, "mr_debug_conv_timing: cannot create events");
+      }
+    g_kt.created = true;
   }
-  g_conv_timing.enabled = enable != 0;
-  if (enable) g_conv_timing.count = 0;
+  g_kt.enabled = enable != 0;
+  if (enable)
+    for (int k = 0; k < KT_KERNELS; ++k) g_kt.count[k] = 0;
   return MR_OK;
 }
-/* after a device synchronise: number of timed launches (<= 256 kept) and their mean duration in ms */
-__attribute__((visibility("default"))) int mr_debug_conv_timing_read(int64_t* launches, float* mean_ms) {
+/* after a device synchronise: number of timed launches (<= 256 kept) and their mean duration in ms; which = 0 conv forward,
+ * 1 fused tail forward (projection + tanh + pooling), 2 fused tail backward (incl. its three small reductions) */
+__attribute__((visibility("default"))) int mr_debug_kernel_timing_read(int which, int64_t* launches, float* mean_ms) {
   using namespace mr;
-  const int64_t n = g_conv_timing.count < CONV_EVT_SLOTS ? g_conv_timing.count : CONV_EVT_SLOTS;
+  MR_REQUIRE(which >= 0 && which < KT_KERNELS, MR_ERR_BAD_SHAPE, "mr_debug_kernel_timing_read: which=%d", which);
+  const int64_t n = g_kt.count[which] < CONV_EVT_SLOTS ? g_kt.count[which] : CONV_EVT_SLOTS;
   double tot = 0;
   for (int64_t i = 0; i < n; ++i) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, g_conv_timing.beg[i], g_conv_timing.end[i]) != cudaSuccess) {
+    if (cudaEventElapsedTime(&ms, g_kt.beg[which][i], g_kt.end[which][i]) != cudaSuccess) {
       cudaGetLastError();
-      return set_err(MR_ERR_LAUNCH, "mr_debug_conv_timing_read: events not complete (synchronise first)");
+      return set_err(MR_ERR_LAUNCH, "mr_debug_kernel_timing_read: events not complete (synchronise first)");
     }
     tot += ms;
   }
-  if (launches) *launches = g_conv_timing.count;
+  if (launches) *launches = g_kt.count[which];
   if (mean_ms) *mean_ms = n ? (float)(tot / n) : 0.f;
   return MR_OK;
+}
+__attribute__((visibility("default"))) int mr_debug_conv_timing_read(int64_t* launches, float* mean_ms) {
+  return mr_debug_kernel_timing_read(0, launches, mean_ms);
 }
 }
