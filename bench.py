@@ -680,12 +680,23 @@ def main():
     args = ap.parse_args()
     if os.environ.get("MINDREC_NO_GRAPH"):
         args.no_graph = True
-    if args.impl == "reference":
-        run_reference(args)
-    elif args.config == 4:
-        run_eval(args)
-    else:
-        run_train(args)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        elif args.config == 4:
+            run_eval(args)
+        else:
+            run_train(args)
+    except BaseException:                                  # noqa: BLE001
+        # a failing rank must END: interpreter shutdown with a live NCCL communicator (and captured graphs holding its kernels) can
+        # block for the launcher's whole time limit while the other ranks wait in a collective
+        import traceback
+        traceback.print_exc()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            os._exit(1)
+        raise
 
 
 if __name__ == "__main__":
