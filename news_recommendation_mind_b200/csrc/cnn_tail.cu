@@ -62,9 +62,6 @@ __device__ __forceinline__ uint32_t ct_off(int r, int piece) {
 }
 
 // 18 warps: 96 registers per thread (the register file is allocated in units of 512 per warp)
-// RD ("row dots on the tensor core", opt-in: MINDREC_TAIL_ROWDOT=1): dp = <d_news, c[l]> of phase A becomes a third MMA,
-// D3 = c tile x (d_news as bf16 high | low rows)^T with N = 16, instead of 8 lanes per row of shared-memory loads and FMAs
-template <bool RD>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 cnn_tail_bwd_kernel(const CnnTailBwdArgs p, const __grid_constant__ CUtensorMap cmap, const __grid_constant__ CUtensorMap kmap) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -78,10 +75,7 @@ cnn_tail_bwd_kernel(const CnnTailBwdArgs p, const __grid_constant__ CUtensorMap 
   uint8_t* sW = sK + 2 * tile_bytes;
   float* sDn = reinterpret_cast<float*>(sW + w_bytes);
   float* sDs = sDn + p.n_side * p.G * dnp;                  // [2 phase-A groups][128]: softmax-backward factor of every tile row
-  float* sRed = sDs + 2 * 128;                              // RD: [2 groups][4 warps][8]: per-warp partial sums of p * dp per title
-  uint8_t* sDnop = reinterpret_cast<uint8_t*>(sRed + (RD ? 2 * 4 * 8 : 0));   // RD: [2 groups][Hp/8 panels][16 rows][16 B]: d_news as the bf16 B
-                                                                       // operand of the row-dot MMA (row g high part, row G + g low part; K-major)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDnop + (RD ? 2 * (size_t)(p.Hp / 8) * 256 : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDs + 2 * 128);
   uint64_t* full = bars;               // [2] TMA: c + key tile landed
   uint64_t* slot_free = bars + 2;      // [2] MMAs that read the stage have completed
   uint64_t* dkp_ready = bars + 4;      // [2] phase A wrote dkp / mask / d_news rows of the stage (128 arrivals)
@@ -90,9 +84,7 @@ cnn_tail_bwd_kernel(const CnnTailBwdArgs p, const __grid_constant__ CUtensorMap 
   uint64_t* d1_empty = bars + 10;      // 256 arrivals
   uint64_t* d2_done = bars + 11;
   uint64_t* w_ready = bars + 12;
-  uint64_t* dn_ready = bars + 13;      // RD: [2] phase-A group wrote its d_news operand and its c tile has landed (128 arrivals)
-  uint64_t* d3_full = bars + 15;       // RD: [2] row dots of the group's tile are in tensor memory
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = p.G, L = p.L, Hp = p.Hp, H = p.H;
@@ -100,15 +92,11 @@ cnn_tail_bwd_kernel(const CnnTailBwdArgs p, const __grid_constant__ CUtensorMap 
 
   pdl_trigger();
   for (uint32_t i = tid * 16; i < 4 * tile_bytes; i += CT_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
-  if (RD)
-    for (uint32_t i = tid * 16; i < 2u * (uint32_t)(p.Hp / 8) * 256u; i += CT_THREADS * 16) *reinterpret_cast<uint4*>(sDnop + i) = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&full[i], 1);
       tc::mbar_init(&slot_free[i], 1);
       tc::mbar_init(&dkp_ready[i], 128);
-      tc::mbar_init(&dn_ready[i], 128);      // (the last two pairs are used by the RD variant only)
-      tc::mbar_init(&d3_full[i], 1);
     }
     for (int i = 0; i < 3; ++i) tc::mbar_init(&e_done[i], 256);
     tc::mbar_init(d1_full, 1);
@@ -148,113 +136,61 @@ cnn_tail_bwd_kernel(const CnnTailBwdArgs p, const __grid_constant__ CUtensorMap 
       qv[e] = (unit_on && h < H) ? __ldg(p.query + h) : 0.f;
     }
     float* ds_s = sDs + a * 128;
-    float* red_s = sRed + a * 32;
-    uint8_t* dnop = sDnop + (size_t)a * (Hp / 8) * 256;
     const int rr = lane >> 3, part = lane & 7;
     const uint8_t* cT = sC + (size_t)a * tile_bytes;
     uint8_t* kT = sK + (size_t)a * tile_bytes;
-    // this thread's tile row (= its TMEM lane in the group's row-dot accumulator)
-    const int rg_ = gl % G, rl_ = gl / G;
-    const uint32_t d3_addr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(3 * Hp + 16 * (int)a);
     uint32_t u = 0;
     for (int64_t tile = blockIdx.x + (int64_t)a * gridDim.x; tile < p.n_tiles; tile += 2 * (int64_t)gridDim.x, ++u) {
       const uint32_t ph = u & 1u, i = 2u * u + a;
       const uint32_t ss = i % (uint32_t)p.n_side, su = i / (uint32_t)p.n_side;          // side stage and its use count
       float* dn_s = sDn + (size_t)ss * G * dnp;
-      const int64_t n_me = tile * G + rg_;
-      const float pl_row = (RD && n_me < p.n_titles && rl_ < L) ? __ldg(prob + n_me * L + rl_) : 0.f;   // RD: one tile row per thread
       CT_TIMED(0, tc::mbar_wait(&e_done[ss], (su & 1u) ^ 1u));   // the epilogue of the side stage's previous tile no longer reads it
-      long long tA0 = 0;
-      if constexpr (RD) {
-        // d_news rows of the tile: fp32 for the epilogue, bf16 high | low parts as the B operand of the row-dot MMA
-        for (int g = wq; g < G; g += 4) {
-          const int64_t n = tile * G + g;
-          for (int h = lane; h < dnp; h += 32) {
-            const float v = (n < p.n_titles && h < H) ? __ldg(d_news + n * H + h) : 0.f;
-            dn_s[g * dnp + h] = v;
-            if (h < Hp) {
-              const __nv_bfloat16 hi = __float2bfloat16(v);
-              uint8_t* o = dnop + (size_t)(h >> 3) * 256 + (h & 7) * 2;
-              *reinterpret_cast<__nv_bfloat16*>(o + g * 16) = hi;
-              *reinterpret_cast<__nv_bfloat16*>(o + (G + g) * 16) = __float2bfloat16(v - __bfloat162float(hi));
-            }
-          }
-        }
-        CT_TIMED(1, tc::mbar_wait(&full[a], ph));
-        tc::tc_fence_before();                     // this thread's tcgen05.ld of the previous tile's row dots, before the MMA overwrites them
-        tc::fence_proxy_async();
-        tc::mbar_arrive(&dn_ready[a]);
-        tA0 = clock64();
-        // dp[r] = <d_news[title of r], c[r]> comes back from the tensor core (one accumulator row per thread)
-        tc::mbar_wait(&d3_full[a], ph);
-        tc::tc_fence_after();
-        float dp;
-        {
-          uint32_t v[16];
-          tc::tmem_ld16(d3_addr, v);
-          tc::tmem_ld_wait();
-          float hi = 0.f, lo = 0.f;
+      for (int g = wq; g < G; g += 4) {
+        const int64_t n = tile * G + g;
+        for (int h = lane; h < dnp; h += 32) dn_s[g * dnp + h] = (n < p.n_titles && h < H) ? __ldg(d_news + n * H + h) : 0.f;
+      }
+      __syncwarp();
+      CT_TIMED(1, tc::mbar_wait(&full[a], ph));
+      asm volatile("bar.sync %0, 128;" ::"r"(3 + (int)a) : "memory");         // nobody of the group still reads the previous tile's ds_s
+      const long long tA0 = clock64();
+      for (int g = wq; g < G; g += 4) {
+        const int64_t n = tile * G + g;
+        const float pl = (n < p.n_titles && lane < L) ? __ldg(prob + n * L + lane) : 0.f;
+        float dr[3][8];
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
-            if (g == rg_) { hi = __uint_as_float(v[g]); lo = __uint_as_float(v[(G == 4 ? 4 : 8) + g]); }
-          dp = hi + lo;
-        }
-        // softmax backward per title: dot_g = sum over the title's rows of p * dp (rows of title g: lanes with lane % G == g)
-        float pd = pl_row * dp;
-        for (int o = G; o < 32; o <<= 1) pd += __shfl_xor_sync(0xffffffffu, pd, o);
-        if (lane < G) red_s[wq * 8 + lane] = pd;
-        asm volatile("bar.sync %0, 128;" ::"r"(3 + (int)a) : "memory");
-        const float dot = (red_s[rg_] + red_s[8 + rg_]) + (red_s[16 + rg_] + red_s[24 + rg_]);
-        if (p.dbg != nullptr) dbg_acc[2] += clock64() - tA0;
-        ds_s[gl] = pl_row * (dp - dot) * inv;                                        // softmax backward (Attention.py:77-80) and 1/sqrt(H); 0 past L
-      } else {
-        for (int g = wq; g < G; g += 4) {
-          const int64_t n = tile * G + g;
-          for (int h = lane; h < dnp; h += 32) dn_s[g * dnp + h] = (n < p.n_titles && h < H) ? __ldg(d_news + n * H + h) : 0.f;
-        }
-        __syncwarp();
-        CT_TIMED(1, tc::mbar_wait(&full[a], ph));
-        asm volatile("bar.sync %0, 128;" ::"r"(3 + (int)a) : "memory");         // nobody of the group still reads the previous tile's ds_s
-        tA0 = clock64();
-        for (int g = wq; g < G; g += 4) {
-          const int64_t n = tile * G + g;
-          const float pl = (n < p.n_titles && lane < L) ? __ldg(prob + n * L + lane) : 0.f;
-          float dr[3][8];
+        for (int v = 0; v < 3; ++v)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) dr[v][e] = (part + 8 * v < pieces) ? dn_s[g * dnp + (part + 8 * v) * 8 + e] : 0.f;
+        // dp[l] = <d_news, c[l]>: 8 lanes per row, 4 rows at a time; the same pass writes the sign bits of c
+        // (c = relu(.) >= +0, so "c > 0" is "the bf16 bits are not zero")
+        float mine = 0.f;
+        // the three 16-byte loads of an iteration are issued before anything is stored, so that their latencies overlap
+        // (the compiler cannot move a shared-memory load above a store it cannot disambiguate)
+#pragma unroll 1
+        for (int it = 0; it < 8; ++it) {
+          const int l = it * 4 + rr, r = l * G + g;
+          uint4 raw[3];
 #pragma unroll
           for (int v = 0; v < 3; ++v)
+            raw[v] = (l < L && part + 8 * v < pieces) ? *reinterpret_cast<const uint4*>(cT + ct_off(r, part + 8 * v)) : make_uint4(0, 0, 0, 0);
+          float d = 0.f;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) dr[v][e] = (part + 8 * v < pieces) ? dn_s[g * dnp + (part + 8 * v) * 8 + e] : 0.f;
-          // dp[l] = <d_news, c[l]>: 8 lanes per row, 4 rows at a time; the same pass writes the sign bits of c
-          // (c = relu(.) >= +0, so "c > 0" is "the bf16 bits are not zero")
-          float mine = 0.f;
-          // the three 16-byte loads of an iteration are issued before anything is stored, so that their latencies overlap
-          // (the compiler cannot move a shared-memory load above a store it cannot disambiguate)
-#pragma unroll 1
-          for (int it = 0; it < 8; ++it) {
-            const int l = it * 4 + rr, r = l * G + g;
-            uint4 raw[3];
+          for (int v = 0; v < 3; ++v) {
+            float f[8];
+            bf8_to_f(raw[v], f);
 #pragma unroll
-            for (int v = 0; v < 3; ++v)
-              raw[v] = (l < L && part + 8 * v < pieces) ? *reinterpret_cast<const uint4*>(cT + ct_off(r, part + 8 * v)) : make_uint4(0, 0, 0, 0);
-            float d = 0.f;
-#pragma unroll
-            for (int v = 0; v < 3; ++v) {
-              float f[8];
-              bf8_to_f(raw[v], f);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) d = fmaf(dr[v][e], f[e], d);
-            }
-            d += __shfl_xor_sync(0xffffffffu, d, 1);
-            d += __shfl_xor_sync(0xffffffffu, d, 2);
-            d += __shfl_xor_sync(0xffffffffu, d, 4);
-            const float sv = __shfl_sync(0xffffffffu, d, (lane & 3) * 8);
-            if ((lane >> 2) == it) mine = sv;
+            for (int e = 0; e < 8; ++e) d = fmaf(dr[v][e], f[e], d);
           }
-          const float dot = warp_sum(pl * mine);
-          if (p.dbg != nullptr) dbg_acc[2] += clock64() - tA0;
-          const float ds = pl * (mine - dot) * inv;                              // softmax backward (Attention.py:77-80) and 1/sqrt(H)
-          ds_s[lane * G + g] = ds;                                               // row r = l * G + g (lanes past L hold 0)
+          d += __shfl_xor_sync(0xffffffffu, d, 1);
+          d += __shfl_xor_sync(0xffffffffu, d, 2);
+          d += __shfl_xor_sync(0xffffffffu, d, 4);
+          const float sv = __shfl_sync(0xffffffffu, d, (lane & 3) * 8);
+          if ((lane >> 2) == it) mine = sv;
         }
+        const float dot = warp_sum(pl * mine);
+        if (p.dbg != nullptr) dbg_acc[2] += clock64() - tA0;
+        const float ds = pl * (mine - dot) * inv;                              // softmax backward (Attention.py:77-80) and 1/sqrt(H)
+        ds_s[lane * G + g] = ds;                                               // row r = l * G + g (lanes past L hold 0)
       }
       asm volatile("bar.sync %0, 128;" ::"r"(3 + (int)a) : "memory");         // the four warps of this group: every row's factor is there
       // dkp over key, same bytes; four rows per pass, loads first (see above)
@@ -424,32 +360,10 @@ cnn_tail_bwd_kernel(const CnnTailBwdArgs p, const __grid_constant__ CUtensorMap 
     const uint32_t b_ps = (uint32_t)Hp * 16u;
     const uint32_t wbase = tc::smem_u32(sW);
     const int nks1 = Hp >> 4;
-    const uint32_t idesc0 = tc::make_idesc(128, 16, 0, 0);
-    const uint32_t dnbase = tc::smem_u32(sDnop);
     tc::mbar_wait(w_ready, 0);
-    const int64_t n_mine = p.n_tiles > (int64_t)blockIdx.x ? (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    // row dots of tile j: D3[group] = c tile (K-major A) x d_news operand^T, N = 16 -- issued one tile AHEAD of the tile's other
-    // MMAs (the groups alternate: group j & 1 starts tile j while the other group is in the long second pass of tile j - 1)
-    auto mma0 = [&](uint32_t j) {
-      const uint32_t s0 = j & 1u, ph0 = (j >> 1) & 1u;
-      tc::mbar_wait(&dn_ready[s0], ph0);
-      tc::tc_fence_after();
-      const uint32_t cb = tc::smem_u32(sC) + s0 * tile_bytes, db0 = dnbase + s0 * (uint32_t)(Hp / 8) * 256u;
-      if (tc::elect_one()) {
-        for (int ks = 0; ks < nks1; ++ks) {
-          const uint64_t da = tc::make_desc_sw(cb + (uint32_t)(ks >> 1) * CT_BLK + (uint32_t)(ks & 1) * 32u, 16, 512, 4, 0);
-          const uint64_t dbb = tc::make_desc(db0 + 2u * (uint32_t)ks * 256u, 256, 128);
-          tc::umma(tmem + (uint32_t)(3 * Hp) + 16u * s0, da, dbb, idesc0, ks > 0 ? 1u : 0u);
-        }
-        tc::umma_commit(&d3_full[s0]);
-      }
-      __syncwarp();
-    };
-    if (RD && n_mine > 0) mma0(0);
     uint32_t i = 0;
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
       const uint32_t s = i & 1u, ph = (i >> 1) & 1u;
-      if (RD && (int64_t)i + 1 < n_mine) mma0(i + 1);
       CT_TIMED(0, tc::mbar_wait(&dkp_ready[s], ph));
       tc::tc_fence_after();
       const uint32_t kbase = tc::smem_u32(sK) + s * tile_bytes, cbase = tc::smem_u32(sC) + s * tile_bytes;
@@ -530,16 +444,6 @@ static bool use_tail() {
   return v != 0;
 }
 
-// opt-in variant of the backward: row dots of phase A on the tensor core (template parameter RD)
-static bool use_rowdot_mma() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MINDREC_TAIL_ROWDOT");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
-  return v != 0;
-}
-
 bool cnn_tail_supported(int64_t L, int64_t Hp) { return use_tail() && L >= 16 && L <= 32 && Hp >= 16 && Hp <= 160 && Hp % 16 == 0; }
 
 // titles per tile: a power of two (4 for 17..32 tokens, 8 for 16), so that a title's rows sit at the same positions modulo 4 whatever
@@ -577,11 +481,8 @@ int cnn_tail_bwd(int64_t n_titles, int64_t L, int64_t H, const __nv_bfloat16* c,
   a.prob = prob; a.d_news = d_news; a.query = query; a.wq_img = wq_img; a.dconv = dconv; a.cmask = cmask;
   const size_t tile_bytes = (size_t)a.nblk * CT_BLK, w_bytes = (size_t)(Hp / 8) * Hp * 16;
   const size_t side = (size_t)a.G * (Hp + 4) * 4;
-  const bool rd = use_rowdot_mma();
-  // ds, barriers (+ RD: partial sums, d_news operands)
-  const size_t fixed = 2 * 128 * 4 + 17 * 8 + 16 + (rd ? 2 * 4 * 8 * 4 + 2 * (size_t)(Hp / 8) * 256 : 0);
-  a.n_side = 4 * tile_bytes + w_bytes + 3 * side + fixed <= 227 * 1024 ? 3 : 2;
-  size_t smem = 4 * tile_bytes + w_bytes + a.n_side * side + fixed;
+  a.n_side = 4 * tile_bytes + w_bytes + 3 * side + 2 * 128 * 4 + 13 * 8 + 16 <= 227 * 1024 ? 3 : 2;
+  size_t smem = 4 * tile_bytes + w_bytes + a.n_side * side + 2 * 128 * 4 + 13 * 8 + 16;
   const size_t a_reach = 3 * tile_bytes + (size_t)a.n_mt * 4 * CT_BLK;       // the MN-major A operand reads whole 128-column groups
   if (smem < a_reach) smem = a_reach;
   MR_REQUIRE(smem <= 227 * 1024, MR_ERR_UNSUPPORTED, "cnn_tail_bwd: %zu bytes of shared memory", smem);
@@ -597,15 +498,13 @@ int cnn_tail_bwd(int64_t n_titles, int64_t L, int64_t H, const __nv_bfloat16* c,
     return rc;
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(cnn_tail_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(cnn_tail_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(cnn_tail_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     MR_REQUIRE(e == cudaSuccess, MR_ERR_LAUNCH, "cnn_tail_bwd: shared-memory opt-in failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   {
     TimedLaunch tl(2, st);
-    if (rd) launch_pdl(cnn_tail_bwd_kernel<true>, dim3((unsigned)grid), dim3(CT_THREADS), smem, st, a, cmap, kmap);
-    else launch_pdl(cnn_tail_bwd_kernel<false>, dim3((unsigned)grid), dim3(CT_THREADS), smem, st, a, cmap, kmap);
+    launch_pdl(cnn_tail_bwd_kernel, dim3((unsigned)grid), dim3(CT_THREADS), smem, st, a, cmap, kmap);
   }
   MR_CHECK_LAUNCH("cnn_tail_bwd_kernel");
   // fixed-order reductions of the per-CTA partials
