@@ -132,15 +132,26 @@ def build_model(cfg, dev, precision):
     return mr.TwoTower(man, mr.BERT_Embedding(man, vocab_size=cfg["V"]), encN, encU).to(dev)
 
 
-def config_dict(args, precision, cfg, extra=None):
+def config_dict(args, cfg, extra=None):
+    """the WORKLOAD of the line -- identical in both arms (`--impl reference` times the reference on this arm's config); what is
+    specific to an implementation (precision, gradient exchange, how the step is launched) goes under `implementation`"""
     d = {"workload": cfg["workload"], "baseline_config": args.config, "global_batch": cfg["B"] * args.gpus, "per_gpu_batch": cfg["B"],
-         "precision": precision, "parallelism": "dp%d" % args.gpus,
-         "grad_sync": ("torch DDP" if getattr(args, "ddp", False) else "trainer.GradSync (in-place NCCL all-reduce, one NCCL stream)") if args.gpus > 1 else "none",
-         "optimizer": "Adam lr 1e-4 / bert_lr 6e-6",
+         "parallelism": "dp%d" % args.gpus, "optimizer": "Adam lr 1e-4 / bert_lr 6e-6",
          "l2": "8 distinct batches cycled; per-step working set (saved activations ~0.5-1 GB) exceeds the 126 MB L2"}
     if extra:
         d.update(extra)
     return d
+
+
+def eval_config(args, cfg):
+    return {"workload": cfg["workload"], "baseline_config": args.config, "parallelism": "dp%d" % args.gpus, "news_sets": cfg["news_sets"],
+            "impressions": cfg["n_impr"],
+            "l2": "every pass re-encodes the whole news set in 32k-title chunks; a chunk's activations (~0.6 GB) exceed the 126 MB L2"}
+
+
+def implementation_dict(args, precision):
+    return {"precision": precision,
+            "grad_sync": ("torch DDP" if getattr(args, "ddp", False) else "trainer.GradSync (in-place NCCL all-reduce, one NCCL stream)") if args.gpus > 1 else "none"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -236,17 +247,22 @@ def run_reference(args):
         val, cores, kind, sample = cpu_eval_baseline(cfg, batches=2 + max(args.steps, 4))
         line = {"impl": "reference", "metric": "eval_news_encoded_per_sec", "value": val, "unit": "news/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * 500 / val, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args, "fp32", cfg),
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": eval_config(args, cfg),
+                "implementation": {"precision": "fp32", "what": "the reference's encode_news on the host cores (oracle/_ref)"},
                 "cpu_baseline": {"value": val, "unit": "news/s", "cores": cores, "kind": kind, "sample": sample},
                 "e2e": {"value": val, "unit": "news/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
     Bs = cfg["B"] if args.config in (2, 3) else 64            # config 5 is ~3x the work per impression: bounded slice
-    val, ms, cores, kind, sample = cpu_train_baseline(cfg, args.warmup, args.steps, Bs=Bs)
+    # the steps asked for, but never more than ~3 minutes of host time (a slow host must still end with a line: the loop stops
+    # early once the budget is spent and `sample` says how many steps were timed)
+    val, ms, cores, kind, sample = cpu_train_baseline(cfg, args.warmup, args.steps, Bs=Bs, budget_s=170)
     line = {"impl": "reference", "metric": "train_impressions_per_sec", "value": val, "unit": "impressions/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args, "fp32", cfg),
+            "config": config_dict(args, cfg),
+            "implementation": {"precision": "fp32", "what": "the reference's models.TwoTower + torch.optim.Adam through the Manager._train loop "
+                                                            "on the host cores (oracle/_ref)" if kind == "reference" else "oracle port on the host cores"},
             "cpu_baseline": {"value": val, "unit": "impressions/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "impressions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -518,7 +534,7 @@ def run_train(args):
                 "unit": "impressions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-                "config": config_dict(args, args.precision, cfg), "clocks": clocks,
+                "config": config_dict(args, cfg), "implementation": implementation_dict(args, args.precision), "clocks": clocks,
                 "e2e": {"value": world * cfg["B"] * args.steps / (ms_e2e * 1e-3), "unit": "impressions/s",
                         "h2d_bytes_per_step": nbytes(host[0]), "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches_eager), "roofline": roof, "roofline_kernels": roof_all, "step_roofline": step_roof,
@@ -527,11 +543,11 @@ def run_train(args):
                 "eager": {"ms_per_step": ms_eager / args.steps, "value": world * cfg["B"] * args.steps / (ms_eager * 1e-3),
                           "launches": int(launches_eager), "note": "the same steps launched kernel by kernel (ctypes -> libmindrec.so, PDL)"},
                 "token_batches": tok_info, "e2e_token_batches": e2e_tok, "eval": eval_info, "dedup": dedup_info}
-        line["config"]["step_execution"] = (
+        line["implementation"]["step_execution"] = (
             "one CUDA-graph replay per step (trainer.GraphStep: forward, loss, backward, %sAdam captured once; launches counted by the "
             "library during capture)" % ("NCCL all-reduces, " if world > 1 else "")) if gstep is not None else \
             "eager launches (ctypes -> libmindrec.so) with programmatic dependent launch" + ("; graph capture failed: " + graph_error if graph_error else "")
-        line["config"]["inputs"] = ("id-only batches (news ids, history mask, user ids, labels); token table resident in HBM, title rows gathered on "
+        line["implementation"]["inputs"] = ("id-only batches (news ids, history mask, user ids, labels); token table resident in HBM, title rows gathered on "
                                     "the device (mr_gather_titles)") if fused else "int64 token batches (the reference's contract)"
         if gstep is not None:
             line["gpu_launches"] = int(launches_eager)            # kernels per `steps` steps: a replay runs the captured launches
@@ -652,8 +668,9 @@ def run_eval(args):
         line = {"metric": "eval_news_encoded_per_sec", "value": test["value"], "unit": "news/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": test["ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-                "config": config_dict(args, args.precision, cfg, {"news_sets": cfg["news_sets"], "impressions": n_impr, "candidates": n_cand,
-                                                                  "history": "looked up in the news table (TwoTower.encode_user_from_table)"}),
+                "config": eval_config(args, cfg),
+                "implementation": dict(implementation_dict(args, args.precision), impressions=n_impr, candidates=n_cand,
+                                       history="looked up in the news table (TwoTower.encode_user_from_table)"),
                 "clocks": clocks, "e2e": {"value": test["e2e"]["value"], "unit": "news/s", "h2d_bytes_per_step": test["e2e"]["h2d_bytes"],
                                           "d2h_bytes_per_step": 0},
                 "gpu_launches": None, "news_encoding": sets,
