@@ -549,6 +549,7 @@ def run_train(args):
             "eager launches (ctypes -> libmindrec.so) with programmatic dependent launch" + ("; graph capture failed: " + graph_error if graph_error else "")
         line["implementation"]["inputs"] = ("id-only batches (news ids, history mask, user ids, labels); token table resident in HBM, title rows gathered on "
                                     "the device (mr_gather_titles)") if fused else "int64 token batches (the reference's contract)"
+        line["step_execution"] = "cuda_graph" if gstep is not None else "eager"          # (details: implementation.step_execution)
         if gstep is not None:
             line["gpu_launches"] = int(launches_eager)            # kernels per `steps` steps: a replay runs the captured launches
             line["graph_replays"] = args.steps
