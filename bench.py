@@ -204,7 +204,7 @@ def cpu_train_baseline(cfg, warmup, steps, Bs=None, budget_s=None):
             break
     total = sum(ts)
     sample = "%s %d-impression step (zero_grad, forward, NLLLoss, backward, Adam), %d steps after %d warm-up" % (
-        "full" if Bs == cfg["B"] else "%d-of-%d-impression slice of the" % (Bs, cfg["B"]), Bs, len(ts), warmup)
+        "full" if Bs == cfg["B"] else "%d-impression slice of the" % Bs, cfg["B"], len(ts), warmup)
     return Bs * len(ts) / total, 1e3 * total / len(ts), torch.get_num_threads(), kind, sample
 
 
