@@ -525,9 +525,16 @@ def run_train(args):
             dedup_info = {"error": repr(exc)[:300]}
 
     # ---------------- second half of the BASELINE metric: evaluation news-encoded/s over the whole news set
-    eval_info = None
+    eval_info, eval_large = None, None
     if fused and not args.quick:
         eval_info = time_news_encoding(env, core, ids, mask, "%s-train news set" % cfg["scale"])
+        # the same on the news set the sharded encoding is meant for: the MIND-large test set of BASELINE configs[3] (120,961 news,
+        # Manager.py:884-914) -- at 8 GPUs the 51k-title set above is all launch and all-gather latency.  (`--config 4` adds scoring.)
+        try:
+            ids_t, mask_t = data.make_news_table(CONFIGS[4]["news_sets"]["large_test"], cfg["L"], seed=7)
+            eval_large = time_news_encoding(env, core, ids_t, mask_t, "large-test news set")
+        except Exception as exc:                               # noqa: BLE001 -- an extra; the headline numbers stand
+            eval_large = {"error": repr(exc)[:300]}
     if rank == 0:
         per_step = ms / args.steps
         line = {"metric": "train_impressions_per_sec", "value": world * cfg["B"] * args.steps / (ms * 1e-3),
@@ -542,7 +549,7 @@ def run_train(args):
                             "note": "four more timed windows of `steps` steps behind the headline region"},
                 "eager": {"ms_per_step": ms_eager / args.steps, "value": world * cfg["B"] * args.steps / (ms_eager * 1e-3),
                           "launches": int(launches_eager), "note": "the same steps launched kernel by kernel (ctypes -> libmindrec.so, PDL)"},
-                "token_batches": tok_info, "e2e_token_batches": e2e_tok, "eval": eval_info, "dedup": dedup_info}
+                "token_batches": tok_info, "e2e_token_batches": e2e_tok, "eval": eval_info, "eval_large_test": eval_large, "dedup": dedup_info}
         line["implementation"]["step_execution"] = (
             "one CUDA-graph replay per step (trainer.GraphStep: forward, loss, backward, %sAdam captured once; launches counted by the "
             "library during capture)" % ("NCCL all-reduces, " if world > 1 else "")) if gstep is not None else \
