@@ -68,3 +68,31 @@ def test_state_dict_keys_match_reference(golden):
         ref = {k: tuple(v.shape) for k, v in g["params"].items()}
         assert ours == ref, (name, set(ours) ^ set(ref))
         assert model.name == "twotower__%s__%s" % (encn, encu)
+
+
+def test_workspace_planning_runs_without_a_gpu_and_is_bounded():
+    """the *_workspace_bytes / *_plan_bytes entry points are pure host arithmetic (caller-owned buffers): callable here,
+    positive and modest at the BASELINE shapes (HBM is for activations and tables, not scratch), -1 on impossible shapes"""
+    import ctypes
+    from news_recommendation_mind_b200._lib import CnnShape, RnnShape
+    lib = _lib.load()
+    MB = 1 << 20
+    for N, L in ((256 * 55, 32), (256 * 110, 48), (32768, 32)):           # config 2/3 step, config 5 step, one evaluation chunk
+        for precision in (0, 1):
+            s = CnnShape(N, L, 300, 150, 30522, precision)
+            fwd = lib.mr_news_cnn_workspace_bytes(ctypes.byref(s), 0)
+            bwd = lib.mr_news_cnn_workspace_bytes(ctypes.byref(s), 1)
+            assert 0 < fwd <= bwd < 8192 * MB, (N, L, precision, fwd, bwd)
+        s = CnnShape(N, L, 300, 150, 30522, 1)
+        assert 0 < lib.mr_news_cnn_bwd_table_workspace_bytes(ctypes.byref(s)) < 8192 * MB
+        assert 0 < lib.mr_token_group_plan_bytes(N * L, 30522) < 64 * MB
+        assert 0 < lib.mr_embed_grad_workspace_bytes(N * L, 300, 30522) < 1024 * MB
+    assert lib.mr_token_group_plan_bytes(-1, 30522) == -1 and lib.mr_token_group_plan_bytes(1 << 31, 30522) == -1
+    assert lib.mr_embed_grad_workspace_bytes(10, 0, 30522) == -1
+    for kind in (0, 1):
+        for precision in (0, 1):
+            r = RnnShape(256, 50, 150, kind, 0, precision)
+            fwd, bwd = lib.mr_rnn_workspace_bytes(ctypes.byref(r), 0), lib.mr_rnn_workspace_bytes(ctypes.byref(r), 1)
+            assert 0 < fwd and 0 < bwd < 1024 * MB, (kind, precision, fwd, bwd)
+    assert lib.mr_linear_workspace_bytes(1024, 150, 300) >= 0
+    assert lib.mr_linear_tc_workspace_bytes(256 * 110 * 48, 300, 300, 30522, 1) > 0
