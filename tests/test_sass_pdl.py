@@ -41,3 +41,46 @@ def test_no_noncoherent_load_above_griddepcontrol_wait():
                 early += 1
     assert kernels_with_wait > 20, kernels_with_wait          # the check looked at the kernels it is meant for
     assert not offenders, offenders
+
+
+def _sass_by_function(obj):
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([exe, "-sass", os.path.join(BUILD, obj)], capture_output=True, text=True).stdout
+    out, fn = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+            out[fn] = []
+        elif fn is not None:
+            out[fn].append(line)
+    return {k: "\n".join(v) for k, v in out.items()}
+
+
+def test_hot_kernels_use_tcgen05_tmem_and_tma():
+    """the tensor path is Blackwell's own (north_star items 2, 3): every hot kernel issues tcgen05.mma (SASS UTCHMMA), reads its
+    accumulators from tensor memory (LDTM), and the operand movers are TMA (UTMALDG) / bulk copies (UBLKCP); the conv forward runs
+    as CTA pairs (UTCHMMA.2CTA, multicast commit); the LSTM recurrences take W_hh from tensor memory (an MMA with a tmem A operand); none of them
+    falls back to the legacy warp-level HMMA pipe."""
+    from news_recommendation_mind_b200 import build
+    build.build()
+    want = {
+        "tapgemm2.o": ("tapgemm2_kernel", ["UTCHMMA.2CTA", "UTCBAR.2CTA.MULTICAST", "LDTM", "UBLKCP"]),     # A rows are GATHERED (token ids): cp.async
+        "cnn_tail.o": ("cnn_tail_fwd_kernel", ["UTCHMMA", "LDTM", "UTMALDG", "UBLKCP"]),
+        "tokred.o": ("tokred_kernel", ["UTCHMMA", "LDTM", "UTMALDG"]),
+        "tapgemm.o": ("tapgemm_kernel", ["UTCHMMA", "LDTM"]),
+        "rnn_tc.o": ("rnn_tc_fwd_kernel", ["UTCHMMA", "LDTM", "STTM"]),
+    }
+    for obj, (kernel, mnemonics) in want.items():
+        fns = {k: v for k, v in _sass_by_function(obj).items() if kernel in k}
+        assert fns, (obj, kernel)
+        for name, text in fns.items():
+            for mn in mnemonics:
+                assert mn in text, (obj, name, mn)
+            assert not re.search(r"\bHMMA\.", text), (obj, name, "legacy mma.sync in a tcgen05 kernel")
+    for kernel in ("cnn_tail_bwd_kernel", "rnn_tc_bwd_kernel"):
+        obj = "cnn_tail.o" if "tail" in kernel else "rnn_tc.o"
+        fns = {k: v for k, v in _sass_by_function(obj).items() if kernel in k}
+        assert fns and all("UTCHMMA" in t and "LDTM" in t for t in fns.values()), kernel
