@@ -82,3 +82,81 @@ def test_metrics_oracle_matches_the_live_cal_metric():
     assert ours == {k: float(ref[k]) for k in ours}, (ours, ref)
     labels, preds = impressions(200, 2, 200, tied=True)
     assert M.ranking_metrics(labels, preds)["auc"] == float(cal_metric(labels, preds, ["auc"])["auc"])
+
+
+def test_grouping_and_partition_match_the_live_reference_utils():
+    """utils.utils._group_lists (split impressions merged by impr_index, utils.py:60-80) and Partition_Sampler (utils.py:267-283)
+    themselves, against oracle/metrics_oracle.py AND the product's host logic (evaluate.group_rows / partition_bounds)."""
+    import numpy as np
+    from oracle import metrics_oracle as M
+    from news_recommendation_mind_b200 import evaluate as ev
+    root = RH.reference_root()
+    sys.path.insert(0, root)
+    try:
+        from utils.utils import _group_lists, Partition_Sampler
+    finally:
+        sys.path.remove(root)
+    rng = np.random.default_rng(5)
+    for trial in range(20):
+        n_rows = int(rng.integers(1, 60))
+        # chunks of one impression are usually adjacent (MIND.py:225-226) but the gathered rows of several ranks are not sorted
+        idx = rng.integers(0, max(2, n_rows // 2), size=n_rows)
+        if trial % 2 == 0:
+            idx = np.sort(idx)
+        sizes = rng.integers(1, 6, size=n_rows)
+        labels = [rng.integers(0, 2, size=s).tolist() for s in sizes]
+        preds = [rng.random(s).tolist() for s in sizes]
+        ref_l, ref_p = _group_lists(idx.tolist(), labels, preds)
+        our_l, our_p = M.group_by_impression(idx.tolist(), labels, preds)
+        assert our_l == ref_l and our_p == ref_p
+        # product: row permutation + group offsets reproduce the same concatenation
+        order, goff = ev.group_rows(torch.as_tensor(idx))
+        rows = list(range(n_rows)) if order is None else order.tolist()
+        got_p = [sum((preds[r] for r in rows[int(goff[g]):int(goff[g + 1])]), []) for g in range(goff.numel() - 1)]
+        assert got_p == ref_p
+    for n, ws in ((10, 3), (7, 7), (1000, 8), (5, 2), (376000, 8)):
+        for r in range(ws):
+            s = Partition_Sampler(range(n), ws, r)
+            assert (s.start, s.end) == M.partition_bounds(n, ws, r) == tuple(ev.partition_bounds(n, ws, r))
+
+
+@pytest.mark.parametrize("encu", ["lstm", "gru", "attn", "lstur"])
+def test_eval_paths_match_the_live_reference(encu):
+    """Manager._eval_fast's calls on the reference itself (Manager.py:498-517): encode_news in eval mode -> the [N+1, H] table,
+    predict_fast over that table (news_reprs installed as init_embedding does, minus the torch.load from data/cache), and the slow
+    eval forward (sigmoid) -- against oracle.encode_news / predict_fast / forward(training=False)."""
+    B, C, S, L, E, H, V, hn, n_news = 6, 9, 8, 10, 32, 16, 200, 4, 25
+    seed = 300 + len(encu)
+    model = RH.build_model("cnn", encu, V=V, E=E, H=H, C=C, S=S, L=L, hn=hn, n_users=40, seed=seed, dropout_p=0.0)
+    gen = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.05 * torch.randn(p.shape, generator=gen))
+    model.eval()
+    x = random_batch(gen, B, C, S, L, V)
+    x["cdd_id"] = torch.randint(0, n_news + 1, (B, C), generator=gen)
+    kw = {}
+    if encu == "lstur":
+        keep = torch.ones(B, dtype=torch.long)             # eval: the user embedding is always kept (no Bernoulli mask at test time)
+        model.encoderU.keep_user = keep
+        kw["keep_user"] = keep
+    params = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    # the news table, row 0 = the empty article [CLS][SEP] (MIND.py:125-127)
+    tok = torch.randint(1, V, (n_news + 1, L), generator=gen)
+    ln = torch.randint(2, L + 1, (n_news + 1,), generator=gen)
+    msk = (torch.arange(L)[None, :] < ln[:, None]).long()
+    tok = tok * msk
+    with torch.no_grad():
+        model.init_encoding()
+        table = model.encode_news({"cdd_encoded_index": tok.unsqueeze(1), "cdd_attn_mask": msk.unsqueeze(1)}).squeeze(-2)
+        model.destroy_encoding()
+        model.news_reprs = torch.nn.Embedding.from_pretrained(table)
+        ref_fast = model.predict_fast(x)
+        ref_slow = model(x)[0]
+    ours_table = O.encode_news(params, tok.unsqueeze(1), msk.unsqueeze(1), "cnn").squeeze(-2)
+    assert torch.allclose(ours_table, table, rtol=1e-5, atol=1e-6)
+    ours_fast = O.predict_fast(params, table, x, encoder_n="cnn", encoder_u=encu, head_num=hn, **kw)
+    ours_slow = O.forward(params, x, False, encoder_n="cnn", encoder_u=encu, head_num=hn, **kw)
+    assert ref_fast.shape == ours_fast.shape == (B, C)
+    assert torch.allclose(ours_fast, ref_fast, rtol=1e-5, atol=1e-6), float((ours_fast - ref_fast).abs().max())
+    assert torch.allclose(ours_slow, ref_slow, rtol=1e-5, atol=1e-6), float((ours_slow - ref_slow).abs().max())
