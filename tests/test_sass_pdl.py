@@ -84,3 +84,31 @@ def test_hot_kernels_use_tcgen05_tmem_and_tma():
         obj = "cnn_tail.o" if "tail" in kernel else "rnn_tc.o"
         fns = {k: v for k, v in _sass_by_function(obj).items() if kernel in k}
         assert fns and all("UTCHMMA" in t and "LDTM" in t for t in fns.values()), kernel
+
+
+def test_hot_kernels_fit_their_register_and_stack_budget():
+    """the persistent tcgen05 kernels are sized against the register file (threads x registers <= 64 K per SM, one CTA per SM) and
+    must not spill: a spill shows up as a stack frame beyond the few bytes ptxas keeps for the 64-bit address arithmetic of the
+    tensor-map / descriptor helpers, or as a LOCAL segment.  Budgets = threads per CTA of the launch (csrc/*.cu) -> registers."""
+    from news_recommendation_mind_b200 import build
+    build.build()
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    # kernel -> (object, threads per CTA as launched, stack bytes tolerated)
+    budget = {
+        "cnn_tail_fwd_kernel": ("cnn_tail.o", 14 * 32, 64),
+        "cnn_tail_bwd_kernel": ("cnn_tail.o", 18 * 32, 64),
+        "tapgemm2_kernel": ("tapgemm2.o", 448, 64),
+        "tokred_kernel": ("tokred.o", 288, 64),
+        "rnn_tc_fwd_kernel": ("rnn_tc.o", 512, 32),
+        "rnn_tc_bwd_kernel": ("rnn_tc.o", 512, 32),
+    }
+    for kernel, (obj, threads, stack_max) in budget.items():
+        txt = subprocess.run([exe, "--dump-resource-usage", os.path.join(BUILD, obj)], capture_output=True, text=True).stdout
+        rows = re.findall(r"Function (\S*%s\S*):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)" % kernel, txt)
+        assert rows, (kernel, obj)
+        for name, reg, stack, _shared, local in rows:
+            assert int(local) == 0, (name, "local memory", local)
+            assert int(stack) <= stack_max, (name, "stack frame (spill?)", stack)
+            assert int(reg) * threads <= 65536, (name, reg, threads)
