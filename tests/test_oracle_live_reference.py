@@ -160,3 +160,72 @@ def test_eval_paths_match_the_live_reference(encu):
     assert ref_fast.shape == ours_fast.shape == (B, C)
     assert torch.allclose(ours_fast, ref_fast, rtol=1e-5, atol=1e-6), float((ours_fast - ref_fast).abs().max())
     assert torch.allclose(ours_slow, ref_slow, rtol=1e-5, atol=1e-6), float((ours_slow - ref_slow).abs().max())
+
+
+@pytest.mark.parametrize("encu", ["lstm", "lstur"])
+def test_checkpoints_interchange_through_the_reference_save_and_load(encu, tmp_path, monkeypatch):
+    """Manager.save / Manager.load THEMSELVES (Manager.py:288-343, unbound, over a stand-in `self` carrying the three attributes
+    they read) move a `.model` file between the reference's TwoTower + torch.optim.Adam and this package's TwoTower + FusedAdam:
+    reference -> file -> ours, ours -> file -> reference, and a DDP-written file (`module.` prefixes) into a bare model."""
+    import types
+    from helpers import build_model, manager_for
+    from news_recommendation_mind_b200 import trainer
+    root = RH.reference_root()
+    sys.path.insert(0, root)
+    try:
+        from utils.Manager import Manager
+    finally:
+        sys.path.remove(root)
+    B, C, S, L, E, H, V, hn = 4, 3, 5, 8, 24, 12, 120, 4
+    ref = RH.build_model("cnn", encu, V=V, E=E, H=H, C=C, S=S, L=L, hn=hn, n_users=40, seed=77, dropout_p=0.0)
+    ref_opt = RH.make_optimizer(ref)
+    gen = torch.Generator().manual_seed(77)
+    ref.train()
+    for _ in range(2):                                      # moments and step counts worth saving
+        x = random_batch(gen, B, C, S, L, V)
+        if encu == "lstur":
+            ref.encoderU.keep_user = torch.ones(B, dtype=torch.long)
+        RH.train_step(ref, ref_opt, x)
+    ours = build_model(manager_for("cnn", encu, C, S, L, E, H, hn, device="cpu"), V)
+    ours_opt = trainer.FusedAdam(ours, lr=1.0, bert_lr=1.0)
+    me = types.SimpleNamespace(name=ours.name, scale="demo", world_size=0)
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("data/model_params/%s" % me.name)
+
+    def same(a, b):
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa) == list(sb)
+        assert all(torch.equal(sa[k], sb[k]) for k in sa)
+
+    def same_opt(fused, adam):
+        assert [g["lr"] for g in fused.param_groups] == [g["lr"] for g in adam.param_groups]
+        fp = [p for g in fused.param_groups for p in g["params"]]
+        ap = [p for g in adam.param_groups for p in g["params"]]
+        assert len(fp) == len(ap)
+        for p, q in zip(fp, ap):
+            if q in adam.state:
+                assert torch.equal(fused.state[p][0], adam.state[q]["exp_avg"]) and torch.equal(fused.state[p][1], adam.state[q]["exp_avg_sq"])
+                assert float(adam.state[q]["step"]) == fused.steps
+    # reference -> ours
+    Manager.save(me, ref, 2, ref_opt)
+    assert os.path.exists("data/model_params/%s/demo_step2.model" % me.name)
+    Manager.load(me, ours, 2, ours_opt)
+    same(ours, ref)
+    same_opt(ours_opt, ref_opt)
+    # ours -> reference (a fresh reference model and optimiser)
+    with torch.no_grad():
+        for p in ours.parameters():
+            p.mul_(1.5)
+    Manager.save(me, ours, 3, ours_opt)
+    ref2 = RH.build_model("cnn", encu, V=V, E=E, H=H, C=C, S=S, L=L, hn=hn, n_users=40, seed=5, dropout_p=0.0)
+    ref2_opt = RH.make_optimizer(ref2, lr=1.0, bert_lr=1.0)
+    Manager.load(me, ref2, 3, ref2_opt)
+    same(ours, ref2)
+    same_opt(ours_opt, ref2_opt)
+    # a file written from a DDP-wrapped model (keys prefixed `module.`) into a bare model, world_size <= 1 (Manager.py:324-332)
+    wrapped = torch.nn.Module()
+    wrapped.module = ref
+    Manager.save(me, wrapped, 4, ref_opt)
+    ours2 = build_model(manager_for("cnn", encu, C, S, L, E, H, hn, device="cpu"), V)
+    Manager.load(me, ours2, 4, trainer.FusedAdam(ours2))
+    same(ours2, ref)
