@@ -229,3 +229,34 @@ def test_checkpoints_interchange_through_the_reference_save_and_load(encu, tmp_p
     ours2 = build_model(manager_for("cnn", encu, C, S, L, E, H, hn, device="cpu"), V)
     Manager.load(me, ours2, 4, trainer.FusedAdam(ours2))
     same(ours2, ref)
+
+
+def test_optimizer_groups_and_schedule_match_the_reference_get_optim():
+    """Manager._get_optim ITSELF (Manager.py:389-422) over this package's TwoTower: the parameters it puts in the `bert` group, the
+    order inside both groups (the state-dict indices of a checkpoint), and the learning rates of the linear warm-up schedule over a
+    whole run -- against trainer.FusedAdam + trainer.LinearWarmupSchedule."""
+    import types
+    from helpers import build_model, manager_for
+    from news_recommendation_mind_b200 import trainer
+    root = RH.reference_root()
+    sys.path.insert(0, root)
+    try:
+        from utils.Manager import Manager
+    finally:
+        sys.path.remove(root)
+    for encn, encu in (("cnn", "lstm"), ("mha", "lstur"), ("cnn", "mha")):
+        ours = build_model(manager_for(encn, encu, 3, 5, 8, 24, 12, 4, device="cpu"), 120)
+        me = types.SimpleNamespace(world_size=0, lr=1e-4, bert_lr=6e-6, scheduler="linear", warmup=4, epochs=3)
+        ref_opt, ref_sched = Manager._get_optim(me, ours, 7)                # 7 steps per epoch x 3 epochs
+        opt = trainer.FusedAdam(ours, lr=me.lr, bert_lr=me.bert_lr)
+        sched = trainer.LinearWarmupSchedule(opt, me.warmup, 7 * me.epochs)
+        assert [[id(p) for p in g["params"]] for g in opt.param_groups] == [[id(p) for p in g["params"]] for g in ref_opt.param_groups]
+        assert len(opt.param_groups[1]["params"]) == 1                      # the word-embedding table alone
+        for _ in range(7 * me.epochs + 2):
+            got, want = [g["lr"] for g in opt.param_groups], [g["lr"] for g in ref_opt.param_groups]
+            assert all(abs(a - b) <= 1e-12 * max(abs(b), 1e-30) + 1e-30 for a, b in zip(got, want)), (got, want)
+            for p in ours.parameters():
+                p.grad = torch.zeros_like(p)
+            ref_opt.step()
+            ref_sched.step()
+            sched.step()
