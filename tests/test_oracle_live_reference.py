@@ -260,3 +260,100 @@ def test_optimizer_groups_and_schedule_match_the_reference_get_optim():
             ref_opt.step()
             ref_sched.step()
             sched.step()
+
+
+def _stage_mind_files(tmp_path, mode, news_ids, news_mask, lines, n_users):
+    """the files utils/MIND.py reads, relative to the working directory: behaviors.tsv, the two id dictionaries and the tokenised
+    news cache (the tokeniser itself needs the network; its output format is MIND.py:139-150: two [N+1, 512] integer arrays)"""
+    import json
+    import pickle
+    d = tmp_path / "data" / "MIND" / ("MINDdemo_%s" % mode)
+    d.mkdir(parents=True)
+    (d / "behaviors.tsv").write_text("".join(lines))
+    dic = tmp_path / "data" / "dictionaries"
+    dic.mkdir(parents=True, exist_ok=True)
+    (dic / ("nid2idx_demo_%s.json" % mode)).write_text(json.dumps({"N%d" % i: i for i in range(1, news_ids.shape[0])}))
+    (dic / "uid2idx_demo.json").write_text(json.dumps({"U%d" % i: i for i in range(1, n_users + 1)}))
+    nc = tmp_path / "data" / "cache" / "MIND" / "news" / "bert" / ("MINDdemo_%s" % mode)
+    nc.mkdir(parents=True)
+    with open(nc / "news.pkl", "wb") as f:
+        pickle.dump({"encoded_news": news_ids.numpy().copy(), "attn_mask": news_mask.numpy().copy()}, f)
+    return "data/MIND/MINDdemo_%s/" % mode
+
+
+def _mind_manager(mode, C, S, L, impr_size):
+    import types
+    m = types.SimpleNamespace(his_size=S, impr_size=impr_size, signal_length=L, npratio=C - 1, shuffle_pos=False, descend_history=False,
+                              bert="bert", mode=mode, rank=-1, world_size=0)
+    m.get_bert_for_cache = lambda: "bert"
+    m.get_special_token_id = lambda tok: {"[PAD]": 0, "[SEP]": 102}[tok]
+    return m
+
+
+def test_batches_follow_the_live_dataset_class(tmp_path, monkeypatch):
+    """utils/MIND.py ITSELF -- MINDBaseDataset.__init__ (init_behaviors from a behaviors.tsv, the impr_size chunking of
+    MIND.py:225-226, the news cache), MIND.__getitem__ (MIND.py:296-405) and the DataLoader's default collate -- over the files of
+    the very samples data.make_train_batch / data.make_eval_impressions draw: same keys, dtypes, shapes and values (the negatives
+    of a training sample up to the order random.sample leaves them in)."""
+    import numpy as np
+    from torch.utils.data import default_collate
+    from news_recommendation_mind_b200 import data
+    root = RH.reference_root()
+    sys.path.insert(0, root)
+    try:
+        from utils.MIND import MIND
+    finally:
+        sys.path.remove(root)
+    monkeypatch.chdir(tmp_path)
+    B, C, S, L, n_news, n_users = 24, 5, 6, 12, 60, 30
+    ids, mask = data.make_news_table(n_news, L, seed=3)
+    # ---------------------------------------------------------------- train
+    x = data.make_train_batch(ids, mask, B, C, S, seed=9, n_users=n_users)
+    # sample 0 becomes a user without history, as data.py lays one out (his_len 0: ids all 0 = the empty article, his_mask[0] = 1,
+    # MIND.py:332-337); the log-normal history lengths of the synthetic data almost never draw one
+    x["his_id"][0] = 0
+    x["his_encoded_index"][0], x["his_attn_mask"][0] = ids[0], mask[0]
+    x["his_mask"][0] = 0
+    x["his_mask"][0, 0] = 1
+    lens = x["his_mask"].squeeze(-1).sum(-1).long()
+    lines = []
+    for b in range(B):
+        his = [int(v) for v in x["his_id"][b] if int(v) != 0]
+        assert len(his) == (int(lens[b]) if int(x["his_id"][b, 0]) != 0 else 0)
+        impr = ["N%d-1" % int(x["cdd_id"][b, 0])] + ["N%d-0" % int(v) for v in x["cdd_id"][b, 1:]]
+        lines.append("%d\tU%d\tt\t%s\t%s\n" % (b + 1, int(x["user_id"][b]), " ".join("N%d" % v for v in his), " ".join(impr)))
+    ds = MIND(_mind_manager("train", C, S, L, 0), _stage_mind_files(tmp_path, "train", ids, mask, lines, n_users))
+    assert len(ds) == B
+    ref = default_collate([ds[i] for i in range(B)])
+    assert set(ref) == set(x)
+    for k in x:
+        assert ref[k].dtype == x[k].dtype and ref[k].shape == x[k].shape, (k, ref[k].dtype, x[k].dtype, ref[k].shape, x[k].shape)
+    for k in ("user_id", "his_id", "his_encoded_index", "his_attn_mask", "his_mask", "cdd_mask", "label"):
+        assert torch.equal(ref[k], x[k]), k
+    assert torch.equal(ref["cdd_id"][:, 0], x["cdd_id"][:, 0])
+    assert torch.equal(ref["cdd_id"][:, 1:].sort(dim=1).values, x["cdd_id"][:, 1:].sort(dim=1).values)
+    assert torch.equal(ref["cdd_encoded_index"], ids[ref["cdd_id"]]) and torch.equal(ref["cdd_attn_mask"], mask[ref["cdd_id"]])
+    # ---------------------------------------------------------------- dev, impressions longer than impr_size cut into chunks
+    impr_size, n_impr = 7, 40
+    ev = data.make_eval_impressions(ids, mask, n_impr, S, seed=4, n_users=n_users, impr_size=impr_size)
+    off = ev["offsets"].tolist()
+    n_rows = len(off) - 1
+    assert n_rows > n_impr                                      # some impressions were cut
+    lines = []
+    for i in range(n_impr):
+        rows = [r for r in range(n_rows) if int(ev["impr_index"][r]) == i]
+        assert rows == list(range(rows[0], rows[-1] + 1))      # chunks of one impression are adjacent
+        his = [int(v) for v in ev["his_id"][rows[0]] if int(v) != 0]
+        cand = ["N%d-%d" % (int(ev["cdd_id"][j]), int(ev["label"][j])) for j in range(off[rows[0]], off[rows[-1] + 1])]
+        lines.append("%d\tU%d\tt\t%s\t%s\n" % (i + 1, int(ev["user_id"][rows[0]]), " ".join("N%d" % v for v in his), " ".join(cand)))
+    ds = MIND(_mind_manager("dev", C, S, L, impr_size), _stage_mind_files(tmp_path, "dev", ids, mask, lines, n_users))
+    assert len(ds) == n_rows
+    for r in range(n_rows):
+        got = default_collate([ds[r]])                          # the dev loader's batch size is 1 (Manager.py:228-238)
+        assert int(got["impr_index"]) == int(ev["impr_index"][r]) + 1          # 1-based in the reference; only equality is used
+        assert int(got["user_id"]) == int(ev["user_id"][r])
+        assert got["cdd_id"][0].tolist() == ev["cdd_id"][off[r]:off[r + 1]].tolist()
+        assert got["label"][0].tolist() == [int(v) for v in ev["label"][off[r]:off[r + 1]]]
+        for k in ("his_id", "his_encoded_index", "his_attn_mask", "his_mask"):
+            assert got[k].dtype == ev[k].dtype and torch.equal(got[k][0], ev[k][r]), (k, r)
+        assert torch.equal(got["cdd_encoded_index"][0], ids[got["cdd_id"][0]])
