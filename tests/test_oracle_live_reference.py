@@ -357,3 +357,52 @@ def test_batches_follow_the_live_dataset_class(tmp_path, monkeypatch):
         for k in ("his_id", "his_encoded_index", "his_attn_mask", "his_mask"):
             assert got[k].dtype == ev[k].dtype and torch.equal(got[k][0], ev[k][r]), (k, r)
         assert torch.equal(got["cdd_encoded_index"][0], ids[got["cdd_id"][0]])
+
+
+@pytest.mark.parametrize("encu", ["lstm", "attn"])
+def test_training_trajectory_matches_the_live_training_loop(encu, tmp_path, monkeypatch):
+    """Manager.train ITSELF (Manager.py:700-722: _get_loss, _get_optim with the linear warm-up schedule, then the _train loop of
+    Manager.py:586-688) drives the reference model over two epochs of four batches; the oracle's train_step (forward, NLLLoss,
+    backward, two-group Adam) with the schedule's learning rates must land on the same losses and the same parameters."""
+    root = RH.reference_root()
+    sys.path.insert(0, root)
+    try:
+        import utils.Manager as MM
+    finally:
+        sys.path.remove(root)
+    monkeypatch.chdir(tmp_path)
+    B, C, S, L, E, H, V, hn = 6, 4, 5, 10, 32, 16, 150, 4
+    model = RH.build_model("cnn", encu, V=V, E=E, H=H, C=C, S=S, L=L, hn=hn, n_users=40, seed=55, dropout_p=0.0)
+    gen = torch.Generator().manual_seed(55)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.05 * torch.randn(p.shape, generator=gen))
+    batches = [random_batch(gen, B, C, S, L, V) for _ in range(4)]
+    params = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    man = object.__new__(MM.Manager)                                      # no argument parsing: the attributes the loop reads
+    for k, v in dict(rank=-1, world_size=0, name="live", scale="small", step=0, interval=10, save_epoch=False, epochs=2, smoothing=0.3,
+                     checkpoint=0, anomaly=False, lr=3e-3, bert_lr=1e-3, scheduler="linear", warmup=3, hold_step=10 ** 9).items():
+        setattr(man, k, v)
+    man._log = lambda res: None                                           # the result log file is not part of the path
+    losses = []
+    real_float = float
+
+    class Spy(torch.nn.NLLLoss):                                          # the loop keeps only the epoch sum of the losses
+        def forward(self, pred, label):
+            out = super().forward(pred, label)
+            losses.append(real_float(out.detach()))
+            return out
+    monkeypatch.setattr(MM.nn, "NLLLoss", Spy)
+    model.train()
+    man.train(model, [batches])
+    assert len(losses) == 8
+    total, warm = 8, 3
+    state, ours = {}, []
+    for s in range(total):
+        f = s / warm if s < warm else max(0.0, (total - s) / (total - warm))          # get_linear_schedule_with_warmup
+        loss, _ = O.train_step(params, state, batches[s % 4], s + 1, lr=3e-3 * f, bert_lr=1e-3 * f, encoder_n="cnn", encoder_u=encu,
+                               head_num=hn)
+        ours.append(loss)
+    assert all(abs(a - b) <= 1e-5 * max(1.0, abs(b)) for a, b in zip(ours, losses)), (ours, losses)
+    for k, ref in model.state_dict().items():
+        torch.testing.assert_close(params[k], ref, rtol=1e-4, atol=1e-4, msg=lambda m: k + ": " + m)
