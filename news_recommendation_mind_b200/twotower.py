@@ -126,7 +126,7 @@ class TwoTower(TwoTowerBaseModel):
         # opt-in (manager.history_from_table): predict_fast looks the clicked-news vectors up in the news table built by
         # init_embedding instead of re-encoding them from tokens (what models/PLM.py:112-113 does).
         # Same bits: the table rows come from the same batch-invariant encoder, row 0 must be the encoded empty article
-        # (evaluate.encode_all_news encodes it; the reference's own table leaves row 0 at zero, Manager.py:496).
+        # (evaluate.encode_all_news encodes it, as the reference's own table build does: MIND_news starts at index 0, MIND.py:462-487).
         self.history_from_table = bool(getattr(manager, "history_from_table", False))
         self.news_tok_ids = self.news_tok_mask = None
 

@@ -406,3 +406,67 @@ def test_training_trajectory_matches_the_live_training_loop(encu, tmp_path, monk
     assert all(abs(a - b) <= 1e-5 * max(1.0, abs(b)) for a, b in zip(ours, losses)), (ours, losses)
     for k, ref in model.state_dict().items():
         torch.testing.assert_close(params[k], ref, rtol=1e-4, atol=1e-4, msg=lambda m: k + ": " + m)
+
+
+@pytest.mark.parametrize("encu", ["lstm", "attn"])
+def test_fast_evaluation_matches_the_live_manager_evaluate(encu, tmp_path, monkeypatch):
+    """Manager.evaluate ITSELF in fast mode (Manager.py:545-584 -> _eval_fast :473-541 -> cal_metric :1276-1344) over the reference's
+    own datasets and DataLoaders (MIND dev with impressions cut at impr_size, MIND_news), on the reference model: the metrics
+    dictionary against the oracle pipeline the GPU tests are held to (encode_news table incl. row 0 = the encoded empty article,
+    predict_fast per chunk, chunks of one impression merged, AUC / MRR / nDCG@5/10 rounded to 4 decimals)."""
+    from torch.utils.data import DataLoader
+    from news_recommendation_mind_b200 import data
+    from oracle import metrics_oracle as M
+    root = RH.reference_root()
+    sys.path.insert(0, root)
+    try:
+        import utils.Manager as MM
+        from utils.MIND import MIND, MIND_news
+    finally:
+        sys.path.remove(root)
+    monkeypatch.chdir(tmp_path)
+    C, S, L, E, H, V, hn, n_news, n_users, impr_size, n_impr = 5, 6, 12, 32, 16, 31000, 4, 60, 30, 7, 40
+    ids, mask = data.make_news_table(n_news, L, seed=3)
+    ev = data.make_eval_impressions(ids, mask, n_impr, S, seed=4, n_users=n_users, impr_size=impr_size)
+    off = ev["offsets"].tolist()
+    n_rows = len(off) - 1
+    lines = []
+    for i in range(n_impr):
+        rows = [r for r in range(n_rows) if int(ev["impr_index"][r]) == i]
+        his = [int(v) for v in ev["his_id"][rows[0]] if int(v) != 0]
+        cand = ["N%d-%d" % (int(ev["cdd_id"][j]), int(ev["label"][j])) for j in range(off[rows[0]], off[rows[-1] + 1])]
+        lines.append("%d\tU%d\tt\t%s\t%s\n" % (i + 1, int(ev["user_id"][rows[0]]), " ".join("N%d" % v for v in his), " ".join(cand)))
+    directory = _stage_mind_files(tmp_path, "dev", ids, mask, lines, n_users)
+    model = RH.build_model("cnn", encu, V=V, E=E, H=H, C=C, S=S, L=L, hn=hn, n_users=n_users, seed=21, dropout_p=0.0)
+    gen = torch.Generator().manual_seed(21)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.05 * torch.randn(p.shape, generator=gen))
+    man = object.__new__(MM.Manager)
+    dm = _mind_manager("dev", C, S, L, impr_size)
+    for k, v in dict(vars(dm), name=model.name, scale="demo", fast=True, smoothing=0.3, checkpoint=0,
+                     metrics=["auc", "mean_mrr", "ndcg@5", "ndcg@10"]).items():
+        setattr(man, k, v)
+    man.get_news_num = lambda: n_news
+    man._log = lambda res: None
+    loaders = [DataLoader(MIND(man, directory), batch_size=1), DataLoader(MIND_news(man, directory), batch_size=7)]
+    ref = man.evaluate(model, loaders, log=False)
+    # ---- the oracle pipeline
+    params = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        table = O.encode_news(params, ids.unsqueeze(1), mask.unsqueeze(1), "cnn").squeeze(-2)
+        assert float(table[0].abs().max()) > 0                              # MIND_news starts at index 0: row 0 IS encoded
+        saved = torch.load("data/cache/tensors/%s/demo/dev/news.pt" % model.name)
+        assert torch.allclose(table, saved, rtol=1e-5, atol=1e-6)
+        idx, labels, preds = [], [], []
+        for r in range(n_rows):
+            x = {"cdd_id": ev["cdd_id"][off[r]:off[r + 1]].unsqueeze(0), "his_encoded_index": ev["his_encoded_index"][r:r + 1],
+                 "his_attn_mask": ev["his_attn_mask"][r:r + 1], "his_mask": ev["his_mask"][r:r + 1], "user_id": ev["user_id"][r:r + 1]}
+            p = O.predict_fast(params, table, x, encoder_n="cnn", encoder_u=encu, head_num=hn)
+            idx.append(int(ev["impr_index"][r]))
+            preds.append(p[0].tolist())
+            labels.append(ev["label"][off[r]:off[r + 1]].tolist())
+    gl, gp = M.group_by_impression(idx, labels, preds)
+    assert len(gl) == n_impr < n_rows
+    ours = M.ranking_metrics(gl, gp)
+    assert ours == {k: float(ref[k]) for k in ours}, (ours, ref)
