@@ -470,3 +470,69 @@ def test_fast_evaluation_matches_the_live_manager_evaluate(encu, tmp_path, monke
     assert len(gl) == n_impr < n_rows
     ours = M.ranking_metrics(gl, gp)
     assert ours == {k: float(ref[k]) for k in ours}, (ours, ref)
+
+
+def test_prediction_file_matches_the_live_manager_test(tmp_path, monkeypatch):
+    """Manager.test ITSELF (Manager.py:815-850: load the checkpoint, _test_fast over the MIND test split -- whose history arrives
+    REVERSED under the default descend_history=False, MIND.py:423-426 --, merge the chunks, write prediction.txt with scipy's ordinal
+    ranks) against the oracle's predictions ranked by metrics_oracle.ordinal_rank (the rule mr_rank_metrics implements bit for bit)
+    and written by evaluate.write_predictions.  The only textual difference allowed is the `.0` scipy >= 1.10 appends to the ranks
+    (the reference's pinned scipy prints integers, and so does the MIND submission format)."""
+    import numpy as np
+    from torch.utils.data import DataLoader
+    from news_recommendation_mind_b200 import data, evaluate as evl
+    from oracle import metrics_oracle as M
+    root = RH.reference_root()
+    sys.path.insert(0, root)
+    try:
+        import utils.Manager as MM
+        from utils.MIND import MIND, MIND_news
+    finally:
+        sys.path.remove(root)
+    monkeypatch.chdir(tmp_path)
+    C, S, L, E, H, V, hn, n_news, n_users, impr_size, n_impr = 5, 6, 12, 32, 16, 31000, 4, 60, 30, 7, 25
+    ids, mask = data.make_news_table(n_news, L, seed=13)
+    ev = data.make_eval_impressions(ids, mask, n_impr, S, seed=14, n_users=n_users, impr_size=impr_size)
+    off = ev["offsets"].tolist()
+    n_rows = len(off) - 1
+    lines = []
+    for i in range(n_impr):
+        rows = [r for r in range(n_rows) if int(ev["impr_index"][r]) == i]
+        his = [int(v) for v in ev["his_id"][rows[0]] if int(v) != 0]
+        cand = ["N%d" % int(ev["cdd_id"][j]) for j in range(off[rows[0]], off[rows[-1] + 1])]          # the test split has no labels
+        lines.append("%d\tU%d\tt\t%s\t%s\n" % (i + 1, int(ev["user_id"][rows[0]]), " ".join("N%d" % v for v in his), " ".join(cand)))
+    directory = _stage_mind_files(tmp_path, "test", ids, mask, lines, n_users)
+    model = RH.build_model("cnn", "lstm", V=V, E=E, H=H, C=C, S=S, L=L, hn=hn, n_users=n_users, seed=31, dropout_p=0.0)
+    model.mode = "test"                                         # TwoTowerBaseModel.py:12 under `-m test`: where init_embedding looks for news.pt
+    gen = torch.Generator().manual_seed(31)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.05 * torch.randn(p.shape, generator=gen))
+    man = object.__new__(MM.Manager)
+    for k, v in dict(vars(_mind_manager("test", C, S, L, impr_size)), name=model.name, scale="demo", fast=True, smoothing=0.3,
+                     checkpoint=5).items():
+        setattr(man, k, v)
+    man.get_news_num = lambda: n_news
+    os.makedirs("data/model_params/%s" % model.name)
+    man.save(model, 5, RH.make_optimizer(model))
+    loaders = [DataLoader(MIND(man, directory), batch_size=1), DataLoader(MIND_news(man, directory), batch_size=7)]
+    man.test(model, loaders)
+    ref_text = open("data/results/%s/demo_step5/prediction.txt" % model.name).read()
+    # ---- ours
+    params = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        table = O.encode_news(params, ids.unsqueeze(1), mask.unsqueeze(1), "cnn").squeeze(-2)
+        idx, preds = [], []
+        for r in range(n_rows):
+            n_his = int((ev["his_id"][r] != 0).sum())
+            order = list(range(n_his))[::-1] + list(range(n_his, S))                                     # MIND.py:423-426
+            x = {"cdd_id": ev["cdd_id"][off[r]:off[r + 1]].unsqueeze(0), "his_encoded_index": ev["his_encoded_index"][r:r + 1][:, order],
+                 "his_attn_mask": ev["his_attn_mask"][r:r + 1][:, order], "his_mask": ev["his_mask"][r:r + 1], "user_id": ev["user_id"][r:r + 1]}
+            idx.append(int(ev["impr_index"][r]))
+            preds.append(O.predict_fast(params, table, x, encoder_n="cnn", encoder_u="lstm", head_num=hn)[0].tolist())
+    merged = M.group_by_impression(idx, preds)[0]
+    ranks = np.concatenate([M.ordinal_rank(np.asarray(p)) for p in merged])
+    offsets = np.concatenate([[0], np.cumsum([len(p) for p in merged])])
+    assert evl.write_predictions("ours.txt", torch.from_numpy(ranks.astype(np.int32)), torch.from_numpy(offsets)) == n_impr
+    assert open("ours.txt").read() == ref_text.replace(".0", "")
+    assert len(ref_text.splitlines()) == n_impr < n_rows
