@@ -169,8 +169,8 @@ def test_metric_parity_on_a_large_dev_set():
     (1.9 M candidates) over 3,000 news: the fp32 CUDA path against the CPU oracle on the same weights, and the bf16 CUDA path
     against both.  fp32: every metric within 5e-5 (half a unit of the 4th decimal) -- measured ~1e-7.  bf16 scores carry
     ~1e-3 relative noise, which swaps neighbours whose scores are closer than that; over 50 k impressions the swaps average
-    out: the bound asserted here (2e-4) is the measured one, and evaluate(..., precision) documents how
-    to get the 4-decimal guarantee (score with the fp32 kernels)."""
+    out: the bound asserted here is 2e-4 on every metric (it holds on the B200).  The 4-decimal guarantee
+    is the fp32 mode's (manager.precision = "fp32": same weights, fp32 kernels), asserted above."""
     from news_recommendation_mind_b200 import evaluate as ev
     n_news, n_impr, S = 3000, 50000, 20
     model, news_ids, news_mask, impr = _eval_setup("fp32", n_news, n_impr, S)
