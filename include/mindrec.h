@@ -3,7 +3,7 @@
  * news-recommendation hot path of tyh666/News-Recommendation-MIND.
  *
  * Every entry point below replaces one piece of PyTorch library work the reference does on the
- * path  models/TwoTower.py -> models/Encoders/* -> models/Modules/Attention.py  (driven by
+ * path  models/TwoTower.py -> models/Encoders/<encoder>.py -> models/Modules/Attention.py  (driven by
  * utils/Manager.py::_train / _eval_fast).  The reference interface each one stands in for is cited
  * as file:line (paths relative to the reference root).
  *

@@ -96,3 +96,18 @@ def test_workspace_planning_runs_without_a_gpu_and_is_bounded():
             assert 0 < fwd and 0 < bwd < 1024 * MB, (kind, precision, fwd, bwd)
     assert lib.mr_linear_workspace_bytes(1024, 150, 300) >= 0
     assert lib.mr_linear_tc_workspace_bytes(256 * 110 * 48, 300, 300, 30522, 1) > 0
+
+
+def test_header_is_plain_c_and_warning_free():
+    """include/mindrec.h is the binding surface of a C / cgo / JNI consumer: it must compile as C (not only as C++ inside nvcc)
+    with -Wall -Wextra -Werror, and every prototype must be usable from a C translation unit."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    hdr = os.path.join(ROOT, "include", "mindrec.h")
+    src = '#include "%s"\nint (*probe_a)(void) = mr_version;\nconst char* (*probe_b)(void) = mr_last_error;\nint main(void) { return MR_OK; }\n' % hdr
+    r = subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", "-"], input=src,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
