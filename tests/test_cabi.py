@@ -111,3 +111,35 @@ def test_header_is_plain_c_and_warning_free():
     r = subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", "-"], input=src,
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_a_c_program_links_and_calls_the_library(tmp_path):
+    """the boundary from a consumer that is not Python: a C99 program including mindrec.h, linked against libmindrec.so, reads the
+    version and -- on a machine without a B200 -- gets a negative status with a reason from a compute entry point instead of a crash
+    or a silent host fallback"""
+    import shutil
+    import subprocess
+    from news_recommendation_mind_b200 import build
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    lib = build.build()
+    src = tmp_path / "probe.c"
+    src.write_text('#include <stdio.h>\n#include "mindrec.h"\n'
+                   "int main(void) {\n"
+                   "  float out[4] = {0};\n"
+                   "  int rc = mr_embed_gather_f32(0, 1, 0, out, 1, 4, 8, 0);\n"
+                   '  printf("%d %d %d %s\\n", mr_version(), mr_device_check(0), rc, mr_last_error());\n'
+                   "  return 0;\n}\n")
+    exe = tmp_path / "probe"
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        lib, "-Wl,-rpath," + os.path.dirname(lib)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    version, dev_rc, rc, reason = out.stdout.strip().split(" ", 3)
+    assert int(version) >= 1
+    if not torch.cuda.is_available():
+        assert int(dev_rc) < 0 and int(rc) < 0 and reason
+    else:
+        assert int(rc) < 0 and reason                                  # null pointers are refused, nothing is launched
