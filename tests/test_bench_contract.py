@@ -38,3 +38,21 @@ def test_reference_arm_other_ranks_exit_without_work():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert r.returncode == 0 and not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def test_algorithmic_work_figures_are_the_surveys():
+    """the figures `roofline` / `step_roofline` are computed from are SURVEY.md 8(d)'s (padding and recompute not counted):
+    1.720 GFLOP per training impression at config 2, 1.684 with the MHA user encoder, 5.08 at config 5; 270,000 FLOP per token in
+    the conv forward; the peaks come from the driver-written MEASURED_PEAKS.json when present, else the profiling guide's fallback."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert abs(bench.flop_per_impression(bench.CONFIGS[2]) / 1e9 - 1.7204) < 1e-3
+    assert abs(bench.flop_per_impression(bench.CONFIGS[3]) / 1e9 - 1.684) < 2e-3
+    assert abs(bench.flop_per_impression(bench.CONFIGS[5]) / 1e9 - 5.08) < 1e-2
+    assert bench.FLOP_PER_TOKEN_CONV == 2 * 3 * 300 * 150
+    pk = bench.peaks()
+    assert set(pk) == {"hbm", "tf_burst", "tf_sustained", "source"} and pk["source"] in ("measured", "fallback")
+    if pk["source"] == "measured":
+        m = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        assert (pk["hbm"], pk["tf_burst"], pk["tf_sustained"]) == (m["hbm_gbs"], m["bf16_tflops"], m["bf16_tflops_sustained"])
+    assert 5000 < pk["hbm"] < 8000 and pk["tf_sustained"] <= pk["tf_burst"] < 2300
