@@ -246,7 +246,7 @@ def run_reference(args):
     if args.config == 4:
         val, cores, kind, sample = cpu_eval_baseline(cfg, batches=2 + max(args.steps, 4))
         line = {"impl": "reference", "metric": "eval_news_encoded_per_sec", "value": val, "unit": "news/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * 500 / val, "higher_is_better": True, "scaling": "weak",
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * 500 / val, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": eval_config(args, cfg),
                 "implementation": {"precision": "fp32", "what": "the reference's encode_news on the host cores (oracle/_ref)"},
                 "cpu_baseline": {"value": val, "unit": "news/s", "cores": cores, "kind": kind, "sample": sample},
