@@ -1,7 +1,7 @@
 """Diagnosis of an order-dependent failure of the bf16 LSTM user encoder at B=700 (8 sequences per CTA): calls mr_rnn_user_fwd
 directly with a POISONED workspace and saved-tensor buffers and reports where the hidden states differ from the oracle."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 from ctypes import byref
