@@ -143,3 +143,38 @@ def test_a_c_program_links_and_calls_the_library(tmp_path):
         assert int(dev_rc) < 0 and int(rc) < 0 and reason
     else:
         assert int(rc) < 0 and reason                                  # null pointers are refused, nothing is launched
+
+
+def test_only_the_checkers_import_the_oracle():
+    """oracle/ is test infrastructure: the product package never imports it (a product path through the oracle would void every
+    parity claim); outside tests/ only bench.py (its `cpu_baseline` / `--impl reference` legs) and __graft_entry__.py (smoke(), and
+    build() staging the checker) may."""
+    import ast
+    allowed = {"bench.py", "__graft_entry__.py"}
+    offenders = []
+    for base, dirs, files in os.walk(ROOT):
+        rel = os.path.relpath(base, ROOT)
+        dirs[:] = [d for d in dirs if not d.startswith(".") and d not in ("__pycache__", "gpurun_out", "build", "_ref", "baseline")]
+        if os.path.islink(base) or rel.split(os.sep)[0] in ("tests", "oracle"):
+            continue
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            path = os.path.join(base, f)
+            tree = ast.parse(open(path).read())
+            for node in ast.walk(tree):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom) and node.module:
+                    names = [node.module]
+                if any(n == "oracle" or n.startswith("oracle.") for n in names) and os.path.relpath(path, ROOT) not in allowed:
+                    offenders.append(os.path.relpath(path, ROOT))
+    assert not offenders, offenders
+    # bench.py: the oracle only inside the two CPU legs
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    tree = ast.parse(src)
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        uses = any(isinstance(n, ast.ImportFrom) and n.module == "oracle" for n in ast.walk(fn))
+        if uses:
+            assert fn.name in ("_reference_available", "cpu_train_baseline", "cpu_eval_baseline", "run_reference"), fn.name
