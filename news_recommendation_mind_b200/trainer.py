@@ -36,15 +36,25 @@ class FusedAdam:
         # begin_step() before every replay, so that the captured launch stays valid for every step
         self.dyn = None
         self._dyn_host = None
+        self._dyn_ring, self._dyn_done, self._dyn_slot = None, None, 0
         self._dyn_ids = None             # ids of the parameters the (captured) launch updates, in launch order
 
     DYN_BLOCK = 4 + 24                   # floats per launch: {1/bc1, 1/sqrt(bc2), grad_scale, -, lr[24]} (mr_adam_step_multi_dyn)
+    DYN_SLOTS = 8                        # pinned host copies of the block: how many steps the host may run ahead of the device
 
     def enable_device_step_scalars(self, device):
         n_params = sum(len(g["params"]) for g in self.param_groups)
         n_blocks = max(1, (n_params + 23) // 24)
         self.dyn = torch.zeros(n_blocks * self.DYN_BLOCK, dtype=torch.float32, device=device)
-        self._dyn_host = torch.zeros(n_blocks * self.DYN_BLOCK, dtype=torch.float32).pin_memory()
+        # The upload is asynchronous from pinned memory: the DMA reads the host block when the copy EXECUTES, not when it is
+        # queued.  A loop that replays steps without synchronising (the host is ~15x faster than a step) would overwrite a single
+        # host block long before the copies of the earlier steps run, and those steps would see later steps' bias corrections and
+        # learning rates.  Hence a ring of blocks, each guarded by an event recorded right behind its copy: a block is rewritten
+        # only after the copy that last read it has run (which also keeps the host at most DYN_SLOTS steps ahead).
+        self._dyn_ring = [torch.zeros(n_blocks * self.DYN_BLOCK, dtype=torch.float32).pin_memory() for _ in range(self.DYN_SLOTS)]
+        self._dyn_done = [None] * self.DYN_SLOTS
+        self._dyn_slot = 0
+        self._dyn_host = self._dyn_ring[0]
 
     def _dyn_items(self):
         """the (parameter, lr) list in group order"""
@@ -53,6 +63,12 @@ class FusedAdam:
     def _write_dyn(self):
         """upload the step-dependent scalars: bias corrections, grad_scale and the CURRENT learning rate of every tensor of the
         launch (a schedule or load_state_dict may have moved them since the capture); stream ordered, asynchronous"""
+        ring, k = self._dyn_ring, self._dyn_slot
+        if ring is not None:
+            self._dyn_slot = (k + 1) % len(ring)
+            if self._dyn_done[k] is not None:
+                self._dyn_done[k].synchronize()          # the copy that last read this block has run (normally long ago)
+            self._dyn_host = ring[k]
         h = self._dyn_host
         ids = self._dyn_ids
         lrs = [lr for p, lr in self._dyn_items() if (ids is None and p.requires_grad) or (ids is not None and id(p) in ids)]
@@ -65,6 +81,10 @@ class FusedAdam:
             if chunk:
                 h[o + 4:o + 4 + len(chunk)] = torch.tensor(chunk, dtype=torch.float32)
         self.dyn.copy_(h, non_blocking=True)
+        if ring is not None:
+            ev = self._dyn_done[k] if self._dyn_done[k] is not None else torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.dyn.device))
+            self._dyn_done[k] = ev
 
     def begin_step(self):
         """graph mode: advance the step counter and refresh the device block before the (captured) step runs"""

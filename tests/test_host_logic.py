@@ -260,3 +260,62 @@ def test_dedup_plan_reconstructs_the_slots():
     n = int(torch.unique(flat).numel())
     assert b["uniq_id"].numel() == 128 and torch.all(b["uniq_id"][n:] == 0) and torch.all(b["uniq_id"][1:n] > b["uniq_id"][:n - 1])
     assert data.dedup_plan(b["cdd_id"], b["his_id"], n - 1) is None and data.dedup_plan(b["cdd_id"], b["his_id"])[2] == n
+
+
+def test_step_scalar_upload_survives_a_host_that_runs_ahead(monkeypatch):
+    """FusedAdam's graph mode uploads the step scalars with an asynchronous copy from pinned memory: the DMA reads the host block
+    when the copy EXECUTES.  Model of that: a device queue that snapshots the source only when it drains (at an event
+    synchronisation or at the end).  20 steps queued without a single synchronisation must each see their OWN bias corrections and
+    learning rate -- true with the ring of event-guarded blocks, false with one block (the bug this guards against)."""
+    queue, seen = [], []
+
+    class Dev:                                                      # stands in for the CUDA tensor `dyn` and its stream
+        device = "fake"
+
+        def copy_(self, h, non_blocking=False):
+            queue.append(("copy", h))                               # a reference: nothing is read yet
+
+    def drain(upto=None):
+        while queue:
+            item = queue.pop(0)
+            if item[0] == "copy":
+                seen.append(item[1].clone())                        # the DMA runs now
+            elif item[1] is upto:
+                return
+
+    class Ev:
+        def record(self, stream):
+            queue.append(("event", self))
+
+        def synchronize(self):
+            if any(it[0] == "event" and it[1] is self for it in queue):
+                drain(self)
+
+    monkeypatch.setattr(torch.cuda, "Event", Ev)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: None)
+    m = torch.nn.Linear(3, 2)
+
+    def run(slots):
+        queue.clear()
+        seen.clear()
+        opt = trainer.FusedAdam(m, lr=1e-2, bert_lr=1e-3)
+        opt.dyn = Dev()
+        n = trainer.FusedAdam.DYN_BLOCK
+        if slots:
+            opt._dyn_ring, opt._dyn_done, opt._dyn_slot = [torch.zeros(n) for _ in range(slots)], [None] * slots, 0
+        else:
+            opt._dyn_host = torch.zeros(n)                          # the round-1/2 layout: one host block
+        sched = trainer.LinearWarmupSchedule(opt, 5, 40)
+        for _ in range(20):
+            opt.begin_step()
+            sched.step()
+        drain()
+        return [(float(h[0]), float(h[4])) for h in seen]
+
+    want = [(1.0 / (1.0 - 0.9 ** s), 1e-2 * min(s - 1, 5) / 5 if s - 1 < 5 else 1e-2 * (40 - (s - 1)) / 35) for s in range(1, 21)]
+    got = run(trainer.FusedAdam.DYN_SLOTS)
+    assert len(got) == 20
+    for (a, b), (c, d) in zip(got, want):
+        assert abs(a - c) <= 1e-6 * c and abs(b - d) <= 1e-9 + 1e-6 * d, (got, want)
+    stale = run(0)
+    assert len(set(stale)) == 1 and stale[0] != got[0]              # one block: every queued copy read the LAST step's values
